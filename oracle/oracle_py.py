@@ -1,0 +1,303 @@
+"""ctypes binding of the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py.  The product package
+(roskfpos_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+class KoInfo(C.Structure):
+    _fields_ = [("status", C.c_int), ("ml_iters", C.c_int), ("cost_evals", C.c_int),
+                ("gain_evals", C.c_int), ("ignored", C.c_int), ("cost", C.c_double)]
+
+
+class KoT6(C.Structure):
+    _fields_ = [("accel_noise", C.c_double), ("ignore_worst", C.c_int),
+                ("ignore_cost_threshold", C.c_double), ("pos", C.c_double * 3),
+                ("vel", C.c_double * 3), ("P", C.c_double * 36)]
+
+
+class KoK8(C.Structure):
+    _fields_ = [("accel_noise", C.c_double), ("jolt", C.c_double), ("tag_z", C.c_double),
+                ("use_fixed_height", C.c_int),
+                ("px4_height", C.c_double), ("px4_arm1", C.c_double), ("px4_arm2", C.c_double),
+                ("px4_cov_vel", C.c_double), ("px4_cov_gyro", C.c_double),
+                ("imu_fixed_cov_acc", C.c_int), ("imu_cov_acc", C.c_double),
+                ("imu_fixed_cov_gyro", C.c_int), ("imu_cov_gyro", C.c_double),
+                ("mag_offset", C.c_double), ("mag_cov", C.c_double),
+                ("pos", C.c_double * 2), ("vel", C.c_double * 2), ("acc", C.c_double * 2),
+                ("angle", C.c_double), ("omega", C.c_double), ("P", C.c_double * 64),
+                ("has_mag", C.c_int), ("has_px4", C.c_int), ("has_imu", C.c_int),
+                ("px4_itime", C.c_double), ("px4_vx", C.c_double), ("px4_vy", C.c_double),
+                ("px4_gz", C.c_double), ("px4_cv", C.c_double), ("px4_cg", C.c_double),
+                ("imu_wz", C.c_double), ("imu_cwz", C.c_double), ("imu_ax", C.c_double),
+                ("imu_ay", C.c_double), ("imu_cxy", C.c_double * 4),
+                ("mag_angle", C.c_double), ("mag_c", C.c_double)]
+
+
+class KoT9(C.Structure):
+    _fields_ = [("accel_noise", C.c_double), ("jolt", C.c_double), ("pos", C.c_double * 3),
+                ("vel", C.c_double * 3), ("acc", C.c_double * 3), ("P", C.c_double * 81),
+                ("has_imu", C.c_int), ("imu_a", C.c_double * 3), ("imu_cov", C.c_double * 9)]
+
+
+def build(force: bool = False) -> str:
+    so = os.path.join(_HERE, "liboracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        _LIB.ko_sse.restype = C.c_double
+        _LIB.ko_max_threads.restype = C.c_int
+    return _LIB
+
+
+def _p(a, ct=C.c_double):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(ct))
+
+
+def _vp(a):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+FMT = {np.dtype(np.float64): 0, np.dtype(np.int32): 1, np.dtype(np.uint16): 2}
+
+
+def max_threads() -> int:
+    return lib().ko_max_threads()
+
+
+# --------------------------------------------------------------------- dense
+def inv(A):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    n = A.shape[0]
+    out = np.empty_like(A)
+    rc = lib().ko_inv(n, _p(A), _p(out))
+    return rc, out
+
+
+def pinv(A):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    out = np.empty_like(A)
+    lib().ko_pinv(A.shape[0], _p(A), _p(out))
+    return out
+
+
+def solve(A, b, equilibrate=False):
+    A = np.ascontiguousarray(A, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    x = np.empty_like(b)
+    rc = lib().ko_solve(A.shape[0], _p(A), _p(b), _p(x), int(equilibrate))
+    return rc, x
+
+
+# ------------------------------------------------------------------------ ML
+def ml_epoch(ranges, anchors, errs, start, use2d=False, variant=0, n_ignore=0, best_mode=0,
+             b1_zero_z=False):
+    ranges = np.ascontiguousarray(ranges, dtype=np.float64)
+    anchors = np.ascontiguousarray(anchors, dtype=np.float64)
+    errs = np.ascontiguousarray(np.broadcast_to(errs, ranges.shape), dtype=np.float64)
+    start = np.ascontiguousarray(start, dtype=np.float64)
+    pos = np.zeros(3)
+    cov = np.zeros(9)
+    it = C.c_int(0)
+    sel = np.zeros(2, dtype=np.int32)
+    rc = lib().ko_ml_epoch(len(ranges), _p(ranges), _p(anchors), _p(errs), _p(start), int(use2d),
+                           int(variant), int(n_ignore), int(best_mode), int(b1_zero_z), _p(pos),
+                           _p(cov), C.byref(it), _p(sel, C.c_int32))
+    d = 2 if use2d else 3
+    return dict(rc=rc, pos=pos, cov=cov[:d * d].reshape(d, d).copy(), iters=it.value,
+                used_mask=int(sel[0]), index=int(sel[1]))
+
+
+def ml_batch(ranges, anchors, err, start, use2d=False, variant=0, n_ignore=0, best_mode=0,
+             threads=0):
+    """ranges [M][N] (f64 m / i32 mm / u16 mm); err scalar or [M][N]."""
+    ranges = np.ascontiguousarray(ranges)
+    M, N = ranges.shape
+    anchors = np.ascontiguousarray(anchors, dtype=np.float64)
+    err_arr = None if np.isscalar(err) else np.ascontiguousarray(err, dtype=np.float64)
+    start = np.ascontiguousarray(start, dtype=np.float64)
+    pos = np.zeros((3, N)); cov = np.zeros((9, N))
+    iters = np.zeros(N, dtype=np.int32); sel = np.zeros((2, N), dtype=np.int32)
+    status = np.zeros(N, dtype=np.int32)
+    lib().ko_ml_batch(C.c_int64(N), M, _p(anchors), _vp(ranges), FMT[ranges.dtype],
+                      C.c_double(err if err_arr is None else 0.0), _p(err_arr), _p(start),
+                      int(use2d), int(variant), int(n_ignore), int(best_mode), _p(pos), _p(cov),
+                      _p(iters, C.c_int32), _p(sel, C.c_int32), _p(status, C.c_int32), int(threads))
+    return dict(pos=pos, cov=cov, iters=iters, sel=sel, status=status)
+
+
+# ------------------------------------------------------------------- replays
+def t6_replay(x0, P0, ranges, anchors, dt, err, accel_noise=0.5, ignore_worst=False, thr=0.0,
+              want_traj=False, threads=0):
+    """x0 [3][N], P0 [36][N] or None (zeros); ranges [T][M][N]; dt scalar or [T]."""
+    ranges = np.ascontiguousarray(ranges)
+    T, M, N = ranges.shape
+    anchors = np.ascontiguousarray(anchors, dtype=np.float64)
+    dt = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, dtype=np.float64), (T,)))
+    err_arr = None if np.isscalar(err) else np.ascontiguousarray(err, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64, order="C", copy=True).reshape(3, N)
+    P = np.zeros((36, N)) if P0 is None else np.array(P0, dtype=np.float64, order="C", copy=True).reshape(36, N)
+    traj = np.zeros((T, 3, N)) if want_traj else None
+    sel = np.zeros((T, N), dtype=np.int32)
+    counters = np.zeros(4)
+    status = np.zeros(N, dtype=np.int32)
+    lib().ko_t6_replay(C.c_int64(N), T, M, _p(anchors), _p(dt), _vp(ranges), FMT[ranges.dtype],
+                       C.c_double(err if err_arr is None else 0.0), _p(err_arr),
+                       C.c_double(accel_noise), int(ignore_worst), C.c_double(thr), _p(x), _p(P),
+                       _p(traj), _p(sel, C.c_int32), _p(counters), _p(status, C.c_int32), int(threads))
+    return dict(x=x, P=P, traj=traj, sel=sel, counters=counters, status=status)
+
+
+def t9_replay(x0, P0, ranges, anchors, dt, err, accel_noise=0.5, jolt=0.5, want_traj=False,
+              threads=0):
+    ranges = np.ascontiguousarray(ranges)
+    T, M, N = ranges.shape
+    anchors = np.ascontiguousarray(anchors, dtype=np.float64)
+    dt = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, dtype=np.float64), (T,)))
+    err_arr = None if np.isscalar(err) else np.ascontiguousarray(err, dtype=np.float64)
+    x = np.array(x0, dtype=np.float64, order="C", copy=True).reshape(9, N)
+    P = np.zeros((81, N)) if P0 is None else np.array(P0, dtype=np.float64, order="C", copy=True).reshape(81, N)
+    traj = np.zeros((T, 3, N)) if want_traj else None
+    counters = np.zeros(4)
+    status = np.zeros(N, dtype=np.int32)
+    lib().ko_t9_replay(C.c_int64(N), T, M, _p(anchors), _p(dt), _vp(ranges), FMT[ranges.dtype],
+                       C.c_double(err if err_arr is None else 0.0), _p(err_arr),
+                       C.c_double(accel_noise), C.c_double(jolt), _p(x), _p(P), _p(traj),
+                       _p(counters), _p(status, C.c_int32), int(threads))
+    return dict(x=x, P=P, traj=traj, counters=counters, status=status)
+
+
+# ------------------------------------------------------- single-filter objects
+class T6:
+    def __init__(self, accel_noise, ignore_worst, thr, p0):
+        self.f = KoT6()
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        lib().ko_t6_init(C.byref(self.f), C.c_double(accel_noise), int(ignore_worst),
+                         C.c_double(thr), _p(p0))
+        self.info = KoInfo()
+
+    def new_toa(self, dt, ranges, anchors, errs):
+        ranges = np.ascontiguousarray(ranges, dtype=np.float64)
+        anchors = np.ascontiguousarray(anchors, dtype=np.float64)
+        errs = np.ascontiguousarray(np.broadcast_to(errs, ranges.shape), dtype=np.float64)
+        lib().ko_t6_new_toa(C.byref(self.f), C.c_double(dt), len(ranges), _p(ranges), _p(anchors),
+                            _p(errs), C.byref(self.info))
+        return self.info
+
+    @property
+    def pos(self):
+        return np.array(self.f.pos)
+
+    @property
+    def P(self):
+        return np.array(self.f.P).reshape(6, 6)
+
+    def get_pose(self, dt):
+        pos = np.zeros(3); P = np.zeros(36)
+        lib().ko_t6_get_pose(C.byref(self.f), C.c_double(dt), _p(pos), _p(P))
+        return pos, P.reshape(6, 6)
+
+
+class K8:
+    def __init__(self, accel_noise, init_angle, jolt, p0, **cfg):
+        self.f = KoK8()
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        lib().ko_k8_init(C.byref(self.f), C.c_double(accel_noise), C.c_double(init_angle),
+                         C.c_double(jolt), _p(p0))
+        for k, v in cfg.items():
+            setattr(self.f, k, v)
+        self.info = KoInfo()
+
+    def new_toa(self, dt, ranges, anchors, errs, b1_zero_z=False):
+        ranges = np.ascontiguousarray(ranges, dtype=np.float64)
+        anchors = np.ascontiguousarray(anchors, dtype=np.float64)
+        errs = np.ascontiguousarray(np.broadcast_to(errs, ranges.shape), dtype=np.float64)
+        lib().ko_k8_new_toa(C.byref(self.f), C.c_double(dt), len(ranges), _p(ranges), _p(anchors),
+                            _p(errs), int(b1_zero_z), C.byref(self.info))
+        return self.info
+
+    def new_px4(self, dt, ix, iy, irz, itime_us, quality):
+        lib().ko_k8_new_px4(C.byref(self.f), C.c_double(dt), C.c_double(ix), C.c_double(iy),
+                            C.c_double(irz), C.c_double(itime_us), int(quality), C.byref(self.info))
+        return self.info
+
+    def new_imu(self, dt, angvel, cov_av, acc, cov_acc):
+        a = [np.ascontiguousarray(v, dtype=np.float64) for v in (angvel, cov_av, acc, cov_acc)]
+        lib().ko_k8_new_imu(C.byref(self.f), C.c_double(dt), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]),
+                            C.byref(self.info))
+        return self.info
+
+    def new_mag(self, dt, mag):
+        mag = np.ascontiguousarray(mag, dtype=np.float64)
+        lib().ko_k8_new_mag(C.byref(self.f), C.c_double(dt), _p(mag), C.byref(self.info))
+        return self.info
+
+    def new_compass(self, dt, compass):
+        lib().ko_k8_new_compass(C.byref(self.f), C.c_double(dt), C.c_double(compass),
+                                C.byref(self.info))
+        return self.info
+
+    @property
+    def x(self):
+        f = self.f
+        return np.array([f.pos[0], f.pos[1], f.vel[0], f.vel[1], f.acc[0], f.acc[1], f.angle, f.omega])
+
+    @property
+    def P(self):
+        return np.array(self.f.P).reshape(8, 8)
+
+    def get_pose(self, dt):
+        x = np.zeros(8); P = np.zeros(64)
+        lib().ko_k8_get_pose(C.byref(self.f), C.c_double(dt), _p(x), _p(P))
+        return x, P.reshape(8, 8)
+
+
+class T9:
+    def __init__(self, accel_noise, jolt, p0):
+        self.f = KoT9()
+        p0 = np.ascontiguousarray(p0, dtype=np.float64)
+        lib().ko_t9_init(C.byref(self.f), C.c_double(accel_noise), C.c_double(jolt), _p(p0))
+        self.info = KoInfo()
+
+    def new_toa(self, dt, ranges, anchors, errs):
+        ranges = np.ascontiguousarray(ranges, dtype=np.float64)
+        anchors = np.ascontiguousarray(anchors, dtype=np.float64)
+        errs = np.ascontiguousarray(np.broadcast_to(errs, ranges.shape), dtype=np.float64)
+        lib().ko_t9_new_toa(C.byref(self.f), C.c_double(dt), len(ranges), _p(ranges), _p(anchors),
+                            _p(errs), C.byref(self.info))
+        return self.info
+
+    def new_imu(self, dt, acc, cov_acc):
+        acc = np.ascontiguousarray(acc, dtype=np.float64)
+        cov_acc = np.ascontiguousarray(cov_acc, dtype=np.float64)
+        lib().ko_t9_new_imu(C.byref(self.f), C.c_double(dt), _p(acc), _p(cov_acc), C.byref(self.info))
+        return self.info
+
+    @property
+    def x(self):
+        f = self.f
+        return np.array(list(f.pos) + list(f.vel) + list(f.acc))
+
+    @property
+    def P(self):
+        return np.array(self.f.P).reshape(9, 9)
