@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- EKF filter-updates/s @ 8 anchors (BASELINE.json metric).
+
+One bench "step" = one pass of the hot path over one batch: reset N filters to
+their initial positions, replay T ranging epochs through the persistent IEKF
+kernel (KalmanFilterTOA, 8 anchors, int32-mm SoA range log resident in HBM),
+reduce the error statistics.  value = N_total * T * K / elapsed.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  torchrun --nproc-per-node N bench.py --gpus N ...      (one rank per GPU)
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ekf_filter_updates_per_sec_8anchors"
+UNIT = "updates/s"
+
+
+def w_alg_t6(m, i_ml, i_c, i_g):
+    """Algorithmic FLOP per T6 update, SURVEY.md §8(d) formula W_alg (v1); the
+    iteration counts are the MEASURED per-update means from the device counters."""
+    w_pred = 4 * 3 * 6 + 12 + 15 + 2 * 3
+    w_mlit = 59 * m + 60
+    w_cost = 13 * m + (2 * 3 * m + 3 * m) + 3
+    w_gain = (1 + 3) * m + m * (36 + 2 * 6 * 3 + 4 * 6 + 4 * 3 + 3) + 6
+    return w_pred + i_ml * w_mlit + 12 * m + 2 * m + i_c * w_cost + i_g * w_gain
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); smax.append(float(r[2])); pw.append(float(r[3]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(pw) if pw else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# --------------------------------------------------------------------------- CPU
+def cpu_reference(n_anchors, tsteps, seconds, threads=0):
+    """Times the CPU oracle (the as-written restatement of the reference's filter,
+    oracle/) on a bounded sample of the bench workload.  Returns a cpu_baseline dict."""
+    from oracle import oracle_py as O
+    from roskfpos_b200 import synth
+    anc = synth.anchors_for(n_anchors)
+    threads = threads or O.max_threads()
+    kind = "port"
+
+    def run(nf):
+        truth = synth.truth_lissajous(nf, tsteps, 0.1, seed=synth.SEED + 7)
+        r = synth.ranges_mm(truth[1:], anc, seed=synth.SEED + 8)
+        t0 = time.perf_counter()
+        out = O.t6_replay(truth[0], None, r, anc, 0.1, 0.01, threads=threads)
+        return time.perf_counter() - t0, out
+
+    probe_n = 64 * threads
+    tp, _ = run(probe_n)
+    rate = probe_n * tsteps / max(tp, 1e-6)
+    nf = int(max(probe_n, min(rate * seconds / tsteps, 4_000_000)))
+    tt, out = run(nf)
+    upd = nf * tsteps
+    return {"value": upd / tt, "unit": UNIT, "cores": threads, "kind": kind,
+            "sample": f"{nf} filters x {tsteps} steps, {n_anchors} anchors, T6 (KalmanFilterTOA) oracle "
+                      f"restatement, gcc -O3 + OpenMP, {tt:.1f} s",
+            "mean_iters": {"ml": out["counters"][0] / upd, "cost": out["counters"][1] / upd,
+                           "gain": out["counters"][2] / upd}}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = args.steps, args.warmup
+    per = max(2.0, min(20.0, 100.0 / max(K + W, 1)))
+    vals = []
+    last = None
+    for i in range(W + K):
+        last = cpu_reference(args.anchors, args.tsteps, per)
+        if i >= W:
+            vals.append(last["value"])
+    v = float(np.mean(vals))
+    last["value"] = v
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": K, "warmup": W, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"T6 IEKF replay, {args.anchors} anchors, CPU sample (see cpu_baseline.sample)"},
+            "cpu_baseline": last,
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- GPU
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from roskfpos_b200 import lib as L, synth
+    from roskfpos_b200.batch import Batch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path "
+                         "(use --impl reference for the CPU baseline)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    N, T, M, K, W = args.filters, args.tsteps, args.anchors, args.steps, args.warmup
+
+    anc = synth.anchors_for(M)
+    ranges, x0, truth_end = synth.device_ranges_mm(N, T, anc, 0.1, dev, seed=synth.SEED + 1000 * rank)
+    x0_full = torch.zeros((6, N), device=dev, dtype=torch.float64)
+    x0_full[:3] = x0
+    batch = Batch(L.MODEL_T6, N, device=local, anchors=anc, accel_noise=0.5)
+    stream = torch.cuda.current_stream()
+    stats = torch.zeros(4, device=dev, dtype=torch.float64)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        batch.set_state(x0_full, None, stream=stream)
+        batch.replay_toa(0.1, ranges, err=0.01, stream=stream)
+        s = batch.error_stats(truth_end, stream=stream)
+        if world > 1:  # the only collective: the final statistics reduction
+            stats.copy_(torch.as_tensor(s))
+            dist.all_reduce(stats)
+            s = stats.cpu().numpy()
+        return s
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(W):
+        step_resident()
+    batch.counters(reset=True)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    e0.record(stream)
+    for k in range(K):
+        batch.set_state(x0_full, None, stream=stream)
+        kev[k][0].record(stream)
+        batch.replay_toa(0.1, ranges, err=0.01, stream=stream)
+        kev[k][1].record(stream)
+        s = batch.error_stats(truth_end, stream=stream)
+        if world > 1:
+            stats.copy_(torch.as_tensor(s))
+            dist.all_reduce(stats)
+            s = stats.cpu().numpy()
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    cnt = batch.counters(reset=True)
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * N * T * K / (ms_max * 1e-3)
+    rmse = float(np.sqrt(s[0] / max(s[2], 1)))
+
+    # ---- end to end through the C ABI with HOST (pinned) buffers
+    e2e = None
+    if not args.no_e2e:
+        h_ranges = torch.empty(ranges.shape, dtype=ranges.dtype, pin_memory=True)
+        h_ranges.copy_(ranges)
+        h_x0 = torch.empty(x0_full.shape, dtype=torch.float64, pin_memory=True)
+        h_x0.copy_(x0_full)
+        h_truth = torch.empty(truth_end.shape, dtype=torch.float64, pin_memory=True)
+        h_truth.copy_(truth_end)
+        h_pos = torch.empty((6, N), dtype=torch.float64, pin_memory=True)
+        hr, hx, ht, hp = h_ranges.numpy(), h_x0.numpy(), h_truth.numpy(), h_pos.numpy()
+        import ctypes as C
+
+        def step_e2e():
+            batch.set_state(hx, None, stream=stream)                      # H2D x0
+            batch.replay_toa(0.1, hr, err=0.01, stream=stream)            # H2D range log, chunked+overlapped
+            s_ = batch.error_stats(ht, stream=stream)                     # H2D truth, D2H 4 doubles
+            L.check(L.lib().kfpos_batch_get_state(batch._h, C.c_void_p(hp.ctypes.data), None, None,
+                                                  C.c_void_p(stream.cuda_stream)), "get_state")  # D2H x
+            return s_
+        for _ in range(max(1, min(W, 2))):
+            step_e2e()
+        barrier()
+        Ke = max(1, min(K, 3))
+        t0 = time.perf_counter()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record(stream)
+        for _ in range(Ke):
+            s2 = step_e2e()
+        f1.record(stream)
+        barrier()
+        wall = (time.perf_counter() - t0) * 1e3
+        ems = max(f0.elapsed_time(f1), 0.0)
+        te = torch.tensor([max(ems, wall if world == 1 else ems)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * N * T * Ke / (float(te.item()) * 1e-3), "unit": UNIT,
+               "h2d_bytes_per_step": int(h_ranges.numel() * h_ranges.element_size() + 8 * 6 * N + 8 * 3 * N),
+               "d2h_bytes_per_step": int(8 * 6 * N + 32), "steps": Ke,
+               "ms_per_step": float(te.item()) / Ke}
+        del h_ranges, hr
+
+    # ---- roofline of the dominant kernel (t6_replay_kernel): FP64 CUDA-core bound
+    upd = max(cnt["updates"], 1.0)
+    i_ml, i_c, i_g = cnt["ml_iters"] / upd, cnt["cost_evals"] / upd, cnt["gain_evals"] / upd
+    w_alg = w_alg_t6(M, i_ml, i_c, i_g)
+    peak = C_double_peak(local)
+    ach = w_alg * N * T / (kernel_ms * 1e-3)
+    peaks, peak_src = load_peaks()
+    alg_bytes = N * T * M * ranges.element_size() + N * (3 + 21) * 8 * 2
+    roof = {"bound": "fp64", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
+            "frac": ach / peak if peak else None, "traffic": None,
+            "peak_source": "measured live: kfpos_measure_fp64_peak (DFMA-only kernel, best of 5)",
+            "kernel": "t6_replay_kernel<8,false,false>", "kernel_ms": kernel_ms,
+            "flop_per_update": w_alg, "mean_iters": {"ml": i_ml, "cost": i_c, "gain": i_g},
+            "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                    "peak_source": peak_src, "bytes_per_update": alg_bytes / (N * T)}}
+
+    if rank == 0:
+        cpu = None if args.no_cpu else cpu_reference(M, min(T, 100), args.cpu_seconds)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+                "ms_per_step": ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"T6 (KalmanFilterTOA) IEKF replay: {N} filters/GPU x {T} epochs, "
+                                       f"{M} anchors, int32-mm ranges, dt 0.1 s, P0=0, fixed initial position",
+                           "filters_per_gpu": N, "epochs_per_step": T, "anchors": M,
+                           "l2_policy": f"inputs larger than L2 ({ranges.numel() * ranges.element_size() / 1e6:.0f} MB range log per step)",
+                           "parallelism": f"filters sharded by index over {world} GPU(s); one all-reduce of 4 doubles per step"},
+                "rmse_m": rmse, "bad_updates": cnt["bad"],
+                "e2e": e2e, "gpu_launches": 3 * K, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line))
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def C_double_peak(device):
+    import ctypes as C
+    from roskfpos_b200 import lib as L
+    v = C.c_double(0.0)
+    L.check(L.lib().kfpos_measure_fp64_peak(int(device), C.byref(v)), "kfpos_measure_fp64_peak")
+    return v.value
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--filters", type=int, default=1 << 20, help="filters per GPU")
+    ap.add_argument("--tsteps", type=int, default=100, help="ranging epochs per bench step")
+    ap.add_argument("--anchors", type=int, default=8)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

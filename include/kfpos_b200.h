@@ -1,0 +1,236 @@
+/*
+ * kfpos_b200.h -- C ABI of libkfpos_b200.so: batched, B200-native (sm_100a)
+ * replacement for the numeric filter core of GTEC-UDC/roskfpos.
+ *
+ * One opaque handle = a BATCH of N independent filters of one model and one
+ * configuration on one GPU.  Each entry point cites the reference interface it
+ * replaces (paths relative to /root/reference/src/kfpos/):
+ *
+ *   PositionEstimationAlgorithm      algorithms/PositionEstimationAlgorithm.h:8-37
+ *   MLLocation                       algorithms/MLLocation.h:25-76
+ *   KalmanFilterTOA (T6)             algorithms/KalmanFilterTOA.h:18-55
+ *   KalmanFilter (K8)                algorithms/KalmanFilter.h:28-134
+ *   KalmanFilterTOAIMU (T9)          algorithms/KalmanFilterTOAIMU.h:15-79
+ *   sole caller                      publishers/Posgenerator.cpp:99-141,476-496,510-548
+ *
+ * Conventions
+ *  - every function returns 0 (KFPOS_OK) or a negative kfpos_status code and
+ *    never throws; per-filter numerical events (singular solve, NaN, too few
+ *    rangings) are reported in the per-filter `status` words, not the return code;
+ *  - "SoA [k][N]" = k rows of N contiguous values, filter index fastest;
+ *  - data pointers may be HOST or DEVICE pointers (the library asks the CUDA
+ *    runtime which); device pointers must belong to the batch's device;
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default
+ *    stream); work is enqueued on it, calls taking host pointers synchronise it
+ *    before returning;
+ *  - calls on one handle must be serialised by the caller (the reference is
+ *    single-threaded: publishers/node_pos.cpp:176-181); handles are independent;
+ *  - there is NO CPU fallback: without a usable CUDA device every call fails
+ *    with KFPOS_ERR_CUDA.
+ */
+#ifndef KFPOS_B200_H
+#define KFPOS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KFPOS_ABI_VERSION 1
+#define KFPOS_MAX_ANCHORS 32 /* anchor slots per epoch (reference MAX_NUM_ANCS = 64; PG.h:102) */
+
+typedef struct kfpos_batch kfpos_batch;
+
+/* return codes */
+enum kfpos_status_code {
+    KFPOS_OK = 0,
+    KFPOS_ERR_INVALID = -1,     /* bad argument / wrong model for this call   */
+    KFPOS_ERR_CUDA = -2,        /* CUDA runtime error or no device            */
+    KFPOS_ERR_NOMEM = -3,       /* allocation failed                          */
+    KFPOS_ERR_NOT_READY = -4,   /* anchors / state not set yet                */
+    KFPOS_ERR_UNSUPPORTED = -5, /* configuration outside the kernels' domain  */
+    KFPOS_ERR_PARSE = -6        /* malformed XML configuration string         */
+};
+
+/* models = the factory ids of PosGenerator::setAlgorithm (PG.cpp:510-538) */
+enum kfpos_model {
+    KFPOS_MODEL_ML = 0, /* MLLocation                                  */
+    KFPOS_MODEL_T6 = 1, /* KalmanFilterTOA: 6-state, rangings only     */
+    KFPOS_MODEL_K8 = 2, /* KalmanFilter: 8-state, UWB+PX4Flow+IMU+mag  */
+    KFPOS_MODEL_T9 = 3  /* KalmanFilterTOAIMU: 9-state, rangings+accel */
+};
+
+/* range tensor element formats; a value <= 0 means "no ranging" (TOA.cpp:50) */
+enum kfpos_range_fmt {
+    KFPOS_FMT_F64_M = 0,  /* double, metres (what newTOAMeasurement receives)              */
+    KFPOS_FMT_I32_MM = 1, /* int32 millimetres, the PosGenerator table format (PG.cpp:213) */
+    KFPOS_FMT_U16_MM = 2  /* uint16 millimetres (ranges < 65.5 m)                          */
+};
+
+/* per-filter status bits (OR-ed over the steps since the last set_state) */
+#define KFPOS_ST_OK 0
+#define KFPOS_ST_NO_MEAS 1   /* a TOA update had no valid ranging                           */
+#define KFPOS_ST_ML_FEW 2    /* inner ML had < 3/4 rangings and returned its start point     */
+#define KFPOS_ST_SINGULAR 4  /* a solve hit a singular matrix: update skipped (TOA.cpp:151)  */
+#define KFPOS_ST_NAN 8       /* non-finite state after an update                             */
+#define KFPOS_ST_ML_NAN 16   /* T6 NaN guard fired (TOA.cpp:270-272)                         */
+#define KFPOS_ST_MAXITER 32  /* IEKF used all iterations without meeting the break test      */
+#define KFPOS_ST_ASYM_R 64   /* K8 IMU covariance block not symmetric (cov[1] != cov[3])     */
+
+/* ML variants (MLLocation.h:5-7) and best-group criteria (MLLocation.h:10-11) */
+#define KFPOS_ML_VARIANT_NORMAL 0
+#define KFPOS_ML_VARIANT_IGNORE_N 1
+#define KFPOS_ML_VARIANT_BEST 2
+#define KFPOS_BEST_MODE_XYZ 0
+#define KFPOS_BEST_MODE_Z 1
+
+/*
+ * Flat configuration: the constructor arguments of the four classes plus the
+ * attributes of the five XML files KalmanFilter::loadConfigurationFiles reads
+ * (KF.cpp:749-893).  Field comments give the reference name.
+ */
+typedef struct kfpos_config {
+    /* constructor / launch parameters (node_pos.cpp:48-113) */
+    double accel_noise;           /* accelerationNoise (all KFs)                    */
+    double jolt;                  /* jolt (K8, T9)                                  */
+    double initial_angle;         /* initialAngle (K8)                              */
+    int32_t ignore_worst_anchor;  /* ignoreWorstAnchorMode (T6)                     */
+    int32_t _pad0;
+    double ignore_cost_threshold; /* ignoreCostThreshold (T6)                       */
+    /* MLLocation ctor (ML.h:30) + config_pos.xml <algorithm .../> */
+    int32_t use2d;                /* use2d                                          */
+    int32_t variant;              /* variant                                        */
+    int32_t num_ignored_rangings; /* numIgnoredRangings                             */
+    int32_t best_mode;            /* bestMode                                       */
+    double min_z, max_z;          /* minZ, maxZ (output gate; documentation only)   */
+    double ml_start[3];           /* previousEstimation: (1,1,4) by default         */
+    /* config_uwb.xml <uwb .../>  (KF.cpp:793-800) */
+    int32_t use_fixed_height;     /* useFixedHeight                                 */
+    int32_t tag_id;               /* tagId (loaded, never read)                     */
+    double fixed_height;          /* fixedHeight -> mUWBtagZ                        */
+    /* config_px4flow.xml <px4flow .../>  (KF.cpp:766-779) */
+    int32_t px4_use_fixed_sensor_height; /* useFixedSensorHeight (never read)       */
+    int32_t _pad1;
+    double px4_sensor_height;     /* sensorHeight -> mPX4flowHeight                 */
+    double px4_arm_p0;            /* armP0 -> mPX4FlowArmP1                         */
+    double px4_arm_p1;            /* armP1 -> mPX4FlowArmP2                         */
+    double px4_sensor_init_angle; /* sensorInitAngle (never read)                   */
+    double px4_cov_velocity;      /* covarianceVelocity                             */
+    double px4_cov_gyro_z;        /* covarianceGyroZ                                */
+    /* config_imu.xml <imu .../>  (KF.cpp:815-824) */
+    int32_t imu_use_fixed_cov_acc;    /* useFixedCovarianceAcceleration             */
+    int32_t imu_use_fixed_cov_gyro_z; /* useFixedCovarianceAngularVelocityZ         */
+    double imu_cov_acc;               /* covarianceAcceleration                     */
+    double imu_cov_gyro_z;            /* covarianceAngularVelocityZ                 */
+    /* config_mag.xml <mag .../>  (KF.cpp:839-844) */
+    double mag_angle_offset;      /* angleOffset                                    */
+    double mag_cov;               /* covarianceMag                                  */
+} kfpos_config;
+
+/* Fills the defaults the reference uses when an attribute/param is absent (all 0;
+ * ml_start = (1,1,4), PG.cpp:531). */
+void kfpos_config_default(kfpos_config *cfg);
+
+/* Parses ONE of the reference's XML configuration strings (the content of
+ * config_uwb / config_px4flow / config_imu / config_mag / config_pos .xml) and
+ * overwrites the matching fields; unknown elements are ignored, missing
+ * attributes get the reference default 0.  Replaces KF.cpp:749-893.           */
+int kfpos_config_load_xml(kfpos_config *cfg, const char *xml);
+
+const char *kfpos_strerror(int code);
+int kfpos_abi_version(void);
+
+/* ------------------------------------------------------------------ lifetime
+ * Replaces the constructors + init() (TOA.cpp:5-40, KF.cpp:6-62,
+ * TOAIMU.cpp:6-46, ML.cpp:3-22).  State is zero, covariance zero, no latched
+ * sensor samples -- the fixed-initial-position constructors. */
+int kfpos_batch_create(kfpos_batch **out, int device, int model, int64_t n_filters,
+                       const kfpos_config *cfg);
+void kfpos_batch_destroy(kfpos_batch *b);
+int64_t kfpos_batch_size(const kfpos_batch *b);
+int kfpos_batch_state_dim(const kfpos_batch *b); /* 3 (ML), 6, 8, 9 */
+
+/* Anchor table shared by the batch: the `beacons` argument of newTOAMeasurement
+ * (PEA.h:16; built by PG.cpp:476-496 from the anchor index order).  xyz [n][3]. */
+int kfpos_batch_set_anchors(kfpos_batch *b, int n_anchors, const double *xyz);
+
+/* State and covariance (checkpoint/restore).  x: SoA [n][N]; P: SoA [n*n][N]
+ * row-major full matrix, or NULL for the reference's initial P0 = 0.
+ * State layouts: T6 [px,py,pz,vx,vy,vz]  (v is always 0: TOA.cpp:110-112)
+ *                K8 [px,py,vx,vy,ax,ay,theta,omega]  (a always 0: KF.cpp:287-291)
+ *                T9 [px,py,pz,vx,vy,vz,ax,ay,az]     (a always 0: TOAIMU.cpp:165-168)
+ * Also clears the per-filter status, selection and latched-sensor flags.      */
+int kfpos_batch_set_state(kfpos_batch *b, const double *x, const double *P, void *stream);
+int kfpos_batch_get_state(kfpos_batch *b, double *x, double *P, int32_t *status, void *stream);
+
+/* ---------------------------------------------------------------- EKF steps
+ * One newTOAMeasurement per filter (PEA.h:16; TOA.cpp:43-61, KF.cpp:64-97,
+ * TOAIMU.cpp:49-73): predict with `dt` (the reference measures it with
+ * steady_clock), inner ML solve, iterated update.
+ * ranges: SoA [n_anchors][N] in `fmt`; err_var: per-ranging errorEstimation SoA
+ * [n_anchors][N] or NULL to use the scalar `err_scalar` for every ranging.     */
+int kfpos_batch_step_toa(kfpos_batch *b, double dt, const void *ranges, int fmt,
+                         double err_scalar, const double *err_var, void *stream);
+
+/* T steps in ONE persistent kernel with state and covariance held on chip.
+ * dt: HOST array [T]; ranges: SoA [T][n_anchors][N]; err_var NULL or same shape.
+ * Optional outputs (NULL to skip): traj SoA [T][3][N] position after each step;
+ * sel SoA [T][N] int32 anchor slot ignored by T6's leave-one-out, -1 if none.   */
+int kfpos_batch_replay_toa(kfpos_batch *b, int n_steps, const double *dt, const void *ranges,
+                           int fmt, double err_scalar, const double *err_var, double *traj,
+                           int32_t *sel, void *stream);
+
+/* newPX4FlowMeasurement (PEA.h:15; KF.cpp:100-133).  K8 only.  SoA [N] each.   */
+int kfpos_batch_step_px4(kfpos_batch *b, double dt, const double *integration_x,
+                         const double *integration_y, const double *integration_rot_z,
+                         const double *integration_time_us, const int32_t *quality, void *stream);
+/* newIMUMeasurement (PEA.h:17; KF.cpp:137-176, TOAIMU.cpp:76-92).  K8 and T9.
+ * ang_vel, lin_acc: SoA [3][N]; cov_ang_vel, cov_acc: SoA [9][N] or NULL (= 0).  */
+int kfpos_batch_step_imu(kfpos_batch *b, double dt, const double *ang_vel,
+                         const double *cov_ang_vel, const double *lin_acc, const double *cov_acc,
+                         void *stream);
+/* newMAGMeasurement (PEA.h:18; KF.cpp:179-193).  K8 only.  mag: SoA [3][N].     */
+int kfpos_batch_step_mag(kfpos_batch *b, double dt, const double *mag, void *stream);
+/* newCompassMeasurement (PEA.h:19; KF.cpp:195-221).  K8 only.  compass: [N] rad. */
+int kfpos_batch_step_compass(kfpos_batch *b, double dt, const double *compass, void *stream);
+
+/* getPose (PEA.h:14; TOA.cpp:438-473, KF.cpp:709-747, TOAIMU.cpp:476-510):
+ * predict-only to `dt` after the last update, state untouched.  x_pred SoA
+ * [n][N], P_pred SoA [n*n][N] (either may be NULL).                              */
+int kfpos_batch_get_pose(kfpos_batch *b, double dt, double *x_pred, double *P_pred, void *stream);
+
+/* ----------------------------------------------------------------------- ML
+ * newTOAMeasurement + getPose of MLLocation (ML.cpp:421-486) for N independent
+ * epochs; variant / use2d / num_ignored_rangings / best_mode / ml_start from the
+ * batch config.  ranges SoA [n_anchors][N].  Outputs (NULL to skip):
+ * pos SoA [3][N]; cov SoA [9][N] (3x3 row-major, the 2x2 block top-left when
+ * use2d); iters [N] total Newton iterations; sel SoA [2][N]: row 0 = bit mask of
+ * the anchor slots used by the final solve, row 1 = #dropped (variant 1) or the
+ * subset index in prev_permutation order (variant 2); status [N].               */
+int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt, double err_scalar,
+                         const double *err_var, double *pos, double *cov, int32_t *iters,
+                         int32_t *sel, int32_t *status, void *stream);
+
+/* ------------------------------------------------------------- diagnostics
+ * Work counters accumulated on the device since the last reset, as doubles:
+ * [0] updates, [1] inner-ML Newton iterations, [2] IEKF cost evaluations,
+ * [3] IEKF gain computations, [4] updates with status != OK, [5] anchors
+ * ignored by leave-one-out, [6..7] reserved.                                    */
+int kfpos_batch_get_counters(kfpos_batch *b, double out[8], int reset, void *stream);
+
+/* Error statistics against a truth position SoA [3][N] (host or device):
+ * out[0] = sum |p - truth|^2, out[1] = same over x,y only, out[2] = filters
+ * counted (finite), out[3] = filters with status != OK.  The sum is a
+ * fixed-shape tree over fixed 1024-filter chunks, so it does not depend on the
+ * launch geometry; multi-GPU callers add the per-rank vectors (one all-reduce). */
+int kfpos_batch_error_stats(kfpos_batch *b, const double *truth, double out[4], void *stream);
+
+/* Roofline denominator for this FP64 CUDA-core path (no reference equivalent):
+ * times a DFMA-only kernel on `device` and returns the sustained FLOP/s.        */
+int kfpos_measure_fp64_peak(int device, double *flops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KFPOS_B200_H */

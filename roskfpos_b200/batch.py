@@ -1,0 +1,215 @@
+"""Python host side of the C ABI: a `Batch` of N independent filters on one GPU.
+
+Arrays may be numpy arrays (host: the library stages them) or CUDA torch tensors
+(device: passed through untouched).  torch is only used for device memory and
+streams; all arithmetic happens inside libkfpos_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+
+from . import lib as L
+
+_FMT_NP = {np.dtype(np.float64): L.FMT_F64_M, np.dtype(np.int32): L.FMT_I32_MM,
+           np.dtype(np.uint16): L.FMT_U16_MM}
+
+
+def _is_torch(a) -> bool:
+    return type(a).__module__.startswith("torch")
+
+
+def _ptr(a, dtype=None):
+    """(void* address, keep-alive object) of a numpy array / torch tensor / None."""
+    if a is None:
+        return None, None
+    if _is_torch(a):
+        if not a.is_contiguous():
+            raise ValueError("tensor arguments must be contiguous")
+        return C.c_void_p(a.data_ptr()), a
+    arr = np.ascontiguousarray(a, dtype=dtype)
+    return C.c_void_p(arr.ctypes.data), arr
+
+
+def _fmt_of(a) -> int:
+    if _is_torch(a):
+        import torch
+        return {torch.float64: L.FMT_F64_M, torch.int32: L.FMT_I32_MM, torch.uint16: L.FMT_U16_MM,
+                torch.int16: L.FMT_U16_MM}[a.dtype]
+    return _FMT_NP[np.asarray(a).dtype]
+
+
+def _stream_ptr(stream) -> Optional[C.c_void_p]:
+    if stream is None:
+        return None
+    return C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+
+
+def make_config(**kw) -> L.KfposConfig:
+    cfg = L.KfposConfig()
+    L.lib().kfpos_config_default(C.byref(cfg))
+    xml = kw.pop("xml", None)
+    for blob in ([xml] if isinstance(xml, (str, bytes)) else (xml or [])):
+        data = blob.encode() if isinstance(blob, str) else blob
+        L.check(L.lib().kfpos_config_load_xml(C.byref(cfg), data), "kfpos_config_load_xml")
+    for k, v in kw.items():
+        if k == "ml_start":
+            for i in range(3):
+                cfg.ml_start[i] = float(v[i])
+        else:
+            if not hasattr(cfg, k):
+                raise AttributeError(f"kfpos_config has no field {k!r}")
+            setattr(cfg, k, v)
+    return cfg
+
+
+class Batch:
+    """N identical-configuration filters (or ML epoch slots) on one GPU."""
+
+    def __init__(self, model: int, n_filters: int, config: Optional[L.KfposConfig] = None,
+                 device: int = 0, anchors=None, **cfg_kw):
+        self._h = C.c_void_p()
+        self.cfg = config if config is not None else make_config(**cfg_kw)
+        self.model = model
+        self.N = int(n_filters)
+        L.check(L.lib().kfpos_batch_create(C.byref(self._h), int(device), int(model),
+                                           C.c_int64(self.N), C.byref(self.cfg)), "kfpos_batch_create")
+        self.n = L.lib().kfpos_batch_state_dim(self._h)
+        self.n_anchors = 0
+        if anchors is not None:
+            self.set_anchors(anchors)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            L.lib().kfpos_batch_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ------------------------------------------------------------------ setup
+    def set_anchors(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        L.check(L.lib().kfpos_batch_set_anchors(self._h, len(xyz), C.c_void_p(xyz.ctypes.data)),
+                "kfpos_batch_set_anchors")
+        self.n_anchors = len(xyz)
+
+    def set_state(self, x, P=None, stream=None):
+        """x: [n][N] (rows beyond those given are zero if x has fewer rows); P [n*n][N] or None."""
+        if not _is_torch(x):
+            x = np.asarray(x, dtype=np.float64).reshape(-1, self.N)
+            if x.shape[0] < self.n:
+                x = np.vstack([x, np.zeros((self.n - x.shape[0], self.N))])
+        px, kx = _ptr(x, np.float64)
+        pP, kP = _ptr(P, np.float64)
+        L.check(L.lib().kfpos_batch_set_state(self._h, px, pP, _stream_ptr(stream)), "kfpos_batch_set_state")
+
+    def get_state(self, want_P=True, stream=None):
+        x = np.empty((self.n, self.N))
+        P = np.empty((self.n * self.n, self.N)) if want_P else None
+        st = np.empty(self.N, dtype=np.int32)
+        L.check(L.lib().kfpos_batch_get_state(self._h, C.c_void_p(x.ctypes.data),
+                                              C.c_void_p(P.ctypes.data) if want_P else None,
+                                              C.c_void_p(st.ctypes.data), _stream_ptr(stream)),
+                "kfpos_batch_get_state")
+        return x, P, st
+
+    def get_state_into(self, x=None, P=None, status=None, stream=None):
+        """Device-to-device variant of get_state for torch tensors."""
+        L.check(L.lib().kfpos_batch_get_state(self._h, _ptr(x)[0], _ptr(P)[0], _ptr(status)[0],
+                                              _stream_ptr(stream)), "kfpos_batch_get_state")
+
+    # ------------------------------------------------------------------ steps
+    def _err(self, err):
+        if err is None or np.isscalar(err):
+            return float(0.0 if err is None else err), None, None
+        p, keep = _ptr(err, np.float64)
+        return 0.0, p, keep
+
+    def step_toa(self, dt, ranges, err=0.01, stream=None):
+        es, ep, keep = self._err(err)
+        pr, kr = _ptr(ranges)
+        L.check(L.lib().kfpos_batch_step_toa(self._h, float(dt), pr, _fmt_of(ranges), es, ep,
+                                             _stream_ptr(stream)), "kfpos_batch_step_toa")
+
+    def replay_toa(self, dt, ranges, err=0.01, traj=None, sel=None, want_traj=False, want_sel=False,
+                   stream=None):
+        """ranges [T][M][N]; dt scalar or [T].  Returns (traj, sel) (numpy, or the tensors given)."""
+        T = int(ranges.shape[0])
+        dts = np.ascontiguousarray(np.broadcast_to(np.asarray(dt, dtype=np.float64), (T,)))
+        es, ep, keep = self._err(err)
+        pr, kr = _ptr(ranges)
+        if traj is None and want_traj:
+            traj = np.empty((T, 3, self.N))
+        if sel is None and want_sel:
+            sel = np.empty((T, self.N), dtype=np.int32)
+        L.check(L.lib().kfpos_batch_replay_toa(self._h, T, C.c_void_p(dts.ctypes.data), pr,
+                                               _fmt_of(ranges), es, ep, _ptr(traj)[0], _ptr(sel)[0],
+                                               _stream_ptr(stream)), "kfpos_batch_replay_toa")
+        return traj, sel
+
+    def step_px4(self, dt, ix, iy, irz, itime_us, quality, stream=None):
+        a = [_ptr(v, np.float64) for v in (ix, iy, irz, itime_us)]
+        q = _ptr(quality, np.int32)
+        L.check(L.lib().kfpos_batch_step_px4(self._h, float(dt), a[0][0], a[1][0], a[2][0], a[3][0], q[0],
+                                             _stream_ptr(stream)), "kfpos_batch_step_px4")
+
+    def step_imu(self, dt, ang_vel, lin_acc, cov_ang_vel=None, cov_acc=None, stream=None):
+        a = [_ptr(v, np.float64) for v in (ang_vel, cov_ang_vel, lin_acc, cov_acc)]
+        L.check(L.lib().kfpos_batch_step_imu(self._h, float(dt), a[0][0], a[1][0], a[2][0], a[3][0],
+                                             _stream_ptr(stream)), "kfpos_batch_step_imu")
+
+    def step_mag(self, dt, mag, stream=None):
+        p, k = _ptr(mag, np.float64)
+        L.check(L.lib().kfpos_batch_step_mag(self._h, float(dt), p, _stream_ptr(stream)), "kfpos_batch_step_mag")
+
+    def step_compass(self, dt, compass, stream=None):
+        p, k = _ptr(compass, np.float64)
+        L.check(L.lib().kfpos_batch_step_compass(self._h, float(dt), p, _stream_ptr(stream)),
+                "kfpos_batch_step_compass")
+
+    def get_pose(self, dt, stream=None):
+        x = np.empty((self.n, self.N))
+        P = np.empty((self.n * self.n, self.N))
+        L.check(L.lib().kfpos_batch_get_pose(self._h, float(dt), C.c_void_p(x.ctypes.data),
+                                             C.c_void_p(P.ctypes.data), _stream_ptr(stream)),
+                "kfpos_batch_get_pose")
+        return x, P
+
+    # --------------------------------------------------------------------- ML
+    def ml_solve(self, ranges, err=0.01, out=None, stream=None):
+        """ranges [M][N].  Returns dict(pos [3][N], cov [9][N], iters, sel [2][N], status)."""
+        es, ep, keep = self._err(err)
+        pr, kr = _ptr(ranges)
+        if out is None:
+            out = dict(pos=np.empty((3, self.N)), cov=np.empty((9, self.N)),
+                       iters=np.empty(self.N, dtype=np.int32), sel=np.empty((2, self.N), dtype=np.int32),
+                       status=np.empty(self.N, dtype=np.int32))
+        L.check(L.lib().kfpos_batch_ml_solve(self._h, pr, _fmt_of(ranges), es, ep,
+                                             _ptr(out.get("pos"))[0], _ptr(out.get("cov"))[0],
+                                             _ptr(out.get("iters"))[0], _ptr(out.get("sel"))[0],
+                                             _ptr(out.get("status"))[0], _stream_ptr(stream)),
+                "kfpos_batch_ml_solve")
+        return out
+
+    # ------------------------------------------------------------ diagnostics
+    def counters(self, reset=False, stream=None):
+        buf = (C.c_double * 8)()
+        L.check(L.lib().kfpos_batch_get_counters(self._h, C.byref(buf), int(reset), _stream_ptr(stream)),
+                "kfpos_batch_get_counters")
+        v = list(buf)
+        return dict(updates=v[0], ml_iters=v[1], cost_evals=v[2], gain_evals=v[3], bad=v[4], ignored=v[5])
+
+    def error_stats(self, truth, stream=None):
+        buf = (C.c_double * 4)()
+        p, k = _ptr(truth, np.float64)
+        L.check(L.lib().kfpos_batch_error_stats(self._h, p, C.byref(buf), _stream_ptr(stream)),
+                "kfpos_batch_error_stats")
+        return np.array(list(buf))

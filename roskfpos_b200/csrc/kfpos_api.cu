@@ -1,0 +1,560 @@
+// kfpos_api.cu -- the C ABI of include/kfpos_b200.h: handle lifetime, host/device
+// pointer handling, staging, and dispatch to the kernels.  No torch types, no
+// CPU fallback: every path ends in a kernel launch or an error code.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/kfpos_b200.h"
+#include "kfpos_kernels.cuh"
+
+using namespace kfpos;
+
+#define CK(call)                                        \
+    do {                                                \
+        cudaError_t _e = (call);                        \
+        if (_e != cudaSuccess) return map_cuda_err(_e); \
+    } while (0)
+
+static int map_cuda_err(cudaError_t e) {
+    if (e == cudaErrorMemoryAllocation) return KFPOS_ERR_NOMEM;
+    return KFPOS_ERR_CUDA;
+}
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr int N_SCRATCH = 8;
+
+} // namespace
+
+struct kfpos_batch {
+    int device = 0;
+    int model = 0;
+    int64_t N = 0;
+    int n = 0;  // state dimension
+    int np = 0; // packed covariance entries
+    kfpos_config cfg;
+    AnchorTable anchors;
+    bool have_anchors = false;
+    double *d_x = nullptr;      // SoA [n][N]
+    double *d_P = nullptr;      // SoA [np][N]
+    int32_t *d_status = nullptr;
+    unsigned long long *d_counters = nullptr;
+    double *d_partials = nullptr, *d_out4 = nullptr;
+    // K8 / T9 latched sensor samples, SoA rows (see kfpos_k8.cuh)
+    double *d_latch = nullptr;
+    int32_t *d_has = nullptr;
+    DevBuf scratch[N_SCRATCH];
+    DevBuf stage[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// true when `p` can be dereferenced by a kernel on this device without staging
+bool on_device(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+size_t fmt_size(int fmt) { return fmt == KFPOS_FMT_F64_M ? 8 : (fmt == KFPOS_FMT_I32_MM ? 4 : 2); }
+
+// input staging: device pointers pass through, host pointers are copied into
+// scratch slot `slot`
+int stage_in(kfpos_batch *b, int slot, const void *src, size_t bytes, cudaStream_t s, const void **out) {
+    if (!src) { *out = nullptr; return KFPOS_OK; }
+    if (on_device(src)) { *out = src; return KFPOS_OK; }
+    CK(b->scratch[slot].reserve(bytes));
+    CK(cudaMemcpyAsync(b->scratch[slot].p, src, bytes, cudaMemcpyHostToDevice, s));
+    *out = b->scratch[slot].p;
+    return KFPOS_OK;
+}
+
+// output staging: returns the device pointer the kernel should write
+int stage_out(kfpos_batch *b, int slot, void *dst, size_t bytes, void **dev, bool *needs_copy) {
+    *needs_copy = false;
+    if (!dst) { *dev = nullptr; return KFPOS_OK; }
+    if (on_device(dst)) { *dev = dst; return KFPOS_OK; }
+    CK(b->scratch[slot].reserve(bytes));
+    *dev = b->scratch[slot].p;
+    *needs_copy = true;
+    return KFPOS_OK;
+}
+
+int state_dim(int model) {
+    switch (model) {
+    case KFPOS_MODEL_ML: return 3;
+    case KFPOS_MODEL_T6: return 6;
+    case KFPOS_MODEL_K8: return 8;
+    case KFPOS_MODEL_T9: return 9;
+    }
+    return 0;
+}
+
+RangeStream make_rs(const kfpos_batch *b, const void *ranges, int fmt, double err_scalar, const double *err) {
+    RangeStream rs;
+    rs.ranges = ranges;
+    rs.err = err;
+    rs.err_scalar = err_scalar;
+    rs.fmt = fmt;
+    rs.m_slots = b->anchors.n;
+    return rs;
+}
+
+} // namespace
+
+// ------------------------------------------------------------------------ misc
+extern "C" int kfpos_abi_version(void) { return KFPOS_ABI_VERSION; }
+
+extern "C" const char *kfpos_strerror(int code) {
+    switch (code) {
+    case KFPOS_OK: return "ok";
+    case KFPOS_ERR_INVALID: return "invalid argument";
+    case KFPOS_ERR_CUDA: return "CUDA error or no CUDA device (this library has no CPU fallback)";
+    case KFPOS_ERR_NOMEM: return "out of device memory";
+    case KFPOS_ERR_NOT_READY: return "anchors or state not set";
+    case KFPOS_ERR_UNSUPPORTED: return "unsupported configuration";
+    case KFPOS_ERR_PARSE: return "malformed XML configuration";
+    }
+    return "unknown error";
+}
+
+// -------------------------------------------------------------------- lifetime
+extern "C" int kfpos_batch_create(kfpos_batch **out, int device, int model, int64_t n_filters,
+                                  const kfpos_config *cfg) {
+    if (!out || !cfg || n_filters <= 0 || state_dim(model) == 0) return KFPOS_ERR_INVALID;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return KFPOS_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return KFPOS_ERR_CUDA;
+    kfpos_batch *b = new (std::nothrow) kfpos_batch();
+    if (!b) return KFPOS_ERR_NOMEM;
+    b->device = device;
+    b->model = model;
+    b->N = n_filters;
+    b->n = state_dim(model);
+    b->np = b->n * (b->n + 1) / 2;
+    b->cfg = *cfg;
+    memset(&b->anchors, 0, sizeof b->anchors);
+    const size_t N = (size_t)n_filters;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void **p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+        if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
+    };
+    alloc((void **)&b->d_counters, CNT_N * sizeof(unsigned long long));
+    if (model != KFPOS_MODEL_ML) {
+        alloc((void **)&b->d_x, sizeof(double) * b->n * N);
+        alloc((void **)&b->d_P, sizeof(double) * b->np * N);
+        alloc((void **)&b->d_status, sizeof(int32_t) * N);
+        alloc((void **)&b->d_partials, sizeof(double) * 4 * ((N + 1023) / 1024));
+        alloc((void **)&b->d_out4, sizeof(double) * 4);
+    }
+    if (model == KFPOS_MODEL_K8 || model == KFPOS_MODEL_T9) {
+        alloc((void **)&b->d_latch, sizeof(double) * 16 * N);
+        alloc((void **)&b->d_has, sizeof(int32_t) * N);
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&b->ev_copied[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_done[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        kfpos_batch_destroy(b);
+        return map_cuda_err(e);
+    }
+    *out = b;
+    return KFPOS_OK;
+}
+
+extern "C" void kfpos_batch_destroy(kfpos_batch *b) {
+    if (!b) return;
+    DeviceGuard g(b->device);
+    cudaDeviceSynchronize();
+    cudaFree(b->d_x);
+    cudaFree(b->d_P);
+    cudaFree(b->d_status);
+    cudaFree(b->d_counters);
+    cudaFree(b->d_partials);
+    cudaFree(b->d_out4);
+    cudaFree(b->d_latch);
+    cudaFree(b->d_has);
+    for (auto &s : b->scratch) s.release();
+    for (auto &s : b->stage) s.release();
+    for (int i = 0; i < 2; ++i) {
+        if (b->ev_copied[i]) cudaEventDestroy(b->ev_copied[i]);
+        if (b->ev_done[i]) cudaEventDestroy(b->ev_done[i]);
+    }
+    if (b->copy_stream) cudaStreamDestroy(b->copy_stream);
+    cudaGetLastError();
+    delete b;
+}
+
+extern "C" int64_t kfpos_batch_size(const kfpos_batch *b) { return b ? b->N : 0; }
+extern "C" int kfpos_batch_state_dim(const kfpos_batch *b) { return b ? b->n : 0; }
+
+extern "C" int kfpos_batch_set_anchors(kfpos_batch *b, int n_anchors, const double *xyz) {
+    if (!b || !xyz || n_anchors < 0 || n_anchors > KFPOS_MAX_ANCHORS) return KFPOS_ERR_INVALID;
+    std::vector<double> host(3 * (size_t)n_anchors);
+    if (on_device(xyz)) {
+        DeviceGuard g(b->device);
+        CK(cudaMemcpy(host.data(), xyz, host.size() * sizeof(double), cudaMemcpyDeviceToHost));
+    } else {
+        memcpy(host.data(), xyz, host.size() * sizeof(double));
+    }
+    memset(&b->anchors, 0, sizeof b->anchors);
+    for (int i = 0; i < n_anchors; ++i) {
+        b->anchors.x[i] = host[3 * i];
+        b->anchors.y[i] = host[3 * i + 1];
+        b->anchors.z[i] = host[3 * i + 2];
+    }
+    b->anchors.n = n_anchors;
+    b->have_anchors = true;
+    return KFPOS_OK;
+}
+
+extern "C" int kfpos_batch_set_state(kfpos_batch *b, const double *x, const double *P, void *stream) {
+    if (!b || b->model == KFPOS_MODEL_ML || !x) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N;
+    const bool xd = on_device(x);
+    CK(cudaMemcpyAsync(b->d_x, x, sizeof(double) * b->n * N, xd ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    if (P) {
+        const void *pf = nullptr;
+        int rc = stage_in(b, 0, P, sizeof(double) * b->n * b->n * N, s, &pf);
+        if (rc) return rc;
+        CK(launch_pack_cov(b->n, b->N, (const double *)pf, b->d_P, s));
+    } else {
+        CK(cudaMemsetAsync(b->d_P, 0, sizeof(double) * b->np * N, s));
+    }
+    CK(cudaMemsetAsync(b->d_status, 0, sizeof(int32_t) * N, s));
+    if (b->d_has) CK(cudaMemsetAsync(b->d_has, 0, sizeof(int32_t) * N, s));
+    if (b->d_latch) CK(cudaMemsetAsync(b->d_latch, 0, sizeof(double) * 16 * N, s));
+    if (!xd || (P && !on_device(P))) CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
+extern "C" int kfpos_batch_get_state(kfpos_batch *b, double *x, double *P, int32_t *status, void *stream) {
+    if (!b || b->model == KFPOS_MODEL_ML) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N;
+    bool sync = false;
+    if (x) {
+        const bool d = on_device(x);
+        CK(cudaMemcpyAsync(x, b->d_x, sizeof(double) * b->n * N, d ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        sync |= !d;
+    }
+    if (P) {
+        void *dev;
+        bool copy;
+        const size_t bytes = sizeof(double) * b->n * b->n * N;
+        int rc = stage_out(b, 0, P, bytes, &dev, &copy);
+        if (rc) return rc;
+        CK(launch_unpack_cov(b->n, b->N, b->d_P, (double *)dev, s));
+        if (copy) {
+            CK(cudaMemcpyAsync(P, dev, bytes, cudaMemcpyDeviceToHost, s));
+            sync = true;
+        }
+    }
+    if (status) {
+        const bool d = on_device(status);
+        CK(cudaMemcpyAsync(status, b->d_status, sizeof(int32_t) * N, d ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s));
+        sync |= !d;
+    }
+    if (sync) CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
+// ------------------------------------------------------------------- TOA steps
+namespace {
+
+// launches the model's replay kernel over T steps whose ranges (and optional
+// per-ranging errors) are already on the device
+int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_ranges, int fmt,
+                  double err_scalar, const double *d_err, double *d_traj, int32_t *d_sel, cudaStream_t s);
+
+} // namespace
+
+extern "C" int kfpos_batch_replay_toa(kfpos_batch *b, int n_steps, const double *dt, const void *ranges,
+                                      int fmt, double err_scalar, const double *err_var, double *traj,
+                                      int32_t *sel, void *stream) {
+    if (!b || b->model == KFPOS_MODEL_ML || n_steps < 0 || !dt || !ranges) return KFPOS_ERR_INVALID;
+    if (fmt < 0 || fmt > 2) return KFPOS_ERR_INVALID;
+    if (!b->have_anchors) return KFPOS_ERR_NOT_READY;
+    if (n_steps == 0) return KFPOS_OK;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N, M = (size_t)b->anchors.n;
+    const int T = n_steps;
+
+    // dt: small, always staged
+    CK(b->scratch[1].reserve(sizeof(double) * T));
+    CK(cudaMemcpyAsync(b->scratch[1].p, dt, sizeof(double) * T,
+                       on_device(dt) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    const double *d_dt = (const double *)b->scratch[1].p;
+
+    void *d_traj = nullptr, *d_sel = nullptr;
+    bool copy_traj = false, copy_sel = false;
+    int rc = stage_out(b, 2, traj, sizeof(double) * 3 * N * T, &d_traj, &copy_traj);
+    if (rc) return rc;
+    rc = stage_out(b, 3, sel, sizeof(int32_t) * N * T, &d_sel, &copy_sel);
+    if (rc) return rc;
+
+    const bool r_dev = on_device(ranges);
+    const bool e_dev = !err_var || on_device(err_var);
+    if (r_dev && e_dev) {
+        rc = launch_replay(b, T, d_dt, ranges, fmt, err_scalar, err_var, (double *)d_traj, (int32_t *)d_sel, s);
+        if (rc) return rc;
+    } else if (!r_dev && err_var == nullptr) {
+        // HOST range log: stream it through two device staging buffers, the copy
+        // of chunk c+1 overlapping the replay kernel of chunk c.
+        const size_t step_bytes = M * N * fmt_size(fmt);
+        size_t chunk_steps = (size_t)(((size_t)256 << 20) / (step_bytes ? step_bytes : 1));
+        if (chunk_steps < 1) chunk_steps = 1;
+        if (chunk_steps > (size_t)T) chunk_steps = (size_t)T;
+        for (int i = 0; i < 2; ++i) CK(b->stage[i].reserve(chunk_steps * step_bytes));
+        CK(cudaEventRecord(b->ev_done[0], s));
+        CK(cudaEventRecord(b->ev_done[1], s));
+        int c = 0;
+        for (size_t t0 = 0; t0 < (size_t)T; t0 += chunk_steps, ++c) {
+            const int k = c & 1;
+            const size_t tc = (t0 + chunk_steps <= (size_t)T) ? chunk_steps : (size_t)T - t0;
+            CK(cudaStreamWaitEvent(b->copy_stream, b->ev_done[k], 0));
+            CK(cudaMemcpyAsync(b->stage[k].p, (const char *)ranges + t0 * step_bytes, tc * step_bytes,
+                               cudaMemcpyHostToDevice, b->copy_stream));
+            CK(cudaEventRecord(b->ev_copied[k], b->copy_stream));
+            CK(cudaStreamWaitEvent(s, b->ev_copied[k], 0));
+            rc = launch_replay(b, (int)tc, d_dt + t0, b->stage[k].p, fmt, err_scalar, nullptr,
+                               d_traj ? (double *)d_traj + t0 * 3 * N : nullptr,
+                               d_sel ? (int32_t *)d_sel + t0 * N : nullptr, s);
+            if (rc) return rc;
+            CK(cudaEventRecord(b->ev_done[k], s));
+        }
+    } else {
+        // host ranges with per-ranging errors (or mixed): stage both whole
+        const void *d_r = nullptr, *d_e = nullptr;
+        rc = stage_in(b, 4, ranges, M * N * T * fmt_size(fmt), s, &d_r);
+        if (rc) return rc;
+        rc = stage_in(b, 5, err_var, sizeof(double) * M * N * T, s, &d_e);
+        if (rc) return rc;
+        rc = launch_replay(b, T, d_dt, d_r, fmt, err_scalar, (const double *)d_e, (double *)d_traj,
+                           (int32_t *)d_sel, s);
+        if (rc) return rc;
+    }
+    if (copy_traj) CK(cudaMemcpyAsync(traj, d_traj, sizeof(double) * 3 * N * T, cudaMemcpyDeviceToHost, s));
+    if (copy_sel) CK(cudaMemcpyAsync(sel, d_sel, sizeof(int32_t) * N * T, cudaMemcpyDeviceToHost, s));
+    if (copy_traj || copy_sel || !r_dev || !e_dev) CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
+extern "C" int kfpos_batch_step_toa(kfpos_batch *b, double dt, const void *ranges, int fmt, double err_scalar,
+                                    const double *err_var, void *stream) {
+    return kfpos_batch_replay_toa(b, 1, &dt, ranges, fmt, err_scalar, err_var, nullptr, nullptr, stream);
+}
+
+namespace {
+
+int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_ranges, int fmt,
+                  double err_scalar, const double *d_err, double *d_traj, int32_t *d_sel, cudaStream_t s) {
+    const RangeStream rs = make_rs(b, d_ranges, fmt, err_scalar, d_err);
+    switch (b->model) {
+    case KFPOS_MODEL_T6: {
+        T6Params p;
+        p.anchors = b->anchors;
+        p.rs = rs;
+        p.N = b->N;
+        p.T = T;
+        p.ignore_worst = b->cfg.ignore_worst_anchor;
+        p.ignore_thr = b->cfg.ignore_cost_threshold;
+        p.accel_noise = b->cfg.accel_noise;
+        p.dt = d_dt;
+        p.x = b->d_x;
+        p.P = b->d_P;
+        p.status = b->d_status;
+        p.traj = d_traj;
+        p.sel = d_sel;
+        p.counters = b->d_counters;
+        CK(launch_t6_replay(p, s));
+        return KFPOS_OK;
+    }
+    default: return KFPOS_ERR_UNSUPPORTED;
+    }
+}
+
+} // namespace
+
+// ---------------------------------------------------------- other sensor steps
+extern "C" int kfpos_batch_step_px4(kfpos_batch *b, double, const double *, const double *, const double *,
+                                    const double *, const int32_t *, void *) {
+    if (!b || b->model != KFPOS_MODEL_K8) return KFPOS_ERR_INVALID;
+    return KFPOS_ERR_UNSUPPORTED;
+}
+extern "C" int kfpos_batch_step_imu(kfpos_batch *b, double, const double *, const double *, const double *,
+                                    const double *, void *) {
+    if (!b || (b->model != KFPOS_MODEL_K8 && b->model != KFPOS_MODEL_T9)) return KFPOS_ERR_INVALID;
+    return KFPOS_ERR_UNSUPPORTED;
+}
+extern "C" int kfpos_batch_step_mag(kfpos_batch *b, double, const double *, void *) {
+    if (!b || b->model != KFPOS_MODEL_K8) return KFPOS_ERR_INVALID;
+    return KFPOS_ERR_UNSUPPORTED;
+}
+extern "C" int kfpos_batch_step_compass(kfpos_batch *b, double, const double *, void *) {
+    if (!b || b->model != KFPOS_MODEL_K8) return KFPOS_ERR_INVALID;
+    return KFPOS_ERR_UNSUPPORTED;
+}
+
+// --------------------------------------------------------------------- getPose
+extern "C" int kfpos_batch_get_pose(kfpos_batch *b, double dt, double *x_pred, double *P_pred, void *stream) {
+    if (!b || b->model == KFPOS_MODEL_ML) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N;
+    void *dx = nullptr, *dP = nullptr;
+    bool cx = false, cP = false;
+    int rc = stage_out(b, 2, x_pred, sizeof(double) * b->n * N, &dx, &cx);
+    if (rc) return rc;
+    rc = stage_out(b, 3, P_pred, sizeof(double) * b->n * b->n * N, &dP, &cP);
+    if (rc) return rc;
+    switch (b->model) {
+    case KFPOS_MODEL_T6:
+        CK(launch_t6_get_pose(b->N, dt, b->cfg.accel_noise, b->d_x, b->d_P, (double *)dx, (double *)dP, s));
+        break;
+    default: return KFPOS_ERR_UNSUPPORTED;
+    }
+    if (cx) CK(cudaMemcpyAsync(x_pred, dx, sizeof(double) * b->n * N, cudaMemcpyDeviceToHost, s));
+    if (cP) CK(cudaMemcpyAsync(P_pred, dP, sizeof(double) * b->n * b->n * N, cudaMemcpyDeviceToHost, s));
+    if (cx || cP) CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
+// -------------------------------------------------------------------------- ML
+extern "C" int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt, double err_scalar,
+                                    const double *err_var, double *pos, double *cov, int32_t *iters,
+                                    int32_t *sel, int32_t *status, void *stream) {
+    if (!b || b->model != KFPOS_MODEL_ML || !ranges || fmt < 0 || fmt > 2) return KFPOS_ERR_INVALID;
+    if (!b->have_anchors) return KFPOS_ERR_NOT_READY;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N, M = (size_t)b->anchors.n;
+    const void *d_r = nullptr, *d_e = nullptr;
+    int rc = stage_in(b, 0, ranges, M * N * fmt_size(fmt), s, &d_r);
+    if (rc) return rc;
+    rc = stage_in(b, 1, err_var, sizeof(double) * M * N, s, &d_e);
+    if (rc) return rc;
+    void *d_pos, *d_cov, *d_it, *d_sel, *d_st;
+    bool c_pos, c_cov, c_it, c_sel, c_st;
+    if ((rc = stage_out(b, 2, pos, sizeof(double) * 3 * N, &d_pos, &c_pos))) return rc;
+    if ((rc = stage_out(b, 3, cov, sizeof(double) * 9 * N, &d_cov, &c_cov))) return rc;
+    if ((rc = stage_out(b, 4, iters, sizeof(int32_t) * N, &d_it, &c_it))) return rc;
+    if ((rc = stage_out(b, 5, sel, sizeof(int32_t) * 2 * N, &d_sel, &c_sel))) return rc;
+    if ((rc = stage_out(b, 6, status, sizeof(int32_t) * N, &d_st, &c_st))) return rc;
+    MlParams p;
+    p.anchors = b->anchors;
+    p.rs = make_rs(b, d_r, fmt, err_scalar, (const double *)d_e);
+    p.N = b->N;
+    p.use2d = b->cfg.use2d;
+    p.variant = b->cfg.variant;
+    p.n_ignore = b->cfg.num_ignored_rangings;
+    p.best_mode = b->cfg.best_mode;
+    p.start[0] = b->cfg.ml_start[0];
+    p.start[1] = b->cfg.ml_start[1];
+    p.start[2] = b->cfg.ml_start[2];
+    p.pos = (double *)d_pos;
+    p.cov = (double *)d_cov;
+    p.iters = (int32_t *)d_it;
+    p.sel = (int32_t *)d_sel;
+    p.status = (int32_t *)d_st;
+    p.counters = b->d_counters;
+    CK(launch_ml_solve(p, s));
+    if (c_pos) CK(cudaMemcpyAsync(pos, d_pos, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, s));
+    if (c_cov) CK(cudaMemcpyAsync(cov, d_cov, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, s));
+    if (c_it) CK(cudaMemcpyAsync(iters, d_it, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s));
+    if (c_sel) CK(cudaMemcpyAsync(sel, d_sel, sizeof(int32_t) * 2 * N, cudaMemcpyDeviceToHost, s));
+    if (c_st) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s));
+    if (c_pos || c_cov || c_it || c_sel || c_st || !on_device(ranges)) CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
+// ----------------------------------------------------------------- diagnostics
+extern "C" int kfpos_batch_get_counters(kfpos_batch *b, double out[8], int reset, void *stream) {
+    if (!b || !out) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned long long h[CNT_N];
+    CK(cudaMemcpyAsync(h, b->d_counters, sizeof h, cudaMemcpyDeviceToHost, s));
+    if (reset) CK(cudaMemsetAsync(b->d_counters, 0, sizeof h, s));
+    CK(cudaStreamSynchronize(s));
+    for (int i = 0; i < CNT_N; ++i) out[i] = (double)h[i];
+    return KFPOS_OK;
+}
+
+extern "C" int kfpos_batch_error_stats(kfpos_batch *b, const double *truth, double out[4], void *stream) {
+    if (!b || b->model == KFPOS_MODEL_ML || !truth || !out) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const void *d_truth = nullptr;
+    int rc = stage_in(b, 0, truth, sizeof(double) * 3 * (size_t)b->N, s, &d_truth);
+    if (rc) return rc;
+    CK(launch_error_stats(b->N, b->d_x, b->d_status, (const double *)d_truth, b->d_partials, b->d_out4, s));
+    CK(cudaMemcpyAsync(out, b->d_out4, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
+extern "C" int kfpos_measure_fp64_peak(int device, double *flops_per_s) {
+    if (!flops_per_s) return KFPOS_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+        cudaGetLastError();
+        return KFPOS_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return KFPOS_ERR_CUDA;
+    CK(measure_fp64_peak(flops_per_s));
+    return KFPOS_OK;
+}

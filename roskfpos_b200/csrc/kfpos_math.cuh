@@ -1,0 +1,190 @@
+// kfpos_math.cuh -- small FP64 building blocks shared by the kernels.
+//
+// Everything here is per-thread register arithmetic: the matrices of this path
+// are 2x2 .. 9x9 with structural sparsity and data-dependent control flow, so
+// they run on the FP64 CUDA-core pipe (DFMA), not on tensor cores.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace kfpos {
+
+#define KF_DEV __device__ __forceinline__
+
+// Anchor table, passed by value inside the kernel parameter block: parameters
+// live in the constant bank, and every lane of a warp reads the same anchor at
+// the same time, so each coordinate is a single broadcast constant-cache read
+// that the compiler folds into the DADD/DFMA operand.
+struct AnchorTable {
+    double x[32], y[32], z[32];
+    int n;
+    int _pad;
+};
+
+// Packed symmetric matrix (lower triangle, row-major).  All indices are
+// compile-time constants after unrolling, so `a` lives in registers.
+template <int N>
+struct Sym {
+    static constexpr int SZ = N * (N + 1) / 2;
+    double a[SZ];
+    KF_DEV double &at(int i, int j) { return i >= j ? a[i * (i + 1) / 2 + j] : a[j * (j + 1) / 2 + i]; }
+    KF_DEV double get(int i, int j) const { return i >= j ? a[i * (i + 1) / 2 + j] : a[j * (j + 1) / 2 + i]; }
+};
+
+// wire range -> metres, exactly `(double) ranges[i] / 1000` (PG.cpp:484).
+KF_DEV double mm_to_m(double mm) { return mm / 1000.0; }
+
+KF_DEV double load_range(const void *base, int fmt, int64_t idx) {
+    switch (fmt) {
+    case 0: return __ldg(reinterpret_cast<const double *>(base) + idx);
+    case 1: return mm_to_m((double)__ldg(reinterpret_cast<const int32_t *>(base) + idx));
+    default: return mm_to_m((double)__ldg(reinterpret_cast<const uint16_t *>(base) + idx));
+    }
+}
+
+// normalizeAngle, KF.cpp:699-706 (single wrap)
+KF_DEV double wrap_angle(double a) {
+    const double PI = 3.14159265358979323846;
+    if (a > PI) return a - 2 * PI;
+    else if (a <= -PI) return a + 2 * PI;
+    return a;
+}
+
+// Symmetric 3x3 solve H s = g by cofactors.  H packed [xx, xy, yy, xz, yz, zz]
+// (Sym<3> order).  Returns false when det is 0 or NaN.
+KF_DEV bool solve_sym3(const double (&H)[6], const double (&g)[3], double (&s)[3]) {
+    const double a = H[0], b = H[1], c = H[3], d = H[2], e = H[4], f = H[5];
+    // [a b c; b d e; c e f]
+    const double c00 = d * f - e * e;
+    const double c01 = c * e - b * f;
+    const double c02 = b * e - c * d;
+    const double det = a * c00 + b * c01 + c * c02;
+    if (!(det != 0.0)) return false;
+    const double c11 = a * f - c * c;
+    const double c12 = b * c - a * e;
+    const double c22 = a * d - b * b;
+    const double id = 1.0 / det;
+    s[0] = (c00 * g[0] + c01 * g[1] + c02 * g[2]) * id;
+    s[1] = (c01 * g[0] + c11 * g[1] + c12 * g[2]) * id;
+    s[2] = (c02 * g[0] + c12 * g[1] + c22 * g[2]) * id;
+    return true;
+}
+
+// inverse of a symmetric 3x3 (packed as above) -> packed; false if singular
+KF_DEV bool inv_sym3(const double (&H)[6], double (&I)[6]) {
+    const double a = H[0], b = H[1], c = H[3], d = H[2], e = H[4], f = H[5];
+    const double c00 = d * f - e * e;
+    const double c01 = c * e - b * f;
+    const double c02 = b * e - c * d;
+    const double det = a * c00 + b * c01 + c * c02;
+    if (!(det != 0.0)) return false;
+    const double id = 1.0 / det;
+    I[0] = c00 * id;
+    I[1] = c01 * id;
+    I[2] = (a * f - c * c) * id;
+    I[3] = c02 * id;
+    I[4] = (b * c - a * e) * id;
+    I[5] = (a * d - b * b) * id;
+    return true;
+}
+
+// Symmetric 2x2 solve [a b; b d] s = g
+KF_DEV bool solve_sym2(double a, double b, double d, double g0, double g1, double &s0, double &s1) {
+    const double det = a * d - b * b;
+    if (!(det != 0.0)) return false;
+    const double id = 1.0 / det;
+    s0 = (d * g0 - b * g1) * id;
+    s1 = (a * g1 - b * g0) * id;
+    return true;
+}
+
+// Sequential scalar measurement update of the linear-KF form used inside one
+// IEKF iteration: prior (0, P), row h with non-zeros at the
+// columns set in MASK, innovation reference y, variance R:
+//   s = h P h^T + R ; k = P h^T / s ; dx += k (y - h dx) ; P -= k (P h^T)^T
+// After all rows of an iteration dx = K (eps - J delta) and P = (I - K J) P^-,
+// identical (in exact arithmetic, R block-diagonal) to the reference's dense
+// K = P J^T inv(J P J^T + R)  (TOA.cpp:316-319, KF.cpp:491-495, TOAIMU.cpp:330-334).
+template <int N, unsigned MASK>
+KF_DEV void scalar_update(Sym<N> &P, double (&dx)[N], const double (&h)[N], double y, double R) {
+    double ph[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double s = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if ((MASK >> j) & 1u) {
+                s = first ? P.get(i, j) * h[j] : fma(P.get(i, j), h[j], s);
+                first = false;
+            }
+        ph[i] = s;
+    }
+    double s = R, nu = y;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+        if ((MASK >> j) & 1u) {
+            s = fma(h[j], ph[j], s);
+            nu = fma(-h[j], dx[j], nu);
+        }
+    const double inv_s = 1.0 / s;
+    const double g = nu * inv_s;
+#pragma unroll
+    for (int i = 0; i < N; ++i) dx[i] = fma(ph[i], g, dx[i]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double k = ph[i] * inv_s;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) P.at(i, j) = fma(-k, ph[j], P.at(i, j));
+    }
+}
+
+// 2-row block update for a correlated pair (K8 IMU accel block, KF.cpp:431-434):
+// rows h0,h1 (non-zeros in MASK), innovations y0,y1, R = [[r00,r01],[r01,r11]].
+template <int N, unsigned MASK>
+KF_DEV void block2_update(Sym<N> &P, double (&dx)[N], const double (&h0)[N], const double (&h1)[N],
+                          double y0, double y1, double r00, double r01, double r11) {
+    double p0[N], p1[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            if ((MASK >> j) & 1u) {
+                s0 = fma(P.get(i, j), h0[j], s0);
+                s1 = fma(P.get(i, j), h1[j], s1);
+            }
+        p0[i] = s0;
+        p1[i] = s1;
+    }
+    double s00 = r00, s01 = r01, s11 = r11, n0 = y0, n1 = y1;
+#pragma unroll
+    for (int j = 0; j < N; ++j)
+        if ((MASK >> j) & 1u) {
+            s00 = fma(h0[j], p0[j], s00);
+            s01 = fma(h0[j], p1[j], s01);
+            s11 = fma(h1[j], p1[j], s11);
+            n0 = fma(-h0[j], dx[j], n0);
+            n1 = fma(-h1[j], dx[j], n1);
+        }
+    const double id = 1.0 / (s00 * s11 - s01 * s01);
+    const double i00 = s11 * id, i01 = -s01 * id, i11 = s00 * id;
+    const double g0 = i00 * n0 + i01 * n1, g1 = i01 * n0 + i11 * n1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) dx[i] = fma(p0[i], g0, fma(p1[i], g1, dx[i]));
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const double k0 = p0[i] * i00 + p1[i] * i01;
+        const double k1 = p0[i] * i01 + p1[i] * i11;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) P.at(i, j) = fma(-k0, p0[j], fma(-k1, p1[j], P.at(i, j)));
+    }
+}
+
+// warp-level sum of a per-thread counter, one atomic per warp
+KF_DEV void warp_accumulate(unsigned long long *dst, unsigned v) {
+    unsigned s = __reduce_add_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && s) atomicAdd(dst, (unsigned long long)s);
+}
+
+} // namespace kfpos

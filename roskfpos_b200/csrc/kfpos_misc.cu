@@ -1,0 +1,156 @@
+// kfpos_misc.cu -- layout conversion and statistics kernels.
+#include "kfpos_kernels.cuh"
+
+namespace kfpos {
+
+// full row-major [n*n][N] -> packed lower triangle [n(n+1)/2][N].  The reference
+// covariance is symmetric up to rounding; the lower triangle is kept.
+__global__ void pack_cov_kernel(int n, int64_t N, const double *full, double *packed) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= N) return;
+    int k = 0;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j, ++k) packed[(int64_t)k * N + f] = full[(int64_t)(i * n + j) * N + f];
+}
+
+__global__ void unpack_cov_kernel(int n, int64_t N, const double *packed, double *full) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= N) return;
+    int k = 0;
+    for (int i = 0; i < n; ++i)
+        for (int j = 0; j <= i; ++j, ++k) {
+            const double v = packed[(int64_t)k * N + f];
+            full[(int64_t)(i * n + j) * N + f] = v;
+            full[(int64_t)(j * n + i) * N + f] = v;
+        }
+}
+
+cudaError_t launch_pack_cov(int n, int64_t N, const double *full, double *packed, cudaStream_t s) {
+    if (N <= 0) return cudaSuccess;
+    pack_cov_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(n, N, full, packed);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_unpack_cov(int n, int64_t N, const double *packed, double *full, cudaStream_t s) {
+    if (N <= 0) return cudaSuccess;
+    unpack_cov_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(n, N, packed, full);
+    return cudaGetLastError();
+}
+
+// ---- error statistics with a launch-geometry-independent summation order:
+// chunk c covers filters [1024c, 1024c+1024); inside a chunk thread i sums the 4
+// filters {i, i+256, i+512, i+768} in that order, then a fixed 256-leaf binary
+// tree in shared memory.  Chunk partials are then folded by ONE block in a fixed
+// order (thread i takes chunks i, i+256, ... ; same tree).
+constexpr int ST_CHUNK = 1024, ST_THREADS = 256;
+
+__device__ void tree_reduce4(double (&v)[4], double (*sh)[ST_THREADS]) {
+    const int t = threadIdx.x;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sh[q][t] = v[q];
+    __syncthreads();
+    for (int s = ST_THREADS / 2; s > 0; s >>= 1) {
+        if (t < s) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sh[q][t] += sh[q][t + s];
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) v[q] = sh[q][0];
+}
+
+__global__ void __launch_bounds__(ST_THREADS)
+error_stats_chunks(int64_t N, const double *x, const int32_t *status, const double *truth, double *partials) {
+    __shared__ double sh[4][ST_THREADS];
+    double v[4] = {0, 0, 0, 0};
+    const int64_t base = (int64_t)blockIdx.x * ST_CHUNK;
+    for (int r = 0; r < ST_CHUNK / ST_THREADS; ++r) {
+        const int64_t f = base + threadIdx.x + (int64_t)r * ST_THREADS;
+        if (f < N) {
+            const double ex = x[f] - truth[f], ey = x[N + f] - truth[N + f], ez = x[2 * N + f] - truth[2 * N + f];
+            const double e2 = ex * ex + ey * ey + ez * ez;
+            if (isfinite(e2)) {
+                v[0] += e2;
+                v[1] += ex * ex + ey * ey;
+                v[2] += 1.0;
+            }
+            if (status && status[f] != 0) v[3] += 1.0;
+        }
+    }
+    tree_reduce4(v, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) partials[(int64_t)blockIdx.x * 4 + q] = v[q];
+    }
+}
+
+__global__ void __launch_bounds__(ST_THREADS) error_stats_final(int64_t n_chunks, const double *partials, double *out4) {
+    __shared__ double sh[4][ST_THREADS];
+    double v[4] = {0, 0, 0, 0};
+    for (int64_t c = threadIdx.x; c < n_chunks; c += ST_THREADS) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] += partials[c * 4 + q];
+    }
+    tree_reduce4(v, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out4[q] = v[q];
+    }
+}
+
+cudaError_t launch_error_stats(int64_t N, const double *x, const int32_t *status, const double *truth,
+                               double *partials, double *out4, cudaStream_t s) {
+    const int64_t n_chunks = (N + ST_CHUNK - 1) / ST_CHUNK;
+    if (n_chunks > 0) error_stats_chunks<<<(unsigned)n_chunks, ST_THREADS, 0, s>>>(N, x, status, truth, partials);
+    error_stats_final<<<1, ST_THREADS, 0, s>>>(n_chunks, partials, out4);
+    return cudaGetLastError();
+}
+
+
+// ---- FP64 roofline denominator: a DFMA-only kernel (8 independent chains per
+// thread, 2 resident 256-thread blocks per SM-quarter) timed with CUDA events.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double v0 = threadIdx.x, v1 = v0 + 1, v2 = v0 + 2, v3 = v0 + 3, v4 = v0 + 4, v5 = v0 + 5, v6 = v0 + 6, v7 = v0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            v0 = fma(v0, a, b); v1 = fma(v1, a, b); v2 = fma(v2, a, b); v3 = fma(v3, a, b);
+            v4 = fma(v4, a, b); v5 = fma(v5, a, b); v6 = fma(v6, a, b); v7 = fma(v7, a, b);
+        }
+    }
+    const double r = ((v0 + v1) + (v2 + v3)) + ((v4 + v5) + (v6 + v7));
+    if (r == 12345.678) out[0] = r; // never true: keeps the chains alive
+}
+
+cudaError_t measure_fp64_peak(double *flops_per_s) {
+    cudaDeviceProp prop;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if ((e = cudaGetDeviceProperties(&prop, dev)) != cudaSuccess) return e;
+    double *d = nullptr;
+    if ((e = cudaMalloc(&d, sizeof(double))) != cudaSuccess) return e;
+    cudaEvent_t t0, t1;
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(t0);
+        fp64_peak_kernel<<<blocks, 256>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(t1);
+        if ((e = cudaEventSynchronize(t1)) != cudaSuccess) break;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, t0, t1);
+        const double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+        if (rep > 0 && ms > 0 && flops / (ms * 1e-3) > best) best = flops / (ms * 1e-3);
+    }
+    cudaEventDestroy(t0);
+    cudaEventDestroy(t1);
+    cudaFree(d);
+    *flops_per_s = best;
+    return e;
+}
+
+} // namespace kfpos

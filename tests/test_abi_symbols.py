@@ -1,0 +1,51 @@
+"""The C-ABI library loads (no GPU needed) and exports every symbol the header declares."""
+import ctypes
+import re
+
+from roskfpos_b200 import lib as L
+
+
+def declared_symbols():
+    src = open(L.HEADER_PATH).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(kfpos_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    names = declared_symbols()
+    assert len(names) >= 20
+    l = ctypes.CDLL(L.SO_PATH)
+    for n in names:
+        assert hasattr(l, n), f"{n} declared in include/kfpos_b200.h but not exported"
+    assert set(names) == set(L.SIGNATURES), set(names) ^ set(L.SIGNATURES)
+
+
+def test_abi_version_and_strerror(kflib):
+    l = kflib.lib()
+    assert l.kfpos_abi_version() == 1
+    assert b"no CPU fallback" in l.kfpos_strerror(-2)
+
+
+def test_no_cpu_fallback_without_gpu(kflib):
+    """Without a CUDA device the product must fail loudly, never compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        return
+    from roskfpos_b200.batch import Batch
+    try:
+        Batch(kflib.MODEL_T6, 8, accel_noise=0.5)
+    except kflib.KfposError as e:
+        assert e.code == -2
+    else:
+        raise AssertionError("Batch() succeeded without a GPU")
+
+
+def test_config_struct_layout(kflib):
+    """ctypes mirror and the C struct agree on size (checked through load_xml writes)."""
+    from roskfpos_b200.batch import make_config
+    cfg = make_config(xml=['<config><mag angleOffset="0.25" covarianceMag="0.0001"/></config>',
+                           '<config><imu useFixedCovarianceAcceleration="1" covarianceAcceleration="0.003" '
+                           'useFixedCovarianceAngularVelocityZ="1" covarianceAngularVelocityZ="0.089"/></config>'])
+    assert cfg.mag_angle_offset == 0.25 and cfg.mag_cov == 0.0001
+    assert cfg.imu_use_fixed_cov_acc == 1 and cfg.imu_cov_gyro_z == 0.089
+    assert list(cfg.ml_start) == [1.0, 1.0, 4.0]

@@ -1,0 +1,158 @@
+"""GPU parity: KalmanFilterTOA batches through the C ABI vs the CPU oracle."""
+import numpy as np
+import pytest
+
+from roskfpos_b200 import synth
+from tests.util import REL_TOL, rel_err_cov, rel_err_state
+
+pytestmark = pytest.mark.gpu
+
+
+def run_gpu(kflib, x0, r, anc, dt, err, P0=None, want_traj=False, want_sel=False, **cfg):
+    from roskfpos_b200.batch import Batch
+    N = r.shape[-1]
+    with Batch(kflib.MODEL_T6, N, anchors=anc, **cfg) as b:
+        b.set_state(x0, P0)
+        traj, sel = b.replay_toa(dt, r, err=err, want_traj=want_traj, want_sel=want_sel)
+        x, P, st = b.get_state()
+        cnt = b.counters()
+    return dict(x=x, P=P, status=st, traj=traj, sel=sel, counters=cnt)
+
+
+@pytest.mark.parametrize("m,N,T", [(4, 2000, 30), (8, 4096, 40), (16, 1000, 20), (6, 777, 25)])
+def test_t6_replay_parity(kflib, oracle, m, N, T):
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=100 + m)
+    r = synth.ranges_mm(truth[1:], anc, seed=200 + m)
+    ref = oracle.t6_replay(truth[0], None, r, anc, 0.1, 0.01, want_traj=True)
+    got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, want_traj=True, accel_noise=0.5)
+    assert rel_err_state(got["x"][:3], ref["x"]) < REL_TOL
+    assert np.all(got["x"][3:] == 0.0)
+    assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
+    assert rel_err_state(got["traj"], ref["traj"]) < REL_TOL
+    # identical work: iteration counters equal
+    c = got["counters"]
+    assert c["updates"] == N * T
+    assert [c["ml_iters"], c["cost_evals"], c["gain_evals"]] == list(ref["counters"][:3])
+    assert np.array_equal(got["status"] & ~32, ref["status"] & ~32)
+
+
+@pytest.mark.parametrize("fmt", [np.float64, np.int32, np.uint16])
+def test_t6_range_formats(kflib, oracle, fmt):
+    N, T, m = 1500, 10, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=5)
+    mm = synth.ranges_mm(truth[1:], anc, seed=6)
+    r = (mm.astype(np.float64) / 1000) if fmt is np.float64 else mm.astype(fmt)
+    ref = oracle.t6_replay(truth[0], None, r, anc, 0.1, 0.01)
+    got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, accel_noise=0.5)
+    assert rel_err_state(got["x"][:3], ref["x"]) < REL_TOL
+    assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
+
+
+def test_t6_missing_rangings_and_variable_dt(kflib, oracle):
+    """Ragged epochs: 30 % of the rangings missing (<= 0), so some epochs have < 4 (ML returns
+    its start) or 0 rangings (predict only); dt varies per step; per-ranging errorEstimation."""
+    N, T, m = 3000, 25, 8
+    anc = synth.anchors_for(m)
+    rng = np.random.default_rng(9)
+    dt = rng.uniform(0.02, 0.3, size=T)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=7)
+    r = synth.ranges_mm(truth[1:], anc, seed=8, p_missing=0.3)
+    r[3, :, :50] = 0          # whole epochs empty
+    r[5, 3:, 50:120] = -5     # only 3 valid
+    err = rng.uniform(0.005, 0.05, size=r.shape)
+    ref = oracle.t6_replay(truth[0], None, r, anc, dt, err)
+    got = run_gpu(kflib, truth[0], r, anc, dt, err, accel_noise=0.5)
+    assert rel_err_state(got["x"][:3], ref["x"]) < REL_TOL
+    assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
+    assert np.array_equal(got["status"] & ~32, ref["status"] & ~32)
+    assert (ref["status"] & 1).any() and (ref["status"] & 2).any()
+
+
+def test_t6_step_api_equals_replay(kflib):
+    """T calls of step_toa == one replay of T steps (state/P round-trip through HBM)."""
+    from roskfpos_b200.batch import Batch
+    N, T, m = 2048, 6, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=11)
+    r = synth.ranges_mm(truth[1:], anc, seed=12)
+    a = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, accel_noise=0.5)
+    with Batch(kflib.MODEL_T6, N, anchors=anc, accel_noise=0.5) as b:
+        b.set_state(truth[0])
+        for t in range(T):
+            b.step_toa(0.1, r[t], err=0.01)
+        x, P, st = b.get_state()
+    assert np.array_equal(x, a["x"]) and np.array_equal(P, a["P"])
+
+
+def test_t6_restore_state(kflib, oracle):
+    """set_state(x, P) restores a checkpoint: split replay == whole replay (to rounding of the
+    symmetric packing) and matches the oracle continued from the same checkpoint."""
+    N, T, m = 1024, 12, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=21)
+    r = synth.ranges_mm(truth[1:], anc, seed=22)
+    first = oracle.t6_replay(truth[0], None, r[:6], anc, 0.1, 0.01)
+    ref = oracle.t6_replay(first["x"], first["P"], r[6:], anc, 0.1, 0.01)
+    got = run_gpu(kflib, first["x"], r[6:], anc, 0.1, 0.01, P0=first["P"], accel_noise=0.5)
+    assert rel_err_state(got["x"][:3], ref["x"]) < REL_TOL
+    assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
+
+
+@pytest.mark.parametrize("thr", [0.0, 0.5, 5.0])
+def test_t6_leave_one_out_selection(kflib, oracle, thr):
+    """ignoreWorstAnchorMode (TOA.cpp:185-238): ignored anchor index bit-exact."""
+    N, T, m = 1500, 12, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=31)
+    r = synth.ranges_mm(truth[1:], anc, seed=32, p_nlos=0.15)
+    ref = oracle.t6_replay(truth[0], None, r, anc, 0.1, 0.01, ignore_worst=True, thr=thr)
+    got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, want_sel=True, accel_noise=0.5,
+                  ignore_worst_anchor=1, ignore_cost_threshold=thr)
+    assert np.array_equal(got["sel"], ref["sel"])
+    assert (ref["sel"] >= 0).any()
+    assert rel_err_state(got["x"][:3], ref["x"]) < REL_TOL
+    assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
+
+
+def test_t6_get_pose(kflib, oracle):
+    from roskfpos_b200.batch import Batch
+    N, m = 64, 4
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, 3, 0.1, seed=41)
+    r = synth.ranges_mm(truth[1:], anc, seed=42)
+    with Batch(kflib.MODEL_T6, N, anchors=anc, accel_noise=0.5) as b:
+        b.set_state(truth[0])
+        b.replay_toa(0.1, r)
+        x0, P0, _ = b.get_state()
+        xp, Pp = b.get_pose(0.037)
+        x1, P1, _ = b.get_state()
+    assert np.array_equal(x0, x1) and np.array_equal(P0, P1)  # non-mutating
+    for f in (0, 17, 63):
+        o = oracle.T6(0.5, False, 0.0, x0[:3, f])
+        for k in range(36):
+            o.f.P[k] = P0[k, f]
+        pos, Pref = o.get_pose(0.037)
+        assert np.allclose(xp[:3, f], pos, rtol=0, atol=1e-12)
+        assert np.abs(Pp[:, f].reshape(6, 6) - Pref).max() <= 1e-12 * np.abs(Pref).max()
+
+
+def test_t6_error_stats_and_determinism(kflib):
+    from roskfpos_b200.batch import Batch
+    N, T, m = 5000, 8, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=51)
+    r = synth.ranges_mm(truth[1:], anc, seed=52)
+    outs = []
+    for _ in range(2):
+        with Batch(kflib.MODEL_T6, N, anchors=anc, accel_noise=0.5) as b:
+            b.set_state(truth[0])
+            b.replay_toa(0.1, r)
+            x, _, st = b.get_state(want_P=False)
+            outs.append((x, b.error_stats(truth[-1])))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(outs[0][1], outs[1][1])  # fixed-shape tree: bit-identical
+    e2 = ((outs[0][0][:3] - truth[-1]) ** 2).sum(axis=0)
+    s = outs[0][1]
+    assert s[2] == N and abs(s[0] - e2.sum()) <= 1e-12 * e2.sum()
