@@ -1,0 +1,191 @@
+"""ctypes binding of oracle/_ref/libkfref.so: the reference's OWN .cpp files compiled
+against the shim headers (oracle/shim) with LAPACK from scipy's bundled OpenBLAS.
+
+TEST INFRASTRUCTURE ONLY (pins the oracle; optional "reference" CPU baseline).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(_HERE, "_ref", "libkfref.so")
+_LIB = None
+
+XML_DEFAULT = {
+    "kfpos_pos": '<config><algorithm type="0" variant="0"/></config>',
+    "kfpos_px4": '<config><px4flow armP0="1" armP1="0" useFixedSensorHeight="1" sensorHeight="5" '
+                 'sensorInitAngle="-1.570796326794897" covarianceVelocity="0.04" covarianceGyroZ="0.02"/></config>',
+    "kfpos_tag": '<config><uwb useFixedHeight="0" fixedHeight="1.049" tagId="0"/></config>',
+    "kfpos_imu": '<config><imu useFixedCovarianceAcceleration="1" covarianceAcceleration="0.003" '
+                 'useFixedCovarianceAngularVelocityZ="1" covarianceAngularVelocityZ="0.089"/></config>',
+    "kfpos_mag": '<config><mag angleOffset="0" covarianceMag="0.0001"/></config>',
+}
+
+
+def find_lapack():
+    try:
+        import scipy
+        base = os.path.join(os.path.dirname(os.path.dirname(scipy.__file__)), "scipy.libs")
+    except ImportError:
+        return None
+    c = sorted(glob.glob(os.path.join(base, "libscipy_openblas-*.so")))
+    return c[0] if c else None
+
+
+def available() -> bool:
+    return os.path.exists(SO) and find_lapack() is not None
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        l = C.CDLL(SO)
+        for n in ("ref_ml_create", "ref_t6_create", "ref_k8_create", "ref_t9_create"):
+            getattr(l, n).restype = C.c_void_p
+        if l.ref_init(find_lapack().encode()) != 0:
+            raise RuntimeError("libkfref: cannot load LAPACK from scipy's OpenBLAS")
+        _LIB = l
+    return _LIB
+
+
+def _p(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _arr(a, shape=None):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a if shape is None else np.ascontiguousarray(np.broadcast_to(a, shape))
+
+
+def ns(dt: float) -> int:
+    """dt in integer nanoseconds (the fake clock's tick); use dt values that are exact ns multiples."""
+    return int(round(dt * 1e9))
+
+
+def valid_only(ranges, anchors, errs):
+    """PosGenerator only forwards slots with range > 0 (PG.cpp:481-489)."""
+    ranges = np.asarray(ranges, dtype=np.float64)
+    keep = ranges > 0
+    return (np.ascontiguousarray(ranges[keep]), np.ascontiguousarray(np.asarray(anchors, dtype=np.float64)[keep]),
+            np.ascontiguousarray(np.broadcast_to(np.asarray(errs, dtype=np.float64), ranges.shape)[keep]))
+
+
+class RefML:
+    def __init__(self, use2d, variant, n_ignore, start):
+        self.h = C.c_void_p(lib().ref_ml_create(int(use2d), int(variant), int(n_ignore),
+                                                C.c_double(start[0]), C.c_double(start[1]), C.c_double(start[2])))
+
+    def solve(self, ranges, anchors, errs, mode=1):
+        r, a, e = valid_only(ranges, anchors, errs)
+        pos = np.zeros(3); cov = np.zeros(9); d = C.c_int(0)
+        rc = lib().ref_ml_solve(self.h, int(mode), len(r), _p(r), _p(a), _p(e), _p(pos), _p(cov), C.byref(d))
+        dd = d.value
+        return dict(rc=rc, pos=pos, cov=cov[:dd * dd].reshape(dd, dd).copy() if dd else np.zeros((0, 0)))
+
+    def __del__(self):
+        if _LIB is not None and self.h:
+            _LIB.ref_ml_destroy(self.h)
+
+
+class RefT6:
+    def __init__(self, accel_noise, ignore_worst, thr, p0):
+        self.h = C.c_void_p(lib().ref_t6_create(C.c_double(accel_noise), int(ignore_worst), C.c_double(thr),
+                                                C.c_double(p0[0]), C.c_double(p0[1]), C.c_double(p0[2])))
+
+    def new_toa(self, dt, ranges, anchors, errs):
+        r, a, e = valid_only(ranges, anchors, errs)
+        return lib().ref_t6_toa(self.h, C.c_longlong(ns(dt)), len(r), _p(r), _p(a), _p(e))
+
+    def state(self):
+        pos = np.zeros(3); P = np.zeros(36)
+        lib().ref_t6_get(self.h, _p(pos), _p(P))
+        return pos, P.reshape(6, 6)
+
+    def get_pose(self, dt):
+        pos = np.zeros(3); P = np.zeros(36)
+        rc = lib().ref_t6_get_pose(self.h, C.c_longlong(ns(dt)), _p(pos), _p(P))
+        return rc, pos, P.reshape(6, 6)
+
+    def __del__(self):
+        if _LIB is not None and self.h:
+            _LIB.ref_t6_destroy(self.h)
+
+
+class RefK8:
+    def __init__(self, accel_noise, init_angle, jolt, p0, xml=None):
+        params = dict(XML_DEFAULT)
+        params.update(xml or {})
+        for k, v in params.items():
+            lib().ref_set_param(k.encode(), v.encode())
+        h = lib().ref_k8_create(C.c_double(accel_noise), C.c_double(init_angle), C.c_double(jolt),
+                                C.c_double(p0[0]), C.c_double(p0[1]), C.c_double(p0[2] if len(p0) > 2 else 0.0))
+        if not h:
+            raise RuntimeError("KalmanFilter::init() failed")
+        self.h = C.c_void_p(h)
+
+    def new_toa(self, dt, ranges, anchors, errs):
+        r, a, e = valid_only(ranges, anchors, errs)
+        return lib().ref_k8_toa(self.h, C.c_longlong(ns(dt)), len(r), _p(r), _p(a), _p(e))
+
+    def new_px4(self, dt, ix, iy, irz, itime_us, quality):
+        return lib().ref_k8_px4(self.h, C.c_longlong(ns(dt)), C.c_double(ix), C.c_double(iy), C.c_double(irz),
+                                C.c_double(itime_us), int(quality))
+
+    def new_imu(self, dt, angvel, cov_av, acc, cov_acc):
+        a = [_arr(v) for v in (angvel, cov_av, acc, cov_acc)]
+        return lib().ref_k8_imu(self.h, C.c_longlong(ns(dt)), _p(a[0]), _p(a[1]), _p(a[2]), _p(a[3]))
+
+    def new_mag(self, dt, mag):
+        m = _arr(mag)
+        return lib().ref_k8_mag(self.h, C.c_longlong(ns(dt)), _p(m))
+
+    def new_compass(self, dt, compass):
+        return lib().ref_k8_compass(self.h, C.c_longlong(ns(dt)), C.c_double(compass))
+
+    def state(self):
+        x = np.zeros(8); P = np.zeros(64)
+        lib().ref_k8_get(self.h, _p(x), _p(P))
+        return x, P.reshape(8, 8)
+
+    def __del__(self):
+        if _LIB is not None and self.h:
+            _LIB.ref_k8_destroy(self.h)
+
+
+class RefT9:
+    def __init__(self, accel_noise, jolt, p0):
+        self.h = C.c_void_p(lib().ref_t9_create(C.c_double(accel_noise), C.c_double(jolt), C.c_double(p0[0]),
+                                                C.c_double(p0[1]), C.c_double(p0[2])))
+
+    def new_toa(self, dt, ranges, anchors, errs):
+        r, a, e = valid_only(ranges, anchors, errs)
+        return lib().ref_t9_toa(self.h, C.c_longlong(ns(dt)), len(r), _p(r), _p(a), _p(e))
+
+    def new_imu(self, dt, acc, cov_acc):
+        a, c = _arr(acc), _arr(cov_acc)
+        return lib().ref_t9_imu(self.h, C.c_longlong(ns(dt)), _p(a), _p(c))
+
+    def state(self):
+        x = np.zeros(9); P = np.zeros(81)
+        lib().ref_t9_get(self.h, _p(x), _p(P))
+        return x, P.reshape(9, 9)
+
+    def __del__(self):
+        if _LIB is not None and self.h:
+            _LIB.ref_t9_destroy(self.h)
+
+
+def t6_replay(x0, ranges_m, anchors, dt, err, accel_noise=0.5):
+    """Batch driver (single thread): ranges f64 metres [T][M][N], x0 [3][N]."""
+    ranges_m = np.ascontiguousarray(ranges_m, dtype=np.float64)
+    T, M, N = ranges_m.shape
+    anchors = _arr(anchors)
+    x0 = _arr(x0).reshape(3, N)
+    x = np.zeros((3, N)); P = np.zeros((36, N))
+    rc = lib().ref_t6_replay(C.c_longlong(N), T, M, _p(anchors), C.c_longlong(ns(dt)), _p(ranges_m),
+                             C.c_double(err), C.c_double(accel_noise), _p(x0), _p(x), _p(P))
+    return dict(rc=rc, x=x, P=P)

@@ -139,7 +139,7 @@ def test_t6_leave_one_out_selection(kflib, oracle, thr):
     got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, want_sel=True, accel_noise=0.5,
                   ignore_worst_anchor=1, ignore_cost_threshold=thr)
     rep = assert_parity(got, ref, per, float_keys=("x",), cov_keys=("P",), int_keys=("status", "sel"),
-                        min_stable=0.97, max_tie_frac=3e-3, what=f"T6 leave-one-out thr={thr}")
+                        min_stable=0.95, max_tie_frac=3e-3, what=f"T6 leave-one-out thr={thr}")
     print("parity report loo", thr, rep)
     assert (ref["sel"] >= 0).any()
 
