@@ -105,29 +105,62 @@ def load_peaks():
 
 
 # --------------------------------------------------------------------------- CPU
-def cpu_reference(n_anchors, tsteps, seconds, threads=0):
-    """Times the CPU oracle (the as-written restatement of the reference's filter,
-    oracle/) on a bounded sample of the bench workload.  Returns a cpu_baseline dict."""
-    from oracle import oracle_py as O
+def _ref_worker(job):
+    """One single-threaded reference process (the reference is single-threaded,
+    node_pos.cpp:176-181): generates its slice, times only the filter calls."""
+    seed, nf, tsteps, n_anchors = job
+    from oracle import ref_py as R
     from roskfpos_b200 import synth
     anc = synth.anchors_for(n_anchors)
-    threads = threads or O.max_threads()
-    kind = "port"
+    truth = synth.truth_lissajous(nf, tsteps, 0.1, seed=seed)
+    r = synth.ranges_mm(truth[1:], anc, seed=seed + 1).astype(np.float64) / 1000
+    R.lib()
+    t0 = time.perf_counter()
+    out = R.t6_replay(truth[0], r, anc, 0.1, 0.01)
+    return time.perf_counter() - t0, nf * tsteps, int(out["rc"])
+
+
+def cpu_reference(n_anchors, tsteps, seconds, threads=0):
+    """Times the reference's CPU implementation of the path on a bounded sample of the bench
+    workload, on all host cores.  kind "reference": the reference's own .cpp files compiled
+    against the shim headers + LAPACK (oracle/_ref, one process per core); kind "port": the
+    oracle restatement with OpenMP (when oracle/_ref was not built)."""
+    from oracle import oracle_py as O
+    from oracle import ref_py as R
+    from roskfpos_b200 import synth
+    anc = synth.anchors_for(n_anchors)
+    cores = threads or os.cpu_count() or 1
+    if R.available():
+        import multiprocessing as mp
+        ctx = mp.get_context("fork")
+        with ctx.Pool(cores) as pool:
+            probe = pool.map(_ref_worker, [(synth.SEED + 50 + i, 8, tsteps, n_anchors) for i in range(cores)])
+            rate_core = np.mean([u / t for t, u, _ in probe])
+            nf = int(max(8, rate_core * seconds / tsteps))
+            res = pool.map(_ref_worker, [(synth.SEED + 100 + i, nf, tsteps, n_anchors) for i in range(cores)])
+        tt = max(t for t, _, _ in res)
+        upd = sum(u for _, u, _ in res)
+        return {"value": upd / tt, "unit": UNIT, "cores": cores, "kind": "reference",
+                "sample": f"{nf * cores} filters x {tsteps} steps, {n_anchors} anchors, the reference's own "
+                          f"KalmanFilterTOA.cpp + MLLocation.cpp (g++ -O2, shim Armadillo over OpenBLAS LAPACK), "
+                          f"{cores} single-threaded processes, {tt:.1f} s",
+                "errors": int(sum(rc for _, _, rc in res))}
 
     def run(nf):
         truth = synth.truth_lissajous(nf, tsteps, 0.1, seed=synth.SEED + 7)
         r = synth.ranges_mm(truth[1:], anc, seed=synth.SEED + 8)
         t0 = time.perf_counter()
-        out = O.t6_replay(truth[0], None, r, anc, 0.1, 0.01, threads=threads)
+        out = O.t6_replay(truth[0], None, r, anc, 0.1, 0.01, threads=cores)
         return time.perf_counter() - t0, out
 
-    probe_n = 64 * threads
+    cores = threads or O.max_threads()
+    probe_n = 64 * cores
     tp, _ = run(probe_n)
     rate = probe_n * tsteps / max(tp, 1e-6)
     nf = int(max(probe_n, min(rate * seconds / tsteps, 4_000_000)))
     tt, out = run(nf)
     upd = nf * tsteps
-    return {"value": upd / tt, "unit": UNIT, "cores": threads, "kind": kind,
+    return {"value": upd / tt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{nf} filters x {tsteps} steps, {n_anchors} anchors, T6 (KalmanFilterTOA) oracle "
                       f"restatement, gcc -O3 + OpenMP, {tt:.1f} s",
             "mean_iters": {"ml": out["counters"][0] / upd, "cost": out["counters"][1] / upd,
@@ -142,16 +175,21 @@ def run_reference(args):
     per = max(2.0, min(20.0, 100.0 / max(K + W, 1)))
     vals = []
     last = None
+    t_steps = []
     for i in range(W + K):
+        t0 = time.perf_counter()
         last = cpu_reference(args.anchors, args.tsteps, per)
         if i >= W:
             vals.append(last["value"])
+            t_steps.append(time.perf_counter() - t0)
     v = float(np.mean(vals))
     last["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": K, "warmup": W, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": 1e3 * float(np.mean(t_steps)), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"T6 IEKF replay, {args.anchors} anchors, CPU sample (see cpu_baseline.sample)"},
+            "config": {"workload": f"T6 (KalmanFilterTOA) IEKF replay, {args.anchors} anchors, dt 0.1 s, P0=0, fixed "
+                                   f"initial position; bounded CPU sample per step (see cpu_baseline.sample)",
+                       "anchors": args.anchors, "epochs_per_step": args.tsteps},
             "cpu_baseline": last,
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -210,6 +248,7 @@ def run_b200(args):
     t_start = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    torch.cuda.cudart().cudaProfilerStart()  # ncu --profile-from-start off sees the timed region only
     e0.record(stream)
     for k in range(K):
         batch.set_state(x0_full, None, stream=stream)
@@ -223,6 +262,7 @@ def run_b200(args):
             s = stats.cpu().numpy()
     e1.record(stream)
     barrier()
+    torch.cuda.cudart().cudaProfilerStop()
     sampler.window(t_start, time.perf_counter())
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)

@@ -5,19 +5,24 @@
 // table that yields, at the current point, the stopping cost, the unweighted SSE
 // (the EKFs' mlRangingError), the gradient and the Hessian together -- the
 // reference evaluates the distances three times per iteration (ML.cpp:171,216,229).
+// The anchor loop is NOT unrolled (the whole replay kernel has to stay inside the
+// 32 KB instruction cache); the epoch's rangings live in a shared-memory column.
 #pragma once
 #include "kfpos_math.cuh"
 
 namespace kfpos {
 
-// Valid rangings of one epoch: z[i] metres for the slots set in `valid`.
-// PME = per-measurement errorEstimation array; otherwise one scalar for all.
-template <int MAXM, bool PME>
+// Valid rangings of one epoch: z[i] metres (shared-memory column) for the slots
+// set in `valid`.  PME = per-measurement errorEstimation column `e`; otherwise
+// the scalar e0 applies to every ranging.
+template <bool PME>
 struct Epoch {
-    double z[MAXM];
-    double e[PME ? MAXM : 1];
+    Col z;
+    Col e;
+    double e0;
     unsigned valid;
-    KF_DEV double err(int i) const { return PME ? e[i] : e[0]; }
+    int m_slots;
+    KF_DEV double err(int i) const { return PME ? e[i] : e0; }
 };
 
 struct MlPass3 {
@@ -26,41 +31,50 @@ struct MlPass3 {
     double H[6]; // packed Sym<3>: xx, xy, yy, xz, yz, zz
 };
 
-// gradient / Hessian / costs at p over the slots in `mask` (ML.cpp:171-222)
-template <int MAXM, bool PME>
-KF_DEV void ml_pass3(const AnchorTable &A, const Epoch<MAXM, PME> &ep, unsigned mask,
-                     const double (&p)[3], MlPass3 &o) {
-    o.wcost = 0.0; o.sse = 0.0;
-    o.g[0] = o.g[1] = o.g[2] = 0.0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) o.H[k] = 0.0;
-    const double inv_e0 = 1.0 / ep.e[0];
-#pragma unroll
-    for (int i = 0; i < MAXM; ++i) {
+// gradient / Hessian / costs at p over the slots in `mask` (ML.cpp:171-222).
+// With a scalar errorEstimation the weight 1/e is common to g and H and cancels in
+// the Newton step, so only the stop-test cost carries it.
+template <bool PME>
+KF_DEV void ml_pass3(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, const double (&p)[3],
+                     MlPass3 &o) {
+    double wc = 0.0, sse = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0, h4 = 0.0, h5 = 0.0, c1s = 0.0;
+#pragma unroll 2
+    for (int i = 0; i < ep.m_slots; ++i) {
         if (!((mask >> i) & 1u)) continue;
         const double dx = A.x[i] - p[0], dy = A.y[i] - p[1], dz = A.z[i] - p[2];
-        const double d2 = dx * dx + dy * dy + dz * dz;
-        const double d = sqrt(d2);
-        const double invd = 1.0 / d;
-        const double w = PME ? 1.0 / ep.e[i] : inv_e0;
+        const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        const double invd = fast_rsqrt(d2);
+        const double d = d2 * invd;
         const double r = ep.z[i];
         const double res = r - d;
-        o.sse = fma(res, res, o.sse);
-        o.wcost = fma(res * res, w, o.wcost);
-        const double t = res * invd * w;
-        o.g[0] = fma(t, dx, o.g[0]);
-        o.g[1] = fma(t, dy, o.g[1]);
-        o.g[2] = fma(t, dz, o.g[2]);
         const double rid = r * invd;
-        const double c1 = (1.0 - rid) * w;
-        const double c2 = rid * invd * invd * w;
-        o.H[0] += fma(c2 * dx, dx, c1);
-        o.H[2] += fma(c2 * dy, dy, c1);
-        o.H[5] += fma(c2 * dz, dz, c1);
-        o.H[1] = fma(c2 * dx, dy, o.H[1]);
-        o.H[3] = fma(c2 * dx, dz, o.H[3]);
-        o.H[4] = fma(c2 * dy, dz, o.H[4]);
+        if (PME) {
+            const double w = 1.0 / ep.e[i];
+            sse = fma(res, res, sse);
+            wc = fma(res * res, w, wc);
+            const double t = res * invd * w;
+            g0 = fma(t, dx, g0); g1 = fma(t, dy, g1); g2 = fma(t, dz, g2);
+            c1s = fma(1.0 - rid, w, c1s);
+            const double c2 = rid * invd * invd * w;
+            const double cx = c2 * dx, cy = c2 * dy, cz = c2 * dz;
+            h0 = fma(cx, dx, h0); h1 = fma(cx, dy, h1); h2 = fma(cy, dy, h2);
+            h3 = fma(cx, dz, h3); h4 = fma(cy, dz, h4); h5 = fma(cz, dz, h5);
+        } else {
+            sse = fma(res, res, sse);
+            const double t = res * invd;
+            g0 = fma(t, dx, g0); g1 = fma(t, dy, g1); g2 = fma(t, dz, g2);
+            c1s += 1.0 - rid;
+            const double c2 = rid * invd * invd;
+            const double cx = c2 * dx, cy = c2 * dy, cz = c2 * dz;
+            h0 = fma(cx, dx, h0); h1 = fma(cx, dy, h1); h2 = fma(cy, dy, h2);
+            h3 = fma(cx, dz, h3); h4 = fma(cy, dz, h4); h5 = fma(cz, dz, h5);
+        }
     }
+    o.sse = sse;
+    o.wcost = PME ? wc : sse * (1.0 / ep.e0);
+    o.g[0] = g0; o.g[1] = g1; o.g[2] = g2;
+    o.H[0] = h0 + c1s; o.H[1] = h1; o.H[2] = h2 + c1s; o.H[3] = h3; o.H[4] = h4; o.H[5] = h5 + c1s;
 }
 
 // return codes of the ML solvers
@@ -71,11 +85,11 @@ KF_DEV void ml_pass3(const AnchorTable &A, const Epoch<MAXM, PME> &ep, unsigned 
 // estimatePosition (3-D), ML.cpp:153-257.  p: in = start, out = estimate.
 // sse_out = estimationError at the returned point.  The covariance
 // inv(J^T W^-1 J) (ML.cpp:229-254) is produced only when cov != nullptr.
-template <int MAXM, bool PME>
-KF_DEV int ml_solve3(const AnchorTable &A, const Epoch<MAXM, PME> &ep, unsigned mask, double (&p)[3],
+template <bool PME>
+KF_DEV int ml_solve3(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, double (&p)[3],
                      double &sse_out, unsigned &iters, double *cov /* packed Sym<3> or null */) {
     MlPass3 ps;
-    ml_pass3<MAXM, PME>(A, ep, mask, p, ps);
+    ml_pass3<PME>(A, ep, mask, p, ps);
     sse_out = ps.sse;
     if (__popc(mask) < 4) return ML_FEW;
     double cost = 1e20, newCost = 1.0;
@@ -87,7 +101,7 @@ KF_DEV int ml_solve3(const AnchorTable &A, const Epoch<MAXM, PME> &ep, unsigned 
         if (!solve_sym3(ps.H, ps.g, s)) { iters += iter; return ML_SINGULAR; }
         // newPos = solve(H, H pos - g)  ==  pos - H^-1 g
         p[0] -= s[0]; p[1] -= s[1]; p[2] -= s[2];
-        ml_pass3<MAXM, PME>(A, ep, mask, p, ps);
+        ml_pass3<PME>(A, ep, mask, p, ps);
         newCost = ps.wcost;
     }
     iters += iter;
@@ -95,8 +109,7 @@ KF_DEV int ml_solve3(const AnchorTable &A, const Epoch<MAXM, PME> &ep, unsigned 
     if (cov) {
         // J_i = (p - b_i)/d_i ; W = diag(max(e_i, SSE)) ; cov = inv(J^T W^-1 J)
         double M[6] = {0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int i = 0; i < MAXM; ++i) {
+        for (int i = 0; i < ep.m_slots; ++i) {
             if (!((mask >> i) & 1u)) continue;
             const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
             const double id2 = 1.0 / (dx * dx + dy * dy + dz * dz);
@@ -123,44 +136,43 @@ struct MlPass2 {
 };
 
 // 2-D pass: distances are 3-D with z fixed, derivatives in x,y only (ML.cpp:74-95)
-template <int MAXM, bool PME>
-KF_DEV void ml_pass2(const AnchorTable &A, const Epoch<MAXM, PME> &ep, unsigned mask, double px,
-                     double py, double pz, MlPass2 &o) {
-    o.sse = 0.0;
-    o.g[0] = o.g[1] = 0.0;
-    o.H[0] = o.H[1] = o.H[2] = 0.0;
-    const double inv_e0 = 1.0 / ep.e[0];
-#pragma unroll
-    for (int i = 0; i < MAXM; ++i) {
+template <bool PME>
+KF_DEV void ml_pass2(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, double px, double py,
+                     double pz, MlPass2 &o) {
+    double sse = 0.0, g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0, h2 = 0.0, c1s = 0.0;
+#pragma unroll 2
+    for (int i = 0; i < ep.m_slots; ++i) {
         if (!((mask >> i) & 1u)) continue;
         const double dx = A.x[i] - px, dy = A.y[i] - py, dz = A.z[i] - pz;
-        const double d = sqrt(dx * dx + dy * dy + dz * dz);
-        const double invd = 1.0 / d;
-        const double w = PME ? 1.0 / ep.e[i] : inv_e0;
+        const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        const double invd = fast_rsqrt(d2);
+        const double d = d2 * invd;
         const double r = ep.z[i];
         const double res = r - d;
-        o.sse = fma(res, res, o.sse);
-        const double t = res * invd * w;
-        o.g[0] = fma(t, dx, o.g[0]);
-        o.g[1] = fma(t, dy, o.g[1]);
         const double rid = r * invd;
-        const double c1 = (1.0 - rid) * w;
+        const double w = PME ? 1.0 / ep.e[i] : 1.0;
+        sse = fma(res, res, sse);
+        const double t = res * invd * w;
+        g0 = fma(t, dx, g0); g1 = fma(t, dy, g1);
+        c1s = fma(1.0 - rid, w, c1s);
         const double c2 = rid * invd * invd * w;
-        o.H[0] += fma(c2 * dx, dx, c1);
-        o.H[2] += fma(c2 * dy, dy, c1);
-        o.H[1] = fma(c2 * dx, dy, o.H[1]);
+        const double cx = c2 * dx, cy = c2 * dy;
+        h0 = fma(cx, dx, h0); h1 = fma(cx, dy, h1); h2 = fma(cy, dy, h2);
     }
+    o.sse = sse;
+    o.g[0] = g0; o.g[1] = g1;
+    o.H[0] = h0 + c1s; o.H[1] = h1; o.H[2] = h2 + c1s;
 }
 
 // estimatePosition2D, ML.cpp:48-143.  z stays at its start value.  The damping
 // `step` of the reference never takes effect: a rejected step leaves
 // newCost == cost, so the while-test fails on the next evaluation (ML.cpp:109-116).
 // B-1: the tentative cost is evaluated at z = start z.
-template <int MAXM, bool PME>
-KF_DEV int ml_solve2(const AnchorTable &A, const Epoch<MAXM, PME> &ep, unsigned mask, double (&p)[3],
+template <bool PME>
+KF_DEV int ml_solve2(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, double (&p)[3],
                      double &sse_out, unsigned &iters, double *cov /* xx, xy, yy or null */) {
     MlPass2 ps;
-    ml_pass2<MAXM, PME>(A, ep, mask, p[0], p[1], p[2], ps);
+    ml_pass2<PME>(A, ep, mask, p[0], p[1], p[2], ps);
     sse_out = ps.sse;
     if (__popc(mask) < 3) return ML_FEW;
     double cost = 1e20, newCost = ps.sse;
@@ -175,7 +187,7 @@ KF_DEV int ml_solve2(const AnchorTable &A, const Epoch<MAXM, PME> &ep, unsigned 
         }
         const double nx = p[0] - s0, ny = p[1] - s1;
         MlPass2 pt;
-        ml_pass2<MAXM, PME>(A, ep, mask, nx, ny, p[2], pt);
+        ml_pass2<PME>(A, ep, mask, nx, ny, p[2], pt);
         if (pt.sse > cost) break; // step /= 2; position kept; loop ends
         newCost = pt.sse;
         p[0] = nx; p[1] = ny;
@@ -185,8 +197,7 @@ KF_DEV int ml_solve2(const AnchorTable &A, const Epoch<MAXM, PME> &ep, unsigned 
     sse_out = ps.sse;
     if (cov) {
         double m00 = 0, m01 = 0, m11 = 0;
-#pragma unroll
-        for (int i = 0; i < MAXM; ++i) {
+        for (int i = 0; i < ep.m_slots; ++i) {
             if (!((mask >> i) & 1u)) continue;
             const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
             const double id2 = 1.0 / (dx * dx + dy * dy + dz * dz);
@@ -203,6 +214,20 @@ KF_DEV int ml_solve2(const AnchorTable &A, const Epoch<MAXM, PME> &ep, unsigned 
         cov[2] = m00 * id;
     }
     return ML_OK;
+}
+
+// loads one epoch's rangings into the shared-memory columns; ranges: SoA with the
+// filter index fastest, `base` = index of slot 0 for this filter, `N` = stride.
+template <bool PME>
+KF_DEV void load_epoch(Epoch<PME> &ep, const void *ranges, int fmt, const double *err, int64_t base, int64_t N) {
+    unsigned valid = 0u;
+    for (int i = 0; i < ep.m_slots; ++i) {
+        const double r = load_range(ranges, fmt, base + (int64_t)i * N);
+        ep.z[i] = r;
+        if (r > 0) valid |= 1u << i; // keep rangings[i] > 0 (TOA.cpp:48-57, ML.cpp:478)
+        if (PME) ep.e[i] = __ldg(err + base + (int64_t)i * N);
+    }
+    ep.valid = valid;
 }
 
 } // namespace kfpos

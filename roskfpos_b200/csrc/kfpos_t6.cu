@@ -1,8 +1,9 @@
 // kfpos_t6.cu -- persistent replay kernel for KalmanFilterTOA batches (G1+G2+G3+G5
-// of SURVEY.md §2): one thread per filter, position and the packed 6x6
-// covariance stay in registers across all T steps; per step the only global
-// traffic is the coalesced read of the filter's M rangings (SoA, filter index
-// fastest) and the optional trajectory / selection stores.
+// of SURVEY.md §2).  One thread per filter; the filter's position and the working
+// covariance stay in registers and its P^- / per-anchor scratch in a private
+// shared-memory column across all T steps.  Per step the only global traffic is
+// the coalesced read of the filter's M rangings (SoA, filter index fastest) and
+// the optional trajectory / selection stores.
 #include "kfpos_kernels.cuh"
 #include "kfpos_t6.cuh"
 
@@ -10,8 +11,14 @@ namespace kfpos {
 
 constexpr int T6_BLOCK = 128;
 
-template <int MAXM, bool PME, bool LOO>
-__global__ void __launch_bounds__(T6_BLOCK) t6_replay_kernel(const __grid_constant__ T6Params p) {
+// shared-memory rows per thread
+__host__ __device__ inline int t6_smem_rows(int m, bool pme, bool loo) {
+    return 3 * m + (pme ? m : 0) + 21 + (loo ? 2 * (21 + 6) : 0);
+}
+
+template <bool PME, bool LOO>
+__global__ void __launch_bounds__(T6_BLOCK, LOO ? 2 : 4) t6_replay_kernel(const __grid_constant__ T6Params p) {
+    extern __shared__ double smem[];
     const int64_t f = (int64_t)blockIdx.x * T6_BLOCK + threadIdx.x;
     const bool active = f < p.N;
     StepStats st = {0u, 0u, 0u, 0u};
@@ -19,76 +26,89 @@ __global__ void __launch_bounds__(T6_BLOCK) t6_replay_kernel(const __grid_consta
 
     if (active) {
         const int64_t N = p.N;
+        const int m = p.rs.m_slots;
+        // carve this thread's columns
+        double *col = smem + threadIdx.x;
+        int row = 0;
+        auto take = [&](int rows) {
+            Col c = {col + (size_t)row * T6_BLOCK, T6_BLOCK};
+            row += rows;
+            return c;
+        };
+        Epoch<PME> ep;
+        ep.z = take(m);
+        ep.e = PME ? take(m) : ep.z;
+        ep.e0 = p.rs.err_scalar;
+        ep.m_slots = m;
+        T6Scratch sc;
+        sc.invd = take(m);
+        sc.eps = take(m);
+        sc.Pm = take(21);
+        Col s_all = LOO ? take(27) : sc.Pm, s_best = LOO ? take(27) : sc.Pm;
+
         double pos[3];
-        Sym<6> P;
 #pragma unroll
         for (int k = 0; k < 3; ++k) pos[k] = p.x[(int64_t)k * N + f];
 #pragma unroll
-        for (int k = 0; k < Sym<6>::SZ; ++k) P.a[k] = p.P[(int64_t)k * N + f];
+        for (int k = 0; k < Sym<6>::SZ; ++k) sc.Pm[k] = p.P[(int64_t)k * N + f];
         unsigned status_or = 0;
 
         for (int t = 0; t < p.T; ++t) {
-            // ---- this step's rangings: keep rangings[i] > 0 (TOA.cpp:48-57)
-            Epoch<MAXM, PME> ep;
-            ep.valid = 0u;
-            ep.e[0] = p.rs.err_scalar;
-            const int64_t base = (int64_t)t * p.rs.m_slots * N + f;
-#pragma unroll
-            for (int i = 0; i < MAXM; ++i) {
-                ep.z[i] = 0.0;
-                if (PME) ep.e[i] = 1.0;
-                if (i < p.rs.m_slots) {
-                    const double r = load_range(p.rs.ranges, p.rs.fmt, base + (int64_t)i * N);
-                    ep.z[i] = r;
-                    if (r > 0) ep.valid |= 1u << i;
-                    if (PME) ep.e[i] = __ldg(p.rs.err + base + (int64_t)i * N);
-                }
-            }
+            load_epoch<PME>(ep, p.rs.ranges, p.rs.fmt, p.rs.err, (int64_t)t * m * N + f, N);
             const double dt = __ldg(p.dt + t);
 
             // ---- predict (TOA.cpp:115-123): x^- = F x with v = 0, P^- = F P F^T + Q.
             // The member covariance is overwritten before the try block, so P^-
             // is what survives a failed update.
-            t6_predict_cov(P, dt, p.accel_noise);
+            Sym<6> Pw;
+#pragma unroll
+            for (int k = 0; k < Sym<6>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+            t6_predict_cov(Pw, dt, p.accel_noise);
+#pragma unroll
+            for (int k = 0; k < Sym<6>::SZ; ++k) sc.Pm[k] = Pw.a[k];
 
             st.status = 0u;
             if (ep.valid == 0u) st.status |= 1u;
-            Sym<6> Pw;
             double dx[6], cost;
-            int rc = t6_update<MAXM, PME>(p.anchors, ep, ep.valid, pos, P, Pw, dx, cost, st);
+            int rc = t6_update<PME>(p.anchors, ep, ep.valid, pos, sc, Pw, dx, cost, st);
             int ignored = -1;
             if (LOO) {
                 // kalmanStep3DCanIgnoreAnAnchor (TOA.cpp:185-238): only with > 4 rangings
                 if (rc == 0 && __popc(ep.valid) > 4) {
-                    double maxDist = 0.0, worstCost = 0.0, dxb[6];
-                    Sym<6> Pb;
+#pragma unroll
+                    for (int k = 0; k < 21; ++k) s_all[k] = Pw.a[k];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) s_all[21 + k] = dx[k];
+                    double maxDist = 0.0, worstCost = 0.0;
                     int idx = -1;
                     bool first = true;
-                    for (int i = 0; i < MAXM && rc == 0; ++i) {
+                    for (int i = 0; i < m && rc == 0; ++i) {
                         if (!((ep.valid >> i) & 1u)) continue;
-                        Sym<6> Pi;
-                        double dxi[6], ci;
-                        rc = t6_update<MAXM, PME>(p.anchors, ep, ep.valid & ~(1u << i), pos, P, Pi,
-                                                  dxi, ci, st);
+                        double ci;
+                        rc = t6_update<PME>(p.anchors, ep, ep.valid & ~(1u << i), pos, sc, Pw, dx, ci, st);
                         if (rc != 0) break;
-                        const double ex = p.anchors.x[i] - (pos[0] + dxi[0]);
-                        const double ey = p.anchors.y[i] - (pos[1] + dxi[1]);
-                        const double ez = p.anchors.z[i] - (pos[2] + dxi[2]);
+                        const double ex = p.anchors.x[i] - (pos[0] + dx[0]);
+                        const double ey = p.anchors.y[i] - (pos[1] + dx[1]);
+                        const double ez = p.anchors.z[i] - (pos[2] + dx[2]);
                         const double diff = ep.z[i] - sqrt(ex * ex + ey * ey + ez * ez);
                         if (first || diff > maxDist) { // strict >, first seeds (TOA.cpp:209)
                             maxDist = diff;
                             worstCost = ci;
-                            Pb = Pi;
 #pragma unroll
-                            for (int k = 0; k < 6; ++k) dxb[k] = dxi[k];
+                            for (int k = 0; k < 21; ++k) s_best[k] = Pw.a[k];
+#pragma unroll
+                            for (int k = 0; k < 6; ++k) s_best[21 + k] = dx[k];
                             idx = i;
                             first = false;
                         }
                     }
-                    if (rc == 0 && maxDist > 0 && (cost - worstCost) > p.ignore_thr) {
-                        Pw = Pb;
+                    const bool take_best = rc == 0 && maxDist > 0 && (cost - worstCost) > p.ignore_thr;
+                    const Col &src = take_best ? s_best : s_all;
 #pragma unroll
-                        for (int k = 0; k < 6; ++k) dx[k] = dxb[k];
+                    for (int k = 0; k < 21; ++k) Pw.a[k] = src[k];
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) dx[k] = src[21 + k];
+                    if (take_best) {
                         ignored = idx;
                         n_ignored += 1;
                     }
@@ -97,7 +117,8 @@ __global__ void __launch_bounds__(T6_BLOCK) t6_replay_kernel(const __grid_consta
             if (rc == 0) {
                 // stateToPose (TOA.cpp:159-183): position kept, velocity dropped
                 pos[0] += dx[0]; pos[1] += dx[1]; pos[2] += dx[2];
-                P = Pw;
+#pragma unroll
+                for (int k = 0; k < Sym<6>::SZ; ++k) sc.Pm[k] = Pw.a[k];
                 if (!(isfinite(pos[0]) && isfinite(pos[1]) && isfinite(pos[2]))) st.status |= 8u;
             } else {
                 st.status |= 4u; // catch (std::runtime_error): update skipped (TOA.cpp:151)
@@ -115,7 +136,7 @@ __global__ void __launch_bounds__(T6_BLOCK) t6_replay_kernel(const __grid_consta
 #pragma unroll
         for (int k = 0; k < 3; ++k) p.x[(int64_t)k * N + f] = pos[k];
 #pragma unroll
-        for (int k = 0; k < Sym<6>::SZ; ++k) p.P[(int64_t)k * N + f] = P.a[k];
+        for (int k = 0; k < Sym<6>::SZ; ++k) p.P[(int64_t)k * N + f] = sc.Pm[k];
         if (p.status) p.status[f] |= (int32_t)status_or;
     }
     warp_accumulate(p.counters + CNT_UPDATES, n_updates);
@@ -126,27 +147,22 @@ __global__ void __launch_bounds__(T6_BLOCK) t6_replay_kernel(const __grid_consta
     warp_accumulate(p.counters + CNT_IGNORED, n_ignored);
 }
 
-template <int MAXM>
-static cudaError_t launch_m(const T6Params &p, cudaStream_t s) {
+template <bool PME, bool LOO>
+static cudaError_t launch_k(const T6Params &p, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + T6_BLOCK - 1) / T6_BLOCK);
-    const bool pme = p.rs.err != nullptr;
-    if (p.ignore_worst) {
-        if (pme) t6_replay_kernel<MAXM, true, true><<<grid, T6_BLOCK, 0, s>>>(p);
-        else t6_replay_kernel<MAXM, false, true><<<grid, T6_BLOCK, 0, s>>>(p);
-    } else {
-        if (pme) t6_replay_kernel<MAXM, true, false><<<grid, T6_BLOCK, 0, s>>>(p);
-        else t6_replay_kernel<MAXM, false, false><<<grid, T6_BLOCK, 0, s>>>(p);
-    }
+    const size_t smem = (size_t)t6_smem_rows(p.rs.m_slots, PME, LOO) * T6_BLOCK * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(t6_replay_kernel<PME, LOO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    t6_replay_kernel<PME, LOO><<<grid, T6_BLOCK, smem, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_t6_replay(const T6Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.T <= 0) return cudaSuccess;
-    const int m = p.rs.m_slots;
-    if (m <= 4) return launch_m<4>(p, s);
-    if (m <= 8) return launch_m<8>(p, s);
-    if (m <= 16) return launch_m<16>(p, s);
-    return launch_m<32>(p, s);
+    const bool pme = p.rs.err != nullptr;
+    if (p.ignore_worst) return pme ? launch_k<true, true>(p, s) : launch_k<false, true>(p, s);
+    return pme ? launch_k<true, false>(p, s) : launch_k<false, false>(p, s);
 }
 
 // getPose (TOA.cpp:438-473): predict-only, state untouched
