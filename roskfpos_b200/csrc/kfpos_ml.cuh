@@ -216,15 +216,54 @@ KF_DEV int ml_solve2(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, 
     return ML_OK;
 }
 
-// loads one epoch's rangings into the shared-memory columns; ranges: SoA with the
-// filter index fastest, `base` = index of slot 0 for this filter, `N` = stride.
+// ---- asynchronous epoch loads (LDGSTS / cp.async): the rangings of the NEXT
+// epoch stream from HBM straight into a shared-memory column while the current
+// epoch is being processed, so no warp ever waits on DRAM and no registers are
+// spent on staging.  ranges: SoA with the filter index fastest; `base` = element
+// index of slot 0 for this filter, `N` = element stride between slots.
+KF_DEV void cp_async_4(void *dst, const void *src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(src) : "memory");
+}
+KF_DEV void cp_async_8(void *dst, const void *src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(src) : "memory");
+}
+KF_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+KF_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+KF_DEV void prefetch_epoch(const Col &raw, int m, const void *ranges, int fmt, int64_t base, int64_t N) {
+    for (int i = 0; i < m; ++i) {
+        const int64_t idx = base + (int64_t)i * N;
+        if (fmt == 0) cp_async_8(&raw[i], reinterpret_cast<const double *>(ranges) + idx);
+        else if (fmt == 1) cp_async_4(&raw[i], reinterpret_cast<const int32_t *>(ranges) + idx);
+        else // uint16: fetch the aligned 32-bit word that holds the element
+            cp_async_4(&raw[i], reinterpret_cast<const void *>(
+                                    reinterpret_cast<uintptr_t>(reinterpret_cast<const uint16_t *>(ranges) + idx) & ~(uintptr_t)3));
+    }
+    cp_async_commit();
+}
+
+// raw column -> metres + valid mask: keep rangings[i] > 0 (TOA.cpp:48-57, ML.cpp:478)
 template <bool PME>
-KF_DEV void load_epoch(Epoch<PME> &ep, const void *ranges, int fmt, const double *err, int64_t base, int64_t N) {
+KF_DEV void convert_epoch(Epoch<PME> &ep, const Col &raw, const void *ranges, int fmt, const double *err,
+                          int64_t base, int64_t N) {
     unsigned valid = 0u;
     for (int i = 0; i < ep.m_slots; ++i) {
-        const double r = load_range(ranges, fmt, base + (int64_t)i * N);
+        double r;
+        if (fmt == 0) {
+            r = raw[i];
+        } else {
+            const unsigned w = *reinterpret_cast<const unsigned *>(&raw[i]);
+            if (fmt == 1) {
+                r = mm_to_m((double)(int)w);
+            } else {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(reinterpret_cast<const uint16_t *>(ranges) + base + (int64_t)i * N);
+                r = mm_to_m((double)((a & 2) ? (w >> 16) : (w & 0xffffu)));
+            }
+        }
         ep.z[i] = r;
-        if (r > 0) valid |= 1u << i; // keep rangings[i] > 0 (TOA.cpp:48-57, ML.cpp:478)
+        if (r > 0) valid |= 1u << i;
         if (PME) ep.e[i] = __ldg(err + base + (int64_t)i * N);
     }
     ep.valid = valid;

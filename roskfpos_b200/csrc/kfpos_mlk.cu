@@ -36,7 +36,10 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
         ep.e = Col{smem + (size_t)(PME ? m : 0) * ML_BLOCK + threadIdx.x, ML_BLOCK};
         ep.e0 = p.rs.err_scalar;
         ep.m_slots = m;
-        load_epoch<PME>(ep, p.rs.ranges, p.rs.fmt, p.rs.err, f, N);
+        const Col raw = Col{smem + (size_t)(PME ? 2 * m : m) * ML_BLOCK + threadIdx.x, ML_BLOCK};
+        prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, f, N); // all M loads in flight together
+        cp_async_wait_all();
+        convert_epoch<PME>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, f, N);
         const bool use2d = p.use2d != 0;
         const int k = use2d ? 3 : 4; // minRangings (ML.cpp:316,319)
         const double start[3] = {p.start[0], p.start[1], p.start[2]};
@@ -140,12 +143,14 @@ cudaError_t launch_ml_solve(const MlParams &p, cudaStream_t s) {
     if (p.N <= 0) return cudaSuccess;
     const unsigned grid = (unsigned)((p.N + ML_BLOCK - 1) / ML_BLOCK);
     const bool pme = p.rs.err != nullptr;
-    const size_t smem = (size_t)p.rs.m_slots * (pme ? 2 : 1) * ML_BLOCK * sizeof(double);
+    const size_t smem = (size_t)p.rs.m_slots * (pme ? 3 : 2) * ML_BLOCK * sizeof(double);
     if (pme) {
         cudaError_t e = cudaFuncSetAttribute(ml_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         ml_solve_kernel<true><<<grid, ML_BLOCK, smem, s>>>(p);
     } else {
+        cudaError_t e = cudaFuncSetAttribute(ml_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         ml_solve_kernel<false><<<grid, ML_BLOCK, smem, s>>>(p);
     }
     return cudaGetLastError();

@@ -13,7 +13,7 @@ constexpr int T6_BLOCK = 128;
 
 // shared-memory rows per thread
 __host__ __device__ inline int t6_smem_rows(int m, bool pme, bool loo) {
-    return 3 * m + (pme ? m : 0) + 21 + (loo ? 2 * (21 + 6) : 0);
+    return 4 * m + (pme ? m : 0) + 21 + (loo ? 2 * (21 + 6) : 0);
 }
 
 template <bool PME, bool LOO>
@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(T6_BLOCK, LOO ? 2 : 4) t6_replay_kernel(const 
         ep.e = PME ? take(m) : ep.z;
         ep.e0 = p.rs.err_scalar;
         ep.m_slots = m;
+        Col raw = take(m); // landing zone of the cp.async prefetch of the next epoch
         T6Scratch sc;
         sc.invd = take(m);
         sc.eps = take(m);
@@ -53,8 +54,11 @@ __global__ void __launch_bounds__(T6_BLOCK, LOO ? 2 : 4) t6_replay_kernel(const 
         for (int k = 0; k < Sym<6>::SZ; ++k) sc.Pm[k] = p.P[(int64_t)k * N + f];
         unsigned status_or = 0;
 
+        prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, f, N);
         for (int t = 0; t < p.T; ++t) {
-            load_epoch<PME>(ep, p.rs.ranges, p.rs.fmt, p.rs.err, (int64_t)t * m * N + f, N);
+            cp_async_wait_all();
+            convert_epoch<PME>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, (int64_t)t * m * N + f, N);
+            if (t + 1 < p.T) prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, (int64_t)(t + 1) * m * N + f, N);
             const double dt = __ldg(p.dt + t);
 
             // ---- predict (TOA.cpp:115-123): x^- = F x with v = 0, P^- = F P F^T + Q.
