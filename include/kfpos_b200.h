@@ -181,12 +181,16 @@ int kfpos_batch_replay_toa(kfpos_batch *b, int n_steps, const double *dt, const 
                            int fmt, double err_scalar, const double *err_var, double *traj,
                            int32_t *sel, void *stream);
 
-/* newPX4FlowMeasurement (PEA.h:15; KF.cpp:100-133).  K8 only.  SoA [N] each.   */
+/* newPX4FlowMeasurement (PEA.h:15; KF.cpp:100-133).  K8 only.  SoA [N] each.
+ * Filters whose quality is 0 skip the event; its dt is carried to their next one
+ * (the reference returns before reading its clock, KF.cpp:111-113).              */
 int kfpos_batch_step_px4(kfpos_batch *b, double dt, const double *integration_x,
                          const double *integration_y, const double *integration_rot_z,
                          const double *integration_time_us, const int32_t *quality, void *stream);
 /* newIMUMeasurement (PEA.h:17; KF.cpp:137-176, TOAIMU.cpp:76-92).  K8 and T9.
- * ang_vel, lin_acc: SoA [3][N]; cov_ang_vel, cov_acc: SoA [9][N] or NULL (= 0).  */
+ * ang_vel, lin_acc: SoA [3][N]; cov_ang_vel, cov_acc: HOST arrays of 9 doubles
+ * (row-major 3x3) applying to the whole batch, or NULL (= 0).  T9's IMU rows are
+ * the restatement of SURVEY App. B-5 (the reference throws on its first IMU sample). */
 int kfpos_batch_step_imu(kfpos_batch *b, double dt, const double *ang_vel,
                          const double *cov_ang_vel, const double *lin_acc, const double *cov_acc,
                          void *stream);
@@ -194,6 +198,36 @@ int kfpos_batch_step_imu(kfpos_batch *b, double dt, const double *ang_vel,
 int kfpos_batch_step_mag(kfpos_batch *b, double dt, const double *mag, void *stream);
 /* newCompassMeasurement (PEA.h:19; KF.cpp:195-221).  K8 only.  compass: [N] rad. */
 int kfpos_batch_step_compass(kfpos_batch *b, double dt, const double *compass, void *stream);
+
+/* A whole sensor-event schedule in ONE persistent kernel (K8, T9): the batched form
+ * of the reference's callback sequence.  The schedule (kind, dt) is common to the
+ * batch, the payload is per filter.  `offset` = first ROW (units of N elements) of
+ * the event's payload: rows of `ranges` for KFPOS_EV_TOA (row = step * n_anchors),
+ * rows of the f64 tensor `sensors` (SoA [R][N]) otherwise:
+ *   KFPOS_EV_PX4     integration_x, integration_y, integration_rot_z, integration_time_us, quality
+ *   KFPOS_EV_IMU     K8: ang_vel_z, lin_acc_x, lin_acc_y     T9: lin_acc_x, lin_acc_y, lin_acc_z
+ *   KFPOS_EV_MAG     mag_x, mag_y            KFPOS_EV_COMPASS  compass (rad)
+ * aux (KFPOS_EV_IMU, batch-wide covariances): K8: cov_acc[0], cov_acc[1], cov_acc[3],
+ * cov_acc[4], cov_ang_vel[8];  T9: cov_acc[0..8].
+ * events: HOST array.  traj (optional): SoA [n_toa][3][N] = (px, py, theta) for K8,
+ * (px, py, pz) for T9, after each TOA event.                                       */
+enum kfpos_event_kind {
+    KFPOS_EV_TOA = 0,
+    KFPOS_EV_PX4 = 1,
+    KFPOS_EV_IMU = 2,
+    KFPOS_EV_MAG = 3,
+    KFPOS_EV_COMPASS = 4
+};
+typedef struct kfpos_event {
+    int32_t kind;
+    int32_t _pad;
+    double dt;
+    int64_t offset;
+    double aux[9];
+} kfpos_event;
+int kfpos_batch_replay_events(kfpos_batch *b, int n_events, const kfpos_event *events, const void *ranges,
+                              int fmt, double err_scalar, const double *err_var, const double *sensors,
+                              int64_t sensor_rows, double *traj, void *stream);
 
 /* getPose (PEA.h:14; TOA.cpp:438-473, KF.cpp:709-747, TOAIMU.cpp:476-510):
  * predict-only to `dt` after the last update, state untouched.  x_pred SoA

@@ -163,6 +163,23 @@ void ko_t9_replay(int64_t N, int T, int M, const double *anchors, const double *
                   double accel_noise, double jolt, double *x /*[9][N]*/, double *P /*[81][N]*/,
                   double *traj, double *counters, int32_t *status, int threads);
 
+/* sensor-event schedules: same layout as kfpos_event of include/kfpos_b200.h */
+typedef struct {
+    int32_t kind; /* 0 TOA, 1 PX4, 2 IMU, 3 MAG, 4 COMPASS */
+    int32_t _pad;
+    double dt;
+    int64_t offset;
+    double aux[9];
+} ko_event;
+void ko_k8_replay(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
+                  int fmt, double err_scalar, const double *err_arr, const double *sensors, const ko_k8 *cfg,
+                  int b1_zero_z, double *x /*[8][N]*/, double *P /*[64][N]*/, double *traj, double *counters /*[5]*/,
+                  int32_t *status, int threads);
+void ko_t9_events(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
+                  int fmt, double err_scalar, const double *err_arr, const double *sensors, double accel_noise,
+                  double jolt, double *x /*[9][N]*/, double *P /*[81][N]*/, double *traj, double *counters /*[5]*/,
+                  int32_t *status, int threads);
+
 int ko_version(void);
 int ko_max_threads(void);
 

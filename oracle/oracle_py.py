@@ -187,6 +187,76 @@ def t9_replay(x0, P0, ranges, anchors, dt, err, accel_noise=0.5, jolt=0.5, want_
     return dict(x=x, P=P, traj=traj, counters=counters, status=status)
 
 
+class KoEvent(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("dt", C.c_double), ("offset", C.c_int64),
+                ("aux", C.c_double * 9)]
+
+
+def _events(events):
+    arr = (KoEvent * len(events))()
+    for i, ev in enumerate(events):
+        arr[i].kind, arr[i].dt, arr[i].offset = int(ev[0]), float(ev[1]), int(ev[2])
+        if len(ev) > 3 and ev[3] is not None:
+            for k, v in enumerate(ev[3]):
+                arr[i].aux[k] = float(v)
+    return arr
+
+
+def k8_cfg(accel_noise=0.5, jolt=0.5, **cfg):
+    c = KoK8()
+    c.accel_noise, c.jolt = accel_noise, jolt
+    for k, v in cfg.items():
+        setattr(c, k, v)
+    return c
+
+
+def k8_replay(x0, P0, events, ranges, sensors, anchors, err, cfg, b1_zero_z=False, want_traj=False, threads=0):
+    """x0 [8][N]; ranges [T][M][N] or None; sensors [R][N] or None; events: (kind, dt, offset_row[, aux])."""
+    anchors = np.ascontiguousarray(anchors, dtype=np.float64)
+    M = len(anchors)
+    x = np.array(x0, dtype=np.float64, order="C", copy=True)
+    N = x.shape[-1]
+    x = x.reshape(8, N)
+    P = np.zeros((64, N)) if P0 is None else np.array(P0, dtype=np.float64, order="C", copy=True).reshape(64, N)
+    ranges = None if ranges is None else np.ascontiguousarray(ranges)
+    sensors = None if sensors is None else np.ascontiguousarray(sensors, dtype=np.float64)
+    err_arr = None if np.isscalar(err) else np.ascontiguousarray(err, dtype=np.float64)
+    n_toa = sum(1 for e in events if e[0] == 0)
+    traj = np.zeros((n_toa, 3, N)) if want_traj else None
+    counters = np.zeros(5)
+    status = np.zeros(N, dtype=np.int32)
+    arr = _events(events)
+    lib().ko_k8_replay(C.c_int64(N), len(events), arr, M, _p(anchors), _vp(ranges),
+                       FMT[ranges.dtype] if ranges is not None else 0,
+                       C.c_double(err if err_arr is None else 0.0), _p(err_arr), _p(sensors), C.byref(cfg),
+                       int(b1_zero_z), _p(x), _p(P), _p(traj), _p(counters), _p(status, C.c_int32), int(threads))
+    return dict(x=x, P=P, traj=traj, counters=counters, status=status)
+
+
+def t9_events(x0, P0, events, ranges, sensors, anchors, err, accel_noise=0.5, jolt=0.5, want_traj=False,
+              threads=0):
+    anchors = np.ascontiguousarray(anchors, dtype=np.float64)
+    M = len(anchors)
+    x = np.array(x0, dtype=np.float64, order="C", copy=True)
+    N = x.shape[-1]
+    x = x.reshape(9, N)
+    P = np.zeros((81, N)) if P0 is None else np.array(P0, dtype=np.float64, order="C", copy=True).reshape(81, N)
+    ranges = None if ranges is None else np.ascontiguousarray(ranges)
+    sensors = None if sensors is None else np.ascontiguousarray(sensors, dtype=np.float64)
+    err_arr = None if np.isscalar(err) else np.ascontiguousarray(err, dtype=np.float64)
+    n_toa = sum(1 for e in events if e[0] == 0)
+    traj = np.zeros((n_toa, 3, N)) if want_traj else None
+    counters = np.zeros(5)
+    status = np.zeros(N, dtype=np.int32)
+    arr = _events(events)
+    lib().ko_t9_events(C.c_int64(N), len(events), arr, M, _p(anchors), _vp(ranges),
+                       FMT[ranges.dtype] if ranges is not None else 0,
+                       C.c_double(err if err_arr is None else 0.0), _p(err_arr), _p(sensors),
+                       C.c_double(accel_noise), C.c_double(jolt), _p(x), _p(P), _p(traj), _p(counters),
+                       _p(status, C.c_int32), int(threads))
+    return dict(x=x, P=P, traj=traj, counters=counters, status=status)
+
+
 # ------------------------------------------------------- single-filter objects
 class T6:
     def __init__(self, accel_noise, ignore_worst, thr, p0):

@@ -162,9 +162,35 @@ class Batch:
                                              _stream_ptr(stream)), "kfpos_batch_step_px4")
 
     def step_imu(self, dt, ang_vel, lin_acc, cov_ang_vel=None, cov_acc=None, stream=None):
-        a = [_ptr(v, np.float64) for v in (ang_vel, cov_ang_vel, lin_acc, cov_acc)]
-        L.check(L.lib().kfpos_batch_step_imu(self._h, float(dt), a[0][0], a[1][0], a[2][0], a[3][0],
+        """ang_vel, lin_acc: [3][N]; cov_*: 9 doubles (row-major 3x3) for the whole batch or None."""
+        a = [_ptr(v, np.float64) for v in (ang_vel, lin_acc)]
+        c = [None if v is None else np.ascontiguousarray(v, dtype=np.float64).reshape(9) for v in (cov_ang_vel, cov_acc)]
+        cp = [None if v is None else C.c_void_p(v.ctypes.data) for v in c]
+        L.check(L.lib().kfpos_batch_step_imu(self._h, float(dt), a[0][0], cp[0], a[1][0], cp[1],
                                              _stream_ptr(stream)), "kfpos_batch_step_imu")
+
+    def replay_events(self, events, ranges=None, sensors=None, err=0.01, traj=None, want_traj=False, stream=None):
+        """events: list of (kind, dt, offset_row[, aux]) ; ranges [T][M][N] (or [rows][N]); sensors [R][N] f64."""
+        n = len(events)
+        arr = (L.KfposEvent * n)()
+        n_toa = 0
+        for i, ev in enumerate(events):
+            arr[i].kind, arr[i].dt, arr[i].offset = int(ev[0]), float(ev[1]), int(ev[2])
+            if len(ev) > 3 and ev[3] is not None:
+                for k, v in enumerate(ev[3]):
+                    arr[i].aux[k] = float(v)
+            n_toa += ev[0] == L.EV_TOA
+        es, ep, keep = self._err(err)
+        pr, kr = _ptr(ranges)
+        ps, ks = _ptr(sensors, np.float64)
+        srows = 0 if sensors is None else int(np.prod(sensors.shape[:-1]))
+        if traj is None and want_traj:
+            traj = np.empty((n_toa, 3, self.N))
+        fmt = _fmt_of(ranges) if ranges is not None else L.FMT_F64_M
+        L.check(L.lib().kfpos_batch_replay_events(self._h, n, C.cast(arr, C.c_void_p), pr, fmt, es, ep, ps,
+                                                  C.c_int64(srows), _ptr(traj)[0], _stream_ptr(stream)),
+                "kfpos_batch_replay_events")
+        return traj
 
     def step_mag(self, dt, mag, stream=None):
         p, k = _ptr(mag, np.float64)

@@ -65,6 +65,7 @@ struct kfpos_batch {
     double *d_partials = nullptr, *d_out4 = nullptr;
     // K8 / T9 latched sensor samples, SoA rows (see kfpos_k8.cuh)
     double *d_latch = nullptr;
+    double *d_latch_u = nullptr; // batch-wide latched IMU covariances
     int32_t *d_has = nullptr;
     DevBuf scratch[N_SCRATCH];
     DevBuf stage[2];
@@ -196,6 +197,7 @@ extern "C" int kfpos_batch_create(kfpos_batch **out, int device, int model, int6
     if (model == KFPOS_MODEL_K8 || model == KFPOS_MODEL_T9) {
         alloc((void **)&b->d_latch, sizeof(double) * 16 * N);
         alloc((void **)&b->d_has, sizeof(int32_t) * N);
+        alloc((void **)&b->d_latch_u, sizeof(double) * 16);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -222,6 +224,7 @@ extern "C" void kfpos_batch_destroy(kfpos_batch *b) {
     cudaFree(b->d_out4);
     cudaFree(b->d_latch);
     cudaFree(b->d_has);
+    cudaFree(b->d_latch_u);
     for (auto &s : b->scratch) s.release();
     for (auto &s : b->stage) s.release();
     for (int i = 0; i < 2; ++i) {
@@ -274,6 +277,7 @@ extern "C" int kfpos_batch_set_state(kfpos_batch *b, const double *x, const doub
     CK(cudaMemsetAsync(b->d_status, 0, sizeof(int32_t) * N, s));
     if (b->d_has) CK(cudaMemsetAsync(b->d_has, 0, sizeof(int32_t) * N, s));
     if (b->d_latch) CK(cudaMemsetAsync(b->d_latch, 0, sizeof(double) * 16 * N, s));
+    if (b->d_latch_u) CK(cudaMemsetAsync(b->d_latch_u, 0, sizeof(double) * 16, s));
     if (!xd || (P && !on_device(P))) CK(cudaStreamSynchronize(s));
     return KFPOS_OK;
 }
@@ -317,6 +321,8 @@ namespace {
 // per-ranging errors) are already on the device
 int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_ranges, int fmt,
                   double err_scalar, const double *d_err, double *d_traj, int32_t *d_sel, cudaStream_t s);
+int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_ranges, int fmt, double err_scalar,
+               const double *d_err, const double *d_sensors, double *d_traj, cudaStream_t s);
 
 } // namespace
 
@@ -347,7 +353,27 @@ extern "C" int kfpos_batch_replay_toa(kfpos_batch *b, int n_steps, const double 
 
     const bool r_dev = on_device(ranges);
     const bool e_dev = !err_var || on_device(err_var);
-    if (r_dev && e_dev) {
+    if (b->model != KFPOS_MODEL_T6) {
+        // K8 / T9: a TOA-only schedule through the event-stream kernel
+        std::vector<double> hdt(T);
+        if (on_device(dt)) CK(cudaMemcpy(hdt.data(), dt, sizeof(double) * T, cudaMemcpyDeviceToHost));
+        else memcpy(hdt.data(), dt, sizeof(double) * T);
+        std::vector<kfpos_event> evs(T);
+        for (int t = 0; t < T; ++t) {
+            memset(&evs[t], 0, sizeof(kfpos_event));
+            evs[t].kind = KFPOS_EV_TOA;
+            evs[t].dt = hdt[t];
+            evs[t].offset = (int64_t)t * (int64_t)M;
+        }
+        if (sel) return KFPOS_ERR_INVALID; // leave-one-out exists only in T6
+        const void *d_r = nullptr, *d_e = nullptr;
+        rc = stage_in(b, 4, ranges, M * N * T * fmt_size(fmt), s, &d_r);
+        if (rc) return rc;
+        rc = stage_in(b, 5, err_var, sizeof(double) * M * N * T, s, &d_e);
+        if (rc) return rc;
+        rc = run_events(b, T, evs.data(), d_r, fmt, err_scalar, (const double *)d_e, nullptr, (double *)d_traj, s);
+        if (rc) return rc;
+    } else if (r_dev && e_dev) {
         rc = launch_replay(b, T, d_dt, ranges, fmt, err_scalar, err_var, (double *)d_traj, (int32_t *)d_sel, s);
         if (rc) return rc;
     } else if (!r_dev && err_var == nullptr) {
@@ -428,24 +454,205 @@ int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_range
 
 } // namespace
 
-// ---------------------------------------------------------- other sensor steps
-extern "C" int kfpos_batch_step_px4(kfpos_batch *b, double, const double *, const double *, const double *,
-                                    const double *, const int32_t *, void *) {
-    if (!b || b->model != KFPOS_MODEL_K8) return KFPOS_ERR_INVALID;
-    return KFPOS_ERR_UNSUPPORTED;
+// ------------------------------------------------------------ event schedules
+namespace {
+
+K8Cfg make_k8cfg(const kfpos_batch *b) {
+    K8Cfg c;
+    c.accel_noise = b->cfg.accel_noise;
+    c.jolt = b->cfg.jolt;
+    c.tag_z = b->cfg.fixed_height;
+    c.px4_height = b->cfg.px4_sensor_height;
+    c.arm1 = b->cfg.px4_arm_p0;
+    c.arm2 = b->cfg.px4_arm_p1;
+    c.px4_cov_vel = b->cfg.px4_cov_velocity;
+    c.px4_cov_gyro = b->cfg.px4_cov_gyro_z;
+    c.imu_cov_acc = b->cfg.imu_cov_acc;
+    c.imu_cov_gyro = b->cfg.imu_cov_gyro_z;
+    c.mag_offset = b->cfg.mag_angle_offset;
+    c.mag_cov = b->cfg.mag_cov;
+    c.imu_fix_acc = b->cfg.imu_use_fixed_cov_acc;
+    c.imu_fix_gyro = b->cfg.imu_use_fixed_cov_gyro_z;
+    return c;
 }
-extern "C" int kfpos_batch_step_imu(kfpos_batch *b, double, const double *, const double *, const double *,
-                                    const double *, void *) {
-    if (!b || (b->model != KFPOS_MODEL_K8 && b->model != KFPOS_MODEL_T9)) return KFPOS_ERR_INVALID;
-    return KFPOS_ERR_UNSUPPORTED;
+
+// events: HOST array; every data pointer already on the device
+int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_ranges, int fmt, double err_scalar,
+               const double *d_err, const double *d_sensors, double *d_traj, cudaStream_t s) {
+    static_assert(sizeof(kfpos_event) == sizeof(EventDesc), "kfpos_event and EventDesc must have one layout");
+    if (n <= 0) return KFPOS_OK;
+    CK(b->scratch[7].reserve(sizeof(EventDesc) * (size_t)n));
+    CK(cudaMemcpyAsync(b->scratch[7].p, events, sizeof(EventDesc) * (size_t)n, cudaMemcpyHostToDevice, s));
+    const RangeStream rs = make_rs(b, d_ranges, fmt, err_scalar, d_err);
+    switch (b->model) {
+    case KFPOS_MODEL_K8: {
+        K8Params p;
+        p.anchors = b->anchors;
+        p.cfg = make_k8cfg(b);
+        p.rs = rs;
+        p.sensors = d_sensors;
+        p.events = (const EventDesc *)b->scratch[7].p;
+        p.n_events = n;
+        p.N = b->N;
+        p.x = b->d_x;
+        p.P = b->d_P;
+        p.status = b->d_status;
+        p.latch = b->d_latch;
+        p.has = b->d_has;
+        p.latch_u = b->d_latch_u;
+        p.traj = d_traj;
+        p.counters = b->d_counters;
+        CK(launch_k8_replay(p, s));
+        break;
+    }
+    case KFPOS_MODEL_T9: {
+        T9Params p;
+        p.anchors = b->anchors;
+        p.accel_noise = b->cfg.accel_noise;
+        p.jolt = b->cfg.jolt;
+        p.rs = rs;
+        p.sensors = d_sensors;
+        p.events = (const EventDesc *)b->scratch[7].p;
+        p.n_events = n;
+        p.N = b->N;
+        p.x = b->d_x;
+        p.P = b->d_P;
+        p.status = b->d_status;
+        p.latch = b->d_latch;
+        p.has = b->d_has;
+        p.latch_u = b->d_latch_u;
+        p.traj = d_traj;
+        p.counters = b->d_counters;
+        CK(launch_t9_replay(p, s));
+        break;
+    }
+    default: return KFPOS_ERR_INVALID;
+    }
+    // the host event array may be a temporary of the caller
+    CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
 }
-extern "C" int kfpos_batch_step_mag(kfpos_batch *b, double, const double *, void *) {
-    if (!b || b->model != KFPOS_MODEL_K8) return KFPOS_ERR_INVALID;
-    return KFPOS_ERR_UNSUPPORTED;
+
+} // namespace
+
+extern "C" int kfpos_batch_replay_events(kfpos_batch *b, int n_events, const kfpos_event *events, const void *ranges,
+                                         int fmt, double err_scalar, const double *err_var, const double *sensors,
+                                         int64_t sensor_rows, double *traj, void *stream) {
+    if (!b || (b->model != KFPOS_MODEL_K8 && b->model != KFPOS_MODEL_T9) || n_events < 0 || !events)
+        return KFPOS_ERR_INVALID;
+    if (fmt < 0 || fmt > 2) return KFPOS_ERR_INVALID;
+    if (!b->have_anchors) return KFPOS_ERR_NOT_READY;
+    if (n_events == 0) return KFPOS_OK;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N, M = (size_t)b->anchors.n;
+    int64_t range_rows = 0, n_toa = 0;
+    for (int e = 0; e < n_events; ++e) {
+        const kfpos_event &ev = events[e];
+        if (ev.kind < KFPOS_EV_TOA || ev.kind > KFPOS_EV_COMPASS || ev.offset < 0) return KFPOS_ERR_INVALID;
+        if (b->model == KFPOS_MODEL_T9 && ev.kind != KFPOS_EV_TOA && ev.kind != KFPOS_EV_IMU) return KFPOS_ERR_INVALID;
+        if (ev.kind == KFPOS_EV_TOA) {
+            if (!ranges) return KFPOS_ERR_INVALID;
+            if (ev.offset + (int64_t)M > range_rows) range_rows = ev.offset + (int64_t)M;
+            ++n_toa;
+        } else {
+            const int rows = ev.kind == KFPOS_EV_PX4 ? 5 : ev.kind == KFPOS_EV_IMU ? 3 : ev.kind == KFPOS_EV_MAG ? 2 : 1;
+            if (!sensors || ev.offset + rows > sensor_rows) return KFPOS_ERR_INVALID;
+        }
+    }
+    const void *d_r = nullptr, *d_e = nullptr, *d_s = nullptr;
+    int rc = stage_in(b, 4, ranges, (size_t)range_rows * N * fmt_size(fmt), s, &d_r);
+    if (rc) return rc;
+    rc = stage_in(b, 5, err_var, sizeof(double) * (size_t)range_rows * N, s, &d_e);
+    if (rc) return rc;
+    rc = stage_in(b, 6, sensors, sizeof(double) * (size_t)sensor_rows * N, s, &d_s);
+    if (rc) return rc;
+    void *d_traj = nullptr;
+    bool copy_traj = false;
+    rc = stage_out(b, 2, traj, sizeof(double) * 3 * N * (size_t)n_toa, &d_traj, &copy_traj);
+    if (rc) return rc;
+    rc = run_events(b, n_events, events, d_r, fmt, err_scalar, (const double *)d_e, (const double *)d_s,
+                    (double *)d_traj, s);
+    if (rc) return rc;
+    if (copy_traj) {
+        CK(cudaMemcpyAsync(traj, d_traj, sizeof(double) * 3 * N * (size_t)n_toa, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return KFPOS_OK;
 }
-extern "C" int kfpos_batch_step_compass(kfpos_batch *b, double, const double *, void *) {
-    if (!b || b->model != KFPOS_MODEL_K8) return KFPOS_ERR_INVALID;
-    return KFPOS_ERR_UNSUPPORTED;
+
+namespace {
+
+// one non-TOA event whose payload rows are gathered into scratch slot 6
+int single_sensor_event(kfpos_batch *b, int kind, double dt, const double *const *rows, int n_rows,
+                        const double aux[9], cudaStream_t s) {
+    const size_t N = (size_t)b->N;
+    CK(b->scratch[6].reserve(sizeof(double) * N * (size_t)n_rows));
+    double *dst = (double *)b->scratch[6].p;
+    for (int i = 0; i < n_rows; ++i) {
+        if (!rows[i]) return KFPOS_ERR_INVALID;
+        CK(cudaMemcpyAsync(dst + (size_t)i * N, rows[i], sizeof(double) * N,
+                           on_device(rows[i]) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+    }
+    kfpos_event ev;
+    memset(&ev, 0, sizeof ev);
+    ev.kind = kind;
+    ev.dt = dt;
+    ev.offset = 0;
+    if (aux) memcpy(ev.aux, aux, sizeof ev.aux);
+    return run_events(b, 1, &ev, nullptr, KFPOS_FMT_F64_M, 0.0, nullptr, dst, nullptr, s);
+}
+
+} // namespace
+
+extern "C" int kfpos_batch_step_px4(kfpos_batch *b, double dt, const double *integration_x,
+                                    const double *integration_y, const double *integration_rot_z,
+                                    const double *integration_time_us, const int32_t *quality, void *stream) {
+    if (!b || b->model != KFPOS_MODEL_K8 || !quality) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N;
+    const void *d_q = nullptr;
+    int rc = stage_in(b, 5, quality, sizeof(int32_t) * N, s, &d_q);
+    if (rc) return rc;
+    CK(b->scratch[3].reserve(sizeof(double) * N));
+    CK(launch_i32_to_f64(b->N, (const int32_t *)d_q, (double *)b->scratch[3].p, s));
+    const double *rows[5] = {integration_x, integration_y, integration_rot_z, integration_time_us,
+                             (const double *)b->scratch[3].p};
+    return single_sensor_event(b, KFPOS_EV_PX4, dt, rows, 5, nullptr, s);
+}
+
+extern "C" int kfpos_batch_step_imu(kfpos_batch *b, double dt, const double *ang_vel, const double *cov_ang_vel,
+                                    const double *lin_acc, const double *cov_acc, void *stream) {
+    if (!b || (b->model != KFPOS_MODEL_K8 && b->model != KFPOS_MODEL_T9) || !lin_acc) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N;
+    double aux[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (b->model == KFPOS_MODEL_K8) {
+        if (!ang_vel) return KFPOS_ERR_INVALID;
+        if (cov_acc) { aux[0] = cov_acc[0]; aux[1] = cov_acc[1]; aux[2] = cov_acc[3]; aux[3] = cov_acc[4]; }
+        if (cov_ang_vel) aux[4] = cov_ang_vel[8];
+        const double *rows[3] = {ang_vel + 2 * N, lin_acc, lin_acc + N};
+        return single_sensor_event(b, KFPOS_EV_IMU, dt, rows, 3, aux, s);
+    }
+    if (cov_acc) memcpy(aux, cov_acc, sizeof aux);
+    const double *rows[3] = {lin_acc, lin_acc + N, lin_acc + 2 * N};
+    return single_sensor_event(b, KFPOS_EV_IMU, dt, rows, 3, aux, s);
+}
+
+extern "C" int kfpos_batch_step_mag(kfpos_batch *b, double dt, const double *mag, void *stream) {
+    if (!b || b->model != KFPOS_MODEL_K8 || !mag) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    const double *rows[2] = {mag, mag + (size_t)b->N};
+    return single_sensor_event(b, KFPOS_EV_MAG, dt, rows, 2, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int kfpos_batch_step_compass(kfpos_batch *b, double dt, const double *compass, void *stream) {
+    if (!b || b->model != KFPOS_MODEL_K8 || !compass) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    const double *rows[1] = {compass};
+    return single_sensor_event(b, KFPOS_EV_COMPASS, dt, rows, 1, nullptr, (cudaStream_t)stream);
 }
 
 // --------------------------------------------------------------------- getPose
@@ -463,6 +670,12 @@ extern "C" int kfpos_batch_get_pose(kfpos_batch *b, double dt, double *x_pred, d
     switch (b->model) {
     case KFPOS_MODEL_T6:
         CK(launch_t6_get_pose(b->N, dt, b->cfg.accel_noise, b->d_x, b->d_P, (double *)dx, (double *)dP, s));
+        break;
+    case KFPOS_MODEL_K8:
+        CK(launch_k8_get_pose(b->N, dt, b->cfg.accel_noise, b->cfg.jolt, b->d_x, b->d_P, (double *)dx, (double *)dP, s));
+        break;
+    case KFPOS_MODEL_T9:
+        CK(launch_t9_get_pose(b->N, dt, b->cfg.jolt, b->d_x, b->d_P, (double *)dx, (double *)dP, s));
         break;
     default: return KFPOS_ERR_UNSUPPORTED;
     }
@@ -540,7 +753,9 @@ extern "C" int kfpos_batch_error_stats(kfpos_batch *b, const double *truth, doub
     const void *d_truth = nullptr;
     int rc = stage_in(b, 0, truth, sizeof(double) * 3 * (size_t)b->N, s, &d_truth);
     if (rc) return rc;
-    CK(launch_error_stats(b->N, b->d_x, b->d_status, (const double *)d_truth, b->d_partials, b->d_out4, s));
+    // K8 is planar: z is the configured tag height (KF.cpp:328-332)
+    CK(launch_error_stats(b->N, b->d_x, b->model == KFPOS_MODEL_K8 ? -1 : 2, b->cfg.fixed_height, b->d_status,
+                          (const double *)d_truth, b->d_partials, b->d_out4, s));
     CK(cudaMemcpyAsync(out, b->d_out4, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     return KFPOS_OK;

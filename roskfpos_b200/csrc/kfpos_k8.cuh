@@ -1,0 +1,227 @@
+// kfpos_k8.cuh -- KalmanFilter (8-state planar iterated EKF fusing UWB rangings,
+// PX4Flow, IMU and magnetometer/compass), per-thread formulation.
+// Reference: algorithms/KalmanFilter.cpp.  State [px,py,vx,vy,ax,ay,theta,omega].
+#pragma once
+#include "kfpos_kernels.cuh" // K8Cfg, EventDesc
+#include "kfpos_math.cuh"
+#include "kfpos_ml.cuh"
+#include "kfpos_t6.cuh" // StepStats
+
+namespace kfpos {
+
+// symmetric congruence with the elementary matrix E = I + c e_i e_k^T :  P <- E P E^T
+template <int N>
+KF_DEV void sym_add_row(Sym<N> &P, int i, int k, double c) {
+    P.at(i, i) = fma(c, fma(c, P.get(k, k), 2.0 * P.get(i, k)), P.get(i, i));
+#pragma unroll
+    for (int b = 0; b < N; ++b)
+        if (b != i) P.at(i, b) = fma(c, P.get(k, b), P.get(i, b));
+}
+
+// P^- = F P F^T + Q (KF.cpp:583-609).  F = I + N with N(p,v)=t, N(p,a)=t^2/2,
+// N(v,a)=t per axis and N(theta,omega)=t, applied as elementary congruences
+// (E(p<-v,t) E(p<-a,-t^2/2) E(v<-a,t) = F restricted to one axis).
+KF_DEV void k8_predict_cov(Sym<8> &P, double t, double accel_noise, double jolt) {
+    const double h = -0.5 * t * t;
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax) {
+        sym_add_row<8>(P, 2 + ax, 4 + ax, t);
+        sym_add_row<8>(P, ax, 4 + ax, h);
+        sym_add_row<8>(P, ax, 2 + ax, t);
+    }
+    sym_add_row<8>(P, 6, 7, t);
+    const double t3 = t * t * t / 6, t2 = t * t / 2;
+    const double u[3] = {t3, t2, t};
+#pragma unroll
+    for (int ax = 0; ax < 2; ++ax)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) P.at(ax + 2 * a, ax + 2 * b) += jolt * u[b] * u[a];
+    P.at(6, 6) += accel_noise * t2 * t2;
+    P.at(7, 6) += accel_noise * t2 * t;
+    P.at(7, 7) += accel_noise * t * t;
+}
+
+// what one kalmanStep3D call fuses (KF.cpp:365-501): row layout [ranges | px4(3) | imu(3) | mag(1)]
+struct K8Meas {
+    bool has_px4, has_imu, has_mag;
+    double px4_vx, px4_vy, px4_gz, px4_cv, px4_cg; // PX4FlowMeasurement
+    double imu_ax, imu_ay, imu_wz;                 // ImuMeasurement
+    double imu_c00, imu_c01, imu_c11, imu_cw;      //   covarianceAccelerationXY, covarianceAngularVelocityZ
+    double mag_angle, mag_c;                       // MagMeasurement
+};
+
+struct K8Scratch {
+    Col Pm;   // 36 rows: P^-
+    Col invd; // M rows
+    Col eps;  // M rows
+};
+
+// kalmanStep3D (KF.cpp:365-501).  xp: predicted state with theta already wrapped
+// (KF.cpp:305); has_r: ranging rows present (ep.valid may still be empty).
+// Same sequential-scalar formulation as t6_update; the IMU accelerometer pair is
+// a 2x2 block (its covariance may carry off-diagonals, KF.cpp:431-434).
+template <bool PME>
+KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const Epoch<PME> &ep, bool has_r, const K8Meas &ms,
+                     double dt, const double (&xp)[8], const K8Scratch &sc, Sym<8> &Pw, double (&dx)[8],
+                     StepStats &st) {
+    const unsigned mask = has_r ? ep.valid : 0u;
+    double sse = -1.0;
+    if (has_r) { // inner ML 2-D solve from (x^-_0, x^-_1, tagZ) (KF.cpp:403-405)
+        double pml[3] = {xp[0], xp[1], cfg.tag_z};
+        const int rc = ml_solve2<PME>(A, ep, mask, pml, sse, st.ml_iters, nullptr);
+        if (rc == ML_FEW) st.status |= 2u;
+        if (rc == ML_SINGULAR) return ML_SINGULAR;
+        if (mask == 0u) sse = -1.0; // estimationError of an empty list
+    }
+    const double R0 = fmax(sse, ep.e0);
+    const double invR0 = 1.0 / R0;
+    // inverse of the IMU accelerometer block and the scalar variances (arma::inv of the
+    // block-diagonal observationCovariance, KF.cpp:446)
+    const double idet = ms.has_imu ? 1.0 / (ms.imu_c00 * ms.imu_c11 - ms.imu_c01 * ms.imu_c01) : 0.0;
+    const double ii00 = ms.imu_c11 * idet, ii01 = -ms.imu_c01 * idet, ii11 = ms.imu_c00 * idet;
+    const double i_cv = ms.has_px4 ? 1.0 / ms.px4_cv : 0.0, i_cg = ms.has_px4 ? 1.0 / ms.px4_cg : 0.0;
+    const double i_cw = ms.has_imu ? 1.0 / ms.imu_cw : 0.0, i_cm = ms.has_mag ? 1.0 / ms.mag_c : 0.0;
+
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dx[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+    double cost = 1e20, prior = 0.0;
+    bool broke = false;
+    for (int iter = 0; iter < 20; ++iter) {
+        const double px = xp[0] + dx[0], py = xp[1] + dx[1];
+        const double vx = xp[2] + dx[2], vy = xp[3] + dx[3];
+        const double ax = xp[4] + dx[4], ay = xp[5] + dx[5];
+        const double th = xp[6] + dx[6], om = xp[7] + dx[7];
+        // ---- pass A: sensor outputs and cost at the current iterate (KF.cpp:451-469)
+        double c = 0.0;
+#pragma unroll 2
+        for (int i = 0; i < ep.m_slots; ++i) {
+            if (!((mask >> i) & 1u)) continue;
+            const double ex = px - A.x[i], ey = py - A.y[i], ez = cfg.tag_z - A.z[i];
+            const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
+            const double id = fast_rsqrt(d2);
+            const double e = ep.z[i] - d2 * id;
+            sc.invd[i] = id;
+            sc.eps[i] = e;
+            c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
+        }
+        if (!PME) c *= invR0;
+        double sn = 0.0, cs = 1.0, sw = 0.0, cw = 1.0;
+        if (ms.has_px4 || ms.has_imu) sincos(th, &sn, &cs);
+        double e_p0 = 0, e_p1 = 0, e_p2 = 0, e_i0 = 0, e_i1 = 0, e_i2 = 0, e_m = 0;
+        if (ms.has_px4) { // px4flowOutput (KF.cpp:563-571)
+            sincos(om * dt, &sw, &cw);
+            const double it = 1.0 / dt;
+            e_p0 = ms.px4_vx - (cs * vx + sn * vy + it * ((1.0 - cw) * cfg.arm1 - sw * cfg.arm2));
+            e_p1 = ms.px4_vy - (-sn * vx + cs * vy + it * (sw * cfg.arm1 + (1.0 - cw) * cfg.arm2));
+            e_p2 = ms.px4_gz - om;
+            c += (e_p0 * e_p0 + e_p1 * e_p1) * i_cv + e_p2 * e_p2 * i_cg;
+        }
+        if (ms.has_imu) { // imuOutput (KF.cpp:573-581)
+            e_i0 = ms.imu_ax - (cs * ax + sn * ay);
+            e_i1 = ms.imu_ay - (-sn * ax + cs * ay);
+            e_i2 = ms.imu_wz - om;
+            c += e_i0 * (ii00 * e_i0 + ii01 * e_i1) + e_i1 * (ii01 * e_i0 + ii11 * e_i1) + e_i2 * e_i2 * i_cw;
+        }
+        if (ms.has_mag) { // residual wrapped once (KF.cpp:461-463)
+            e_m = wrap_angle(ms.mag_angle - th);
+            c += e_m * e_m * i_cm;
+        }
+        const double newCost = c + prior;
+        st.cost_evals += 1;
+        if (fabs(cost - newCost) / cost < 1e-4) { broke = true; break; }
+        cost = newCost;
+
+        // ---- pass B: sequential updates from (x^-, P^-), rows linearised at the iterate
+        st.gain_evals += 1;
+        if (iter > 0) {
+#pragma unroll
+            for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+        }
+        double dn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        double b0 = 0, b1 = 0, G0 = 0, G1 = 0, G2 = 0; // range rows: J^T R^-1 y, J^T R^-1 J (xy block)
+#pragma unroll 1
+        for (int i = 0; i < ep.m_slots; ++i) {
+            if (!((mask >> i) & 1u)) continue;
+            const double id = sc.invd[i];
+            double h[8] = {(px - A.x[i]) * id, (py - A.y[i]) * id, 0, 0, 0, 0, 0, 0}; // KF.cpp:611-625
+            const double y = fma(h[0], dx[0], fma(h[1], dx[1], sc.eps[i]));
+            const double R = PME ? fmax(sse, ep.e[i]) : R0;
+            scalar_update<8, 0x03u>(Pw, dn, h, y, R);
+            const double iR = PME ? 1.0 / R : 1.0;
+            const double yr = y * iR, h0r = h[0] * iR;
+            b0 = fma(h[0], yr, b0); b1 = fma(h[1], yr, b1);
+            G0 = fma(h0r, h[0], G0); G1 = fma(h0r, h[1], G1); G2 = fma(h[1] * iR, h[1], G2);
+        }
+        if (!PME) { b0 *= invR0; b1 *= invR0; G0 *= invR0; G1 *= invR0; G2 *= invR0; }
+        // Jacobian entries of the sensor rows at the iterate (KF.cpp:627-697)
+        const double j_p06 = -sn * vx + cs * vy, j_p07 = cfg.arm1 * sw - cfg.arm2 * cw;
+        const double j_p16 = -cs * vx - sn * vy, j_p17 = cfg.arm1 * cw + cfg.arm2 * sw;
+        const double j_i06 = -sn * ax + cs * ay, j_i16 = -cs * ax - sn * ay;
+        // y = eps - J delta = eps + J dx   (dx still holds the previous iterate's increment)
+        const double y_p0 = e_p0 + (cs * dx[2] + sn * dx[3] + j_p06 * dx[6] + j_p07 * dx[7]);
+        const double y_p1 = e_p1 + (-sn * dx[2] + cs * dx[3] + j_p16 * dx[6] + j_p17 * dx[7]);
+        const double y_p2 = e_p2 + dx[7];
+        const double y_i0 = e_i0 + (cs * dx[4] + sn * dx[5] + j_i06 * dx[6]);
+        const double y_i1 = e_i1 + (-sn * dx[4] + cs * dx[5] + j_i16 * dx[6]);
+        const double y_i2 = e_i2 + dx[7];
+        const double y_m = e_m + dx[6];
+        if (ms.has_px4) {
+            double h[8] = {0, 0, cs, sn, 0, 0, j_p06, j_p07};
+            scalar_update<8, 0xCCu>(Pw, dn, h, y_p0, ms.px4_cv);
+            h[2] = -sn; h[3] = cs; h[6] = j_p16; h[7] = j_p17;
+            scalar_update<8, 0xCCu>(Pw, dn, h, y_p1, ms.px4_cv);
+            h[7] = 1.0;
+            scalar_update<8, 0x80u>(Pw, dn, h, y_p2, ms.px4_cg);
+        }
+        if (ms.has_imu) {
+            double h0[8] = {0, 0, 0, 0, cs, sn, j_i06, 0}, h1[8] = {0, 0, 0, 0, -sn, cs, j_i16, 0};
+            block2_update<8, 0x70u>(Pw, dn, h0, h1, y_i0, y_i1, ms.imu_c00, ms.imu_c01, ms.imu_c11);
+            h0[7] = 1.0;
+            scalar_update<8, 0x80u>(Pw, dn, h0, y_i2, ms.imu_cw);
+        }
+        if (ms.has_mag) {
+            double h[8] = {0, 0, 0, 0, 0, 0, 1.0, 0};
+            scalar_update<8, 0x40u>(Pw, dn, h, y_m, ms.mag_c);
+        }
+        // ---- prior term for the next cost: w = J^T R^-1 (y - J Delta), delta^T P^+ delta = w . Delta
+        double w[8];
+        w[0] = b0 - (G0 * dn[0] + G1 * dn[1]);
+        w[1] = b1 - (G1 * dn[0] + G2 * dn[1]);
+#pragma unroll
+        for (int k = 2; k < 8; ++k) w[k] = 0.0;
+        if (ms.has_px4) {
+            const double u0 = (y_p0 - (cs * dn[2] + sn * dn[3] + j_p06 * dn[6] + j_p07 * dn[7])) * i_cv;
+            const double u1 = (y_p1 - (-sn * dn[2] + cs * dn[3] + j_p16 * dn[6] + j_p17 * dn[7])) * i_cv;
+            const double u2 = (y_p2 - dn[7]) * i_cg;
+            w[2] += cs * u0 - sn * u1;
+            w[3] += sn * u0 + cs * u1;
+            w[6] += j_p06 * u0 + j_p16 * u1;
+            w[7] += j_p07 * u0 + j_p17 * u1 + u2;
+        }
+        if (ms.has_imu) {
+            const double r0 = y_i0 - (cs * dn[4] + sn * dn[5] + j_i06 * dn[6]);
+            const double r1 = y_i1 - (-sn * dn[4] + cs * dn[5] + j_i16 * dn[6]);
+            const double u0 = ii00 * r0 + ii01 * r1, u1 = ii01 * r0 + ii11 * r1;
+            const double u2 = (y_i2 - dn[7]) * i_cw;
+            w[4] += cs * u0 - sn * u1;
+            w[5] += sn * u0 + cs * u1;
+            w[6] += j_i06 * u0 + j_i16 * u1;
+            w[7] += u2;
+        }
+        if (ms.has_mag) w[6] += (y_m - dn[6]) * i_cm;
+        prior = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            prior = fma(w[k], dn[k], prior);
+            dx[k] = dn[k];
+        }
+    }
+    if (!broke) st.status |= 32u;
+    return 0;
+}
+
+} // namespace kfpos

@@ -52,8 +52,79 @@ struct MlParams {
     unsigned long long *counters;
 };
 
+// ---- sensor event streams (K8, T9).  The schedule (kind, dt) is common to the batch;
+// `offset` is the first ROW (units of N elements) of the event's payload: rows of the
+// range tensor for EV_TOA, rows of the f64 `sensors` tensor otherwise:
+//   EV_PX4: integration_x, integration_y, integration_rot_z, integration_time_us, quality
+//   EV_IMU: K8: ang_vel_z, lin_acc_x, lin_acc_y   T9: lin_acc_x, lin_acc_y, lin_acc_z
+//   EV_MAG: mag_x, mag_y      EV_COMPASS: compass (rad)
+// aux: EV_IMU covariances, common to the batch: K8: cov_acc[0],[1],[3],[4], cov_ang_vel[8];
+// T9: cov_acc[0..8].  Mirrors kfpos_event of include/kfpos_b200.h.
+enum { EV_TOA = 0, EV_PX4 = 1, EV_IMU = 2, EV_MAG = 3, EV_COMPASS = 4 };
+struct EventDesc {
+    int32_t kind;
+    int32_t _pad;
+    double dt;
+    int64_t offset;
+    double aux[9];
+};
+
+// constants of the five XML files + launch parameters (KF.cpp:766-844, node_pos.cpp:48-113)
+struct K8Cfg {
+    double accel_noise, jolt;
+    double tag_z;                  // mUWBtagZ
+    double px4_height, arm1, arm2; // mPX4flowHeight, mPX4FlowArmP1/P2
+    double px4_cov_vel, px4_cov_gyro;
+    double imu_cov_acc, imu_cov_gyro;
+    double mag_offset, mag_cov;
+    int imu_fix_acc, imu_fix_gyro;
+};
+
+struct K8Params {
+    AnchorTable anchors;
+    K8Cfg cfg;
+    RangeStream rs;
+    const double *sensors;   // SoA rows [R][N] f64
+    const EventDesc *events; // device [n_events]
+    int n_events;
+    int64_t N;
+    double *x;       // SoA [8][N]
+    double *P;       // SoA [36][N] packed
+    int32_t *status; // [N]
+    double *latch;   // SoA [8][N]: px4 vx,vy,gz,cv | imu ax,ay,wz | mag angle
+    int32_t *has;    // [N] bit0 px4, bit1 imu, bit2 mag latched
+    double *latch_u; // [4] batch-wide latched IMU covariances c00,c01,c11,cw
+    double *traj;    // SoA [n_toa][3][N] (px, py, theta) after each TOA event, or null
+    unsigned long long *counters;
+};
+
 cudaError_t launch_t6_replay(const T6Params &p, cudaStream_t s);
+cudaError_t launch_k8_replay(const K8Params &p, cudaStream_t s);
+cudaError_t launch_k8_get_pose(int64_t N, double dt, double accel_noise, double jolt, const double *x,
+                               const double *P, double *x_pred, double *P_pred_full, cudaStream_t s);
 cudaError_t launch_ml_solve(const MlParams &p, cudaStream_t s);
+
+struct T9Params {
+    AnchorTable anchors;
+    double accel_noise, jolt;
+    RangeStream rs;
+    const double *sensors;
+    const EventDesc *events;
+    int n_events;
+    int64_t N;
+    double *x;       // SoA [9][N]
+    double *P;       // SoA [45][N] packed
+    int32_t *status; // [N]
+    double *latch;   // SoA rows 0..2: latched acceleration
+    int32_t *has;    // [N] bit1: imu latched
+    double *latch_u; // [9] batch-wide latched 3x3 acceleration covariance
+    double *traj;    // SoA [n_toa][3][N] or null
+    unsigned long long *counters;
+};
+cudaError_t launch_t9_replay(const T9Params &p, cudaStream_t s);
+cudaError_t launch_t9_get_pose(int64_t N, double dt, double jolt, const double *x, const double *P, double *x_pred,
+                               double *P_pred_full, cudaStream_t s);
+cudaError_t launch_i32_to_f64(int64_t N, const int32_t *in, double *out, cudaStream_t s);
 
 // full row-major SoA [n*n][N]  <->  packed lower-triangle SoA [n(n+1)/2][N]
 cudaError_t launch_pack_cov(int n, int64_t N, const double *full, double *packed, cudaStream_t s);
@@ -65,8 +136,9 @@ cudaError_t launch_t6_get_pose(int64_t N, double dt, double accel_noise, const d
 
 // error statistics: partial[chunk][4] over fixed 1024-filter chunks, then a
 // fixed-shape tree in the second kernel -> out[4]
-cudaError_t launch_error_stats(int64_t N, const double *x, const int32_t *status, const double *truth,
-                               double *partials, double *out4, cudaStream_t s);
+// (position = rows 0,1 and row `zrow`, or the constant `zconst` when zrow < 0)
+cudaError_t launch_error_stats(int64_t N, const double *x, int zrow, double zconst, const int32_t *status,
+                               const double *truth, double *partials, double *out4, cudaStream_t s);
 
 // DFMA-only microbenchmark on the current device (the FP64 roofline denominator)
 cudaError_t measure_fp64_peak(double *flops_per_s);

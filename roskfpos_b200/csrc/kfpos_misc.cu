@@ -61,14 +61,16 @@ __device__ void tree_reduce4(double (&v)[4], double (*sh)[ST_THREADS]) {
 }
 
 __global__ void __launch_bounds__(ST_THREADS)
-error_stats_chunks(int64_t N, const double *x, const int32_t *status, const double *truth, double *partials) {
+error_stats_chunks(int64_t N, const double *x, int zrow, double zconst, const int32_t *status, const double *truth,
+                   double *partials) {
     __shared__ double sh[4][ST_THREADS];
     double v[4] = {0, 0, 0, 0};
     const int64_t base = (int64_t)blockIdx.x * ST_CHUNK;
     for (int r = 0; r < ST_CHUNK / ST_THREADS; ++r) {
         const int64_t f = base + threadIdx.x + (int64_t)r * ST_THREADS;
         if (f < N) {
-            const double ex = x[f] - truth[f], ey = x[N + f] - truth[N + f], ez = x[2 * N + f] - truth[2 * N + f];
+            const double pz = zrow >= 0 ? x[(int64_t)zrow * N + f] : zconst;
+            const double ex = x[f] - truth[f], ey = x[N + f] - truth[N + f], ez = pz - truth[2 * N + f];
             const double e2 = ex * ex + ey * ey + ez * ez;
             if (isfinite(e2)) {
                 v[0] += e2;
@@ -99,10 +101,22 @@ __global__ void __launch_bounds__(ST_THREADS) error_stats_final(int64_t n_chunks
     }
 }
 
-cudaError_t launch_error_stats(int64_t N, const double *x, const int32_t *status, const double *truth,
-                               double *partials, double *out4, cudaStream_t s) {
+__global__ void i32_to_f64_kernel(int64_t N, const int32_t *in, double *out) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f < N) out[f] = (double)in[f];
+}
+
+cudaError_t launch_i32_to_f64(int64_t N, const int32_t *in, double *out, cudaStream_t s) {
+    if (N <= 0) return cudaSuccess;
+    i32_to_f64_kernel<<<(unsigned)((N + 255) / 256), 256, 0, s>>>(N, in, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_error_stats(int64_t N, const double *x, int zrow, double zconst, const int32_t *status,
+                               const double *truth, double *partials, double *out4, cudaStream_t s) {
     const int64_t n_chunks = (N + ST_CHUNK - 1) / ST_CHUNK;
-    if (n_chunks > 0) error_stats_chunks<<<(unsigned)n_chunks, ST_THREADS, 0, s>>>(N, x, status, truth, partials);
+    if (n_chunks > 0)
+        error_stats_chunks<<<(unsigned)n_chunks, ST_THREADS, 0, s>>>(N, x, zrow, zconst, status, truth, partials);
     error_stats_final<<<1, ST_THREADS, 0, s>>>(n_chunks, partials, out4);
     return cudaGetLastError();
 }

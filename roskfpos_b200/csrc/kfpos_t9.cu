@@ -1,0 +1,360 @@
+// kfpos_t9.cu -- KalmanFilterTOAIMU (9-state constant-acceleration iterated EKF on
+// rangings + 3-axis accelerometer), persistent event-stream kernel, one thread per
+// filter.  Reference: algorithms/KalmanFilterTOAIMU.cpp.  State [p(3), v(3), a(3)].
+//
+// The ranging path follows the reference exactly (TOAIMU.cpp:242-340).  The IMU rows
+// are the RESTATEMENT of SURVEY App. B-5: the reference reserves 9 rows for 3 values,
+// writes jacobian(row, 9) on a 9-column matrix (std::logic_error on the first IMU
+// sample) and uses diag(a) as dh/da; here: 3 rows, h = a, J = I3 on the acceleration
+// block, R = the 3x3 covarianceAcceleration.
+#include "kfpos_k8.cuh" // sym_add_row
+#include "kfpos_kernels.cuh"
+
+namespace kfpos {
+
+constexpr int T9_BLOCK = 128;
+
+__host__ __device__ inline int t9_smem_rows(int m, bool pme) { return 4 * m + (pme ? m : 0) + 45; }
+
+// P^- = F P F^T + Q (TOAIMU.cpp:392-421)
+KF_DEV void t9_predict_cov(Sym<9> &P, double t, double jolt) {
+    const double h = -0.5 * t * t;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        sym_add_row<9>(P, 3 + ax, 6 + ax, t);
+        sym_add_row<9>(P, ax, 6 + ax, h);
+        sym_add_row<9>(P, ax, 3 + ax, t);
+    }
+    const double t3 = t * t * t / 6, t2 = t * t / 2;
+    const double u[3] = {t3, t2, t};
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b <= a; ++b) P.at(ax + 3 * a, ax + 3 * b) += jolt * u[b] * u[a];
+}
+
+struct T9Scratch {
+    Col Pm, invd, eps;
+};
+
+// 3-row block update on the acceleration block (J = [0 0 I3]), S = P_aa + R packed symmetric
+KF_DEV bool accel_block_update(Sym<9> &P, double (&dn)[9], const double (&y)[3], const double (&R)[6]) {
+    double S[6], Si[6];
+    S[0] = P.get(6, 6) + R[0]; S[1] = P.get(7, 6) + R[1]; S[2] = P.get(7, 7) + R[2];
+    S[3] = P.get(8, 6) + R[3]; S[4] = P.get(8, 7) + R[4]; S[5] = P.get(8, 8) + R[5];
+    if (!inv_sym3(S, Si)) return false;
+    const double n0 = y[0] - dn[6], n1 = y[1] - dn[7], n2 = y[2] - dn[8];
+    // g = S^-1 nu
+    const double g0 = Si[0] * n0 + Si[1] * n1 + Si[3] * n2;
+    const double g1 = Si[1] * n0 + Si[2] * n1 + Si[4] * n2;
+    const double g2 = Si[3] * n0 + Si[4] * n1 + Si[5] * n2;
+    double pa[9][3];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        pa[i][0] = P.get(i, 6); pa[i][1] = P.get(i, 7); pa[i][2] = P.get(i, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dn[i] = fma(pa[i][0], g0, fma(pa[i][1], g1, fma(pa[i][2], g2, dn[i])));
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const double k0 = pa[i][0] * Si[0] + pa[i][1] * Si[1] + pa[i][2] * Si[3];
+        const double k1 = pa[i][0] * Si[1] + pa[i][1] * Si[2] + pa[i][2] * Si[4];
+        const double k2 = pa[i][0] * Si[3] + pa[i][1] * Si[4] + pa[i][2] * Si[5];
+#pragma unroll
+        for (int j = 0; j <= i; ++j)
+            P.at(i, j) = fma(-k0, pa[j][0], fma(-k1, pa[j][1], fma(-k2, pa[j][2], P.at(i, j))));
+    }
+    return true;
+}
+
+// kalmanStep3D (TOAIMU.cpp:242-340)
+template <bool PME>
+KF_DEV int t9_update(const AnchorTable &A, const Epoch<PME> &ep, bool has_r, bool has_imu, const double (&za)[3],
+                     const double (&Ra)[6], const double (&xp)[9], const T9Scratch &sc, Sym<9> &Pw, double (&dx)[9],
+                     StepStats &st) {
+    const unsigned mask = has_r ? ep.valid : 0u;
+    double sse = -1.0;
+    if (has_r) { // TOAIMU.cpp:268-270 (no NaN guard in this class)
+        double pml[3] = {xp[0], xp[1], xp[2]};
+        const int rc = ml_solve3<PME>(A, ep, mask, pml, sse, st.ml_iters, nullptr);
+        if (rc == ML_FEW) st.status |= 2u;
+        if (rc == ML_SINGULAR) return ML_SINGULAR;
+        if (mask == 0u) sse = -1.0;
+    }
+    const double R0 = fmax(sse, ep.e0);
+    const double invR0 = 1.0 / R0;
+    double Rai[6] = {0, 0, 0, 0, 0, 0};
+    if (has_imu && !inv_sym3(Ra, Rai)) return ML_SINGULAR; // arma::inv(observationCovariance) would throw
+
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dx[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+    double cost = 1e20, prior = 0.0;
+    bool broke = false;
+    for (int iter = 0; iter < 20; ++iter) {
+        const double px = xp[0] + dx[0], py = xp[1] + dx[1], pz = xp[2] + dx[2];
+        double c = 0.0;
+#pragma unroll 2
+        for (int i = 0; i < ep.m_slots; ++i) {
+            if (!((mask >> i) & 1u)) continue;
+            const double ex = px - A.x[i], ey = py - A.y[i], ez = pz - A.z[i];
+            const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
+            const double id = fast_rsqrt(d2);
+            const double e = ep.z[i] - d2 * id;
+            sc.invd[i] = id;
+            sc.eps[i] = e;
+            c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
+        }
+        if (!PME) c *= invR0;
+        double ea[3] = {0, 0, 0};
+        if (has_imu) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) ea[k] = za[k] - (xp[6 + k] + dx[6 + k]);
+            c += ea[0] * (Rai[0] * ea[0] + Rai[1] * ea[1] + Rai[3] * ea[2]) +
+                 ea[1] * (Rai[1] * ea[0] + Rai[2] * ea[1] + Rai[4] * ea[2]) +
+                 ea[2] * (Rai[3] * ea[0] + Rai[4] * ea[1] + Rai[5] * ea[2]);
+        }
+        const double newCost = c + prior;
+        st.cost_evals += 1;
+        if (fabs(cost - newCost) / cost < 1e-4) { broke = true; break; }
+        cost = newCost;
+
+        st.gain_evals += 1;
+        if (iter > 0) {
+#pragma unroll
+            for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+        }
+        double dn[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        double b0 = 0, b1 = 0, b2 = 0, G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0;
+#pragma unroll 1
+        for (int i = 0; i < ep.m_slots; ++i) {
+            if (!((mask >> i) & 1u)) continue;
+            const double id = sc.invd[i];
+            double h[9] = {(px - A.x[i]) * id, (py - A.y[i]) * id, (pz - A.z[i]) * id, 0, 0, 0, 0, 0, 0};
+            const double y = fma(h[0], dx[0], fma(h[1], dx[1], fma(h[2], dx[2], sc.eps[i])));
+            const double R = PME ? fmax(sse, ep.e[i]) : R0;
+            scalar_update<9, 0x7u>(Pw, dn, h, y, R);
+            const double iR = PME ? 1.0 / R : 1.0;
+            const double yr = y * iR, h0r = h[0] * iR, h1r = h[1] * iR, h2r = h[2] * iR;
+            b0 = fma(h[0], yr, b0); b1 = fma(h[1], yr, b1); b2 = fma(h[2], yr, b2);
+            G0 = fma(h0r, h[0], G0); G1 = fma(h0r, h[1], G1); G2 = fma(h1r, h[1], G2);
+            G3 = fma(h0r, h[2], G3); G4 = fma(h1r, h[2], G4); G5 = fma(h2r, h[2], G5);
+        }
+        // y_a = eps_a - J delta = eps_a + dx_a
+        const double ya[3] = {ea[0] + dx[6], ea[1] + dx[7], ea[2] + dx[8]};
+        if (has_imu && !accel_block_update(Pw, dn, ya, Ra)) return ML_SINGULAR;
+        double w0 = b0 - (G0 * dn[0] + G1 * dn[1] + G3 * dn[2]);
+        double w1 = b1 - (G1 * dn[0] + G2 * dn[1] + G4 * dn[2]);
+        double w2 = b2 - (G3 * dn[0] + G4 * dn[1] + G5 * dn[2]);
+        prior = w0 * dn[0] + w1 * dn[1] + w2 * dn[2];
+        if (!PME) prior *= invR0;
+        if (has_imu) {
+            const double r0 = ya[0] - dn[6], r1 = ya[1] - dn[7], r2 = ya[2] - dn[8];
+            prior += dn[6] * (Rai[0] * r0 + Rai[1] * r1 + Rai[3] * r2) +
+                     dn[7] * (Rai[1] * r0 + Rai[2] * r1 + Rai[4] * r2) +
+                     dn[8] * (Rai[3] * r0 + Rai[4] * r1 + Rai[5] * r2);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dx[k] = dn[k];
+    }
+    if (!broke) st.status |= 32u;
+    return 0;
+}
+
+template <bool PME>
+__global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_constant__ T9Params p) {
+    extern __shared__ double smem[];
+    const int64_t f = (int64_t)blockIdx.x * T9_BLOCK + threadIdx.x;
+    const bool active = f < p.N;
+    StepStats st = {0u, 0u, 0u, 0u};
+    unsigned n_updates = 0, n_bad = 0;
+    if (active) {
+        const int64_t N = p.N;
+        const int m = p.rs.m_slots;
+        double *col = smem + threadIdx.x;
+        int row = 0;
+        auto take = [&](int rows) {
+            Col c = {col + (size_t)row * T9_BLOCK, T9_BLOCK};
+            row += rows;
+            return c;
+        };
+        Epoch<PME> ep;
+        ep.z = take(m);
+        ep.e = PME ? take(m) : ep.z;
+        ep.e0 = p.rs.err_scalar;
+        ep.m_slots = m;
+        ep.valid = 0u;
+        Col raw = take(m > 3 ? m : 3);
+        T9Scratch sc;
+        sc.invd = take(m);
+        sc.eps = take(m);
+        sc.Pm = take(45);
+
+        double pos[3], vel[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            pos[k] = p.x[(int64_t)k * N + f];
+            vel[k] = p.x[(int64_t)(3 + k) * N + f];
+        }
+#pragma unroll
+        for (int k = 0; k < Sym<9>::SZ; ++k) sc.Pm[k] = p.P[(int64_t)k * N + f];
+        unsigned has = (unsigned)p.has[f];
+        unsigned status_or = 0;
+        double Ra[6]; // packed symmetric part of the latched 3x3 covariance
+        bool asym = false;
+        {
+            const double *c = p.latch_u;
+            Ra[0] = c[0]; Ra[1] = 0.5 * (c[1] + c[3]); Ra[2] = c[4];
+            Ra[3] = 0.5 * (c[2] + c[6]); Ra[4] = 0.5 * (c[5] + c[7]); Ra[5] = c[8];
+        }
+        int n_toa = 0;
+        auto prefetch = [&](const EventDesc &ev) {
+            if (ev.kind == EV_TOA) {
+                prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, ev.offset * N + f, N);
+            } else {
+                for (int i = 0; i < 3; ++i) cp_async_8(&raw[i], p.sensors + (ev.offset + i) * N + f);
+                cp_async_commit();
+            }
+        };
+        if (p.n_events > 0) prefetch(p.events[0]);
+        for (int e = 0; e < p.n_events; ++e) {
+            const EventDesc ev = p.events[e];
+            cp_async_wait_all();
+            st.status = 0u;
+            bool has_r = false, has_imu = false;
+            if (ev.kind == EV_TOA) { // newTOAMeasurement (TOAIMU.cpp:49-73): rangings + latched IMU
+                convert_epoch<PME>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, ev.offset * N + f, N);
+                has_r = true;
+                has_imu = (has >> 1) & 1u;
+            } else { // newIMUMeasurement (TOAIMU.cpp:76-92)
+                p.latch[0 * N + f] = raw[0]; p.latch[1 * N + f] = raw[1]; p.latch[2 * N + f] = raw[2];
+                Ra[0] = ev.aux[0]; Ra[1] = 0.5 * (ev.aux[1] + ev.aux[3]); Ra[2] = ev.aux[4];
+                Ra[3] = 0.5 * (ev.aux[2] + ev.aux[6]); Ra[4] = 0.5 * (ev.aux[5] + ev.aux[7]); Ra[5] = ev.aux[8];
+                asym = ev.aux[1] != ev.aux[3] || ev.aux[2] != ev.aux[6] || ev.aux[5] != ev.aux[7];
+                has |= 2u;
+                has_imu = true;
+            }
+            if (e + 1 < p.n_events) prefetch(p.events[e + 1]);
+            if (has_imu && asym) st.status |= 64u;
+            double za[3] = {0, 0, 0};
+            if (has_imu) {
+                za[0] = p.latch[0 * N + f]; za[1] = p.latch[1 * N + f]; za[2] = p.latch[2 * N + f];
+            }
+            const double dt = ev.dt;
+            // ---- predict (TOAIMU.cpp:165-180): a = 0 at the start of every step
+            Sym<9> Pw;
+#pragma unroll
+            for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+            t9_predict_cov(Pw, dt, p.jolt);
+#pragma unroll
+            for (int k = 0; k < Sym<9>::SZ; ++k) sc.Pm[k] = Pw.a[k];
+            const double xp[9] = {pos[0] + dt * vel[0], pos[1] + dt * vel[1], pos[2] + dt * vel[2],
+                                  vel[0], vel[1], vel[2], 0.0, 0.0, 0.0};
+            if (has_r && ep.valid == 0u) st.status |= 1u;
+            double dx[9];
+            const int rc = t9_update<PME>(p.anchors, ep, has_r, has_imu, za, Ra, xp, sc, Pw, dx, st);
+            if (rc == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { // velocity and position kept, acceleration dropped (:189-194)
+                    pos[k] = xp[k] + dx[k];
+                    vel[k] = xp[3 + k] + dx[3 + k];
+                }
+#pragma unroll
+                for (int k = 0; k < Sym<9>::SZ; ++k) sc.Pm[k] = Pw.a[k];
+                bool fin = true;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) fin = fin && isfinite(pos[k]) && isfinite(vel[k]);
+                if (!fin) st.status |= 8u;
+            } else {
+                st.status |= 4u;
+            }
+            n_updates += 1;
+            if (st.status & ~(32u | 64u)) n_bad += 1;
+            status_or |= st.status;
+            if (ev.kind == EV_TOA) {
+                if (p.traj) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) p.traj[((int64_t)n_toa * 3 + k) * N + f] = pos[k];
+                }
+                ++n_toa;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            p.x[(int64_t)k * N + f] = pos[k];
+            p.x[(int64_t)(3 + k) * N + f] = vel[k];
+            p.x[(int64_t)(6 + k) * N + f] = 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < Sym<9>::SZ; ++k) p.P[(int64_t)k * N + f] = sc.Pm[k];
+        p.has[f] = (int32_t)has;
+        if (p.status) p.status[f] |= (int32_t)status_or;
+        if (f == 0 && (has & 2u)) {
+            // keep the symmetric part as the latched covariance
+            p.latch_u[0] = Ra[0]; p.latch_u[1] = Ra[1]; p.latch_u[2] = Ra[3];
+            p.latch_u[3] = Ra[1]; p.latch_u[4] = Ra[2]; p.latch_u[5] = Ra[4];
+            p.latch_u[6] = Ra[3]; p.latch_u[7] = Ra[4]; p.latch_u[8] = Ra[5];
+        }
+    }
+    warp_accumulate(p.counters + CNT_UPDATES, n_updates);
+    warp_accumulate(p.counters + CNT_ML_ITERS, st.ml_iters);
+    warp_accumulate(p.counters + CNT_COST_EVALS, st.cost_evals);
+    warp_accumulate(p.counters + CNT_GAIN_EVALS, st.gain_evals);
+    warp_accumulate(p.counters + CNT_BAD, n_bad);
+}
+
+cudaError_t launch_t9_replay(const T9Params &p, cudaStream_t s) {
+    if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((p.N + T9_BLOCK - 1) / T9_BLOCK);
+    const bool pme = p.rs.err != nullptr;
+    const size_t smem = (size_t)t9_smem_rows(p.rs.m_slots > 3 ? p.rs.m_slots : 3, pme) * T9_BLOCK * sizeof(double);
+    cudaError_t e;
+    if (pme) {
+        e = cudaFuncSetAttribute(t9_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        t9_replay_kernel<true><<<grid, T9_BLOCK, smem, s>>>(p);
+    } else {
+        e = cudaFuncSetAttribute(t9_replay_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        t9_replay_kernel<false><<<grid, T9_BLOCK, smem, s>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+// getPose (TOAIMU.cpp:476-510): predict-only, state untouched
+__global__ void t9_get_pose_kernel(int64_t N, double dt, double jolt, const double *x, const double *P,
+                                   double *x_pred, double *P_full) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= N) return;
+    Sym<9> S;
+#pragma unroll
+    for (int k = 0; k < Sym<9>::SZ; ++k) S.a[k] = P[(int64_t)k * N + f];
+    t9_predict_cov(S, dt, jolt);
+    if (x_pred) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double v = x[(int64_t)(3 + k) * N + f];
+            x_pred[(int64_t)k * N + f] = x[(int64_t)k * N + f] + dt * v;
+            x_pred[(int64_t)(3 + k) * N + f] = v;
+            x_pred[(int64_t)(6 + k) * N + f] = 0.0;
+        }
+    }
+    if (P_full) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+#pragma unroll
+            for (int j = 0; j < 9; ++j) P_full[(int64_t)(i * 9 + j) * N + f] = S.get(i, j);
+    }
+}
+
+cudaError_t launch_t9_get_pose(int64_t N, double dt, double jolt, const double *x, const double *P, double *x_pred,
+                               double *P_pred_full, cudaStream_t s) {
+    if (N <= 0) return cudaSuccess;
+    t9_get_pose_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(N, dt, jolt, x, P, x_pred, P_pred_full);
+    return cudaGetLastError();
+}
+
+} // namespace kfpos

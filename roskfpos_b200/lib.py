@@ -37,6 +37,15 @@ class KfposConfig(C.Structure):
     ]
 
 
+EV_TOA, EV_PX4, EV_IMU, EV_MAG, EV_COMPASS = 0, 1, 2, 3, 4
+EV_ROWS = {EV_PX4: 5, EV_IMU: 3, EV_MAG: 2, EV_COMPASS: 1}
+
+
+class KfposEvent(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("_pad", C.c_int32), ("dt", C.c_double), ("offset", C.c_int64),
+                ("aux", C.c_double * 9)]
+
+
 _LIB = None
 
 # name -> (restype, argtypes); every symbol include/kfpos_b200.h declares
@@ -59,6 +68,7 @@ SIGNATURES = {
     "kfpos_batch_step_imu": (_I, [_VP, _D, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_batch_step_mag": (_I, [_VP, _D, _VP, _VP]),
     "kfpos_batch_step_compass": (_I, [_VP, _D, _VP, _VP]),
+    "kfpos_batch_replay_events": (_I, [_VP, _I, _VP, _VP, _I, _D, _VP, _VP, _I64, _VP, _VP]),
     "kfpos_batch_get_pose": (_I, [_VP, _D, _VP, _VP, _VP]),
     "kfpos_batch_ml_solve": (_I, [_VP, _VP, _I, _D, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_batch_get_counters": (_I, [_VP, C.POINTER(C.c_double * 8), _I, _VP]),

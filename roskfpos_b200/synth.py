@@ -63,6 +63,115 @@ def ranges_mm(truth: np.ndarray, anchors: np.ndarray, sigma: float = 0.10, seed:
     return np.ascontiguousarray(mm[0] if single else mm)
 
 
+EV_TOA, EV_PX4, EV_IMU, EV_MAG, EV_COMPASS = 0, 1, 2, 3, 4
+# per 0.1 s macro-step (BASELINE configs 3 and 5): 10 IMU samples, 1 compass,
+# 1 TOA epoch (+ 3 PX4Flow frames for the full multi-sensor config); dt sums to 0.1 s and is
+# never 0 (px4flowOutput divides by timeLag, KF.cpp:566)
+MACRO_IMU_MAG = [(EV_IMU, 0.009)] * 10 + [(EV_COMPASS, 0.005), (EV_TOA, 0.005)]
+MACRO_FULL = ([(EV_IMU, 0.008)] * 3 + [(EV_PX4, 0.003)] + [(EV_IMU, 0.008)] * 3 + [(EV_PX4, 0.003)] +
+              [(EV_IMU, 0.008)] * 4 + [(EV_PX4, 0.003)] + [(EV_COMPASS, 0.005), (EV_TOA, 0.006)])
+IMU_AUX = [0.003, 0.0, 0.0, 0.003, 0.089]  # cov_acc[0],[1],[3],[4], cov_ang_vel[8] (config_imu.xml:2)
+PX4_HEIGHT, PX4_T_US = 5.0, 33333.0      # config_px4flow.xml:2
+
+
+def k8_workload(n_filters, n_macro, anchors, seed=SEED, full=False, sigma_r=0.10, xp=None, device=None):
+    """Multi-sensor event stream for KalmanFilter (K8) batches.
+
+    Returns dict(events=[(kind, dt, offset_row, aux)], ranges int32 [T][M][N], sensors f64 [R][N],
+    x0 [8][N], truth_end [3][N] (x, y, tag z)).  `xp` = numpy (default) or torch (then `device`).
+    """
+    macro = MACRO_FULL if full else MACRO_IMU_MAG
+    use_torch = xp is not None and xp.__name__ == "torch"
+    if use_torch:
+        import torch
+        g = torch.Generator(device=device)
+        g.manual_seed(seed)
+        f64 = dict(device=device, dtype=torch.float64)
+        rand = lambda *s: torch.rand(*s, generator=g, **f64)
+        randn = lambda *s: torch.randn(*s, generator=g, **f64)
+        sin, cos, sqrt, floor, stack = torch.sin, torch.cos, torch.sqrt, torch.floor, torch.stack
+        anc = torch.as_tensor(anchors, **f64)
+        full_like = lambda a, v: torch.full_like(a, v)
+    else:
+        rng = np.random.default_rng(seed)
+        rand = lambda *s: rng.random(s)
+        randn = lambda *s: rng.normal(size=s)
+        sin, cos, sqrt, floor, stack = np.sin, np.cos, np.sqrt, np.floor, np.stack
+        anc = np.asarray(anchors, dtype=np.float64)
+        full_like = lambda a, v: np.full_like(a, v)
+    N, M = n_filters, len(anchors)
+    ph = rand(2, N) * (2 * np.pi)
+    th0 = 0.3 + 0.2 * rand(N)
+    om = 0.05
+    tag_z = 1.049
+
+    def kin(t):
+        px = 5 + 3 * sin(0.20 * t + ph[0]); py = 5 + 3 * sin(0.31 * t + ph[1])
+        vx = 0.6 * cos(0.20 * t + ph[0]); vy = 0.93 * cos(0.31 * t + ph[1])
+        ax = -0.12 * sin(0.20 * t + ph[0]); ay = -0.2883 * sin(0.31 * t + ph[1])
+        return px, py, vx, vy, ax, ay, th0 + om * t
+
+    events, rows, rng_rows = [], [], []
+    t = 0.0
+    for _ in range(n_macro):
+        for kind, dt in macro:
+            t += dt
+            px, py, vx, vy, ax, ay, th = kin(t)
+            c, s = cos(th), sin(th)
+            if kind == EV_TOA:
+                d = sqrt((px[None] - anc[:, 0:1]) ** 2 + (py[None] - anc[:, 1:2]) ** 2 + (tag_z - anc[:, 2:3]) ** 2)
+                d = d + sigma_r * randn(M, N)
+                events.append((kind, dt, len(rng_rows) * M, None))
+                rng_rows.append(floor(d * 1000.0))
+            elif kind == EV_IMU:
+                off = len(rows)
+                rows.append(om + np.sqrt(0.089) * randn(N))
+                rows.append(c * ax + s * ay + np.sqrt(0.003) * randn(N))
+                rows.append(-s * ax + c * ay + np.sqrt(0.003) * randn(N))
+                events.append((kind, dt, off, IMU_AUX))
+            elif kind == EV_PX4:
+                off = len(rows)
+                T = PX4_T_US / 1e6
+                rows.append((c * vx + s * vy) * T / PX4_HEIGHT + 2e-4 * randn(N))
+                rows.append((-s * vx + c * vy) * T / PX4_HEIGHT + 2e-4 * randn(N))
+                rows.append(full_like(px, om * T))
+                rows.append(full_like(px, PX4_T_US))
+                rows.append(full_like(px, 200.0))
+                events.append((kind, dt, off, None))
+            else:
+                off = len(rows)
+                a = th + 0.01 * randn(N)
+                rows.append(a - 2 * np.pi * floor((a + np.pi) / (2 * np.pi)))
+                events.append((kind, dt, off, None))
+    px, py, vx, vy, ax, ay, th = kin(0.0)
+    zeros = full_like(px, 0.0)
+    x0 = stack([px, py, vx, vy, zeros, zeros, th, full_like(px, om)])
+    pe = kin(t)
+    truth_end = stack([pe[0], pe[1], full_like(px, tag_z)])
+    ranges = stack(rng_rows)
+    sensors = stack(rows)
+    if use_torch:
+        import torch
+        ranges = ranges.clamp_(min=0).to(torch.int32).contiguous()
+        sensors = sensors.contiguous()
+    else:
+        ranges = np.ascontiguousarray(np.clip(ranges, 0, None).astype(np.int32))
+        sensors = np.ascontiguousarray(sensors)
+    return dict(events=events, ranges=ranges, sensors=sensors, x0=x0, truth_end=truth_end, tag_z=tag_z,
+                n_toa=len(rng_rows), n_events=len(events))
+
+
+K8_XML = ['<config><uwb useFixedHeight="0" fixedHeight="1.049" tagId="0"/></config>',
+          '<config><px4flow armP0="1" armP1="0" useFixedSensorHeight="1" sensorHeight="5" '
+          'sensorInitAngle="-1.570796326794897" covarianceVelocity="0.04" covarianceGyroZ="0.02"/></config>',
+          '<config><imu useFixedCovarianceAcceleration="1" covarianceAcceleration="0.003" '
+          'useFixedCovarianceAngularVelocityZ="1" covarianceAngularVelocityZ="0.089"/></config>',
+          '<config><mag angleOffset="0" covarianceMag="0.0001"/></config>']
+K8_ORACLE_CFG = dict(tag_z=1.049, use_fixed_height=0, px4_height=5.0, px4_arm1=1.0, px4_arm2=0.0,
+                     px4_cov_vel=0.04, px4_cov_gyro=0.02, imu_fixed_cov_acc=1, imu_cov_acc=0.003,
+                     imu_fixed_cov_gyro=1, imu_cov_gyro=0.089, mag_offset=0.0, mag_cov=1e-4)
+
+
 def device_ranges_mm(n_filters: int, n_steps: int, anchors: np.ndarray, dt: float, device,
                      seed: int = SEED, sigma: float = 0.10, dtype=None, step0: int = 0):
     """torch/device version of truth_lissajous + ranges_mm for bench-sized inputs.

@@ -1,0 +1,74 @@
+"""GPU parity: KalmanFilterTOAIMU (T9) through the C ABI: ranging path (reference-exact) and the
+restated IMU rows."""
+import numpy as np
+import pytest
+
+from roskfpos_b200 import synth
+from tests.util import REL_TOL, rel_err_cov, rel_err_state
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("m,N,T", [(8, 4096, 40), (16, 1000, 20)])
+def test_t9_ranging_replay_parity(kflib, oracle, m, N, T):
+    from roskfpos_b200.batch import Batch
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=300 + m)
+    r = synth.ranges_mm(truth[1:], anc, seed=301 + m)
+    x0 = np.zeros((9, N)); x0[:3] = truth[0]
+    ref = oracle.t9_replay(x0, None, r, anc, 0.1, 0.01, want_traj=True)
+    with Batch(kflib.MODEL_T9, N, anchors=anc, accel_noise=0.5, jolt=0.5) as b:
+        b.set_state(x0)
+        traj, _ = b.replay_toa(0.1, r, err=0.01, want_traj=True)
+        x, P, st = b.get_state()
+        cnt = b.counters()
+    assert rel_err_state(x, ref["x"]) < REL_TOL
+    assert rel_err_cov(P, ref["P"]) < REL_TOL
+    assert rel_err_state(traj, ref["traj"]) < REL_TOL
+    assert [cnt["ml_iters"], cnt["cost_evals"], cnt["gain_evals"]] == list(ref["counters"][:3])
+    assert np.all(x[6:] == 0.0)
+
+
+def test_t9_imu_events_and_step_api(kflib, oracle):
+    from roskfpos_b200.batch import Batch
+    N, T, m = 2048, 15, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=401)
+    r = synth.ranges_mm(truth[1:], anc, seed=402)
+    rng = np.random.default_rng(5)
+    cov = np.array([[0.02, 0.002, 0.0], [0.002, 0.03, 0.001], [0.0, 0.001, 0.05]]).ravel()
+    sens = rng.normal(0, 0.2, size=(3 * 2 * T, N))
+    events = []
+    for t in range(T):
+        events.append((2, 0.04, 6 * t, cov))
+        events.append((2, 0.03, 6 * t + 3, cov))
+        events.append((0, 0.03, t * m, None))
+    x0 = np.zeros((9, N)); x0[:3] = truth[0]
+    ref = oracle.t9_events(x0, None, events, r, sens, anc, 0.01)
+    outs = []
+    for mode in ("events", "steps"):
+        with Batch(kflib.MODEL_T9, N, anchors=anc, accel_noise=0.5, jolt=0.5) as b:
+            b.set_state(x0)
+            if mode == "events":
+                b.replay_events(events, ranges=r, sensors=sens, err=0.01)
+            else:
+                for (kind, dt, off, aux) in events:
+                    if kind == 0:
+                        b.step_toa(dt, r.reshape(-1, N)[off:off + m], err=0.01)
+                    else:
+                        b.step_imu(dt, None, sens[off:off + 3], cov_acc=aux)
+            outs.append(b.get_state())
+            xp, Pp = b.get_pose(0.02)
+    for x, P, st in outs:
+        assert rel_err_state(x, ref["x"]) < REL_TOL
+        assert rel_err_cov(P, ref["P"]) < REL_TOL
+    o = oracle.T9(0.5, 0.5, outs[1][0][:3, 7])
+    for k in range(3):
+        o.f.vel[k] = outs[1][0][3 + k, 7]
+    for k in range(81):
+        o.f.P[k] = outs[1][1][k, 7]
+    xr = np.zeros(9); Pr = np.zeros(81)
+    import ctypes as C
+    oracle.lib().ko_t9_get_pose(C.byref(o.f), C.c_double(0.02), xr.ctypes.data_as(C.POINTER(C.c_double)),
+                                Pr.ctypes.data_as(C.POINTER(C.c_double)))
+    assert np.abs(xp[:, 7] - xr).max() < 1e-12 and np.abs(Pp[:, 7] - Pr).max() <= 1e-12 * np.abs(Pr).max()
