@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(K8_BLOCK, 3) k8_replay_kernel(const __grid_con
         for (int k = 0; k < Sym<8>::SZ; ++k) sc.Pm[k] = p.P[(int64_t)k * N + f];
         unsigned has = (unsigned)p.has[f]; // bit0 px4, bit1 imu, bit2 mag latched
         unsigned status_or = 0;
-        double carry = 0.0; // time of events this filter skipped (PX4 quality 0 returns before the clock is read)
+        // time of the events this filter skipped (a PX4 frame of quality 0 returns before the
+        // reference reads its clock, KF.cpp:111-113); persists across launches in latch row 8
+        double carry = p.latch[8 * N + f];
         double ic00 = p.latch_u[0], ic01 = p.latch_u[1], ic11 = p.latch_u[2], icw = p.latch_u[3];
         int n_toa = 0;
 
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(K8_BLOCK, 3) k8_replay_kernel(const __grid_con
 #pragma unroll
         for (int k = 0; k < Sym<8>::SZ; ++k) p.P[(int64_t)k * N + f] = sc.Pm[k];
         p.has[f] = (int32_t)has;
+        p.latch[8 * N + f] = carry;
         if (p.status) p.status[f] |= (int32_t)status_or;
         if (f == 0) {
             p.latch_u[0] = ic00; p.latch_u[1] = ic01; p.latch_u[2] = ic11; p.latch_u[3] = icw;
