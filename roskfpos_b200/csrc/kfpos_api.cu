@@ -600,7 +600,7 @@ int single_sensor_event(kfpos_batch *b, int kind, double dt, const double *const
     ev.dt = dt;
     ev.offset = 0;
     if (aux) memcpy(ev.aux, aux, sizeof ev.aux);
-    return run_events(b, 1, &ev, nullptr, KFPOS_FMT_F64_M, 0.0, nullptr, dst, nullptr, s);
+    return run_events(b, 1, &ev, nullptr, KFPOS_FMT_F64_M, 1.0, nullptr, dst, nullptr, s);
 }
 
 } // namespace

@@ -76,7 +76,7 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const Epoch<PME> &e
         if (mask == 0u) sse = -1.0; // estimationError of an empty list
     }
     const double R0 = fmax(sse, ep.e0);
-    const double invR0 = 1.0 / R0;
+    const double invR0 = mask ? 1.0 / R0 : 0.0; // no ranging rows: nothing is weighted by it
     // inverse of the IMU accelerometer block and the scalar variances (arma::inv of the
     // block-diagonal observationCovariance, KF.cpp:446)
     const double idet = ms.has_imu ? 1.0 / (ms.imu_c00 * ms.imu_c11 - ms.imu_c01 * ms.imu_c01) : 0.0;

@@ -84,7 +84,7 @@ KF_DEV int t9_update(const AnchorTable &A, const Epoch<PME> &ep, bool has_r, boo
         if (mask == 0u) sse = -1.0;
     }
     const double R0 = fmax(sse, ep.e0);
-    const double invR0 = 1.0 / R0;
+    const double invR0 = mask ? 1.0 / R0 : 0.0;
     double Rai[6] = {0, 0, 0, 0, 0, 0};
     if (has_imu && !inv_sym3(Ra, Rai)) return ML_SINGULAR; // arma::inv(observationCovariance) would throw
 
