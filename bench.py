@@ -333,6 +333,14 @@ def run_b200(args):
             "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                     "peak_source": peak_src, "bytes_per_update": alg_bytes / (N * T)}}
 
+    other = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        del ranges
+        torch.cuda.empty_cache()
+        try:
+            other = bench_other_configs(local, dev, args)
+        except Exception as exc:  # secondary numbers must never take the headline line down
+            other = {"error": repr(exc)}
     if rank == 0:
         cpu = None if args.no_cpu else cpu_reference(M, min(T, 100), args.cpu_seconds)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -341,14 +349,105 @@ def run_b200(args):
                 "config": {"workload": f"T6 (KalmanFilterTOA) IEKF replay: {N} filters/GPU x {T} epochs, "
                                        f"{M} anchors, int32-mm ranges, dt 0.1 s, P0=0, fixed initial position",
                            "filters_per_gpu": N, "epochs_per_step": T, "anchors": M,
-                           "l2_policy": f"inputs larger than L2 ({ranges.numel() * ranges.element_size() / 1e6:.0f} MB range log per step)",
+                           "l2_policy": f"inputs larger than L2 ({N * T * M * 4 / 1e6:.0f} MB range log per step)",
                            "parallelism": f"filters sharded by index over {world} GPU(s); one all-reduce of 4 doubles per step"},
                 "rmse_m": rmse, "bad_updates": cnt["bad"],
-                "e2e": e2e, "gpu_launches": 3 * K, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+                "e2e": e2e, "gpu_launches": 3 * K, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                "other_configs": other}
         print(json.dumps(line))
     batch.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_other_configs(local, dev, args):
+    """The remaining BASELINE.json configs as secondary numbers (device-resident inputs, CUDA
+    events, 1 warm-up + 3 timed repetitions each).  Not the headline metric."""
+    import torch
+    from roskfpos_b200 import lib as L, synth
+    from roskfpos_b200.batch import Batch
+    stream = torch.cuda.current_stream()
+    out = {}
+
+    def timed(fn, reps=3):
+        fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps * 1e-3
+
+    # ---- config 2: ML multilateration, 8 anchors, 1 Mi epochs (3-D from (1,1,4), and 2-D)
+    N = 1 << 20
+    anc = synth.anchors_for(8)
+    r, _, _ = synth.device_ranges_mm(N, 1, anc, 0.1, dev, seed=synth.SEED + 5)
+    r = r[0].contiguous()
+    outs = dict(pos=torch.empty((3, N), device=dev, dtype=torch.float64),
+                cov=torch.empty((9, N), device=dev, dtype=torch.float64),
+                iters=torch.empty(N, device=dev, dtype=torch.int32),
+                sel=torch.empty((2, N), device=dev, dtype=torch.int32),
+                status=torch.empty(N, device=dev, dtype=torch.int32))
+    for use2d in (0, 1):
+        with Batch(L.MODEL_ML, N, device=local, anchors=anc, use2d=use2d,
+                   ml_start=[1.0, 1.0, 1.0 if use2d else 4.0]) as b:
+            t = timed(lambda: b.ml_solve(r, err=0.01, out=outs, stream=stream))
+            c = b.counters()
+        out[f"config2_ml_{'2d' if use2d else '3d'}"] = {
+            "epochs_per_s": N / t, "ms": t * 1e3, "epochs": N, "anchors": 8,
+            "mean_newton_iters": c["ml_iters"] / max(c["updates"], 1)}
+    # ---- config 4a/4b: NLOS variants, 16 anchors
+    anc16 = synth.anchors_for(16)
+    N4 = 1 << 22
+    r16, _, _ = synth.device_ranges_mm(N4, 1, anc16, 0.1, dev, seed=synth.SEED + 6)
+    r16 = r16[0].contiguous()
+    o4 = dict(pos=torch.empty((3, N4), device=dev, dtype=torch.float64), cov=None, iters=None,
+              sel=torch.empty((2, N4), device=dev, dtype=torch.int32), status=None)
+    with Batch(L.MODEL_ML, N4, device=local, anchors=anc16, use2d=0, variant=1, num_ignored_rangings=2) as b:
+        t = timed(lambda: b.ml_solve(r16, err=0.01, out=o4, stream=stream))
+    out["config4a_ml_ignore2_16anchors"] = {"epochs_per_s": N4 / t, "ms": t * 1e3, "epochs": N4}
+    Nb = 1 << 17
+    ob = dict(pos=torch.empty((3, Nb), device=dev, dtype=torch.float64), cov=None, iters=None,
+              sel=torch.empty((2, Nb), device=dev, dtype=torch.int32), status=None)
+    rb = r16[:, :Nb].contiguous()
+    with Batch(L.MODEL_ML, Nb, device=local, anchors=anc16, use2d=1, variant=2, ml_start=[1.0, 1.0, 1.0]) as b:
+        t = timed(lambda: b.ml_solve(rb, err=0.01, out=ob, stream=stream), reps=1)
+    out["config4b_ml_best3_of_16_2d"] = {"epochs_per_s": Nb / t, "ms": t * 1e3, "epochs": Nb,
+                                         "subset_solves_per_epoch": 560 + 1}
+    del r16, rb, o4, ob
+    # ---- config 4c: T6 leave-one-out (ignoreWorstAnchorMode), 16 anchors
+    Nl, Tl = 1 << 18, 10
+    rl, x0l, _ = synth.device_ranges_mm(Nl, Tl, anc16, 0.1, dev, seed=synth.SEED + 7)
+    x0f = torch.zeros((6, Nl), device=dev, dtype=torch.float64)
+    x0f[:3] = x0l
+    with Batch(L.MODEL_T6, Nl, device=local, anchors=anc16, accel_noise=0.5, ignore_worst_anchor=1,
+               ignore_cost_threshold=0.5) as b:
+        def run():
+            b.set_state(x0f, None, stream=stream)
+            b.replay_toa(0.1, rl, err=0.01, stream=stream)
+        t = timed(run)
+    out["config4c_t6_leave_one_out_16anchors"] = {"updates_per_s": Nl * Tl / t, "ms": t * 1e3,
+                                                  "filters": Nl, "epochs": Tl, "solves_per_update": 17}
+    del rl
+    # ---- configs 3 and 5: K8 multi-sensor event streams, 8 anchors, 1 Mi filters
+    for name, full, n_macro in (("config3_k8_imu_mag", False, 5), ("config5_k8_full_multisensor", True, 4)):
+        Nk = 1 << 20
+        w = synth.k8_workload(Nk, n_macro, anc, seed=synth.SEED + 8, full=full, xp=torch, device=dev)
+        with Batch(L.MODEL_K8, Nk, device=local, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5) as b:
+            def run():
+                b.set_state(w["x0"], None, stream=stream)
+                b.replay_events(w["events"], ranges=w["ranges"], sensors=w["sensors"], err=0.01, stream=stream)
+            t = timed(run)
+            c = b.counters()
+            s4 = b.error_stats(w["truth_end"], stream=stream)
+        out[name] = {"toa_updates_per_s": Nk * w["n_toa"] / t, "all_event_updates_per_s": Nk * w["n_events"] / t,
+                     "ms": t * 1e3, "filters": Nk, "events": w["n_events"], "toa_events": w["n_toa"],
+                     "rmse_xy_m": float(np.sqrt(s4[1] / max(s4[2], 1))), "bad_updates": c["bad"],
+                     "input_mb": (w["sensors"].numel() * 8 + w["ranges"].numel() * 4) / 1e6}
+        del w
+    return out
 
 
 def C_double_peak(device):
@@ -371,6 +470,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary BASELINE configs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
