@@ -201,6 +201,7 @@ def run_b200(args):
     import torch.distributed as dist
     from roskfpos_b200 import lib as L, synth
     from roskfpos_b200.batch import Batch
+    from roskfpos_b200.shard import reduce_stats
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the product has no CPU path "
@@ -220,7 +221,6 @@ def run_b200(args):
     x0_full[:3] = x0
     batch = Batch(L.MODEL_T6, N, device=local, anchors=anc, accel_noise=0.5)
     stream = torch.cuda.current_stream()
-    stats = torch.zeros(4, device=dev, dtype=torch.float64)
 
     def barrier():
         if world > 1:
@@ -231,10 +231,7 @@ def run_b200(args):
         batch.set_state(x0_full, None, stream=stream)
         batch.replay_toa(0.1, ranges, err=0.01, stream=stream)
         s = batch.error_stats(truth_end, stream=stream)
-        if world > 1:  # the only collective: the final statistics reduction
-            stats.copy_(torch.as_tensor(s))
-            dist.all_reduce(stats)
-            s = stats.cpu().numpy()
+        s, _, _ = reduce_stats(s, device=dev)  # the only collective: the final statistics reduction
         return s
 
     # ---- device-resident throughput (`value`)
@@ -256,10 +253,7 @@ def run_b200(args):
         batch.replay_toa(0.1, ranges, err=0.01, stream=stream)
         kev[k][1].record(stream)
         s = batch.error_stats(truth_end, stream=stream)
-        if world > 1:
-            stats.copy_(torch.as_tensor(s))
-            dist.all_reduce(stats)
-            s = stats.cpu().numpy()
+        s, _, _ = reduce_stats(s, device=dev)
     e1.record(stream)
     barrier()
     torch.cuda.cudart().cudaProfilerStop()
