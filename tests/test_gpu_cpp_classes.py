@@ -61,13 +61,13 @@ def test_cpp_kalman_filter_multi_sensor(exe, oracle):
             script.append(f"toa {dt!r} 0.01 {fmt(rr[off:off + 8])}")
             o.new_toa(dt, rr[off:off + 8], anc, 0.01)
         elif kind == synth.EV_IMU:
-            script.append(f"imu {dt!r} 0 0 {s[off]!r} {s[off + 1]!r} {s[off + 2]!r} 0 {fmt(cav)} {fmt(cac)}")
+            script.append(f"imu {dt!r} 0 0 {fmt(s[off:off + 3])} 0 {fmt(cav)} {fmt(cac)}")
             o.new_imu(dt, [0, 0, s[off]], cav, [s[off + 1], s[off + 2], 0], cac)
         elif kind == synth.EV_PX4:
-            script.append(f"px4 {dt!r} {s[off]!r} {s[off + 1]!r} {s[off + 2]!r} {s[off + 3]!r} {int(s[off + 4])}")
+            script.append(f"px4 {dt!r} {fmt(s[off:off + 4])} {int(s[off + 4])}")
             o.new_px4(dt, s[off], s[off + 1], s[off + 2], s[off + 3], int(s[off + 4]))
         else:
-            script.append(f"compass {dt!r} {s[off]!r}")
+            script.append(f"compass {dt!r} {fmt(s[off:off + 1])}")
             o.new_compass(dt, s[off])
     script.append("pose")
     p = run(exe, script)[-1]
