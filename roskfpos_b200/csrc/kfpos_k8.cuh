@@ -67,10 +67,12 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const Epoch<PME> &e
                      double dt, const double (&xp)[8], const K8Scratch &sc, Sym<8> &Pw, double (&dx)[8],
                      StepStats &st) {
     const unsigned mask = has_r ? ep.valid : 0u;
-    double sse = -1.0;
-    if (has_r) { // inner ML 2-D solve from (x^-_0, x^-_1, tagZ) (KF.cpp:403-405)
+    double sse = -1.0, sse_xp = 0.0;
+    if (has_r) { // inner ML 2-D solve from (x^-_0, x^-_1, tagZ) (KF.cpp:403-405); its first pass
+                 // leaves 1/d_i and eps_i at x^- in the scratch columns for the first cost evaluation
         double pml[3] = {xp[0], xp[1], cfg.tag_z};
-        const int rc = ml_solve2<PME>(A, ep, mask, pml, sse, st.ml_iters, nullptr);
+        const DistStore ds = {sc.invd, sc.eps};
+        const int rc = ml_solve2<PME, true>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &ds, &sse_xp);
         if (rc == ML_FEW) st.status |= 2u;
         if (rc == ML_SINGULAR) return ML_SINGULAR;
         if (mask == 0u) sse = -1.0; // estimationError of an empty list
@@ -97,16 +99,28 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const Epoch<PME> &e
         const double th = xp[6] + dx[6], om = xp[7] + dx[7];
         // ---- pass A: sensor outputs and cost at the current iterate (KF.cpp:451-469)
         double c = 0.0;
+        if (iter == 0) { // x = x^-: distances already in the scratch columns
+            if (PME) {
+                for (int i = 0; i < ep.m_slots; ++i) {
+                    if (!((mask >> i) & 1u)) continue;
+                    const double e = sc.eps[i];
+                    c = fma(e * e, 1.0 / fmax(sse, ep.e[i]), c);
+                }
+            } else {
+                c = sse_xp;
+            }
+        } else {
 #pragma unroll 2
-        for (int i = 0; i < ep.m_slots; ++i) {
-            if (!((mask >> i) & 1u)) continue;
-            const double ex = px - A.x[i], ey = py - A.y[i], ez = cfg.tag_z - A.z[i];
-            const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
-            const double id = fast_rsqrt(d2);
-            const double e = ep.z[i] - d2 * id;
-            sc.invd[i] = id;
-            sc.eps[i] = e;
-            c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
+            for (int i = 0; i < ep.m_slots; ++i) {
+                if (!((mask >> i) & 1u)) continue;
+                const double ex = px - A.x[i], ey = py - A.y[i], ez = cfg.tag_z - A.z[i];
+                const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
+                const double id = fast_rsqrt(d2);
+                const double e = ep.z[i] - d2 * id;
+                sc.invd[i] = id;
+                sc.eps[i] = e;
+                c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
+            }
         }
         if (!PME) c *= invR0;
         double sn = 0.0, cs = 1.0, sw = 0.0, cw = 1.0;

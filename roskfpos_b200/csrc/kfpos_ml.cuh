@@ -34,9 +34,15 @@ struct MlPass3 {
 // gradient / Hessian / costs at p over the slots in `mask` (ML.cpp:171-222).
 // With a scalar errorEstimation the weight 1/e is common to g and H and cancels in
 // the Newton step, so only the stop-test cost carries it.
-template <bool PME>
+// STORE: also park 1/d_i and r_i - d_i in the scratch columns -- the first pass runs at the
+// predicted position, exactly where the IEKF's first cost evaluation needs them.
+struct DistStore {
+    Col invd, eps;
+};
+
+template <bool PME, bool STORE = false>
 KF_DEV void ml_pass3(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, const double (&p)[3],
-                     MlPass3 &o) {
+                     MlPass3 &o, const DistStore *ds = nullptr) {
     double wc = 0.0, sse = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
     double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0, h4 = 0.0, h5 = 0.0, c1s = 0.0;
 #pragma unroll 2
@@ -49,6 +55,10 @@ KF_DEV void ml_pass3(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, 
         const double r = ep.z[i];
         const double res = r - d;
         const double rid = r * invd;
+        if (STORE) {
+            ds->invd[i] = invd;
+            ds->eps[i] = res;
+        }
         if (PME) {
             const double w = 1.0 / ep.e[i];
             sse = fma(res, res, sse);
@@ -85,12 +95,14 @@ KF_DEV void ml_pass3(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, 
 // estimatePosition (3-D), ML.cpp:153-257.  p: in = start, out = estimate.
 // sse_out = estimationError at the returned point.  The covariance
 // inv(J^T W^-1 J) (ML.cpp:229-254) is produced only when cov != nullptr.
-template <bool PME>
+template <bool PME, bool STORE = false>
 KF_DEV int ml_solve3(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, double (&p)[3],
-                     double &sse_out, unsigned &iters, double *cov /* packed Sym<3> or null */) {
+                     double &sse_out, unsigned &iters, double *cov /* packed Sym<3> or null */,
+                     const DistStore *ds = nullptr, double *sse_start = nullptr) {
     MlPass3 ps;
-    ml_pass3<PME>(A, ep, mask, p, ps);
+    ml_pass3<PME, STORE>(A, ep, mask, p, ps, ds);
     sse_out = ps.sse;
+    if (sse_start) *sse_start = ps.sse;
     if (__popc(mask) < 4) return ML_FEW;
     double cost = 1e20, newCost = 1.0;
     unsigned iter = 0;
@@ -136,9 +148,9 @@ struct MlPass2 {
 };
 
 // 2-D pass: distances are 3-D with z fixed, derivatives in x,y only (ML.cpp:74-95)
-template <bool PME>
+template <bool PME, bool STORE = false>
 KF_DEV void ml_pass2(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, double px, double py,
-                     double pz, MlPass2 &o) {
+                     double pz, MlPass2 &o, const DistStore *ds = nullptr) {
     double sse = 0.0, g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0, h2 = 0.0, c1s = 0.0;
 #pragma unroll 2
     for (int i = 0; i < ep.m_slots; ++i) {
@@ -150,6 +162,10 @@ KF_DEV void ml_pass2(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, 
         const double r = ep.z[i];
         const double res = r - d;
         const double rid = r * invd;
+        if (STORE) {
+            ds->invd[i] = invd;
+            ds->eps[i] = res;
+        }
         const double w = PME ? 1.0 / ep.e[i] : 1.0;
         sse = fma(res, res, sse);
         const double t = res * invd * w;
@@ -168,12 +184,14 @@ KF_DEV void ml_pass2(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, 
 // `step` of the reference never takes effect: a rejected step leaves
 // newCost == cost, so the while-test fails on the next evaluation (ML.cpp:109-116).
 // B-1: the tentative cost is evaluated at z = start z.
-template <bool PME>
+template <bool PME, bool STORE = false>
 KF_DEV int ml_solve2(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, double (&p)[3],
-                     double &sse_out, unsigned &iters, double *cov /* xx, xy, yy or null */) {
+                     double &sse_out, unsigned &iters, double *cov /* xx, xy, yy or null */,
+                     const DistStore *ds = nullptr, double *sse_start = nullptr) {
     MlPass2 ps;
-    ml_pass2<PME>(A, ep, mask, p[0], p[1], p[2], ps);
+    ml_pass2<PME, STORE>(A, ep, mask, p[0], p[1], p[2], ps, ds);
     sse_out = ps.sse;
+    if (sse_start) *sse_start = ps.sse;
     if (__popc(mask) < 3) return ML_FEW;
     double cost = 1e20, newCost = ps.sse;
     unsigned iter = 0;

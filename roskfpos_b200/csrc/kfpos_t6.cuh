@@ -58,15 +58,16 @@ KF_DEV int t6_update(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, 
                      const T6Scratch &sc, Sym<6> &Pw, double (&dx)[6], double &cost_out, StepStats &st) {
     // ---- inner ML solve from the predicted position (TOA.cpp:268-273)
     double pml[3] = {xp[0], xp[1], xp[2]};
-    double sse;
-    const int rc = ml_solve3<PME>(A, ep, mask, pml, sse, st.ml_iters, nullptr);
+    double sse, sse_xp;
+    // the first Newton pass runs at xp: it also leaves 1/d_i and eps_i(xp) in the scratch
+    // columns for the IEKF's first cost evaluation
+    const DistStore ds = {sc.invd, sc.eps};
+    const int rc = ml_solve3<PME, true>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &ds, &sse_xp);
     if (rc == ML_FEW) st.status |= 2u;
     if (rc == ML_SINGULAR) return ML_SINGULAR;
-    if (isnan(pml[0]) || isnan(pml[1]) || isnan(pml[2])) { // TOA.cpp:270-272
+    if (isnan(pml[0]) || isnan(pml[1]) || isnan(pml[2])) { // TOA.cpp:270-272: back to xp
         st.status |= 16u;
-        MlPass3 ps;
-        ml_pass3<PME>(A, ep, mask, xp, ps);
-        sse = ps.sse;
+        sse = sse_xp;
     }
     if (mask == 0u) sse = -1.0; // estimationError of an empty list (ML.cpp:265-267)
 
@@ -85,16 +86,28 @@ KF_DEV int t6_update(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, 
         const double px = xp[0] + dx[0], py = xp[1] + dx[1], pz = xp[2] + dx[2];
         // ---- pass A: cost at the current iterate (TOA.cpp:297-305)
         double c = 0.0;
+        if (iter == 0) { // x = xp: distances already in the scratch columns
+            if (PME) {
+                for (int i = 0; i < ep.m_slots; ++i) {
+                    if (!((mask >> i) & 1u)) continue;
+                    const double e = sc.eps[i];
+                    c = fma(e * e, 1.0 / fmax(sse, ep.e[i]), c);
+                }
+            } else {
+                c = sse_xp;
+            }
+        } else {
 #pragma unroll 2
-        for (int i = 0; i < ep.m_slots; ++i) {
-            if (!((mask >> i) & 1u)) continue;
-            const double ex = px - A.x[i], ey = py - A.y[i], ez = pz - A.z[i];
-            const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
-            const double id = fast_rsqrt(d2);
-            const double e = ep.z[i] - d2 * id;
-            sc.invd[i] = id;
-            sc.eps[i] = e;
-            c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
+            for (int i = 0; i < ep.m_slots; ++i) {
+                if (!((mask >> i) & 1u)) continue;
+                const double ex = px - A.x[i], ey = py - A.y[i], ez = pz - A.z[i];
+                const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
+                const double id = fast_rsqrt(d2);
+                const double e = ep.z[i] - d2 * id;
+                sc.invd[i] = id;
+                sc.eps[i] = e;
+                c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
+            }
         }
         const double newCost = (PME ? c : c * invR0) + prior;
         st.cost_evals += 1;

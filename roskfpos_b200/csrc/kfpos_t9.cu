@@ -75,10 +75,11 @@ KF_DEV int t9_update(const AnchorTable &A, const Epoch<PME> &ep, bool has_r, boo
                      const double (&Ra)[6], const double (&xp)[9], const T9Scratch &sc, Sym<9> &Pw, double (&dx)[9],
                      StepStats &st) {
     const unsigned mask = has_r ? ep.valid : 0u;
-    double sse = -1.0;
+    double sse = -1.0, sse_xp = 0.0;
     if (has_r) { // TOAIMU.cpp:268-270 (no NaN guard in this class)
         double pml[3] = {xp[0], xp[1], xp[2]};
-        const int rc = ml_solve3<PME>(A, ep, mask, pml, sse, st.ml_iters, nullptr);
+        const DistStore ds = {sc.invd, sc.eps};
+        const int rc = ml_solve3<PME, true>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &ds, &sse_xp);
         if (rc == ML_FEW) st.status |= 2u;
         if (rc == ML_SINGULAR) return ML_SINGULAR;
         if (mask == 0u) sse = -1.0;
@@ -97,16 +98,28 @@ KF_DEV int t9_update(const AnchorTable &A, const Epoch<PME> &ep, bool has_r, boo
     for (int iter = 0; iter < 20; ++iter) {
         const double px = xp[0] + dx[0], py = xp[1] + dx[1], pz = xp[2] + dx[2];
         double c = 0.0;
+        if (iter == 0) { // x = x^-: distances already in the scratch columns
+            if (PME) {
+                for (int i = 0; i < ep.m_slots; ++i) {
+                    if (!((mask >> i) & 1u)) continue;
+                    const double e = sc.eps[i];
+                    c = fma(e * e, 1.0 / fmax(sse, ep.e[i]), c);
+                }
+            } else {
+                c = sse_xp;
+            }
+        } else {
 #pragma unroll 2
-        for (int i = 0; i < ep.m_slots; ++i) {
-            if (!((mask >> i) & 1u)) continue;
-            const double ex = px - A.x[i], ey = py - A.y[i], ez = pz - A.z[i];
-            const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
-            const double id = fast_rsqrt(d2);
-            const double e = ep.z[i] - d2 * id;
-            sc.invd[i] = id;
-            sc.eps[i] = e;
-            c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
+            for (int i = 0; i < ep.m_slots; ++i) {
+                if (!((mask >> i) & 1u)) continue;
+                const double ex = px - A.x[i], ey = py - A.y[i], ez = pz - A.z[i];
+                const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
+                const double id = fast_rsqrt(d2);
+                const double e = ep.z[i] - d2 * id;
+                sc.invd[i] = id;
+                sc.eps[i] = e;
+                c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
+            }
         }
         if (!PME) c *= invR0;
         double ea[3] = {0, 0, 0};
