@@ -5,7 +5,6 @@
 #include "kfpos_kernels.cuh" // K8Cfg, EventDesc
 #include "kfpos_math.cuh"
 #include "kfpos_ml.cuh"
-#include "kfpos_t6.cuh" // StepStats
 
 namespace kfpos {
 

@@ -39,26 +39,26 @@ KF_DEV double mm_to_m(double mm) {
     return fma(fma(-q, 1000.0, mm), 0.001, q);
 }
 
-// Reciprocal and reciprocal square root for well-scaled positive arguments
-// (distances in metres, innovation variances): MUFU seed (>= 20 bits) + two
-// Newton steps on the FP64 pipe, <= 1 ulp, no slow-path branch or subroutine.
-// 0 -> inf/NaN like the IEEE operations they replace.
+// Reciprocal and reciprocal square root for well-scaled arguments (distances in
+// metres, innovation variances, determinants): MUFU seed (relative error e <= 2^-20,
+// the unit reads the upper 32 bits of the operand) + ONE cubic correction on the FP64 pipe
+//   1/x       = y (1 + e + e^2)            + O(e^3),  e = 1 - x y
+//   1/sqrt(x) = y (1 + e/2 + 3 e^2 / 8)    + O(e^3),  e = 1 - x y^2
+// => <= 1 ulp (checked against IEEE division / sqrt by kfpos_selftest_math), 3 / 5 FP64
+// instructions, no slow-path branch.  0 -> inf/NaN like the IEEE operations they replace;
+// denormal arguments are flushed (never reached by this path's quantities).
 KF_DEV double fast_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    const double e = fma(-x, y, 1.0);
+    return fma(y, fma(e, e, e), y);
 }
 
 KF_DEV double fast_rsqrt(double x) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x * y, y, 1.0);
-    y = fma(0.5 * y, e, y);
-    e = fma(-x * y, y, 1.0);
-    return fma(0.5 * y, e, y);
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
 // one column of a per-thread array kept in shared memory: element i of thread t
@@ -98,7 +98,7 @@ KF_DEV bool solve_sym3(const double (&H)[6], const double (&g)[3], double (&s)[3
     const double c11 = a * f - c * c;
     const double c12 = b * c - a * e;
     const double c22 = a * d - b * b;
-    const double id = 1.0 / det;
+    const double id = fast_rcp(det);
     s[0] = (c00 * g[0] + c01 * g[1] + c02 * g[2]) * id;
     s[1] = (c01 * g[0] + c11 * g[1] + c12 * g[2]) * id;
     s[2] = (c02 * g[0] + c12 * g[1] + c22 * g[2]) * id;
@@ -127,7 +127,7 @@ KF_DEV bool inv_sym3(const double (&H)[6], double (&I)[6]) {
 KF_DEV bool solve_sym2(double a, double b, double d, double g0, double g1, double &s0, double &s1) {
     const double det = a * d - b * b;
     if (!(det != 0.0)) return false;
-    const double id = 1.0 / det;
+    const double id = fast_rcp(det);
     s0 = (d * g0 - b * g1) * id;
     s1 = (a * g1 - b * g0) * id;
     return true;
@@ -215,6 +215,11 @@ KF_DEV void block2_update(Sym<N> &P, double (&dx)[N], const double (&h0)[N], con
         for (int j = 0; j <= i; ++j) P.at(i, j) = fma(-k0, p0[j], fma(-k1, p1[j], P.at(i, j)));
     }
 }
+
+// per-thread work counters of one replay (summed into the device counters at the end)
+struct StepStats {
+    unsigned ml_iters, cost_evals, gain_evals, status;
+};
 
 // warp-level sum of a per-thread counter, one atomic per warp
 KF_DEV void warp_accumulate(unsigned long long *dst, unsigned v) {

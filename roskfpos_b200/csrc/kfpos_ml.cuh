@@ -287,4 +287,56 @@ KF_DEV void convert_epoch(Epoch<PME> &ep, const Col &raw, const void *ranges, in
     ep.valid = valid;
 }
 
+// Packed landing zone: 32-bit words for the mm wire formats (half the shared memory of a
+// double column), doubles for the f64 format.  Element i of thread t lives at word/double
+// index i * stride + t of the region (conflict-free either way).
+struct RawCol {
+    void *p;
+    int stride;
+    KF_DEV unsigned *w(int i) const { return reinterpret_cast<unsigned *>(p) + i * stride; }
+    KF_DEV double *d(int i) const { return reinterpret_cast<double *>(p) + i * stride; }
+};
+KF_DEV RawCol make_raw(double *region, int fmt, int tid, int block) {
+    RawCol r;
+    r.p = fmt == 0 ? static_cast<void *>(region + tid) : static_cast<void *>(reinterpret_cast<unsigned *>(region) + tid);
+    r.stride = block;
+    return r;
+}
+
+KF_DEV void prefetch_epoch(const RawCol &raw, int m, const void *ranges, int fmt, int64_t base, int64_t N) {
+    for (int i = 0; i < m; ++i) {
+        const int64_t idx = base + (int64_t)i * N;
+        if (fmt == 0) cp_async_8(raw.d(i), reinterpret_cast<const double *>(ranges) + idx);
+        else if (fmt == 1) cp_async_4(raw.w(i), reinterpret_cast<const int32_t *>(ranges) + idx);
+        else // uint16: fetch the aligned 32-bit word that holds the element
+            cp_async_4(raw.w(i), reinterpret_cast<const void *>(
+                                     reinterpret_cast<uintptr_t>(reinterpret_cast<const uint16_t *>(ranges) + idx) & ~(uintptr_t)3));
+    }
+    cp_async_commit();
+}
+
+template <bool PME>
+KF_DEV void convert_epoch(Epoch<PME> &ep, const RawCol &raw, const void *ranges, int fmt, const double *err,
+                          int64_t base, int64_t N) {
+    unsigned valid = 0u;
+    for (int i = 0; i < ep.m_slots; ++i) {
+        double r;
+        if (fmt == 0) {
+            r = *raw.d(i);
+        } else {
+            const unsigned w = *raw.w(i);
+            if (fmt == 1) {
+                r = mm_to_m((double)(int)w);
+            } else {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(reinterpret_cast<const uint16_t *>(ranges) + base + (int64_t)i * N);
+                r = mm_to_m((double)((a & 2) ? (w >> 16) : (w & 0xffffu)));
+            }
+        }
+        ep.z[i] = r;
+        if (r > 0) valid |= 1u << i;
+        if (PME) ep.e[i] = __ldg(err + base + (int64_t)i * N);
+    }
+    ep.valid = valid;
+}
+
 } // namespace kfpos

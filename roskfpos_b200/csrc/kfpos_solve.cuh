@@ -1,0 +1,441 @@
+// kfpos_solve.cuh -- per-thread ML (Newton) multilateration and the information-form
+// ranging pass of the iterated EKFs: the B200 formulation of
+// MLLocation::estimatePosition / estimatePosition2D (ML.cpp:48-257) and of the ranging
+// rows of kalmanStep3D* (TOA.cpp:293-326, KF.cpp:451-495, TOAIMU.cpp:303-334).
+//
+// One thread owns one filter / epoch.  The SM sub-partition dispatches one FP64
+// instruction every ~2.3 cycles and any other instruction in 1 (profiles/README.md), so the
+// kernels are bound by  2.3 * (#FP64 instr) + (#other instr):  everything here is written
+// to minimise that sum --
+//   * MT > 0: the anchor count is a compile-time constant, the anchor loops are fully
+//     unrolled, the anchor coordinates fold into the DADD operands as constant-bank
+//     references, the epoch's ranges live in registers, and a missing ranging is handled
+//     by zeroing its 1/d and r (two predicated moves) instead of a branch;
+//   * MT == 0: run-time anchor count, rolled loops, ranges in a shared-memory column;
+//   * one Newton iteration = ONE pass over the anchors (stop cost, SSE, gradient,
+//     Hessian together; the reference evaluates the distances three times);
+//   * one IEKF iteration = ONE pass (cost, b = J^T R^-1 y, G = J^T R^-1 J) + a 3x3 / 2x2 solve;
+//   * reciprocal / reciprocal square root = MUFU seed + one cubic correction.
+#pragma once
+#include "kfpos_math.cuh"
+
+namespace kfpos {
+
+// Valid rangings of one epoch in metres.  PME = per-measurement errorEstimation column
+// `e` (shared memory); otherwise the scalar e0 applies to every ranging.
+template <bool PME, int MT = 0>
+struct EpochT {
+    Col z; // MT == 0: shared-memory column
+    Col e;
+    double zr[MT > 0 ? MT : 1]; // MT > 0: registers
+    double e0;
+    unsigned valid;
+    int m_slots;
+    KF_DEV int m() const { return MT > 0 ? MT : m_slots; }
+    KF_DEV double r(int i) const { return MT > 0 ? zr[i] : z[i]; }
+    // run-time index (MT > 0: a select chain over the register copy)
+    KF_DEV double z_at(int i) const {
+        if (MT == 0) return z[i];
+        double v = 0.0;
+#pragma unroll
+        for (int k = 0; k < (MT > 0 ? MT : 1); ++k) v = (k == i) ? zr[k] : v;
+        return v;
+    }
+    KF_DEV double err(int i) const { return PME ? e[i] : e0; }
+};
+
+// fabs(cost - newCost) / cost > 1e-3  (ML.cpp:67,165), bit-exact without the division
+// unless the quotient is within 1e-9 of the threshold.
+KF_DEV bool rel_change_gt(double cost, double newCost) {
+    const double q = fabs(cost - newCost);
+    if (cost > 0.0) {
+        const double t = 1e-3 * cost;
+        if (q > t * 1.000000001) return true;
+        if (q < t * 0.999999999) return false;
+    }
+    return q / cost > 1e-3;
+}
+// fabs(cost - newCost) / cost < tol  (TOA.cpp:307, KF.cpp:470, TOAIMU.cpp:312)
+KF_DEV bool rel_change_lt(double cost, double newCost, double tol) {
+    const double q = fabs(cost - newCost);
+    if (cost > 0.0) {
+        const double t = tol * cost;
+        if (q < t * 0.999999999) return true;
+        if (q > t * 1.000000001) return false;
+    }
+    return q / cost < tol;
+}
+
+struct MlPass3 {
+    double wcost, sse;
+    double g[3];
+    double H[6]; // packed Sym<3>: xx, xy, yy, xz, yz, zz
+};
+
+// gradient / Hessian / costs at p over the slots in `mask` (ML.cpp:171-222).
+// With a scalar errorEstimation the weight 1/e is common to g and H and cancels in
+// the Newton step, so only the stop-test cost carries it.
+template <bool PME, int MT>
+KF_DEV void ml_pass3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, int nvalid,
+                     const double (&p)[3], MlPass3 &o) {
+    double wc = 0.0, sse = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
+    double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0, h4 = 0.0, h5 = 0.0, c1s = 0.0;
+#pragma unroll(MT > 0 ? MT : 2)
+    for (int i = 0; i < ep.m(); ++i) {
+        const bool on = (mask >> i) & 1u;
+        if (MT == 0 && !on) continue;
+        const double dx = A.x[i] - p[0], dy = A.y[i] - p[1], dz = A.z[i] - p[2];
+        const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        double invd = fast_rsqrt(d2);
+        double r = ep.r(i);
+        if (MT > 0) { // a missing ranging contributes exact zeros
+            invd = on ? invd : 0.0;
+            r = on ? r : 0.0;
+        }
+        const double res = fma(-d2, invd, r);
+        const double rid = r * invd;
+        if (PME) {
+            const double w = fast_rcp(ep.e[i]);
+            sse = fma(res, res, sse);
+            wc = fma(res * res, w, wc);
+            const double t = res * invd * w;
+            g0 = fma(t, dx, g0); g1 = fma(t, dy, g1); g2 = fma(t, dz, g2);
+            c1s = fma(1.0 - rid, w, c1s);
+            const double c2 = rid * invd * invd * w;
+            const double cx = c2 * dx, cy = c2 * dy, cz = c2 * dz;
+            h0 = fma(cx, dx, h0); h1 = fma(cx, dy, h1); h2 = fma(cy, dy, h2);
+            h3 = fma(cx, dz, h3); h4 = fma(cy, dz, h4); h5 = fma(cz, dz, h5);
+        } else {
+            sse = fma(res, res, sse);
+            const double t = res * invd;
+            g0 = fma(t, dx, g0); g1 = fma(t, dy, g1); g2 = fma(t, dz, g2);
+            c1s += rid; // sum of (1 - r/d) = nvalid - sum r/d
+            const double c2 = rid * (invd * invd);
+            const double cx = c2 * dx, cy = c2 * dy, cz = c2 * dz;
+            h0 = fma(cx, dx, h0); h1 = fma(cx, dy, h1); h2 = fma(cy, dy, h2);
+            h3 = fma(cx, dz, h3); h4 = fma(cy, dz, h4); h5 = fma(cz, dz, h5);
+        }
+    }
+    if (!PME) c1s = (double)nvalid - c1s;
+    o.sse = sse;
+    o.wcost = PME ? wc : sse * fast_rcp(ep.e0);
+    o.g[0] = g0; o.g[1] = g1; o.g[2] = g2;
+    o.H[0] = h0 + c1s; o.H[1] = h1; o.H[2] = h2 + c1s; o.H[3] = h3; o.H[4] = h4; o.H[5] = h5 + c1s;
+}
+
+// return codes of the ML solvers
+#define ML_OK 0
+#define ML_FEW 1       // fewer than minRangings: position = start (ML.cpp:54-58,158-161)
+#define ML_SINGULAR -1 // arma::solve / inv would throw
+
+// estimatePosition (3-D), ML.cpp:153-257.  p: in = start, out = estimate.
+// sse_out = estimationError at the returned point, sse_start = at the start point.
+// The covariance inv(J^T W^-1 J) (ML.cpp:229-254) is produced only when cov != nullptr.
+// iter_cap < 10000 makes the solver resumable: when `iter_cap` iterations were not enough it
+// returns ML_MORE with (cost, iter) in `rs` and the current point in p; calling it again with
+// that `rs` continues the same iteration sequence (the ML kernel parks such epochs in a
+// queue so that a few slow epochs do not hold their whole warp for 10000 iterations).
+struct MlResume {
+    double cost;
+    unsigned iter; // 0 = fresh start
+};
+#define ML_MORE 2
+
+template <bool PME, int MT>
+KF_DEV int ml_solve3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, double (&p)[3],
+                     double &sse_out, unsigned &iters, double *cov /* packed Sym<3> or null */,
+                     double *sse_start = nullptr, unsigned iter_cap = 10000u, MlResume *rs = nullptr) {
+    const int nvalid = __popc(mask);
+    MlPass3 ps;
+    double cost = 1e20, newCost = 1.0;
+    unsigned iter = 0;
+    bool first = true;
+    if (rs && rs->iter) { // resume: the pass below recomputes newCost at p
+        cost = rs->cost;
+        iter = rs->iter;
+        first = false;
+    }
+    for (;;) {
+        ml_pass3<PME, MT>(A, ep, mask, nvalid, p, ps);
+        if (first) {
+            first = false;
+            if (sse_start) *sse_start = ps.sse;
+            if (nvalid < 4) { sse_out = ps.sse; return ML_FEW; }
+        } else {
+            newCost = ps.wcost;
+        }
+        if (!(rel_change_gt(cost, newCost) && iter < 10000u)) break;
+        if (iter >= iter_cap) {
+            rs->cost = cost;
+            rs->iter = iter;
+            return ML_MORE;
+        }
+        iter += 1;
+        cost = newCost;
+        double s[3];
+        if (!solve_sym3(ps.H, ps.g, s)) { iters += iter; return ML_SINGULAR; }
+        // newPos = solve(H, H pos - g)  ==  pos - H^-1 g
+        p[0] -= s[0]; p[1] -= s[1]; p[2] -= s[2];
+    }
+    iters += iter;
+    sse_out = ps.sse;
+    if (cov) {
+        // J_i = (p - b_i)/d_i ; W = diag(max(e_i, SSE)) ; cov = inv(J^T W^-1 J)
+        double M[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = 0; i < ep.m_slots; ++i) {
+            if (!((mask >> i) & 1u)) continue;
+            const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
+            const double id2 = 1.0 / (dx * dx + dy * dy + dz * dz);
+            const double w = id2 / fmax(ep.err(i), ps.sse);
+            M[0] = fma(w * dx, dx, M[0]);
+            M[1] = fma(w * dx, dy, M[1]);
+            M[2] = fma(w * dy, dy, M[2]);
+            M[3] = fma(w * dx, dz, M[3]);
+            M[4] = fma(w * dy, dz, M[4]);
+            M[5] = fma(w * dz, dz, M[5]);
+        }
+        double I[6];
+        if (!inv_sym3(M, I)) return ML_SINGULAR;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) cov[k] = I[k];
+    }
+    return ML_OK;
+}
+
+struct MlPass2 {
+    double sse;
+    double g[2];
+    double H[3]; // xx, xy, yy
+};
+
+// 2-D pass: distances are 3-D with z fixed, derivatives in x,y only (ML.cpp:74-95)
+template <bool PME, int MT>
+KF_DEV void ml_pass2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, int nvalid, double px,
+                     double py, double pz, MlPass2 &o) {
+    double sse = 0.0, g0 = 0.0, g1 = 0.0, h0 = 0.0, h1 = 0.0, h2 = 0.0, c1s = 0.0;
+#pragma unroll(MT > 0 ? MT : 2)
+    for (int i = 0; i < ep.m(); ++i) {
+        const bool on = (mask >> i) & 1u;
+        if (MT == 0 && !on) continue;
+        const double dx = A.x[i] - px, dy = A.y[i] - py, dz = A.z[i] - pz;
+        const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        double invd = fast_rsqrt(d2);
+        double r = ep.r(i);
+        if (MT > 0) {
+            invd = on ? invd : 0.0;
+            r = on ? r : 0.0;
+        }
+        const double res = fma(-d2, invd, r);
+        const double rid = r * invd;
+        sse = fma(res, res, sse);
+        if (PME) {
+            const double w = fast_rcp(ep.e[i]);
+            const double t = res * invd * w;
+            g0 = fma(t, dx, g0); g1 = fma(t, dy, g1);
+            c1s = fma(1.0 - rid, w, c1s);
+            const double c2 = rid * invd * invd * w;
+            const double cx = c2 * dx, cy = c2 * dy;
+            h0 = fma(cx, dx, h0); h1 = fma(cx, dy, h1); h2 = fma(cy, dy, h2);
+        } else {
+            const double t = res * invd;
+            g0 = fma(t, dx, g0); g1 = fma(t, dy, g1);
+            c1s += rid;
+            const double c2 = rid * (invd * invd);
+            const double cx = c2 * dx, cy = c2 * dy;
+            h0 = fma(cx, dx, h0); h1 = fma(cx, dy, h1); h2 = fma(cy, dy, h2);
+        }
+    }
+    if (!PME) c1s = (double)nvalid - c1s;
+    o.sse = sse;
+    o.g[0] = g0; o.g[1] = g1;
+    o.H[0] = h0 + c1s; o.H[1] = h1; o.H[2] = h2 + c1s;
+}
+
+// estimatePosition2D, ML.cpp:48-143.  z stays at its start value.  The damping
+// `step` of the reference never takes effect: a rejected step leaves
+// newCost == cost, so the while-test fails on the next evaluation (ML.cpp:109-116).
+// B-1: the tentative cost is evaluated at z = start z.
+template <bool PME, int MT>
+KF_DEV int ml_solve2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, double (&p)[3],
+                     double &sse_out, unsigned &iters, double *cov /* xx, xy, yy or null */,
+                     double *sse_start = nullptr) {
+    const int nvalid = __popc(mask);
+    MlPass2 ps, pt;
+    double cost = 1e20, newCost = 0.0;
+    double nx = p[0], ny = p[1];
+    unsigned iter = 0;
+    bool first = true;
+    for (;;) {
+        ml_pass2<PME, MT>(A, ep, mask, nvalid, nx, ny, p[2], pt);
+        if (first) {
+            first = false;
+            ps = pt;
+            newCost = pt.sse;
+            if (sse_start) *sse_start = pt.sse;
+            if (nvalid < 3) { sse_out = pt.sse; return ML_FEW; }
+        } else {
+            if (pt.sse > cost) break; // step /= 2; position kept; the while-test then fails
+            newCost = pt.sse;
+            p[0] = nx; p[1] = ny;
+            ps = pt;
+        }
+        if (!(rel_change_gt(cost, newCost) && iter < 10000u)) break;
+        iter += 1;
+        cost = newCost;
+        double s0, s1;
+        if (!solve_sym2(ps.H[0], ps.H[1], ps.H[2], ps.g[0], ps.g[1], s0, s1)) {
+            iters += iter;
+            return ML_SINGULAR;
+        }
+        nx = p[0] - s0; ny = p[1] - s1;
+    }
+    iters += iter;
+    sse_out = ps.sse;
+    if (cov) {
+        double m00 = 0, m01 = 0, m11 = 0;
+        for (int i = 0; i < ep.m_slots; ++i) {
+            if (!((mask >> i) & 1u)) continue;
+            const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
+            const double id2 = 1.0 / (dx * dx + dy * dy + dz * dz);
+            const double w = id2 / fmax(ep.err(i), ps.sse);
+            m00 = fma(w * dx, dx, m00);
+            m01 = fma(w * dx, dy, m01);
+            m11 = fma(w * dy, dy, m11);
+        }
+        const double det = m00 * m11 - m01 * m01;
+        if (!(det != 0.0)) return ML_SINGULAR;
+        const double id = 1.0 / det;
+        cov[0] = m11 * id;
+        cov[1] = -m01 * id;
+        cov[2] = m00 * id;
+    }
+    return ML_OK;
+}
+
+// ---- information-form ranging pass of one IEKF iteration at the iterate p = x^- + dx:
+//   c = sum eps_i^2 / R_i,  b = sum h_i y_i / R_i,  G = sum h_i h_i^T / R_i   (packed xx,xy,yy,xz,yz,zz)
+// with h_i = (p - a_i)/d_i, eps_i = r_i - d_i, y_i = eps_i + h_i . dx  (= eps - J delta, delta = -dx)
+// and R_i = max(sse, e_i).  With a scalar errorEstimation R is common: the sums are returned
+// UNSCALED and the caller multiplies by 1/R once.  D = 3: all three components; D = 2: the
+// rows only touch x,y (K8; z is the fixed tag height), G packed xx,xy,yy.
+template <bool PME, int MT, int D>
+KF_DEV void iekf_pass(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, double sse, double px,
+                      double py, double pz, const double (&dx)[3], double &c_out, double (&b)[3], double (&G)[6]) {
+    double c = 0.0, b0 = 0.0, b1 = 0.0, b2 = 0.0;
+    double G0 = 0.0, G1 = 0.0, G2 = 0.0, G3 = 0.0, G4 = 0.0, G5 = 0.0;
+#pragma unroll(MT > 0 ? MT : 2)
+    for (int i = 0; i < ep.m(); ++i) {
+        const bool on = (mask >> i) & 1u;
+        if (MT == 0 && !on) continue;
+        const double ex = px - A.x[i], ey = py - A.y[i], ez = pz - A.z[i];
+        const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
+        double id = fast_rsqrt(d2);
+        double r = ep.r(i);
+        if (MT > 0) {
+            id = on ? id : 0.0;
+            r = on ? r : 0.0;
+        }
+        const double e = fma(-d2, id, r);
+        const double h0 = ex * id, h1 = ey * id, h2 = D == 3 ? ez * id : 0.0;
+        const double y = D == 3 ? fma(h0, dx[0], fma(h1, dx[1], fma(h2, dx[2], e))) : fma(h0, dx[0], fma(h1, dx[1], e));
+        if (PME) {
+            const double iR = fast_rcp(fmax(sse, ep.e[i]));
+            c = fma(e * e, iR, c);
+            const double yr = y * iR;
+            const double h0r = h0 * iR, h1r = h1 * iR;
+            b0 = fma(h0, yr, b0); b1 = fma(h1, yr, b1);
+            G0 = fma(h0r, h0, G0); G1 = fma(h0r, h1, G1); G2 = fma(h1r, h1, G2);
+            if (D == 3) {
+                b2 = fma(h2, yr, b2);
+                G3 = fma(h0r, h2, G3); G4 = fma(h1r, h2, G4); G5 = fma(h2 * iR, h2, G5);
+            }
+        } else {
+            c = fma(e, e, c);
+            b0 = fma(h0, y, b0); b1 = fma(h1, y, b1);
+            G0 = fma(h0, h0, G0); G1 = fma(h0, h1, G1); G2 = fma(h1, h1, G2);
+            if (D == 3) {
+                b2 = fma(h2, y, b2);
+                G3 = fma(h0, h2, G3); G4 = fma(h1, h2, G4); G5 = fma(h2, h2, G5);
+            }
+        }
+    }
+    c_out = c;
+    b[0] = b0; b[1] = b1; b[2] = b2;
+    G[0] = G0; G[1] = G1; G[2] = G2; G[3] = G3; G[4] = G4; G[5] = G5;
+}
+
+// ---- asynchronous epoch loads (LDGSTS / cp.async): the rangings of the NEXT
+// epoch stream from HBM straight into a shared-memory landing zone while the current
+// epoch is being processed, so no warp ever waits on DRAM and no registers are
+// spent on staging.  ranges: SoA with the filter index fastest; `base` = element
+// index of slot 0 for this filter, `N` = element stride between slots.
+KF_DEV void cp_async_4(void *dst, const void *src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(src) : "memory");
+}
+KF_DEV void cp_async_8(void *dst, const void *src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(src) : "memory");
+}
+KF_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+KF_DEV void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// Landing zone: 32-bit words for the mm wire formats (half the shared memory of a
+// double column), doubles for the f64 format.  Element i of thread t lives at word/double
+// index i * stride + t of the region (conflict-free either way).
+struct RawCol {
+    void *p;
+    int stride;
+    KF_DEV unsigned *w(int i) const { return reinterpret_cast<unsigned *>(p) + i * stride; }
+    KF_DEV double *d(int i) const { return reinterpret_cast<double *>(p) + i * stride; }
+};
+KF_DEV RawCol make_raw(double *region, int fmt, int tid, int block) {
+    RawCol r;
+    r.p = fmt == 0 ? static_cast<void *>(region + tid) : static_cast<void *>(reinterpret_cast<unsigned *>(region) + tid);
+    r.stride = block;
+    return r;
+}
+// doubles of shared memory per thread a landing zone of `rows` elements needs
+__host__ __device__ inline int raw_rows(int fmt, int rows) { return fmt == 0 ? rows : (rows + 1) / 2; }
+
+KF_DEV void prefetch_epoch(const RawCol &raw, int m, const void *ranges, int fmt, int64_t base, int64_t N) {
+#pragma unroll 4
+    for (int i = 0; i < m; ++i) {
+        const int64_t idx = base + (int64_t)i * N;
+        if (fmt == 0) cp_async_8(raw.d(i), reinterpret_cast<const double *>(ranges) + idx);
+        else if (fmt == 1) cp_async_4(raw.w(i), reinterpret_cast<const int32_t *>(ranges) + idx);
+        else // uint16: fetch the aligned 32-bit word that holds the element
+            cp_async_4(raw.w(i), reinterpret_cast<const void *>(
+                                     reinterpret_cast<uintptr_t>(reinterpret_cast<const uint16_t *>(ranges) + idx) & ~(uintptr_t)3));
+    }
+    cp_async_commit();
+}
+
+// landing zone -> metres + valid mask: keep rangings[i] > 0 (TOA.cpp:48-57, ML.cpp:478)
+template <bool PME, int MT>
+KF_DEV void convert_epoch(EpochT<PME, MT> &ep, const RawCol &raw, const void *ranges, int fmt, const double *err,
+                          int64_t base, int64_t N) {
+    unsigned valid = 0u;
+#pragma unroll(MT > 0 ? MT : 1)
+    for (int i = 0; i < ep.m(); ++i) {
+        double r;
+        if (fmt == 0) {
+            r = *raw.d(i);
+        } else {
+            const unsigned w = *raw.w(i);
+            if (fmt == 1) {
+                r = mm_to_m((double)(int)w);
+            } else {
+                const uintptr_t a = reinterpret_cast<uintptr_t>(reinterpret_cast<const uint16_t *>(ranges) + base + (int64_t)i * N);
+                r = mm_to_m((double)((a & 2) ? (w >> 16) : (w & 0xffffu)));
+            }
+        }
+        if (MT > 0) ep.zr[i] = r;
+        else ep.z[i] = r;
+        if (r > 0) valid |= 1u << i;
+        if (PME) ep.e[i] = __ldg(err + base + (int64_t)i * N);
+    }
+    ep.valid = valid;
+}
+
+} // namespace kfpos

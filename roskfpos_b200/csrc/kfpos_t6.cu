@@ -10,23 +10,29 @@
 namespace kfpos {
 
 constexpr int T6_BLOCK = 128;
+#ifndef T6_MINB
+#define T6_MINB 4 // 128 registers; more resident warps do not help a dispatch-bound kernel (profiles/README.md)
+#endif
 
-// shared-memory rows per thread
-__host__ __device__ inline int t6_smem_rows(int m, bool pme, bool loo) {
-    return 4 * m + (pme ? m : 0) + 21 + (loo ? 2 * (21 + 6) : 0);
+// shared-memory rows (doubles) per thread: [metres column when MT == 0], [errorEstimation
+// column], P^-, landing zone of the prefetch
+__host__ __device__ inline int t6_smem_rows(int m, int fmt, bool pme, bool in_regs) {
+    return (in_regs ? 0 : m) + (pme ? m : 0) + 21 + raw_rows(fmt, m);
 }
 
-template <bool PME, bool LOO>
-__global__ void __launch_bounds__(T6_BLOCK, LOO ? 2 : 4) t6_replay_kernel(const __grid_constant__ T6Params p) {
+// MT > 0: compile-time anchor count (unrolled anchor loops, ranges in registers); MT == 0: run-time.
+template <bool PME, bool LOO, int MT>
+__global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __grid_constant__ T6Params p) {
     extern __shared__ double smem[];
     const int64_t f = (int64_t)blockIdx.x * T6_BLOCK + threadIdx.x;
     const bool active = f < p.N;
+    const unsigned wmask = __ballot_sync(0xffffffffu, active);
     StepStats st = {0u, 0u, 0u, 0u};
     unsigned n_updates = 0, n_bad = 0, n_ignored = 0;
 
     if (active) {
         const int64_t N = p.N;
-        const int m = p.rs.m_slots;
+        const int m = MT > 0 ? MT : p.rs.m_slots;
         // carve this thread's columns
         double *col = smem + threadIdx.x;
         int row = 0;
@@ -35,94 +41,88 @@ __global__ void __launch_bounds__(T6_BLOCK, LOO ? 2 : 4) t6_replay_kernel(const 
             row += rows;
             return c;
         };
-        Epoch<PME> ep;
-        ep.z = take(m);
-        ep.e = PME ? take(m) : ep.z;
+        EpochT<PME, MT> ep;
+        const Col Pm = take(21);
+        ep.z = MT > 0 ? Pm : take(m);
+        ep.e = PME ? take(m) : Pm;
         ep.e0 = p.rs.err_scalar;
         ep.m_slots = m;
-        Col raw = take(m); // landing zone of the cp.async prefetch of the next epoch
-        T6Scratch sc;
-        sc.invd = take(m);
-        sc.eps = take(m);
-        sc.Pm = take(21);
-        Col s_all = LOO ? take(27) : sc.Pm, s_best = LOO ? take(27) : sc.Pm;
+        // landing zone of the cp.async prefetch of the next epoch
+        const RawCol raw = make_raw(smem + (size_t)row * T6_BLOCK, p.rs.fmt, threadIdx.x, T6_BLOCK);
 
         double pos[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) pos[k] = p.x[(int64_t)k * N + f];
 #pragma unroll
-        for (int k = 0; k < Sym<6>::SZ; ++k) sc.Pm[k] = p.P[(int64_t)k * N + f];
+        for (int k = 0; k < Sym<6>::SZ; ++k) Pm[k] = p.P[(int64_t)k * N + f];
         unsigned status_or = 0;
 
         prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, f, N);
         for (int t = 0; t < p.T; ++t) {
-            cp_async_wait_all();
-            convert_epoch<PME>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, (int64_t)t * m * N + f, N);
-            if (t + 1 < p.T) prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, (int64_t)(t + 1) * m * N + f, N);
             const double dt = __ldg(p.dt + t);
 
             // ---- predict (TOA.cpp:115-123): x^- = F x with v = 0, P^- = F P F^T + Q.
             // The member covariance is overwritten before the try block, so P^-
             // is what survives a failed update.
-            Sym<6> Pw;
+            {
+                Sym<6> Pw;
 #pragma unroll
-            for (int k = 0; k < Sym<6>::SZ; ++k) Pw.a[k] = sc.Pm[k];
-            t6_predict_cov(Pw, dt, p.accel_noise);
+                for (int k = 0; k < Sym<6>::SZ; ++k) Pw.a[k] = Pm[k];
+                t6_predict_cov(Pw, dt, p.accel_noise);
 #pragma unroll
-            for (int k = 0; k < Sym<6>::SZ; ++k) sc.Pm[k] = Pw.a[k];
+                for (int k = 0; k < Sym<6>::SZ; ++k) Pm[k] = Pw.a[k];
+            }
+            // ---- this epoch's rangings (landed during the previous epoch); start the next fetch
+            cp_async_wait_all();
+            convert_epoch<PME, MT>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, (int64_t)t * m * N + f, N);
+            if (t + 1 < p.T) prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, (int64_t)(t + 1) * m * N + f, N);
 
             st.status = 0u;
             if (ep.valid == 0u) st.status |= 1u;
-            double dx[6], cost;
-            int rc = t6_update<PME>(p.anchors, ep, ep.valid, pos, sc, Pw, dx, cost, st);
-            int ignored = -1;
-            if (LOO) {
-                // kalmanStep3DCanIgnoreAnAnchor (TOA.cpp:185-238): only with > 4 rangings
-                if (rc == 0 && __popc(ep.valid) > 4) {
-#pragma unroll
-                    for (int k = 0; k < 21; ++k) s_all[k] = Pw.a[k];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) s_all[21 + k] = dx[k];
-                    double maxDist = 0.0, worstCost = 0.0;
-                    int idx = -1;
-                    bool first = true;
-                    for (int i = 0; i < m && rc == 0; ++i) {
-                        if (!((ep.valid >> i) & 1u)) continue;
-                        double ci;
-                        rc = t6_update<PME>(p.anchors, ep, ep.valid & ~(1u << i), pos, sc, Pw, dx, ci, st);
-                        if (rc != 0) break;
-                        const double ex = p.anchors.x[i] - (pos[0] + dx[0]);
-                        const double ey = p.anchors.y[i] - (pos[1] + dx[1]);
-                        const double ez = p.anchors.z[i] - (pos[2] + dx[2]);
-                        const double diff = ep.z[i] - sqrt(ex * ex + ey * ey + ez * ez);
-                        if (first || diff > maxDist) { // strict >, first seeds (TOA.cpp:209)
-                            maxDist = diff;
-                            worstCost = ci;
-#pragma unroll
-                            for (int k = 0; k < 21; ++k) s_best[k] = Pw.a[k];
-#pragma unroll
-                            for (int k = 0; k < 6; ++k) s_best[21 + k] = dx[k];
-                            idx = i;
-                            first = false;
-                        }
+            T6Result res;
+            int rc, ignored = -1;
+            if (!LOO) {
+                rc = t6_update<PME, MT>(p.anchors, ep, ep.valid, pos, Pm, res, st, wmask);
+                __syncwarp(wmask);
+            } else {
+                // kalmanStep3DCanIgnoreAnAnchor (TOA.cpp:185-238): the all-anchor solve (i = -1),
+                // then -- only with > 4 rangings -- one solve per left-out anchor, all from the same P^-
+                T6Result best;
+                double maxDist = 0.0;
+                int idx = -1;
+                bool first = true;
+                const int n_try = __popc(ep.valid) > 4 ? m : 0;
+                rc = 0;
+                for (int i = -1; i < n_try && rc == 0; ++i) {
+                    if (i >= 0 && !((ep.valid >> i) & 1u)) continue;
+                    T6Result ri;
+                    rc = t6_update<PME, MT>(p.anchors, ep, i < 0 ? ep.valid : (ep.valid & ~(1u << i)), pos, Pm, ri, st);
+                    if (rc != 0) break;
+                    if (i < 0) {
+                        res = ri;
+                        continue;
                     }
-                    const bool take_best = rc == 0 && maxDist > 0 && (cost - worstCost) > p.ignore_thr;
-                    const Col &src = take_best ? s_best : s_all;
-#pragma unroll
-                    for (int k = 0; k < 21; ++k) Pw.a[k] = src[k];
-#pragma unroll
-                    for (int k = 0; k < 6; ++k) dx[k] = src[21 + k];
-                    if (take_best) {
-                        ignored = idx;
-                        n_ignored += 1;
+                    const double ex = p.anchors.x[i] - (pos[0] + ri.dx[0]);
+                    const double ey = p.anchors.y[i] - (pos[1] + ri.dx[1]);
+                    const double ez = p.anchors.z[i] - (pos[2] + ri.dx[2]);
+                    const double diff = ep.z_at(i) - sqrt(ex * ex + ey * ey + ez * ez);
+                    if (first || diff > maxDist) { // strict >, first seeds (TOA.cpp:209)
+                        maxDist = diff;
+                        best = ri;
+                        idx = i;
+                        first = false;
                     }
+                }
+                if (rc == 0 && idx >= 0 && maxDist > 0 && (res.cost - best.cost) > p.ignore_thr) {
+                    res = best;
+                    ignored = idx;
+                    n_ignored += 1;
                 }
             }
             if (rc == 0) {
                 // stateToPose (TOA.cpp:159-183): position kept, velocity dropped
-                pos[0] += dx[0]; pos[1] += dx[1]; pos[2] += dx[2];
-#pragma unroll
-                for (int k = 0; k < Sym<6>::SZ; ++k) sc.Pm[k] = Pw.a[k];
+                pos[0] += res.dx[0]; pos[1] += res.dx[1]; pos[2] += res.dx[2];
+                t6_apply_cov(Pm, res.M);
                 if (!(isfinite(pos[0]) && isfinite(pos[1]) && isfinite(pos[2]))) st.status |= 8u;
             } else {
                 st.status |= 4u; // catch (std::runtime_error): update skipped (TOA.cpp:151)
@@ -140,7 +140,7 @@ __global__ void __launch_bounds__(T6_BLOCK, LOO ? 2 : 4) t6_replay_kernel(const 
 #pragma unroll
         for (int k = 0; k < 3; ++k) p.x[(int64_t)k * N + f] = pos[k];
 #pragma unroll
-        for (int k = 0; k < Sym<6>::SZ; ++k) p.P[(int64_t)k * N + f] = sc.Pm[k];
+        for (int k = 0; k < Sym<6>::SZ; ++k) p.P[(int64_t)k * N + f] = Pm[k];
         if (p.status) p.status[f] |= (int32_t)status_or;
     }
     warp_accumulate(p.counters + CNT_UPDATES, n_updates);
@@ -151,22 +151,32 @@ __global__ void __launch_bounds__(T6_BLOCK, LOO ? 2 : 4) t6_replay_kernel(const 
     warp_accumulate(p.counters + CNT_IGNORED, n_ignored);
 }
 
-template <bool PME, bool LOO>
+template <bool PME, bool LOO, int MT>
 static cudaError_t launch_k(const T6Params &p, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + T6_BLOCK - 1) / T6_BLOCK);
-    const size_t smem = (size_t)t6_smem_rows(p.rs.m_slots, PME, LOO) * T6_BLOCK * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(t6_replay_kernel<PME, LOO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    const size_t smem = (size_t)t6_smem_rows(p.rs.m_slots, p.rs.fmt, PME, MT > 0) * T6_BLOCK * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(t6_replay_kernel<PME, LOO, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
-    t6_replay_kernel<PME, LOO><<<grid, T6_BLOCK, smem, s>>>(p);
+    t6_replay_kernel<PME, LOO, MT><<<grid, T6_BLOCK, smem, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_t6_replay(const T6Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.T <= 0) return cudaSuccess;
     const bool pme = p.rs.err != nullptr;
-    if (p.ignore_worst) return pme ? launch_k<true, true>(p, s) : launch_k<false, true>(p, s);
-    return pme ? launch_k<true, false>(p, s) : launch_k<false, false>(p, s);
+    const int m = p.rs.m_slots;
+    if (p.ignore_worst) {
+        if (pme) return launch_k<true, true, 0>(p, s);
+        if (m == 8) return launch_k<false, true, 8>(p, s);
+        if (m == 16) return launch_k<false, true, 16>(p, s);
+        return launch_k<false, true, 0>(p, s);
+    }
+    if (pme) return launch_k<true, false, 0>(p, s);
+    if (m == 4) return launch_k<false, false, 4>(p, s);
+    if (m == 8) return launch_k<false, false, 8>(p, s);
+    if (m == 16) return launch_k<false, false, 16>(p, s);
+    return launch_k<false, false, 0>(p, s);
 }
 
 // getPose (TOA.cpp:438-473): predict-only, state untouched

@@ -2,13 +2,9 @@
 // rangings), per-thread formulation.  Reference: algorithms/KalmanFilterTOA.cpp.
 #pragma once
 #include "kfpos_math.cuh"
-#include "kfpos_ml.cuh"
+#include "kfpos_solve.cuh"
 
 namespace kfpos {
-
-struct StepStats {
-    unsigned ml_iters, cost_evals, gain_evals, status;
-};
 
 // P^- = F P F^T + Q for F = [[I, tI],[0, I]] and the per-axis Q of
 // predictionErrorCovariance (TOA.cpp:362-391), in place on the packed matrix.
@@ -35,34 +31,80 @@ KF_DEV void t6_predict_cov(Sym<6> &P, double t, double accel_noise) {
     }
 }
 
-// Per-thread scratch columns in shared memory used by one IEKF update.
-struct T6Scratch {
-    Col Pm;   // 21 rows: P^- (read at the start of every gain pass)
-    Col invd; // MAXM rows: 1/dist at the current iterate (pass A -> pass B)
-    Col eps;  // MAXM rows: z - dist at the current iterate
+// Result of one IEKF update in factored form: x = x^- + dx (position part; the
+// velocity increment is never used, TOA.cpp:159-183) and P = P^- - B M B^T with
+// B = P^-[:, 0:3] and M symmetric 3x3 (packed Sym<3> order xx, xy, yy, xz, yz, zz).
+struct T6Result {
+    double dx[3];
+    double M[6];
+    double cost;
 };
+
+// Solves one information-form IEKF gain step for 3-D ranging rows:
+//   N = I + G A;  s = N^-1 b;  dx = A s;  M = N^-1 G;  returns w . dx with w = b - G dx
+// A = position block of P^- (packed xx, yx, yy, zx, zy, zz), G packed the same way.
+KF_DEV double info_gain3(const double (&a)[6], const double (&b)[3], const double (&G)[6], double (&dx)[3],
+                         double (&M)[6]) {
+    const double a00 = a[0], a10 = a[1], a11 = a[2], a20 = a[3], a21 = a[4], a22 = a[5];
+    const double G0 = G[0], G1 = G[1], G2 = G[2], G3 = G[3], G4 = G[4], G5 = G[5];
+    const double n00 = fma(G0, a00, fma(G1, a10, fma(G3, a20, 1.0)));
+    const double n01 = fma(G0, a10, fma(G1, a11, G3 * a21));
+    const double n02 = fma(G0, a20, fma(G1, a21, G3 * a22));
+    const double n10 = fma(G1, a00, fma(G2, a10, G4 * a20));
+    const double n11 = fma(G1, a10, fma(G2, a11, fma(G4, a21, 1.0)));
+    const double n12 = fma(G1, a20, fma(G2, a21, G4 * a22));
+    const double n20 = fma(G3, a00, fma(G4, a10, G5 * a20));
+    const double n21 = fma(G3, a10, fma(G4, a11, G5 * a21));
+    const double n22 = fma(G3, a20, fma(G4, a21, fma(G5, a22, 1.0)));
+    const double c00 = fma(n11, n22, -n12 * n21), c01 = fma(n02, n21, -n01 * n22), c02 = fma(n01, n12, -n02 * n11);
+    const double c10 = fma(n12, n20, -n10 * n22), c11 = fma(n00, n22, -n02 * n20), c12 = fma(n02, n10, -n00 * n12);
+    const double c20 = fma(n10, n21, -n11 * n20), c21 = fma(n01, n20, -n00 * n21), c22 = fma(n00, n11, -n01 * n10);
+    const double idet = fast_rcp(fma(n00, c00, fma(n01, c10, n02 * c20)));
+    const double s0 = fma(c00, b[0], fma(c01, b[1], c02 * b[2])) * idet;
+    const double s1 = fma(c10, b[0], fma(c11, b[1], c12 * b[2])) * idet;
+    const double s2 = fma(c20, b[0], fma(c21, b[1], c22 * b[2])) * idet;
+    dx[0] = fma(a00, s0, fma(a10, s1, a20 * s2));
+    dx[1] = fma(a10, s0, fma(a11, s1, a21 * s2));
+    dx[2] = fma(a20, s0, fma(a21, s1, a22 * s2));
+    M[0] = fma(c00, G0, fma(c01, G1, c02 * G3)) * idet;
+    M[1] = fma(c10, G0, fma(c11, G1, c12 * G3)) * idet;
+    M[2] = fma(c10, G1, fma(c11, G2, c12 * G4)) * idet;
+    M[3] = fma(c20, G0, fma(c21, G1, c22 * G3)) * idet;
+    M[4] = fma(c20, G1, fma(c21, G2, c22 * G4)) * idet;
+    M[5] = fma(c20, G3, fma(c21, G4, c22 * G5)) * idet;
+    const double w0 = b[0] - fma(G0, dx[0], fma(G1, dx[1], G3 * dx[2]));
+    const double w1 = b[1] - fma(G1, dx[0], fma(G2, dx[1], G4 * dx[2]));
+    const double w2 = b[2] - fma(G3, dx[0], fma(G4, dx[1], G5 * dx[2]));
+    return fma(w0, dx[0], fma(w1, dx[1], w2 * dx[2]));
+}
 
 // kalmanStep3DIgnoreAnchor (TOA.cpp:242-338) on the slots in `mask`.
 //   xp : predicted position (predicted velocity is 0: TOA.cpp:110-120)
-//   sc.Pm : P^- (kept);  Pw: out = (I - K J) P^- ;  dx: out = x - x^- (6)
+//   Pm : P^- (shared-memory column, read only)
 // Returns ML_SINGULAR when a solve failed (the reference's catch at TOA.cpp:151
-// then skips the update), else 0.  `cost_out` = last assigned IEKF cost.
+// then skips the update), else 0.  `out.cost` = last assigned IEKF cost.
 //
-// Formulation (validated against the dense oracle): inside one
-// IEKF iteration the gain step is a linear-KF update from (x^-, P^-), processed
-// one ranging at a time as rank-1 updates of a register copy of P^-; the prior
-// term delta^T pinv(P^-) delta of the cost equals w . dx with
-// w = J^T R^-1 (y - J dx), accumulated on the fly (b = J^T R^-1 y, G = J^T R^-1 J).
-template <bool PME>
-KF_DEV int t6_update(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, const double (&xp)[3],
-                     const T6Scratch &sc, Sym<6> &Pw, double (&dx)[6], double &cost_out, StepStats &st) {
+// Formulation (validated against the dense oracle).  Every ranging row is
+// [h_i^T 0] with h_i the unit vector anchor -> tag, and R is diagonal, so with
+// A = P^-[0:3,0:3], B = P^-[:,0:3], G = J^T R^-1 J (3x3) and b = J^T R^-1 (eps - J delta):
+//   K (eps - J delta) = B (I + G A)^-1 b        (push-through identity: no inverse of P^-, no m x m inverse)
+//   (I - K J) P^-     = P^- - B (I + G A)^-1 G B^T
+// so one IEKF iteration is ONE pass over the anchors that accumulates the cost, b and G
+// (independent FMAs, no serial rank-1 chain) followed by a 3x3 solve.  I + G A has
+// eigenvalues >= 1 (G, A positive semi-definite): it is never singular, also for the
+// rank-3 first step P^- = Q.  The prior term delta^T pinv(P^-) delta of the cost equals
+// w . dx with w = b - G dx (delta = -P^- w lies in the range of P^-).
+// wmask != 0: the lanes in wmask all call this function together; they are re-converged
+// after the Newton loop (whose trip count differs per lane) so that the IEKF loop is issued
+// once per warp and not once per group of lanes that left the Newton loop together.
+template <bool PME, int MT>
+KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, const double (&xp)[3],
+                     const Col &Pm, T6Result &out, StepStats &st, unsigned wmask = 0u) {
     // ---- inner ML solve from the predicted position (TOA.cpp:268-273)
     double pml[3] = {xp[0], xp[1], xp[2]};
     double sse, sse_xp;
-    // the first Newton pass runs at xp: it also leaves 1/d_i and eps_i(xp) in the scratch
-    // columns for the IEKF's first cost evaluation
-    const DistStore ds = {sc.invd, sc.eps};
-    const int rc = ml_solve3<PME, true>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &ds, &sse_xp);
+    const int rc = ml_solve3<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &sse_xp);
+    if (wmask) __syncwarp(wmask);
     if (rc == ML_FEW) st.status |= 2u;
     if (rc == ML_SINGULAR) return ML_SINGULAR;
     if (isnan(pml[0]) || isnan(pml[1]) || isnan(pml[2])) { // TOA.cpp:270-272: back to xp
@@ -72,95 +114,60 @@ KF_DEV int t6_update(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, 
     if (mask == 0u) sse = -1.0; // estimationError of an empty list (ML.cpp:265-267)
 
     // R_ii = max(mlRangingError, errorEstimation_i) (TOA.cpp:281)
-    const double R0 = fmax(sse, ep.e0);
-    const double invR0 = 1.0 / R0;
+    const double invR0 = fast_rcp(fmax(sse, ep.e0));
+    double a[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) a[k] = Pm[k]; // position block of P^-
 
+    double dx[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-    for (int k = 0; k < 6; ++k) dx[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < Sym<6>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+    for (int k = 0; k < 6; ++k) out.M[k] = 0.0;
     double cost = 1e20;
     double prior = 0.0; // delta^T pinv(P^-) delta
     bool broke = false;
     for (int iter = 0; iter < 10; ++iter) {
-        const double px = xp[0] + dx[0], py = xp[1] + dx[1], pz = xp[2] + dx[2];
-        // ---- pass A: cost at the current iterate (TOA.cpp:297-305)
-        double c = 0.0;
-        if (iter == 0) { // x = xp: distances already in the scratch columns
-            if (PME) {
-                for (int i = 0; i < ep.m_slots; ++i) {
-                    if (!((mask >> i) & 1u)) continue;
-                    const double e = sc.eps[i];
-                    c = fma(e * e, 1.0 / fmax(sse, ep.e[i]), c);
-                }
-            } else {
-                c = sse_xp;
-            }
-        } else {
-#pragma unroll 2
-            for (int i = 0; i < ep.m_slots; ++i) {
-                if (!((mask >> i) & 1u)) continue;
-                const double ex = px - A.x[i], ey = py - A.y[i], ez = pz - A.z[i];
-                const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
-                const double id = fast_rsqrt(d2);
-                const double e = ep.z[i] - d2 * id;
-                sc.invd[i] = id;
-                sc.eps[i] = e;
-                c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
-            }
-        }
+        // ---- one pass: cost at the current iterate (TOA.cpp:297-305) and the
+        //      information-form accumulators of the rows linearised there (TOA.cpp:313-320)
+        double c, b[3], G[6];
+        iekf_pass<PME, MT, 3>(A, ep, mask, sse, xp[0] + dx[0], xp[1] + dx[1], xp[2] + dx[2], dx, c, b, G);
         const double newCost = (PME ? c : c * invR0) + prior;
         st.cost_evals += 1;
-        if (fabs(cost - newCost) / cost < 1e-3) { broke = true; break; }
+        if (rel_change_lt(cost, newCost, 1e-3)) { broke = true; break; }
         cost = newCost;
-        // ---- pass B: sequential scalar updates from (x^-, P^-) with the rows
-        //      linearised at the current iterate (TOA.cpp:313-320)
         st.gain_evals += 1;
-        if (iter > 0) {
+        if (!PME) {
 #pragma unroll
-            for (int k = 0; k < Sym<6>::SZ; ++k) Pw.a[k] = sc.Pm[k];
-        }
-        double dn[6] = {0, 0, 0, 0, 0, 0};
-        double b0 = 0, b1 = 0, b2 = 0;                      // J^T R^-1 y
-        double G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0; // J^T R^-1 J (position block, packed)
-#pragma unroll 1
-        for (int i = 0; i < ep.m_slots; ++i) {
-            if (!((mask >> i) & 1u)) continue;
-            const double id = sc.invd[i];
-            double h[6];
-            h[0] = (px - A.x[i]) * id;
-            h[1] = (py - A.y[i]) * id;
-            h[2] = (pz - A.z[i]) * id;
-            h[3] = h[4] = h[5] = 0.0;
-            // y = eps - J delta, delta = x^- - x = -dx
-            const double y = fma(h[0], dx[0], fma(h[1], dx[1], fma(h[2], dx[2], sc.eps[i])));
-            const double R = PME ? fmax(sse, ep.e[i]) : R0;
-            scalar_update<6, 0x7u>(Pw, dn, h, y, R);
-            if (PME) {
-                const double iR = 1.0 / R;
-                const double yr = y * iR;
-                b0 = fma(h[0], yr, b0); b1 = fma(h[1], yr, b1); b2 = fma(h[2], yr, b2);
-                const double h0r = h[0] * iR, h1r = h[1] * iR, h2r = h[2] * iR;
-                G0 = fma(h0r, h[0], G0); G1 = fma(h0r, h[1], G1); G2 = fma(h1r, h[1], G2);
-                G3 = fma(h0r, h[2], G3); G4 = fma(h1r, h[2], G4); G5 = fma(h2r, h[2], G5);
-            } else { // common R: scale once after the loop
-                b0 = fma(h[0], y, b0); b1 = fma(h[1], y, b1); b2 = fma(h[2], y, b2);
-                G0 = fma(h[0], h[0], G0); G1 = fma(h[0], h[1], G1); G2 = fma(h[1], h[1], G2);
-                G3 = fma(h[0], h[2], G3); G4 = fma(h[1], h[2], G4); G5 = fma(h[2], h[2], G5);
-            }
-        }
+            for (int k = 0; k < 3; ++k) b[k] *= invR0;
 #pragma unroll
-        for (int k = 0; k < 6; ++k) dx[k] = dn[k];
-        // w = J^T R^-1 (y - J dx) ; delta^T P^+ delta = w . dx   (position part only)
-        const double w0 = b0 - (G0 * dx[0] + G1 * dx[1] + G3 * dx[2]);
-        const double w1 = b1 - (G1 * dx[0] + G2 * dx[1] + G4 * dx[2]);
-        const double w2 = b2 - (G3 * dx[0] + G4 * dx[1] + G5 * dx[2]);
-        prior = w0 * dx[0] + w1 * dx[1] + w2 * dx[2];
-        if (!PME) prior *= invR0;
+            for (int k = 0; k < 6; ++k) G[k] *= invR0;
+        }
+        prior = info_gain3(a, b, G, dx, out.M);
     }
     if (!broke) st.status |= 32u;
-    cost_out = cost;
+    out.dx[0] = dx[0]; out.dx[1] = dx[1]; out.dx[2] = dx[2];
+    out.cost = cost;
     return 0;
+}
+
+// P^+ = P^- - B M B^T, B = P^-[:, 0:3]  (the reference's (I - K J) P^-, TOA.cpp:326), in
+// place on the shared-memory column: only B (18 values) is held in registers.
+KF_DEV void t6_apply_cov(const Col &Pm, const double (&M)[6]) {
+    double B[6][3];
+#pragma unroll
+    for (int i = 0; i < 6; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) B[i][k] = (i >= k) ? Pm[i * (i + 1) / 2 + k] : Pm[k * (k + 1) / 2 + i];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double c0 = fma(B[i][0], M[0], fma(B[i][1], M[1], B[i][2] * M[3]));
+        const double c1 = fma(B[i][0], M[1], fma(B[i][1], M[2], B[i][2] * M[4]));
+        const double c2 = fma(B[i][0], M[3], fma(B[i][1], M[4], B[i][2] * M[5]));
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const int k = i * (i + 1) / 2 + j;
+            Pm[k] = fma(-c0, B[j][0], fma(-c1, B[j][1], fma(-c2, B[j][2], Pm[k])));
+        }
+    }
 }
 
 } // namespace kfpos
