@@ -9,13 +9,20 @@
 namespace kfpos {
 
 constexpr int K8_BLOCK = 128;
+#ifndef K8_MINB
+#define K8_MINB 2 // 255 registers: the register copy of P (72) + increments + Jacobian entries
+#endif
 
-__host__ __device__ inline int k8_raw_rows(int m) { return m > 5 ? m : 5; }
-__host__ __device__ inline int k8_smem_rows(int m, bool pme) { return 3 * m + k8_raw_rows(m) + (pme ? m : 0) + 36; }
+// shared-memory rows (doubles) per thread: P^- (36), latched sensor samples (8), the landing
+// zone of the event prefetch (rangings or <= 5 sensor values), [metres column when MT == 0],
+// [errorEstimation column]
+__host__ __device__ inline int k8_land_rows(int m, int fmt) { return raw_rows(fmt, m) > 5 ? raw_rows(fmt, m) : 5; }
+__host__ __device__ inline int k8_smem_rows(int m, int fmt, bool pme, bool in_regs) {
+    return 36 + 8 + k8_land_rows(m, fmt) + (in_regs ? 0 : m) + (pme ? m : 0);
+}
 
-KF_DEV int event_rows(int kind, int m) {
+KF_DEV int event_rows(int kind) {
     switch (kind) {
-    case EV_TOA: return m;
     case EV_PX4: return 5;
     case EV_IMU: return 3;
     case EV_MAG: return 2;
@@ -23,28 +30,29 @@ KF_DEV int event_rows(int kind, int m) {
     }
 }
 
-KF_DEV void prefetch_event(const Col &raw, const EventDesc &ev, int m, const RangeStream &rs, const double *sensors,
-                           int64_t N, int64_t f) {
+KF_DEV void prefetch_event(const RawColPriv &raw, const Col &land, const EventDesc &ev, int m, const RangeStream &rs,
+                           const double *sensors, int64_t N, int64_t f) {
     if (ev.kind == EV_TOA) {
         prefetch_epoch(raw, m, rs.ranges, rs.fmt, ev.offset * N + f, N);
     } else {
-        const int rows = event_rows(ev.kind, m);
-        for (int i = 0; i < rows; ++i) cp_async_8(&raw[i], sensors + (ev.offset + i) * N + f);
+        const int rows = event_rows(ev.kind);
+        for (int i = 0; i < rows; ++i) cp_async_8(&land[i], sensors + (ev.offset + i) * N + f);
         cp_async_commit();
     }
 }
 
-template <bool PME>
-__global__ void __launch_bounds__(K8_BLOCK, 3) k8_replay_kernel(const __grid_constant__ K8Params p) {
+template <bool PME, int MT>
+__global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __grid_constant__ K8Params p) {
     extern __shared__ double smem[];
     const int64_t f = (int64_t)blockIdx.x * K8_BLOCK + threadIdx.x;
     const bool active = f < p.N;
+    const unsigned wmask = __ballot_sync(0xffffffffu, active);
     StepStats st = {0u, 0u, 0u, 0u};
     unsigned n_updates = 0, n_bad = 0;
 
     if (active) {
         const int64_t N = p.N;
-        const int m = p.rs.m_slots;
+        const int m = MT > 0 ? MT : p.rs.m_slots;
         double *col = smem + threadIdx.x;
         int row = 0;
         auto take = [&](int rows) {
@@ -52,24 +60,26 @@ __global__ void __launch_bounds__(K8_BLOCK, 3) k8_replay_kernel(const __grid_con
             row += rows;
             return c;
         };
-        Epoch<PME> ep;
-        ep.z = take(m);
-        ep.e = PME ? take(m) : ep.z;
+        const Col Pm = take(36);
+        // latched samples: px4 vx,vy,gz,cv | imu ax,ay,wz | mag angle   (KF.h:92-130)
+        const Col latch = take(8);
+        const Col land = take(k8_land_rows(m, p.rs.fmt));
+        const RawColPriv raw = {land}; // rangings land in the same private column
+        EpochT<PME, MT> ep;
+        ep.z = MT > 0 ? Pm : take(m);
+        ep.e = PME ? take(m) : Pm;
         ep.e0 = p.rs.err_scalar;
         ep.m_slots = m;
         ep.valid = 0u;
-        Col raw = take(k8_raw_rows(m));
-        K8Scratch sc;
-        sc.invd = take(m);
-        sc.eps = take(m);
-        sc.Pm = take(36);
 
         // persistent members: position, velocity, angle, angular speed (acceleration is never
         // written back: KF.cpp:287-291,315-318)
         double px = p.x[0 * N + f], py = p.x[1 * N + f], vx = p.x[2 * N + f], vy = p.x[3 * N + f];
         double th = p.x[6 * N + f], om = p.x[7 * N + f];
 #pragma unroll
-        for (int k = 0; k < Sym<8>::SZ; ++k) sc.Pm[k] = p.P[(int64_t)k * N + f];
+        for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = p.P[(int64_t)k * N + f];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) latch[k] = p.latch[(int64_t)k * N + f];
         unsigned has = (unsigned)p.has[f]; // bit0 px4, bit1 imu, bit2 mag latched
         unsigned status_or = 0;
         // time of the events this filter skipped (a PX4 frame of quality 0 returns before the
@@ -78,33 +88,33 @@ __global__ void __launch_bounds__(K8_BLOCK, 3) k8_replay_kernel(const __grid_con
         double ic00 = p.latch_u[0], ic01 = p.latch_u[1], ic11 = p.latch_u[2], icw = p.latch_u[3];
         int n_toa = 0;
 
-        if (p.n_events > 0) prefetch_event(raw, p.events[0], m, p.rs, p.sensors, N, f);
+        if (p.n_events > 0) prefetch_event(raw, land, p.events[0], m, p.rs, p.sensors, N, f);
         for (int e = 0; e < p.n_events; ++e) {
             const EventDesc ev = p.events[e];
             cp_async_wait_all();
             st.status = 0u;
             K8Meas ms;
             ms.has_px4 = ms.has_imu = ms.has_mag = false;
+            ms.latch = latch;
             ms.px4_cg = p.cfg.px4_cov_gyro;
             ms.mag_c = p.cfg.mag_cov;
             bool has_r = false, skip = false;
             switch (ev.kind) {
             case EV_TOA: { // newTOAMeasurement (KF.cpp:64-97): rangings + latched px4 / imu / mag
-                convert_epoch<PME>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, ev.offset * N + f, N);
+                convert_epoch<PME, MT>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, ev.offset * N + f, N);
                 has_r = true;
                 ms.has_px4 = has & 1u; ms.has_imu = (has >> 1) & 1u; ms.has_mag = (has >> 2) & 1u;
                 break;
             }
             case EV_PX4: { // newPX4FlowMeasurement (KF.cpp:100-133)
-                const double ix = raw[0], iy = raw[1], irz = raw[2], itus = raw[3];
-                const int quality = (int)raw[4];
+                const double ix = land[0], iy = land[1], irz = land[2], itus = land[3];
+                const int quality = (int)land[4];
                 if (quality == 0) { skip = true; break; }
                 const double it = itus / 1000000.0;
                 const double pvy = iy / it * p.cfg.px4_height, pvx = ix / it * p.cfg.px4_height;
                 const double cv = itus > 0 ? p.cfg.px4_cov_vel / it * p.cfg.px4_height / quality
                                            : p.cfg.px4_cov_vel * quality;
-                p.latch[0 * N + f] = pvx; p.latch[1 * N + f] = pvy; p.latch[2 * N + f] = irz / it;
-                p.latch[3 * N + f] = cv;
+                latch[0] = pvx; latch[1] = pvy; latch[2] = irz / it; latch[3] = cv;
                 has |= 1u;
                 ms.has_px4 = true;
                 break;
@@ -115,78 +125,81 @@ __global__ void __launch_bounds__(K8_BLOCK, 3) k8_replay_kernel(const __grid_con
                 ic11 = p.cfg.imu_fix_acc ? p.cfg.imu_cov_acc : ev.aux[3];
                 icw = p.cfg.imu_fix_gyro ? p.cfg.imu_cov_gyro : ev.aux[4];
                 if (ev.aux[1] != ev.aux[2]) st.status |= 64u; // asymmetric block: symmetric part used
-                p.latch[6 * N + f] = raw[0]; p.latch[4 * N + f] = raw[1]; p.latch[5 * N + f] = raw[2];
+                const double wz = land[0], lax = land[1], lay = land[2];
+                latch[6] = wz; latch[4] = lax; latch[5] = lay;
                 has |= 2u;
                 ms.has_imu = true;
                 break;
             }
             case EV_MAG: { // newMAGMeasurement (KF.cpp:179-193): mag only, angle not normalised
-                p.latch[7 * N + f] = atan2(raw[1], raw[0]) - p.cfg.mag_offset;
+                latch[7] = atan2(land[1], land[0]) - p.cfg.mag_offset;
                 has |= 4u;
                 ms.has_mag = true;
                 break;
             }
             default: { // newCompassMeasurement (KF.cpp:195-221): mag + latched px4 + latched imu
-                p.latch[7 * N + f] = wrap_angle(raw[0]);
+                latch[7] = wrap_angle(land[0]);
                 has |= 4u;
                 ms.has_mag = true;
                 ms.has_px4 = has & 1u; ms.has_imu = (has >> 1) & 1u;
                 break;
             }
             }
-            if (e + 1 < p.n_events) prefetch_event(raw, p.events[e + 1], m, p.rs, p.sensors, N, f);
-            if (skip) { carry += ev.dt; continue; }
-            const double dt = ev.dt + carry;
-            carry = 0.0;
-            if (ms.has_px4) {
-                ms.px4_vx = p.latch[0 * N + f]; ms.px4_vy = p.latch[1 * N + f];
-                ms.px4_gz = p.latch[2 * N + f]; ms.px4_cv = p.latch[3 * N + f];
-            }
-            if (ms.has_imu) {
-                ms.imu_ax = p.latch[4 * N + f]; ms.imu_ay = p.latch[5 * N + f]; ms.imu_wz = p.latch[6 * N + f];
-                ms.imu_c00 = ic00; ms.imu_c01 = ic01; ms.imu_c11 = ic11; ms.imu_cw = icw;
-            }
-            if (ms.has_mag) ms.mag_angle = p.latch[7 * N + f];
-
-            // ---- predict (KF.cpp:287-305): a = 0 at the start of every step
-            Sym<8> Pw;
-#pragma unroll
-            for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = sc.Pm[k];
-            k8_predict_cov(Pw, dt, p.cfg.accel_noise, p.cfg.jolt);
-#pragma unroll
-            for (int k = 0; k < Sym<8>::SZ; ++k) sc.Pm[k] = Pw.a[k];
-            const double xp[8] = {px + dt * vx, py + dt * vy, vx, vy, 0.0, 0.0, wrap_angle(th + dt * om), om};
-
-            if (has_r && ep.valid == 0u) st.status |= 1u;
-            double dx[8];
-            const int rc = k8_update<PME>(p.anchors, p.cfg, ep, has_r, ms, dt, xp, sc, Pw, dx, st);
-            if (rc == 0) {
-                px = xp[0] + dx[0]; py = xp[1] + dx[1];
-                vx = xp[2] + dx[2]; vy = xp[3] + dx[3];
-                th = xp[6] + dx[6]; om = xp[7] + dx[7]; // written back un-wrapped (KF.cpp:317)
-#pragma unroll
-                for (int k = 0; k < Sym<8>::SZ; ++k) sc.Pm[k] = Pw.a[k];
-                if (!(isfinite(px) && isfinite(py) && isfinite(vx) && isfinite(vy) && isfinite(th) && isfinite(om)))
-                    st.status |= 8u;
+            if (e + 1 < p.n_events) prefetch_event(raw, land, p.events[e + 1], m, p.rs, p.sensors, N, f);
+            if (skip) {
+                carry += ev.dt;
             } else {
-                st.status |= 4u; // the reference would abort on this uncaught exception; the update is skipped
-            }
-            n_updates += 1;
-            if (st.status & ~(32u | 64u)) n_bad += 1;
-            status_or |= st.status;
-            if (ev.kind == EV_TOA) {
-                if (p.traj) {
-                    p.traj[((int64_t)n_toa * 3 + 0) * N + f] = px;
-                    p.traj[((int64_t)n_toa * 3 + 1) * N + f] = py;
-                    p.traj[((int64_t)n_toa * 3 + 2) * N + f] = th;
+                const double dt = ev.dt + carry;
+                carry = 0.0;
+
+                // ---- predict (KF.cpp:287-305): a = 0 at the start of every step
+                Sym<8> Pw;
+#pragma unroll
+                for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k];
+                k8_predict_cov(Pw, dt, p.cfg.accel_noise, p.cfg.jolt);
+#pragma unroll
+                for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = Pw.a[k];
+                const double xp[8] = {px + dt * vx, py + dt * vy, vx, vy, 0.0, 0.0, wrap_angle(th + dt * om), om};
+
+                if (ms.has_imu) {
+                    ms.imu_c00 = ic00; ms.imu_c01 = ic01; ms.imu_c11 = ic11; ms.imu_cw = icw;
                 }
-                ++n_toa;
+
+                if (has_r && ep.valid == 0u) st.status |= 1u;
+                double dx[8];
+                const int rc = k8_update<PME, MT>(p.anchors, p.cfg, ep, has_r, ms, dt, xp, Pm, Pw, dx, st, wmask);
+                if (rc == 0) {
+                    px = xp[0] + dx[0]; py = xp[1] + dx[1];
+                    vx = xp[2] + dx[2]; vy = xp[3] + dx[3];
+                    th = xp[6] + dx[6]; om = xp[7] + dx[7]; // written back un-wrapped (KF.cpp:317)
+#pragma unroll
+                    for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = Pw.a[k];
+                    if (!(isfinite(px) && isfinite(py) && isfinite(vx) && isfinite(vy) && isfinite(th) && isfinite(om)))
+                        st.status |= 8u;
+                } else {
+                    st.status |= 4u; // the reference would abort on this uncaught exception; the update is skipped
+                }
+                n_updates += 1;
+                if (st.status & ~(32u | 64u)) n_bad += 1;
+                status_or |= st.status;
+                if (ev.kind == EV_TOA) {
+                    if (p.traj) {
+                        p.traj[((int64_t)n_toa * 3 + 0) * N + f] = px;
+                        p.traj[((int64_t)n_toa * 3 + 1) * N + f] = py;
+                        p.traj[((int64_t)n_toa * 3 + 2) * N + f] = th;
+                    }
+                    ++n_toa;
+                }
+
             }
+            __syncwarp(wmask); // the IEKF trip count differs per lane
         }
         p.x[0 * N + f] = px; p.x[1 * N + f] = py; p.x[2 * N + f] = vx; p.x[3 * N + f] = vy;
         p.x[4 * N + f] = 0.0; p.x[5 * N + f] = 0.0; p.x[6 * N + f] = th; p.x[7 * N + f] = om;
 #pragma unroll
-        for (int k = 0; k < Sym<8>::SZ; ++k) p.P[(int64_t)k * N + f] = sc.Pm[k];
+        for (int k = 0; k < Sym<8>::SZ; ++k) p.P[(int64_t)k * N + f] = Pm[k];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) p.latch[(int64_t)k * N + f] = latch[k];
         p.has[f] = (int32_t)has;
         p.latch[8 * N + f] = carry;
         if (p.status) p.status[f] |= (int32_t)status_or;
@@ -201,22 +214,21 @@ __global__ void __launch_bounds__(K8_BLOCK, 3) k8_replay_kernel(const __grid_con
     warp_accumulate(p.counters + CNT_BAD, n_bad);
 }
 
+template <bool PME, int MT>
+static cudaError_t launch_k(const K8Params &p, cudaStream_t s) {
+    const unsigned grid = (unsigned)((p.N + K8_BLOCK - 1) / K8_BLOCK);
+    const size_t smem = (size_t)k8_smem_rows(p.rs.m_slots, p.rs.fmt, PME, MT > 0) * K8_BLOCK * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(k8_replay_kernel<PME, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k8_replay_kernel<PME, MT><<<grid, K8_BLOCK, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_k8_replay(const K8Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((p.N + K8_BLOCK - 1) / K8_BLOCK);
-    const bool pme = p.rs.err != nullptr;
-    const size_t smem = (size_t)k8_smem_rows(p.rs.m_slots, pme) * K8_BLOCK * sizeof(double);
-    cudaError_t e;
-    if (pme) {
-        e = cudaFuncSetAttribute(k8_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k8_replay_kernel<true><<<grid, K8_BLOCK, smem, s>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(k8_replay_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        k8_replay_kernel<false><<<grid, K8_BLOCK, smem, s>>>(p);
-    }
-    return cudaGetLastError();
+    if (p.rs.err != nullptr) return launch_k<true, 0>(p, s);
+    if (p.rs.m_slots == 8) return launch_k<false, 8>(p, s);
+    return launch_k<false, 0>(p, s);
 }
 
 // getPose (KF.cpp:709-747): predict-only, state untouched

@@ -4,7 +4,7 @@
 #pragma once
 #include "kfpos_kernels.cuh" // K8Cfg, EventDesc
 #include "kfpos_math.cuh"
-#include "kfpos_ml.cuh"
+#include "kfpos_solve.cuh"
 
 namespace kfpos {
 
@@ -45,131 +45,105 @@ KF_DEV void k8_predict_cov(Sym<8> &P, double t, double accel_noise, double jolt)
 // what one kalmanStep3D call fuses (KF.cpp:365-501): row layout [ranges | px4(3) | imu(3) | mag(1)]
 struct K8Meas {
     bool has_px4, has_imu, has_mag;
-    double px4_vx, px4_vy, px4_gz, px4_cv, px4_cg; // PX4FlowMeasurement
-    double imu_ax, imu_ay, imu_wz;                 // ImuMeasurement
-    double imu_c00, imu_c01, imu_c11, imu_cw;      //   covarianceAccelerationXY, covarianceAngularVelocityZ
-    double mag_angle, mag_c;                       // MagMeasurement
-};
-
-struct K8Scratch {
-    Col Pm;   // 36 rows: P^-
-    Col invd; // M rows
-    Col eps;  // M rows
+    double imu_c00, imu_c01, imu_c11, imu_cw; // covarianceAccelerationXY, covarianceAngularVelocityZ
+    double px4_cg, mag_c;                     // covarianceGyroZ, covarianceMag (XML constants)
+    // latched samples (shared-memory column, read where they are used so that they do not
+    // occupy registers across the iteration):
+    //   [0..3] PX4Flow vx, vy, gz, cv   [4..6] IMU ax, ay, wz   [7] magnetometer angle
+    Col latch;
 };
 
 // kalmanStep3D (KF.cpp:365-501).  xp: predicted state with theta already wrapped
 // (KF.cpp:305); has_r: ranging rows present (ep.valid may still be empty).
-// Same sequential-scalar formulation as t6_update; the IMU accelerometer pair is
-// a 2x2 block (its covariance may carry off-diagonals, KF.cpp:431-434).
-template <bool PME>
-KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const Epoch<PME> &ep, bool has_r, const K8Meas &ms,
-                     double dt, const double (&xp)[8], const K8Scratch &sc, Sym<8> &Pw, double (&dx)[8],
-                     StepStats &st) {
+//   Pm : P^- (shared-memory column, read only);  Pw: out = (I - K J) P^-;  dx: out = x - x^-
+// One IEKF iteration = one pass over the anchors (cost + information-form accumulators of the
+// ranging rows, kfpos_solve.cuh) + the sensor residuals; its gain step applies the ranging rows
+// as ONE 2x2 block update and the <= 7 sensor rows as sequential scalar updates (the IMU
+// accelerometer pair as a 2x2 block: its covariance may carry off-diagonals, KF.cpp:431-434).
+// wmask: lanes that run this event together, re-converged after the Newton loop (0 = none).
+template <bool PME, int MT>
+KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const EpochT<PME, MT> &ep, bool has_r, const K8Meas &ms,
+                     double dt, const double (&xp)[8], const Col &Pm, Sym<8> &Pw, double (&dx)[8], StepStats &st,
+                     unsigned wmask) {
     const unsigned mask = has_r ? ep.valid : 0u;
-    double sse = -1.0, sse_xp = 0.0;
-    if (has_r) { // inner ML 2-D solve from (x^-_0, x^-_1, tagZ) (KF.cpp:403-405); its first pass
-                 // leaves 1/d_i and eps_i at x^- in the scratch columns for the first cost evaluation
+    double sse = -1.0;
+    int rc = ML_OK;
+    if (has_r) { // inner ML 2-D solve from (x^-_0, x^-_1, tagZ) (KF.cpp:403-405)
         double pml[3] = {xp[0], xp[1], cfg.tag_z};
-        const DistStore ds = {sc.invd, sc.eps};
-        const int rc = ml_solve2<PME, true>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &ds, &sse_xp);
-        if (rc == ML_FEW) st.status |= 2u;
-        if (rc == ML_SINGULAR) return ML_SINGULAR;
+        rc = ml_solve2<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr);
         if (mask == 0u) sse = -1.0; // estimationError of an empty list
+        // has_r is a property of the event, common to the batch: every lane of wmask is here
+        if (wmask) __syncwarp(wmask);
     }
-    const double R0 = fmax(sse, ep.e0);
-    const double invR0 = mask ? 1.0 / R0 : 0.0; // no ranging rows: nothing is weighted by it
+    if (rc == ML_FEW) st.status |= 2u;
+    if (rc == ML_SINGULAR) return ML_SINGULAR;
+    const double invR0 = mask ? fast_rcp(fmax(sse, ep.e0)) : 0.0; // no ranging rows: nothing is weighted by it
     // inverse of the IMU accelerometer block and the scalar variances (arma::inv of the
     // block-diagonal observationCovariance, KF.cpp:446)
     const double idet = ms.has_imu ? 1.0 / (ms.imu_c00 * ms.imu_c11 - ms.imu_c01 * ms.imu_c01) : 0.0;
     const double ii00 = ms.imu_c11 * idet, ii01 = -ms.imu_c01 * idet, ii11 = ms.imu_c00 * idet;
-    const double i_cv = ms.has_px4 ? 1.0 / ms.px4_cv : 0.0, i_cg = ms.has_px4 ? 1.0 / ms.px4_cg : 0.0;
+    const double px4_cv = ms.has_px4 ? ms.latch[3] : 1.0;
+    const double i_cv = ms.has_px4 ? 1.0 / px4_cv : 0.0, i_cg = ms.has_px4 ? 1.0 / ms.px4_cg : 0.0;
     const double i_cw = ms.has_imu ? 1.0 / ms.imu_cw : 0.0, i_cm = ms.has_mag ? 1.0 / ms.mag_c : 0.0;
 
 #pragma unroll
     for (int k = 0; k < 8; ++k) dx[k] = 0.0;
 #pragma unroll
-    for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+    for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k];
     double cost = 1e20, prior = 0.0;
     bool broke = false;
     for (int iter = 0; iter < 20; ++iter) {
-        const double px = xp[0] + dx[0], py = xp[1] + dx[1];
         const double vx = xp[2] + dx[2], vy = xp[3] + dx[3];
         const double ax = xp[4] + dx[4], ay = xp[5] + dx[5];
         const double th = xp[6] + dx[6], om = xp[7] + dx[7];
-        // ---- pass A: sensor outputs and cost at the current iterate (KF.cpp:451-469)
-        double c = 0.0;
-        if (iter == 0) { // x = x^-: distances already in the scratch columns
-            if (PME) {
-                for (int i = 0; i < ep.m_slots; ++i) {
-                    if (!((mask >> i) & 1u)) continue;
-                    const double e = sc.eps[i];
-                    c = fma(e * e, 1.0 / fmax(sse, ep.e[i]), c);
-                }
-            } else {
-                c = sse_xp;
-            }
-        } else {
-#pragma unroll 2
-            for (int i = 0; i < ep.m_slots; ++i) {
-                if (!((mask >> i) & 1u)) continue;
-                const double ex = px - A.x[i], ey = py - A.y[i], ez = cfg.tag_z - A.z[i];
-                const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
-                const double id = fast_rsqrt(d2);
-                const double e = ep.z[i] - d2 * id;
-                sc.invd[i] = id;
-                sc.eps[i] = e;
-                c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
-            }
+        // ---- sensor outputs and cost at the current iterate (KF.cpp:451-469); the ranging pass
+        //      also accumulates b = J^T R^-1 y and G = J^T R^-1 J of the rows linearised there
+        double c = 0.0, b[3] = {0.0, 0.0, 0.0}, G[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (mask) {
+            const double dx3[3] = {dx[0], dx[1], 0.0};
+            iekf_pass<PME, MT, 2>(A, ep, mask, sse, xp[0] + dx[0], xp[1] + dx[1], cfg.tag_z, dx3, c, b, G);
+            if (!PME) c *= invR0;
         }
-        if (!PME) c *= invR0;
         double sn = 0.0, cs = 1.0, sw = 0.0, cw = 1.0;
         if (ms.has_px4 || ms.has_imu) sincos(th, &sn, &cs);
         double e_p0 = 0, e_p1 = 0, e_p2 = 0, e_i0 = 0, e_i1 = 0, e_i2 = 0, e_m = 0;
         if (ms.has_px4) { // px4flowOutput (KF.cpp:563-571)
             sincos(om * dt, &sw, &cw);
             const double it = 1.0 / dt;
-            e_p0 = ms.px4_vx - (cs * vx + sn * vy + it * ((1.0 - cw) * cfg.arm1 - sw * cfg.arm2));
-            e_p1 = ms.px4_vy - (-sn * vx + cs * vy + it * (sw * cfg.arm1 + (1.0 - cw) * cfg.arm2));
-            e_p2 = ms.px4_gz - om;
+            e_p0 = ms.latch[0] - (cs * vx + sn * vy + it * ((1.0 - cw) * cfg.arm1 - sw * cfg.arm2));
+            e_p1 = ms.latch[1] - (-sn * vx + cs * vy + it * (sw * cfg.arm1 + (1.0 - cw) * cfg.arm2));
+            e_p2 = ms.latch[2] - om;
             c += (e_p0 * e_p0 + e_p1 * e_p1) * i_cv + e_p2 * e_p2 * i_cg;
         }
         if (ms.has_imu) { // imuOutput (KF.cpp:573-581)
-            e_i0 = ms.imu_ax - (cs * ax + sn * ay);
-            e_i1 = ms.imu_ay - (-sn * ax + cs * ay);
-            e_i2 = ms.imu_wz - om;
+            e_i0 = ms.latch[4] - (cs * ax + sn * ay);
+            e_i1 = ms.latch[5] - (-sn * ax + cs * ay);
+            e_i2 = ms.latch[6] - om;
             c += e_i0 * (ii00 * e_i0 + ii01 * e_i1) + e_i1 * (ii01 * e_i0 + ii11 * e_i1) + e_i2 * e_i2 * i_cw;
         }
         if (ms.has_mag) { // residual wrapped once (KF.cpp:461-463)
-            e_m = wrap_angle(ms.mag_angle - th);
+            e_m = wrap_angle(ms.latch[7] - th);
             c += e_m * e_m * i_cm;
         }
         const double newCost = c + prior;
         st.cost_evals += 1;
-        if (fabs(cost - newCost) / cost < 1e-4) { broke = true; break; }
+        if (rel_change_lt(cost, newCost, 1e-4)) { broke = true; break; }
         cost = newCost;
 
-        // ---- pass B: sequential updates from (x^-, P^-), rows linearised at the iterate
+        // ---- gain step from (x^-, P^-), rows linearised at the iterate (KF.cpp:472-495)
         st.gain_evals += 1;
         if (iter > 0) {
 #pragma unroll
-            for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+            for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k];
         }
         double dn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        double b0 = 0, b1 = 0, G0 = 0, G1 = 0, G2 = 0; // range rows: J^T R^-1 y, J^T R^-1 J (xy block)
-#pragma unroll 1
-        for (int i = 0; i < ep.m_slots; ++i) {
-            if (!((mask >> i) & 1u)) continue;
-            const double id = sc.invd[i];
-            double h[8] = {(px - A.x[i]) * id, (py - A.y[i]) * id, 0, 0, 0, 0, 0, 0}; // KF.cpp:611-625
-            const double y = fma(h[0], dx[0], fma(h[1], dx[1], sc.eps[i]));
-            const double R = PME ? fmax(sse, ep.e[i]) : R0;
-            scalar_update<8, 0x03u>(Pw, dn, h, y, R);
-            const double iR = PME ? 1.0 / R : 1.0;
-            const double yr = y * iR, h0r = h[0] * iR;
-            b0 = fma(h[0], yr, b0); b1 = fma(h[1], yr, b1);
-            G0 = fma(h0r, h[0], G0); G1 = fma(h0r, h[1], G1); G2 = fma(h[1] * iR, h[1], G2);
+        if (mask) { // ranging rows (KF.cpp:611-625): one 2x2 information-form block
+            if (!PME) {
+                b[0] *= invR0; b[1] *= invR0;
+                G[0] *= invR0; G[1] *= invR0; G[2] *= invR0;
+            }
+            info_block<8, 2>(Pw, dn, b, G);
         }
-        if (!PME) { b0 *= invR0; b1 *= invR0; G0 *= invR0; G1 *= invR0; G2 *= invR0; }
         // Jacobian entries of the sensor rows at the iterate (KF.cpp:627-697)
         const double j_p06 = -sn * vx + cs * vy, j_p07 = cfg.arm1 * sw - cfg.arm2 * cw;
         const double j_p16 = -cs * vx - sn * vy, j_p17 = cfg.arm1 * cw + cfg.arm2 * sw;
@@ -184,9 +158,9 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const Epoch<PME> &e
         const double y_m = e_m + dx[6];
         if (ms.has_px4) {
             double h[8] = {0, 0, cs, sn, 0, 0, j_p06, j_p07};
-            scalar_update<8, 0xCCu>(Pw, dn, h, y_p0, ms.px4_cv);
+            scalar_update<8, 0xCCu>(Pw, dn, h, y_p0, px4_cv);
             h[2] = -sn; h[3] = cs; h[6] = j_p16; h[7] = j_p17;
-            scalar_update<8, 0xCCu>(Pw, dn, h, y_p1, ms.px4_cv);
+            scalar_update<8, 0xCCu>(Pw, dn, h, y_p1, px4_cv);
             h[7] = 1.0;
             scalar_update<8, 0x80u>(Pw, dn, h, y_p2, ms.px4_cg);
         }
@@ -202,8 +176,8 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const Epoch<PME> &e
         }
         // ---- prior term for the next cost: w = J^T R^-1 (y - J Delta), delta^T P^+ delta = w . Delta
         double w[8];
-        w[0] = b0 - (G0 * dn[0] + G1 * dn[1]);
-        w[1] = b1 - (G1 * dn[0] + G2 * dn[1]);
+        w[0] = b[0] - (G[0] * dn[0] + G[1] * dn[1]);
+        w[1] = b[1] - (G[1] * dn[0] + G[2] * dn[1]);
 #pragma unroll
         for (int k = 2; k < 8; ++k) w[k] = 0.0;
         if (ms.has_px4) {

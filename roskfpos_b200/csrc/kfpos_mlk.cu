@@ -1,25 +1,25 @@
 // kfpos_mlk.cu -- batched MLLocation epochs (G4 of SURVEY.md §2): one thread per
 // epoch; variants NORMAL / IGNORE_N / BEST (ML.cpp:307-414, 421-469).
 #include "kfpos_kernels.cuh"
-#include "kfpos_ml.cuh"
+#include "kfpos_solve.cuh"
 
 namespace kfpos {
 
 constexpr int ML_BLOCK = 128;
 
 template <bool PME>
-KF_DEV int ml_any(const AnchorTable &A, const Epoch<PME> &ep, unsigned mask, bool use2d,
+KF_DEV int ml_any(const AnchorTable &A, const EpochT<PME, 0> &ep, unsigned mask, bool use2d,
                   const double (&start)[3], double (&pos)[3], double (&cov)[6], double &sse,
                   unsigned &iters) {
     pos[0] = start[0]; pos[1] = start[1]; pos[2] = start[2];
     if (use2d) {
         double c2[3] = {0, 0, 0};
-        const int rc = ml_solve2<PME>(A, ep, mask, pos, sse, iters, c2);
+        const int rc = ml_solve2<PME, 0>(A, ep, mask, pos, sse, iters, c2);
         cov[0] = c2[0]; cov[1] = c2[1]; cov[2] = c2[2];
         cov[3] = cov[4] = cov[5] = 0.0;
         return rc;
     }
-    return ml_solve3<PME>(A, ep, mask, pos, sse, iters, cov);
+    return ml_solve3<PME, 0>(A, ep, mask, pos, sse, iters, cov);
 }
 
 template <bool PME>
@@ -31,15 +31,15 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
     if (active) {
         const int64_t N = p.N;
         const int m = p.rs.m_slots;
-        Epoch<PME> ep;
+        EpochT<PME, 0> ep;
         ep.z = Col{smem + threadIdx.x, ML_BLOCK};
         ep.e = Col{smem + (size_t)(PME ? m : 0) * ML_BLOCK + threadIdx.x, ML_BLOCK};
         ep.e0 = p.rs.err_scalar;
         ep.m_slots = m;
-        const Col raw = Col{smem + (size_t)(PME ? 2 * m : m) * ML_BLOCK + threadIdx.x, ML_BLOCK};
+        const RawCol raw = make_raw(smem + (size_t)(PME ? 2 * m : m) * ML_BLOCK, p.rs.fmt, threadIdx.x, ML_BLOCK);
         prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, f, N); // all M loads in flight together
         cp_async_wait_all();
-        convert_epoch<PME>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, f, N);
+        convert_epoch<PME, 0>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, f, N);
         const bool use2d = p.use2d != 0;
         const int k = use2d ? 3 : 4; // minRangings (ML.cpp:316,319)
         const double start[3] = {p.start[0], p.start[1], p.start[2]};

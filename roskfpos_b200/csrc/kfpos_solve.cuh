@@ -364,6 +364,140 @@ KF_DEV void iekf_pass(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned 
     G[0] = G0; G[1] = G1; G[2] = G2; G[3] = G3; G[4] = G4; G[5] = G5;
 }
 
+// Solves one information-form IEKF gain step for 3-D ranging rows:
+//   N = I + G A;  s = N^-1 b;  dx = A s (position part of B s);  M = N^-1 G;
+//   returns w . dx with w = b - G dx
+// A = position block of P^- (packed xx, yx, yy, zx, zy, zz), G packed the same way.
+KF_DEV double info_gain3(const double (&a)[6], const double (&b)[3], const double (&G)[6], double (&dx)[3],
+                         double (&M)[6], double (&s)[3]) {
+    const double a00 = a[0], a10 = a[1], a11 = a[2], a20 = a[3], a21 = a[4], a22 = a[5];
+    const double G0 = G[0], G1 = G[1], G2 = G[2], G3 = G[3], G4 = G[4], G5 = G[5];
+    const double n00 = fma(G0, a00, fma(G1, a10, fma(G3, a20, 1.0)));
+    const double n01 = fma(G0, a10, fma(G1, a11, G3 * a21));
+    const double n02 = fma(G0, a20, fma(G1, a21, G3 * a22));
+    const double n10 = fma(G1, a00, fma(G2, a10, G4 * a20));
+    const double n11 = fma(G1, a10, fma(G2, a11, fma(G4, a21, 1.0)));
+    const double n12 = fma(G1, a20, fma(G2, a21, G4 * a22));
+    const double n20 = fma(G3, a00, fma(G4, a10, G5 * a20));
+    const double n21 = fma(G3, a10, fma(G4, a11, G5 * a21));
+    const double n22 = fma(G3, a20, fma(G4, a21, fma(G5, a22, 1.0)));
+    const double c00 = fma(n11, n22, -n12 * n21), c01 = fma(n02, n21, -n01 * n22), c02 = fma(n01, n12, -n02 * n11);
+    const double c10 = fma(n12, n20, -n10 * n22), c11 = fma(n00, n22, -n02 * n20), c12 = fma(n02, n10, -n00 * n12);
+    const double c20 = fma(n10, n21, -n11 * n20), c21 = fma(n01, n20, -n00 * n21), c22 = fma(n00, n11, -n01 * n10);
+    const double idet = fast_rcp(fma(n00, c00, fma(n01, c10, n02 * c20)));
+    const double s0 = fma(c00, b[0], fma(c01, b[1], c02 * b[2])) * idet;
+    const double s1 = fma(c10, b[0], fma(c11, b[1], c12 * b[2])) * idet;
+    const double s2 = fma(c20, b[0], fma(c21, b[1], c22 * b[2])) * idet;
+    s[0] = s0; s[1] = s1; s[2] = s2;
+    dx[0] = fma(a00, s0, fma(a10, s1, a20 * s2));
+    dx[1] = fma(a10, s0, fma(a11, s1, a21 * s2));
+    dx[2] = fma(a20, s0, fma(a21, s1, a22 * s2));
+    M[0] = fma(c00, G0, fma(c01, G1, c02 * G3)) * idet;
+    M[1] = fma(c10, G0, fma(c11, G1, c12 * G3)) * idet;
+    M[2] = fma(c10, G1, fma(c11, G2, c12 * G4)) * idet;
+    M[3] = fma(c20, G0, fma(c21, G1, c22 * G3)) * idet;
+    M[4] = fma(c20, G1, fma(c21, G2, c22 * G4)) * idet;
+    M[5] = fma(c20, G3, fma(c21, G4, c22 * G5)) * idet;
+    const double w0 = b[0] - fma(G0, dx[0], fma(G1, dx[1], G3 * dx[2]));
+    const double w1 = b[1] - fma(G1, dx[0], fma(G2, dx[1], G4 * dx[2]));
+    const double w2 = b[2] - fma(G3, dx[0], fma(G4, dx[1], G5 * dx[2]));
+    return fma(w0, dx[0], fma(w1, dx[1], w2 * dx[2]));
+}
+
+// P^+ = P^- - B M B^T, B = P^-[:, 0:3]  (the reference's (I - K J) P^-), in place on the
+// shared-memory column of the packed NS x NS matrix: only B is held in registers.
+template <int NS>
+KF_DEV void apply_cov_block3(const Col &Pm, const double (&M)[6]) {
+    double B[NS][3];
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) B[i][k] = (i >= k) ? Pm[i * (i + 1) / 2 + k] : Pm[k * (k + 1) / 2 + i];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        const double c0 = fma(B[i][0], M[0], fma(B[i][1], M[1], B[i][2] * M[3]));
+        const double c1 = fma(B[i][0], M[1], fma(B[i][1], M[2], B[i][2] * M[4]));
+        const double c2 = fma(B[i][0], M[3], fma(B[i][1], M[4], B[i][2] * M[5]));
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            const int k = i * (i + 1) / 2 + j;
+            Pm[k] = fma(-c0, B[j][0], fma(-c1, B[j][1], fma(-c2, B[j][2], Pm[k])));
+        }
+    }
+}
+
+// ---- ranging rows of one IEKF gain step as ONE block update of a register-resident (P, dn):
+// on entry P = P^- and dn = 0; on exit P = P^- - B M B^T and dn = B s with
+//   A = P^-[0:D,0:D], B = P^-[:,0:D], N = I + G A, s = N^-1 b, M = N^-1 G
+// (= the sequential rank-1 updates of all m ranging rows; push-through identity, see kfpos_t6.cuh).
+// The remaining sensor rows (PX4Flow / IMU / magnetometer) are then applied sequentially to (P, dn).
+template <int NS, int D>
+KF_DEV void info_block(Sym<NS> &P, double (&dn)[NS], const double (&b)[3], const double (&G)[6]) {
+    double s[3] = {0.0, 0.0, 0.0}, M[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (D == 2) {
+        const double a00 = P.get(0, 0), a10 = P.get(1, 0), a11 = P.get(1, 1);
+        const double n00 = fma(G[0], a00, fma(G[1], a10, 1.0)), n01 = fma(G[0], a10, G[1] * a11);
+        const double n10 = fma(G[1], a00, G[2] * a10), n11 = fma(G[1], a10, fma(G[2], a11, 1.0));
+        const double idet = fast_rcp(fma(n00, n11, -n01 * n10));
+        s[0] = fma(n11, b[0], -n01 * b[1]) * idet;
+        s[1] = fma(n00, b[1], -n10 * b[0]) * idet;
+        M[0] = fma(n11, G[0], -n01 * G[1]) * idet;
+        M[1] = fma(n11, G[1], -n01 * G[2]) * idet;
+        M[2] = fma(n00, G[2], -n10 * G[1]) * idet;
+    } else {
+        const double a00 = P.get(0, 0), a10 = P.get(1, 0), a11 = P.get(1, 1), a20 = P.get(2, 0), a21 = P.get(2, 1),
+                     a22 = P.get(2, 2);
+        const double G0 = G[0], G1 = G[1], G2 = G[2], G3 = G[3], G4 = G[4], G5 = G[5];
+        const double n00 = fma(G0, a00, fma(G1, a10, fma(G3, a20, 1.0)));
+        const double n01 = fma(G0, a10, fma(G1, a11, G3 * a21));
+        const double n02 = fma(G0, a20, fma(G1, a21, G3 * a22));
+        const double n10 = fma(G1, a00, fma(G2, a10, G4 * a20));
+        const double n11 = fma(G1, a10, fma(G2, a11, fma(G4, a21, 1.0)));
+        const double n12 = fma(G1, a20, fma(G2, a21, G4 * a22));
+        const double n20 = fma(G3, a00, fma(G4, a10, G5 * a20));
+        const double n21 = fma(G3, a10, fma(G4, a11, G5 * a21));
+        const double n22 = fma(G3, a20, fma(G4, a21, fma(G5, a22, 1.0)));
+        const double c00 = fma(n11, n22, -n12 * n21), c01 = fma(n02, n21, -n01 * n22), c02 = fma(n01, n12, -n02 * n11);
+        const double c10 = fma(n12, n20, -n10 * n22), c11 = fma(n00, n22, -n02 * n20), c12 = fma(n02, n10, -n00 * n12);
+        const double c20 = fma(n10, n21, -n11 * n20), c21 = fma(n01, n20, -n00 * n21), c22 = fma(n00, n11, -n01 * n10);
+        const double idet = fast_rcp(fma(n00, c00, fma(n01, c10, n02 * c20)));
+        s[0] = fma(c00, b[0], fma(c01, b[1], c02 * b[2])) * idet;
+        s[1] = fma(c10, b[0], fma(c11, b[1], c12 * b[2])) * idet;
+        s[2] = fma(c20, b[0], fma(c21, b[1], c22 * b[2])) * idet;
+        M[0] = fma(c00, G0, fma(c01, G1, c02 * G3)) * idet;
+        M[1] = fma(c10, G0, fma(c11, G1, c12 * G3)) * idet;
+        M[2] = fma(c10, G1, fma(c11, G2, c12 * G4)) * idet;
+        M[3] = fma(c20, G0, fma(c21, G1, c22 * G3)) * idet;
+        M[4] = fma(c20, G1, fma(c21, G2, c22 * G4)) * idet;
+        M[5] = fma(c20, G3, fma(c21, G4, c22 * G5)) * idet;
+    }
+    double B[NS][D];
+#pragma unroll
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int k = 0; k < D; ++k) B[i][k] = P.get(i, k);
+#pragma unroll
+    for (int i = 0; i < NS; ++i) {
+        double c0, c1, c2 = 0.0;
+        if (D == 2) {
+            dn[i] = fma(B[i][0], s[0], B[i][1] * s[1]);
+            c0 = fma(B[i][0], M[0], B[i][1] * M[1]);
+            c1 = fma(B[i][0], M[1], B[i][1] * M[2]);
+        } else {
+            dn[i] = fma(B[i][0], s[0], fma(B[i][1], s[1], B[i][D - 1] * s[2]));
+            c0 = fma(B[i][0], M[0], fma(B[i][1], M[1], B[i][D - 1] * M[3]));
+            c1 = fma(B[i][0], M[1], fma(B[i][1], M[2], B[i][D - 1] * M[4]));
+            c2 = fma(B[i][0], M[3], fma(B[i][1], M[4], B[i][D - 1] * M[5]));
+        }
+#pragma unroll
+        for (int j = 0; j <= i; ++j) {
+            double v = fma(-c0, B[j][0], fma(-c1, B[j][1], P.get(i, j)));
+            if (D == 3) v = fma(-c2, B[j][D - 1], v);
+            P.at(i, j) = v;
+        }
+    }
+}
+
 // ---- asynchronous epoch loads (LDGSTS / cp.async): the rangings of the NEXT
 // epoch stream from HBM straight into a shared-memory landing zone while the current
 // epoch is being processed, so no warp ever waits on DRAM and no registers are
@@ -395,10 +529,19 @@ KF_DEV RawCol make_raw(double *region, int fmt, int tid, int block) {
     r.stride = block;
     return r;
 }
+// The same landing zone INSIDE a thread's private double column (K8 / T9, where the zone is
+// shared with the f64 sensor payloads of other event kinds and warps drift apart in the
+// schedule): 32-bit element i is half (i & 1) of the thread's double i / 2.
+struct RawColPriv {
+    Col c;
+    KF_DEV unsigned *w(int i) const { return reinterpret_cast<unsigned *>(&c[i >> 1]) + (i & 1); }
+    KF_DEV double *d(int i) const { return &c[i]; }
+};
 // doubles of shared memory per thread a landing zone of `rows` elements needs
 __host__ __device__ inline int raw_rows(int fmt, int rows) { return fmt == 0 ? rows : (rows + 1) / 2; }
 
-KF_DEV void prefetch_epoch(const RawCol &raw, int m, const void *ranges, int fmt, int64_t base, int64_t N) {
+template <class RAW>
+KF_DEV void prefetch_epoch(const RAW &raw, int m, const void *ranges, int fmt, int64_t base, int64_t N) {
 #pragma unroll 4
     for (int i = 0; i < m; ++i) {
         const int64_t idx = base + (int64_t)i * N;
@@ -412,8 +555,8 @@ KF_DEV void prefetch_epoch(const RawCol &raw, int m, const void *ranges, int fmt
 }
 
 // landing zone -> metres + valid mask: keep rangings[i] > 0 (TOA.cpp:48-57, ML.cpp:478)
-template <bool PME, int MT>
-KF_DEV void convert_epoch(EpochT<PME, MT> &ep, const RawCol &raw, const void *ranges, int fmt, const double *err,
+template <bool PME, int MT, class RAW>
+KF_DEV void convert_epoch(EpochT<PME, MT> &ep, const RAW &raw, const void *ranges, int fmt, const double *err,
                           int64_t base, int64_t N) {
     unsigned valid = 0u;
 #pragma unroll(MT > 0 ? MT : 1)

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
             if (rc == 0) {
                 // stateToPose (TOA.cpp:159-183): position kept, velocity dropped
                 pos[0] += res.dx[0]; pos[1] += res.dx[1]; pos[2] += res.dx[2];
-                t6_apply_cov(Pm, res.M);
+                apply_cov_block3<6>(Pm, res.M);
                 if (!(isfinite(pos[0]) && isfinite(pos[1]) && isfinite(pos[2]))) st.status |= 8u;
             } else {
                 st.status |= 4u; // catch (std::runtime_error): update skipped (TOA.cpp:151)

@@ -40,44 +40,6 @@ struct T6Result {
     double cost;
 };
 
-// Solves one information-form IEKF gain step for 3-D ranging rows:
-//   N = I + G A;  s = N^-1 b;  dx = A s;  M = N^-1 G;  returns w . dx with w = b - G dx
-// A = position block of P^- (packed xx, yx, yy, zx, zy, zz), G packed the same way.
-KF_DEV double info_gain3(const double (&a)[6], const double (&b)[3], const double (&G)[6], double (&dx)[3],
-                         double (&M)[6]) {
-    const double a00 = a[0], a10 = a[1], a11 = a[2], a20 = a[3], a21 = a[4], a22 = a[5];
-    const double G0 = G[0], G1 = G[1], G2 = G[2], G3 = G[3], G4 = G[4], G5 = G[5];
-    const double n00 = fma(G0, a00, fma(G1, a10, fma(G3, a20, 1.0)));
-    const double n01 = fma(G0, a10, fma(G1, a11, G3 * a21));
-    const double n02 = fma(G0, a20, fma(G1, a21, G3 * a22));
-    const double n10 = fma(G1, a00, fma(G2, a10, G4 * a20));
-    const double n11 = fma(G1, a10, fma(G2, a11, fma(G4, a21, 1.0)));
-    const double n12 = fma(G1, a20, fma(G2, a21, G4 * a22));
-    const double n20 = fma(G3, a00, fma(G4, a10, G5 * a20));
-    const double n21 = fma(G3, a10, fma(G4, a11, G5 * a21));
-    const double n22 = fma(G3, a20, fma(G4, a21, fma(G5, a22, 1.0)));
-    const double c00 = fma(n11, n22, -n12 * n21), c01 = fma(n02, n21, -n01 * n22), c02 = fma(n01, n12, -n02 * n11);
-    const double c10 = fma(n12, n20, -n10 * n22), c11 = fma(n00, n22, -n02 * n20), c12 = fma(n02, n10, -n00 * n12);
-    const double c20 = fma(n10, n21, -n11 * n20), c21 = fma(n01, n20, -n00 * n21), c22 = fma(n00, n11, -n01 * n10);
-    const double idet = fast_rcp(fma(n00, c00, fma(n01, c10, n02 * c20)));
-    const double s0 = fma(c00, b[0], fma(c01, b[1], c02 * b[2])) * idet;
-    const double s1 = fma(c10, b[0], fma(c11, b[1], c12 * b[2])) * idet;
-    const double s2 = fma(c20, b[0], fma(c21, b[1], c22 * b[2])) * idet;
-    dx[0] = fma(a00, s0, fma(a10, s1, a20 * s2));
-    dx[1] = fma(a10, s0, fma(a11, s1, a21 * s2));
-    dx[2] = fma(a20, s0, fma(a21, s1, a22 * s2));
-    M[0] = fma(c00, G0, fma(c01, G1, c02 * G3)) * idet;
-    M[1] = fma(c10, G0, fma(c11, G1, c12 * G3)) * idet;
-    M[2] = fma(c10, G1, fma(c11, G2, c12 * G4)) * idet;
-    M[3] = fma(c20, G0, fma(c21, G1, c22 * G3)) * idet;
-    M[4] = fma(c20, G1, fma(c21, G2, c22 * G4)) * idet;
-    M[5] = fma(c20, G3, fma(c21, G4, c22 * G5)) * idet;
-    const double w0 = b[0] - fma(G0, dx[0], fma(G1, dx[1], G3 * dx[2]));
-    const double w1 = b[1] - fma(G1, dx[0], fma(G2, dx[1], G4 * dx[2]));
-    const double w2 = b[2] - fma(G3, dx[0], fma(G4, dx[1], G5 * dx[2]));
-    return fma(w0, dx[0], fma(w1, dx[1], w2 * dx[2]));
-}
-
 // kalmanStep3DIgnoreAnchor (TOA.cpp:242-338) on the slots in `mask`.
 //   xp : predicted position (predicted velocity is 0: TOA.cpp:110-120)
 //   Pm : P^- (shared-memory column, read only)
@@ -141,33 +103,13 @@ KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
 #pragma unroll
             for (int k = 0; k < 6; ++k) G[k] *= invR0;
         }
-        prior = info_gain3(a, b, G, dx, out.M);
+        double sgain[3];
+        prior = info_gain3(a, b, G, dx, out.M, sgain);
     }
     if (!broke) st.status |= 32u;
     out.dx[0] = dx[0]; out.dx[1] = dx[1]; out.dx[2] = dx[2];
     out.cost = cost;
     return 0;
-}
-
-// P^+ = P^- - B M B^T, B = P^-[:, 0:3]  (the reference's (I - K J) P^-, TOA.cpp:326), in
-// place on the shared-memory column: only B (18 values) is held in registers.
-KF_DEV void t6_apply_cov(const Col &Pm, const double (&M)[6]) {
-    double B[6][3];
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) B[i][k] = (i >= k) ? Pm[i * (i + 1) / 2 + k] : Pm[k * (k + 1) / 2 + i];
-#pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        const double c0 = fma(B[i][0], M[0], fma(B[i][1], M[1], B[i][2] * M[3]));
-        const double c1 = fma(B[i][0], M[1], fma(B[i][1], M[2], B[i][2] * M[4]));
-        const double c2 = fma(B[i][0], M[3], fma(B[i][1], M[4], B[i][2] * M[5]));
-#pragma unroll
-        for (int j = 0; j <= i; ++j) {
-            const int k = i * (i + 1) / 2 + j;
-            Pm[k] = fma(-c0, B[j][0], fma(-c1, B[j][1], fma(-c2, B[j][2], Pm[k])));
-        }
-    }
 }
 
 } // namespace kfpos

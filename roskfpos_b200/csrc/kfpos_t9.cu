@@ -14,7 +14,12 @@ namespace kfpos {
 
 constexpr int T9_BLOCK = 128;
 
-__host__ __device__ inline int t9_smem_rows(int m, bool pme) { return 4 * m + (pme ? m : 0) + 45; }
+// shared-memory rows (doubles) per thread: P^- (45), landing zone (rangings or 3 accelerations),
+// [metres column when MT == 0], [errorEstimation column]
+__host__ __device__ inline int t9_land_rows(int m, int fmt) { return raw_rows(fmt, m) > 3 ? raw_rows(fmt, m) : 3; }
+__host__ __device__ inline int t9_smem_rows(int m, int fmt, bool pme, bool in_regs) {
+    return 45 + t9_land_rows(m, fmt) + (in_regs ? 0 : m) + (pme ? m : 0);
+}
 
 // P^- = F P F^T + Q (TOAIMU.cpp:392-421)
 KF_DEV void t9_predict_cov(Sym<9> &P, double t, double jolt) {
@@ -34,10 +39,6 @@ KF_DEV void t9_predict_cov(Sym<9> &P, double t, double jolt) {
 #pragma unroll
             for (int b = 0; b <= a; ++b) P.at(ax + 3 * a, ax + 3 * b) += jolt * u[b] * u[a];
 }
-
-struct T9Scratch {
-    Col Pm, invd, eps;
-};
 
 // 3-row block update on the acceleration block (J = [0 0 I3]), S = P_aa + R packed symmetric
 KF_DEV bool accel_block_update(Sym<9> &P, double (&dn)[9], const double (&y)[3], const double (&R)[6]) {
@@ -69,107 +70,118 @@ KF_DEV bool accel_block_update(Sym<9> &P, double (&dn)[9], const double (&y)[3],
     return true;
 }
 
-// kalmanStep3D (TOAIMU.cpp:242-340)
-template <bool PME>
-KF_DEV int t9_update(const AnchorTable &A, const Epoch<PME> &ep, bool has_r, bool has_imu, const double (&za)[3],
-                     const double (&Ra)[6], const double (&xp)[9], const T9Scratch &sc, Sym<9> &Pw, double (&dx)[9],
-                     StepStats &st) {
+// kalmanStep3D (TOAIMU.cpp:242-340).  Pm: P^- (shared-memory column, read only); dx: out = x - x^-.
+// Ranging rows: information form (kfpos_solve.cuh).  Without accelerometer rows the result is
+// FACTORED like T6's: P = P^- - B M B^T with M returned (Pw untouched, return value 1); with them
+// the ranging block is applied to a register copy Pw per gain step, followed by one 3x3 block
+// update for the accelerometer rows, and Pw = (I - K J) P^- is returned (return value 0).
+template <bool PME, int MT>
+KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r, bool has_imu, const double (&za)[3],
+                     const double (&Ra)[6], const double (&xp)[9], const Col &Pm, Sym<9> &Pw, double (&dx)[9],
+                     double (&M)[6], StepStats &st, unsigned wmask) {
     const unsigned mask = has_r ? ep.valid : 0u;
-    double sse = -1.0, sse_xp = 0.0;
+    double sse = -1.0;
+    int rc = ML_OK;
     if (has_r) { // TOAIMU.cpp:268-270 (no NaN guard in this class)
         double pml[3] = {xp[0], xp[1], xp[2]};
-        const DistStore ds = {sc.invd, sc.eps};
-        const int rc = ml_solve3<PME, true>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &ds, &sse_xp);
-        if (rc == ML_FEW) st.status |= 2u;
-        if (rc == ML_SINGULAR) return ML_SINGULAR;
+        rc = ml_solve3<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr);
         if (mask == 0u) sse = -1.0;
+        // has_r is a property of the event, common to the batch: every lane of wmask is here
+        if (wmask) __syncwarp(wmask);
     }
-    const double R0 = fmax(sse, ep.e0);
-    const double invR0 = mask ? 1.0 / R0 : 0.0;
+    if (rc == ML_FEW) st.status |= 2u;
+    if (rc == ML_SINGULAR) return ML_SINGULAR;
+    const double invR0 = mask ? fast_rcp(fmax(sse, ep.e0)) : 0.0;
     double Rai[6] = {0, 0, 0, 0, 0, 0};
     if (has_imu && !inv_sym3(Ra, Rai)) return ML_SINGULAR; // arma::inv(observationCovariance) would throw
 
 #pragma unroll
     for (int k = 0; k < 9; ++k) dx[k] = 0.0;
 #pragma unroll
-    for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+    for (int k = 0; k < 6; ++k) M[k] = 0.0;
     double cost = 1e20, prior = 0.0;
     bool broke = false;
-    for (int iter = 0; iter < 20; ++iter) {
-        const double px = xp[0] + dx[0], py = xp[1] + dx[1], pz = xp[2] + dx[2];
-        double c = 0.0;
-        if (iter == 0) { // x = x^-: distances already in the scratch columns
-            if (PME) {
-                for (int i = 0; i < ep.m_slots; ++i) {
-                    if (!((mask >> i) & 1u)) continue;
-                    const double e = sc.eps[i];
-                    c = fma(e * e, 1.0 / fmax(sse, ep.e[i]), c);
-                }
-            } else {
-                c = sse_xp;
-            }
-        } else {
-#pragma unroll 2
-            for (int i = 0; i < ep.m_slots; ++i) {
-                if (!((mask >> i) & 1u)) continue;
-                const double ex = px - A.x[i], ey = py - A.y[i], ez = pz - A.z[i];
-                const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
-                const double id = fast_rsqrt(d2);
-                const double e = ep.z[i] - d2 * id;
-                sc.invd[i] = id;
-                sc.eps[i] = e;
-                c = PME ? fma(e * e, 1.0 / fmax(sse, ep.e[i]), c) : fma(e, e, c);
-            }
-        }
-        if (!PME) c *= invR0;
-        double ea[3] = {0, 0, 0};
-        if (has_imu) {
+    if (!has_imu) { // ---- ranging rows only: factored form, nothing but 3-vectors and 3x3 matrices in flight
+        double a[6], s[3] = {0.0, 0.0, 0.0};
 #pragma unroll
-            for (int k = 0; k < 3; ++k) ea[k] = za[k] - (xp[6 + k] + dx[6 + k]);
-            c += ea[0] * (Rai[0] * ea[0] + Rai[1] * ea[1] + Rai[3] * ea[2]) +
-                 ea[1] * (Rai[1] * ea[0] + Rai[2] * ea[1] + Rai[4] * ea[2]) +
-                 ea[2] * (Rai[3] * ea[0] + Rai[4] * ea[1] + Rai[5] * ea[2]);
+        for (int k = 0; k < 6; ++k) a[k] = Pm[k];
+        double dxp[3] = {0.0, 0.0, 0.0};
+        for (int iter = 0; iter < 20; ++iter) {
+            double c = 0.0, b[3] = {0.0, 0.0, 0.0}, G[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            if (mask) {
+                iekf_pass<PME, MT, 3>(A, ep, mask, sse, xp[0] + dxp[0], xp[1] + dxp[1], xp[2] + dxp[2], dxp, c, b, G);
+                if (!PME) c *= invR0;
+            }
+            const double newCost = c + prior;
+            st.cost_evals += 1;
+            if (rel_change_lt(cost, newCost, 1e-4)) { broke = true; break; }
+            cost = newCost;
+            st.gain_evals += 1;
+            if (!PME) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) b[k] *= invR0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) G[k] *= invR0;
+            }
+            prior = info_gain3(a, b, G, dxp, M, s);
         }
+        if (!broke) st.status |= 32u;
+        // dx = B s over all nine states (velocity is persisted: TOAIMU.cpp:189-191)
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const double bi0 = Pm[i * (i + 1) / 2 + 0];
+            const double bi1 = i >= 1 ? Pm[i * (i + 1) / 2 + 1] : Pm[1];
+            const double bi2 = i >= 2 ? Pm[i * (i + 1) / 2 + 2] : Pm[3 + i];
+            dx[i] = fma(bi0, s[0], fma(bi1, s[1], bi2 * s[2]));
+        }
+        return 1;
+    }
+#pragma unroll
+    for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = Pm[k];
+    for (int iter = 0; iter < 20; ++iter) {
+        double c = 0.0, b[3] = {0.0, 0.0, 0.0}, G[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+        if (mask) {
+            const double dx3[3] = {dx[0], dx[1], dx[2]};
+            iekf_pass<PME, MT, 3>(A, ep, mask, sse, xp[0] + dx[0], xp[1] + dx[1], xp[2] + dx[2], dx3, c, b, G);
+            if (!PME) c *= invR0;
+        }
+        double ea[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) ea[k] = za[k] - (xp[6 + k] + dx[6 + k]);
+        c += ea[0] * (Rai[0] * ea[0] + Rai[1] * ea[1] + Rai[3] * ea[2]) +
+             ea[1] * (Rai[1] * ea[0] + Rai[2] * ea[1] + Rai[4] * ea[2]) +
+             ea[2] * (Rai[3] * ea[0] + Rai[4] * ea[1] + Rai[5] * ea[2]);
         const double newCost = c + prior;
         st.cost_evals += 1;
-        if (fabs(cost - newCost) / cost < 1e-4) { broke = true; break; }
+        if (rel_change_lt(cost, newCost, 1e-4)) { broke = true; break; }
         cost = newCost;
 
         st.gain_evals += 1;
         if (iter > 0) {
 #pragma unroll
-            for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+            for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = Pm[k];
         }
         double dn[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-        double b0 = 0, b1 = 0, b2 = 0, G0 = 0, G1 = 0, G2 = 0, G3 = 0, G4 = 0, G5 = 0;
-#pragma unroll 1
-        for (int i = 0; i < ep.m_slots; ++i) {
-            if (!((mask >> i) & 1u)) continue;
-            const double id = sc.invd[i];
-            double h[9] = {(px - A.x[i]) * id, (py - A.y[i]) * id, (pz - A.z[i]) * id, 0, 0, 0, 0, 0, 0};
-            const double y = fma(h[0], dx[0], fma(h[1], dx[1], fma(h[2], dx[2], sc.eps[i])));
-            const double R = PME ? fmax(sse, ep.e[i]) : R0;
-            scalar_update<9, 0x7u>(Pw, dn, h, y, R);
-            const double iR = PME ? 1.0 / R : 1.0;
-            const double yr = y * iR, h0r = h[0] * iR, h1r = h[1] * iR, h2r = h[2] * iR;
-            b0 = fma(h[0], yr, b0); b1 = fma(h[1], yr, b1); b2 = fma(h[2], yr, b2);
-            G0 = fma(h0r, h[0], G0); G1 = fma(h0r, h[1], G1); G2 = fma(h1r, h[1], G2);
-            G3 = fma(h0r, h[2], G3); G4 = fma(h1r, h[2], G4); G5 = fma(h2r, h[2], G5);
+        if (mask) {
+            if (!PME) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) b[k] *= invR0;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) G[k] *= invR0;
+            }
+            info_block<9, 3>(Pw, dn, b, G);
         }
         // y_a = eps_a - J delta = eps_a + dx_a
         const double ya[3] = {ea[0] + dx[6], ea[1] + dx[7], ea[2] + dx[8]};
-        if (has_imu && !accel_block_update(Pw, dn, ya, Ra)) return ML_SINGULAR;
-        double w0 = b0 - (G0 * dn[0] + G1 * dn[1] + G3 * dn[2]);
-        double w1 = b1 - (G1 * dn[0] + G2 * dn[1] + G4 * dn[2]);
-        double w2 = b2 - (G3 * dn[0] + G4 * dn[1] + G5 * dn[2]);
+        if (!accel_block_update(Pw, dn, ya, Ra)) return ML_SINGULAR;
+        const double w0 = b[0] - (G[0] * dn[0] + G[1] * dn[1] + G[3] * dn[2]);
+        const double w1 = b[1] - (G[1] * dn[0] + G[2] * dn[1] + G[4] * dn[2]);
+        const double w2 = b[2] - (G[3] * dn[0] + G[4] * dn[1] + G[5] * dn[2]);
         prior = w0 * dn[0] + w1 * dn[1] + w2 * dn[2];
-        if (!PME) prior *= invR0;
-        if (has_imu) {
-            const double r0 = ya[0] - dn[6], r1 = ya[1] - dn[7], r2 = ya[2] - dn[8];
-            prior += dn[6] * (Rai[0] * r0 + Rai[1] * r1 + Rai[3] * r2) +
-                     dn[7] * (Rai[1] * r0 + Rai[2] * r1 + Rai[4] * r2) +
-                     dn[8] * (Rai[3] * r0 + Rai[4] * r1 + Rai[5] * r2);
-        }
+        const double r0 = ya[0] - dn[6], r1 = ya[1] - dn[7], r2 = ya[2] - dn[8];
+        prior += dn[6] * (Rai[0] * r0 + Rai[1] * r1 + Rai[3] * r2) +
+                 dn[7] * (Rai[1] * r0 + Rai[2] * r1 + Rai[4] * r2) +
+                 dn[8] * (Rai[3] * r0 + Rai[4] * r1 + Rai[5] * r2);
 #pragma unroll
         for (int k = 0; k < 9; ++k) dx[k] = dn[k];
     }
@@ -177,16 +189,17 @@ KF_DEV int t9_update(const AnchorTable &A, const Epoch<PME> &ep, bool has_r, boo
     return 0;
 }
 
-template <bool PME>
+template <bool PME, int MT>
 __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_constant__ T9Params p) {
     extern __shared__ double smem[];
     const int64_t f = (int64_t)blockIdx.x * T9_BLOCK + threadIdx.x;
     const bool active = f < p.N;
+    const unsigned wmask = __ballot_sync(0xffffffffu, active);
     StepStats st = {0u, 0u, 0u, 0u};
     unsigned n_updates = 0, n_bad = 0;
     if (active) {
         const int64_t N = p.N;
-        const int m = p.rs.m_slots;
+        const int m = MT > 0 ? MT : p.rs.m_slots;
         double *col = smem + threadIdx.x;
         int row = 0;
         auto take = [&](int rows) {
@@ -194,17 +207,15 @@ __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_con
             row += rows;
             return c;
         };
-        Epoch<PME> ep;
-        ep.z = take(m);
-        ep.e = PME ? take(m) : ep.z;
+        const Col Pm = take(45);
+        const Col land = take(t9_land_rows(m, p.rs.fmt));
+        const RawColPriv raw = {land}; // rangings land in the same private column
+        EpochT<PME, MT> ep;
+        ep.z = MT > 0 ? Pm : take(m);
+        ep.e = PME ? take(m) : Pm;
         ep.e0 = p.rs.err_scalar;
         ep.m_slots = m;
         ep.valid = 0u;
-        Col raw = take(m > 3 ? m : 3);
-        T9Scratch sc;
-        sc.invd = take(m);
-        sc.eps = take(m);
-        sc.Pm = take(45);
 
         double pos[3], vel[3];
 #pragma unroll
@@ -213,9 +224,10 @@ __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_con
             vel[k] = p.x[(int64_t)(3 + k) * N + f];
         }
 #pragma unroll
-        for (int k = 0; k < Sym<9>::SZ; ++k) sc.Pm[k] = p.P[(int64_t)k * N + f];
+        for (int k = 0; k < Sym<9>::SZ; ++k) Pm[k] = p.P[(int64_t)k * N + f];
         unsigned has = (unsigned)p.has[f];
         unsigned status_or = 0;
+        double za[3] = {p.latch[0 * N + f], p.latch[1 * N + f], p.latch[2 * N + f]}; // latched acceleration
         double Ra[6]; // packed symmetric part of the latched 3x3 covariance
         bool asym = false;
         {
@@ -228,7 +240,7 @@ __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_con
             if (ev.kind == EV_TOA) {
                 prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, ev.offset * N + f, N);
             } else {
-                for (int i = 0; i < 3; ++i) cp_async_8(&raw[i], p.sensors + (ev.offset + i) * N + f);
+                for (int i = 0; i < 3; ++i) cp_async_8(&land[i], p.sensors + (ev.offset + i) * N + f);
                 cp_async_commit();
             }
         };
@@ -239,11 +251,11 @@ __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_con
             st.status = 0u;
             bool has_r = false, has_imu = false;
             if (ev.kind == EV_TOA) { // newTOAMeasurement (TOAIMU.cpp:49-73): rangings + latched IMU
-                convert_epoch<PME>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, ev.offset * N + f, N);
+                convert_epoch<PME, MT>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, ev.offset * N + f, N);
                 has_r = true;
                 has_imu = (has >> 1) & 1u;
             } else { // newIMUMeasurement (TOAIMU.cpp:76-92)
-                p.latch[0 * N + f] = raw[0]; p.latch[1 * N + f] = raw[1]; p.latch[2 * N + f] = raw[2];
+                za[0] = land[0]; za[1] = land[1]; za[2] = land[2];
                 Ra[0] = ev.aux[0]; Ra[1] = 0.5 * (ev.aux[1] + ev.aux[3]); Ra[2] = ev.aux[4];
                 Ra[3] = 0.5 * (ev.aux[2] + ev.aux[6]); Ra[4] = 0.5 * (ev.aux[5] + ev.aux[7]); Ra[5] = ev.aux[8];
                 asym = ev.aux[1] != ev.aux[3] || ev.aux[2] != ev.aux[6] || ev.aux[5] != ev.aux[7];
@@ -252,31 +264,32 @@ __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_con
             }
             if (e + 1 < p.n_events) prefetch(p.events[e + 1]);
             if (has_imu && asym) st.status |= 64u;
-            double za[3] = {0, 0, 0};
-            if (has_imu) {
-                za[0] = p.latch[0 * N + f]; za[1] = p.latch[1 * N + f]; za[2] = p.latch[2 * N + f];
-            }
             const double dt = ev.dt;
             // ---- predict (TOAIMU.cpp:165-180): a = 0 at the start of every step
             Sym<9> Pw;
 #pragma unroll
-            for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = sc.Pm[k];
+            for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = Pm[k];
             t9_predict_cov(Pw, dt, p.jolt);
 #pragma unroll
-            for (int k = 0; k < Sym<9>::SZ; ++k) sc.Pm[k] = Pw.a[k];
+            for (int k = 0; k < Sym<9>::SZ; ++k) Pm[k] = Pw.a[k];
             const double xp[9] = {pos[0] + dt * vel[0], pos[1] + dt * vel[1], pos[2] + dt * vel[2],
                                   vel[0], vel[1], vel[2], 0.0, 0.0, 0.0};
             if (has_r && ep.valid == 0u) st.status |= 1u;
-            double dx[9];
-            const int rc = t9_update<PME>(p.anchors, ep, has_r, has_imu, za, Ra, xp, sc, Pw, dx, st);
-            if (rc == 0) {
+            double dx[9], M[6];
+            const int rc = t9_update<PME, MT>(p.anchors, ep, has_r, has_imu, za, Ra, xp, Pm, Pw, dx, M, st, wmask);
+            __syncwarp(wmask); // the IEKF trip count differs per lane
+            if (rc >= 0) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { // velocity and position kept, acceleration dropped (:189-194)
                     pos[k] = xp[k] + dx[k];
                     vel[k] = xp[3 + k] + dx[3 + k];
                 }
+                if (rc == 1) {
+                    apply_cov_block3<9>(Pm, M);
+                } else {
 #pragma unroll
-                for (int k = 0; k < Sym<9>::SZ; ++k) sc.Pm[k] = Pw.a[k];
+                    for (int k = 0; k < Sym<9>::SZ; ++k) Pm[k] = Pw.a[k];
+                }
                 bool fin = true;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) fin = fin && isfinite(pos[k]) && isfinite(vel[k]);
@@ -300,9 +313,10 @@ __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_con
             p.x[(int64_t)k * N + f] = pos[k];
             p.x[(int64_t)(3 + k) * N + f] = vel[k];
             p.x[(int64_t)(6 + k) * N + f] = 0.0;
+            p.latch[(int64_t)k * N + f] = za[k];
         }
 #pragma unroll
-        for (int k = 0; k < Sym<9>::SZ; ++k) p.P[(int64_t)k * N + f] = sc.Pm[k];
+        for (int k = 0; k < Sym<9>::SZ; ++k) p.P[(int64_t)k * N + f] = Pm[k];
         p.has[f] = (int32_t)has;
         if (p.status) p.status[f] |= (int32_t)status_or;
         if (f == 0 && (has & 2u)) {
@@ -319,22 +333,21 @@ __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_con
     warp_accumulate(p.counters + CNT_BAD, n_bad);
 }
 
+template <bool PME, int MT>
+static cudaError_t launch_k(const T9Params &p, cudaStream_t s) {
+    const unsigned grid = (unsigned)((p.N + T9_BLOCK - 1) / T9_BLOCK);
+    const size_t smem = (size_t)t9_smem_rows(p.rs.m_slots, p.rs.fmt, PME, MT > 0) * T9_BLOCK * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(t9_replay_kernel<PME, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    t9_replay_kernel<PME, MT><<<grid, T9_BLOCK, smem, s>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_t9_replay(const T9Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
-    const unsigned grid = (unsigned)((p.N + T9_BLOCK - 1) / T9_BLOCK);
-    const bool pme = p.rs.err != nullptr;
-    const size_t smem = (size_t)t9_smem_rows(p.rs.m_slots > 3 ? p.rs.m_slots : 3, pme) * T9_BLOCK * sizeof(double);
-    cudaError_t e;
-    if (pme) {
-        e = cudaFuncSetAttribute(t9_replay_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        t9_replay_kernel<true><<<grid, T9_BLOCK, smem, s>>>(p);
-    } else {
-        e = cudaFuncSetAttribute(t9_replay_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        t9_replay_kernel<false><<<grid, T9_BLOCK, smem, s>>>(p);
-    }
-    return cudaGetLastError();
+    if (p.rs.err != nullptr) return launch_k<true, 0>(p, s);
+    if (p.rs.m_slots == 8) return launch_k<false, 8>(p, s);
+    return launch_k<false, 0>(p, s);
 }
 
 // getPose (TOAIMU.cpp:476-510): predict-only, state untouched
