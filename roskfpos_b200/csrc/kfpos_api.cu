@@ -66,6 +66,10 @@ struct kfpos_batch {
     // K8 / T9 latched sensor samples, SoA rows (see kfpos_k8.cuh)
     double *d_latch = nullptr;
     double *d_latch_u = nullptr; // batch-wide latched IMU covariances
+    // ML: straggler queue of the Newton solver (kfpos_mlk.cu)
+    void *d_mlq = nullptr;
+    int *d_mlq_count = nullptr;
+    int mlq_cap = 0;
     int32_t *d_has = nullptr;
     DevBuf scratch[N_SCRATCH];
     DevBuf stage[2];
@@ -199,6 +203,15 @@ extern "C" int kfpos_batch_create(kfpos_batch **out, int device, int model, int6
         alloc((void **)&b->d_has, sizeof(int32_t) * N);
         alloc((void **)&b->d_latch_u, sizeof(double) * 16);
     }
+    if (model == KFPOS_MODEL_ML) {
+        if (n_filters > 0x7fffffffLL) {
+            kfpos_batch_destroy(b);
+            return KFPOS_ERR_UNSUPPORTED;
+        }
+        b->mlq_cap = (int)(N / 8 + 4096);
+        alloc(&b->d_mlq, (size_t)b->mlq_cap * 64);
+        alloc((void **)&b->d_mlq_count, sizeof(int));
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&b->ev_copied[i], cudaEventDisableTiming);
@@ -225,6 +238,8 @@ extern "C" void kfpos_batch_destroy(kfpos_batch *b) {
     cudaFree(b->d_latch);
     cudaFree(b->d_has);
     cudaFree(b->d_latch_u);
+    cudaFree(b->d_mlq);
+    cudaFree(b->d_mlq_count);
     for (auto &s : b->scratch) s.release();
     for (auto &s : b->stage) s.release();
     for (int i = 0; i < 2; ++i) {
@@ -723,6 +738,9 @@ extern "C" int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt,
     p.sel = (int32_t *)d_sel;
     p.status = (int32_t *)d_st;
     p.counters = b->d_counters;
+    p.queue = b->d_mlq;
+    p.queue_count = b->d_mlq_count;
+    p.queue_cap = b->mlq_cap;
     CK(launch_ml_solve(p, s));
     if (c_pos) CK(cudaMemcpyAsync(pos, d_pos, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, s));
     if (c_cov) CK(cudaMemcpyAsync(cov, d_cov, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, s));

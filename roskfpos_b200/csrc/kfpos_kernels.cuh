@@ -50,6 +50,9 @@ struct MlParams {
     int32_t *sel;    // SoA [2][N] or null
     int32_t *status; // [N] or null
     unsigned long long *counters;
+    void *queue;      // straggler queue: queue_cap records of 64 bytes (kfpos_mlk.cu)
+    int *queue_count; // device counter
+    int queue_cap;
 };
 
 // ---- sensor event streams (K8, T9).  The schedule (kind, dt) is common to the batch;

@@ -113,3 +113,28 @@ def test_ml_zero_noise_recovers_truth(kflib):
     d = np.sqrt(((truth[None] - anc[:, :, None]) ** 2).sum(axis=1))
     got = gpu_ml(kflib, anc, d, err=0.01)
     assert np.abs(got["pos"] - truth).max() < 1e-5
+
+
+@pytest.mark.parametrize("variant", [0, 1])
+def test_ml_straggler_queue(kflib, oracle, variant):
+    """16 anchors, 3-D from (1,1,4): about one epoch in a thousand needs more than the main
+    kernel's 32 Newton iterations (most of those run to the reference's 10000 cap) and is parked
+    in the straggler queue and resumed by the second launch.  Parked or not, every epoch whose
+    oracle result is stable must agree, iteration counts included; every epoch is counted once."""
+    from roskfpos_b200.batch import Batch
+    N, m = 150000, 16
+    anc, truth, r = epochs(m, N, seed=900 + variant)
+    ref, per = oracle_ml(oracle, r, anc, 0.01, start_for(0), variant=variant, n_ignore=2)
+    with Batch(kflib.MODEL_ML, N, anchors=anc, variant=variant, num_ignored_rangings=2) as b:
+        got = b.ml_solve(r, err=0.01)
+        cnt = b.counters()
+    slow = ref["iters"] > 32 * (2 if variant else 1)
+    assert slow.sum() >= 20, "the workload no longer exercises the queue"
+    assert cnt["updates"] == N and cnt["ml_iters"] == got["iters"].astype(np.int64).sum()
+    keys = dict(float_keys=("pos",), int_keys=("status", "iters", "sel"))
+    rep = assert_parity(got, ref, per, min_stable=0.99, max_tie_frac=1e-3, what=f"stragglers v{variant}", **keys)
+    # the parked epochs on their own: those the oracle calls stable must all agree
+    sub = lambda d: {k: np.asarray(v)[..., slow] for k, v in d.items()}
+    rep_slow = assert_parity(sub(got), sub(ref), [sub(p) for p in per], min_stable=0.0, max_tie_frac=0.05,
+                             what=f"parked epochs v{variant}", **keys)
+    print("parity report stragglers", variant, rep, rep_slow, int(slow.sum()))
