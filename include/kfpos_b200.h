@@ -181,6 +181,13 @@ int kfpos_batch_replay_toa(kfpos_batch *b, int n_steps, const double *dt, const 
                            int fmt, double err_scalar, const double *err_var, double *traj,
                            int32_t *sel, void *stream);
 
+/* T6 only: the same persistent replay with PER-FILTER time steps, for logs assembled by
+ * kfpos_assemble_epochs (every tag has its own report times).  dt_per_filter: SoA [T][N];
+ * a value < 0 means "filter f has no epoch t": neither predict nor update, its trajectory row
+ * repeats the current position.                                                     */
+int kfpos_batch_replay_epochs(kfpos_batch *b, int n_steps, const double *dt_per_filter, const void *ranges,
+                              int fmt, double err_scalar, const double *err_var, double *traj, void *stream);
+
 /* newPX4FlowMeasurement (PEA.h:15; KF.cpp:100-133).  K8 only.  SoA [N] each.
  * Filters whose quality is 0 skip the event; its dt is carried to their next one
  * (the reference returns before reading its clock, KF.cpp:111-113).              */
@@ -245,6 +252,30 @@ int kfpos_batch_get_pose(kfpos_batch *b, double dt, double *x_pred, double *P_pr
 int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt, double err_scalar,
                          const double *err_var, double *pos, double *cov, int32_t *iters,
                          int32_t *sel, int32_t *status, void *stream);
+
+/* --------------------------------------------------------- epoch assembler
+ * The ranging aggregation of PosGenerator (publishers/Posgenerator.cpp:143-281,476-507) for N
+ * independent, time-sorted ranging logs (one tag each; the tagId filter of :203 is the caller's):
+ * rangings are grouped by `seq` into epochs; an epoch is emitted when the next sequence number
+ * starts and when the one-shot 50 ms timer (Posgenerator.h:77) expires after the last ranging
+ * of a sequence (the row stays open: late rangings of the same seq are added and the row is
+ * emitted again, as the reference does).
+ *   inputs, SoA [L][N]: anchor (index into the anchor table; 0xFF or >= n_anchors = padding of
+ *     a ragged log), seq (0..255), range_mm (gtec_msgs/Ranging.range), err (errorEstimation,
+ *     NULL = none; only values > 0 overwrite within a sequence, :94,236), t (arrival time, s);
+ *   outputs: ranges_out int32 SoA [max_epochs][n_anchors][N] (-1 = no ranging, the table's
+ *     initial value :505), err_out f64 same shape or NULL, dt_out f64 SoA [max_epochs][N] = time
+ *     between consecutive reports (first report: first_dt; epochs a log does not have: -1),
+ *     n_epochs [N] or NULL = reports each log produced (may exceed max_epochs: truncated).
+ * flags: 0 = as written, the 256-row table whose new row gets only slot 0 cleared (:251-255,
+ * slots written 256 sequence numbers earlier survive);
+ * KFPOS_ASM_FIX_ROW_CLEAR = clear the whole row.  The outputs feed kfpos_batch_replay_epochs
+ * (KFPOS_FMT_I32_MM).  Synchronises `stream` before returning (internal scratch is freed). */
+#define KFPOS_ASM_FIX_ROW_CLEAR 1
+int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs, int n_anchors, const uint8_t *anchor,
+                          const uint8_t *seq, const int32_t *range_mm, const double *err, const double *t,
+                          int64_t max_epochs, int flags, double first_dt, int32_t *ranges_out, double *err_out,
+                          double *dt_out, int32_t *n_epochs, void *stream);
 
 /* ------------------------------------------------------------- diagnostics
  * Work counters accumulated on the device since the last reset, as doubles:

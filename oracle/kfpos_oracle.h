@@ -183,6 +183,16 @@ void ko_t9_events(int64_t N, int n_events, const ko_event *ev, int M, const doub
 int ko_version(void);
 int ko_max_threads(void);
 
+/* ------------------------------------------------------- ranging aggregation (ko_assemble.c) */
+int64_t ko_assemble(int64_t L, int M, int64_t stride, const uint8_t *anchor, const uint8_t *seq,
+                    const int32_t *range_mm, const double *err, const double *t, int64_t max_epochs,
+                    int fix_b12, double first_dt, int64_t out_stride, int32_t *ranges_out, double *err_out,
+                    double *dt_out);
+void ko_assemble_batch(int64_t N, int64_t L, int M, const uint8_t *anchor, const uint8_t *seq,
+                       const int32_t *range_mm, const double *err, const double *t, int64_t max_epochs,
+                       int fix_b12, double first_dt, int32_t *ranges_out, double *err_out, double *dt_out,
+                       int32_t *n_epochs);
+
 #ifdef __cplusplus
 }
 #endif

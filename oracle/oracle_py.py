@@ -371,3 +371,24 @@ class T9:
     @property
     def P(self):
         return np.array(self.f.P).reshape(9, 9)
+
+
+# ------------------------------------------------- ranging aggregation (Posgenerator.cpp:143-281)
+def assemble(anchor, seq, range_mm, t, n_anchors, max_epochs, err=None, fix_b12=False, first_dt=0.1):
+    """N logs of L messages, SoA [L][N] (a single log may be 1-D).  Returns dict(ranges int32
+    [T][M][N], err [T][M][N], dt [T][N] (-1 = no epoch), n_epochs [N] (may exceed max_epochs))."""
+    anchor = np.ascontiguousarray(np.atleast_2d(np.asarray(anchor, dtype=np.uint8).T).T)
+    L, N = anchor.shape
+    seq = np.ascontiguousarray(np.asarray(seq, dtype=np.uint8).reshape(L, N))
+    range_mm = np.ascontiguousarray(np.asarray(range_mm, dtype=np.int32).reshape(L, N))
+    t = np.ascontiguousarray(np.asarray(t, dtype=np.float64).reshape(L, N))
+    e = None if err is None else np.ascontiguousarray(np.asarray(err, dtype=np.float64).reshape(L, N))
+    M, T = int(n_anchors), int(max_epochs)
+    ro = np.empty((T, M, N), dtype=np.int32)
+    eo = np.empty((T, M, N))
+    dt = np.empty((T, N))
+    ne = np.empty(N, dtype=np.int32)
+    lib().ko_assemble_batch(C.c_int64(N), C.c_int64(L), M, _p(anchor, C.c_uint8), _p(seq, C.c_uint8),
+                            _p(range_mm, C.c_int32), _p(e), _p(t), C.c_int64(T), int(fix_b12),
+                            C.c_double(first_dt), _p(ro, C.c_int32), _p(eo), _p(dt), _p(ne, C.c_int32))
+    return dict(ranges=ro, err=eo, dt=dt, n_epochs=ne)

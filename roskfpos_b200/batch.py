@@ -155,6 +155,19 @@ class Batch:
                                                _stream_ptr(stream)), "kfpos_batch_replay_toa")
         return traj, sel
 
+    def replay_epochs(self, dt_per_filter, ranges, err=0.01, traj=None, want_traj=False, stream=None):
+        """T6: ranges [T][M][N] with per-filter time steps dt_per_filter [T][N] (< 0 = no epoch), the
+        output of assemble_epochs()."""
+        T = int(ranges.shape[0])
+        es, ep, keep = self._err(err)
+        pr, kr = _ptr(ranges)
+        pd, kd = _ptr(dt_per_filter, np.float64)
+        if traj is None and want_traj:
+            traj = np.empty((T, 3, self.N))
+        L.check(L.lib().kfpos_batch_replay_epochs(self._h, T, pd, pr, _fmt_of(ranges), es, ep, _ptr(traj)[0],
+                                                  _stream_ptr(stream)), "kfpos_batch_replay_epochs")
+        return traj
+
     def step_px4(self, dt, ix, iy, irz, itime_us, quality, stream=None):
         a = [_ptr(v, np.float64) for v in (ix, iy, irz, itime_us)]
         q = _ptr(quality, np.int32)
@@ -239,3 +252,24 @@ class Batch:
         L.check(L.lib().kfpos_batch_error_stats(self._h, p, C.byref(buf), _stream_ptr(stream)),
                 "kfpos_batch_error_stats")
         return np.array(list(buf))
+
+
+def assemble_epochs(anchor, seq, range_mm, t, n_anchors, max_epochs, err=None, fix_row_clear=False, first_dt=0.1,
+                    device=0, out=None, stream=None):
+    """Ranging aggregation of PosGenerator for N logs of L messages (SoA [L][N]; numpy or CUDA torch
+    tensors: uint8 anchor index, uint8 seq, int32 range_mm, f64 arrival time, optional f64 err).
+    Returns dict(ranges int32 [T][M][N], err [T][M][N] or None, dt [T][N], n_epochs [N]); `out` may
+    supply device tensors under the same keys."""
+    Lm, N = int(anchor.shape[0]), int(anchor.shape[1])
+    M, T = int(n_anchors), int(max_epochs)
+    if out is None:
+        out = dict(ranges=np.empty((T, M, N), dtype=np.int32), err=None if err is None else np.empty((T, M, N)),
+                   dt=np.empty((T, N)), n_epochs=np.empty(N, dtype=np.int32))
+    keep = [_ptr(anchor, np.uint8), _ptr(seq, np.uint8), _ptr(range_mm, np.int32), _ptr(err, np.float64),
+            _ptr(t, np.float64)]
+    L.check(L.lib().kfpos_assemble_epochs(int(device), N, Lm, M, keep[0][0], keep[1][0], keep[2][0], keep[3][0],
+                                          keep[4][0], T, L.ASM_FIX_ROW_CLEAR if fix_row_clear else 0, float(first_dt),
+                                          _ptr(out["ranges"])[0], _ptr(out.get("err"))[0], _ptr(out["dt"])[0],
+                                          _ptr(out.get("n_epochs"))[0], _stream_ptr(stream)),
+            "kfpos_assemble_epochs")
+    return out

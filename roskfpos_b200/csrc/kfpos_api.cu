@@ -335,7 +335,8 @@ namespace {
 // launches the model's replay kernel over T steps whose ranges (and optional
 // per-ranging errors) are already on the device
 int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_ranges, int fmt,
-                  double err_scalar, const double *d_err, double *d_traj, int32_t *d_sel, cudaStream_t s);
+                  double err_scalar, const double *d_err, double *d_traj, int32_t *d_sel, cudaStream_t s,
+                  const double *d_dt_f = nullptr);
 int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_ranges, int fmt, double err_scalar,
                const double *d_err, const double *d_sensors, double *d_traj, cudaStream_t s);
 
@@ -433,6 +434,33 @@ extern "C" int kfpos_batch_replay_toa(kfpos_batch *b, int n_steps, const double 
     return KFPOS_OK;
 }
 
+extern "C" int kfpos_batch_replay_epochs(kfpos_batch *b, int n_steps, const double *dt_per_filter, const void *ranges,
+                                         int fmt, double err_scalar, const double *err_var, double *traj,
+                                         void *stream) {
+    if (!b || b->model != KFPOS_MODEL_T6 || n_steps < 0 || !dt_per_filter || !ranges) return KFPOS_ERR_INVALID;
+    if (fmt < 0 || fmt > 2) return KFPOS_ERR_INVALID;
+    if (!b->have_anchors) return KFPOS_ERR_NOT_READY;
+    if (n_steps == 0) return KFPOS_OK;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N, M = (size_t)b->anchors.n, T = (size_t)n_steps;
+    const void *d_dtf = nullptr, *d_r = nullptr, *d_e = nullptr;
+    int rc = stage_in(b, 1, dt_per_filter, sizeof(double) * N * T, s, &d_dtf);
+    if (rc) return rc;
+    if ((rc = stage_in(b, 4, ranges, M * N * T * fmt_size(fmt), s, &d_r))) return rc;
+    if ((rc = stage_in(b, 5, err_var, sizeof(double) * M * N * T, s, &d_e))) return rc;
+    void *d_traj = nullptr;
+    bool copy_traj = false;
+    if ((rc = stage_out(b, 2, traj, sizeof(double) * 3 * N * T, &d_traj, &copy_traj))) return rc;
+    rc = launch_replay(b, n_steps, nullptr, d_r, fmt, err_scalar, (const double *)d_e, (double *)d_traj, nullptr, s,
+                       (const double *)d_dtf);
+    if (rc) return rc;
+    if (copy_traj) CK(cudaMemcpyAsync(traj, d_traj, sizeof(double) * 3 * N * T, cudaMemcpyDeviceToHost, s));
+    if (copy_traj || !on_device(ranges) || !on_device(dt_per_filter) || (err_var && !on_device(err_var)))
+        CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
 extern "C" int kfpos_batch_step_toa(kfpos_batch *b, double dt, const void *ranges, int fmt, double err_scalar,
                                     const double *err_var, void *stream) {
     return kfpos_batch_replay_toa(b, 1, &dt, ranges, fmt, err_scalar, err_var, nullptr, nullptr, stream);
@@ -441,7 +469,8 @@ extern "C" int kfpos_batch_step_toa(kfpos_batch *b, double dt, const void *range
 namespace {
 
 int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_ranges, int fmt,
-                  double err_scalar, const double *d_err, double *d_traj, int32_t *d_sel, cudaStream_t s) {
+                  double err_scalar, const double *d_err, double *d_traj, int32_t *d_sel, cudaStream_t s,
+                  const double *d_dt_f) {
     const RangeStream rs = make_rs(b, d_ranges, fmt, err_scalar, d_err);
     switch (b->model) {
     case KFPOS_MODEL_T6: {
@@ -454,6 +483,7 @@ int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_range
         p.ignore_thr = b->cfg.ignore_cost_threshold;
         p.accel_noise = b->cfg.accel_noise;
         p.dt = d_dt;
+        p.dt_f = d_dt_f;
         p.x = b->d_x;
         p.P = b->d_P;
         p.status = b->d_status;
@@ -748,6 +778,94 @@ extern "C" int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt,
     if (c_sel) CK(cudaMemcpyAsync(sel, d_sel, sizeof(int32_t) * 2 * N, cudaMemcpyDeviceToHost, s));
     if (c_st) CK(cudaMemcpyAsync(status, d_st, sizeof(int32_t) * N, cudaMemcpyDeviceToHost, s));
     if (c_pos || c_cov || c_it || c_sel || c_st || !on_device(ranges)) CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
+// ------------------------------------------------------------ epoch assembler
+namespace {
+// temporary device copy of a host array (or the device pointer itself)
+struct TmpIn {
+    const void *d = nullptr;
+    void *own = nullptr;
+    cudaError_t set(const void *src, size_t bytes, cudaStream_t s) {
+        if (!src || on_device(src)) { d = src; return cudaSuccess; }
+        cudaError_t e = cudaMalloc(&own, bytes);
+        if (e != cudaSuccess) return e;
+        d = own;
+        return cudaMemcpyAsync(own, src, bytes, cudaMemcpyHostToDevice, s);
+    }
+    ~TmpIn() { if (own) cudaFree(own); }
+};
+struct TmpOut {
+    void *d = nullptr, *own = nullptr, *host = nullptr;
+    size_t bytes = 0;
+    cudaError_t set(void *dst, size_t n) {
+        if (!dst || on_device(dst)) { d = dst; return cudaSuccess; }
+        cudaError_t e = cudaMalloc(&own, n);
+        if (e != cudaSuccess) return e;
+        d = own; host = dst; bytes = n;
+        return cudaSuccess;
+    }
+    cudaError_t back(cudaStream_t s) { return host ? cudaMemcpyAsync(host, own, bytes, cudaMemcpyDeviceToHost, s) : cudaSuccess; }
+    ~TmpOut() { if (own) cudaFree(own); }
+};
+} // namespace
+
+extern "C" int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs, int n_anchors, const uint8_t *anchor,
+                                     const uint8_t *seq, const int32_t *range_mm, const double *err, const double *t,
+                                     int64_t max_epochs, int flags, double first_dt, int32_t *ranges_out,
+                                     double *err_out, double *dt_out, int32_t *n_epochs, void *stream) {
+    if (n_logs <= 0 || n_msgs < 0 || n_anchors <= 0 || n_anchors > KFPOS_MAX_ANCHORS || max_epochs <= 0)
+        return KFPOS_ERR_INVALID;
+    if (!anchor || !seq || !range_mm || !t || !ranges_out || !dt_out) return KFPOS_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return KFPOS_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return KFPOS_ERR_CUDA;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)n_logs, L = (size_t)n_msgs, M = (size_t)n_anchors, T = (size_t)max_epochs;
+    TmpIn i_a, i_s, i_r, i_e, i_t;
+    TmpOut o_r, o_e, o_dt, o_n;
+    CK(i_a.set(anchor, L * N, s));
+    CK(i_s.set(seq, L * N, s));
+    CK(i_r.set(range_mm, 4 * L * N, s));
+    CK(i_e.set(err, 8 * L * N, s));
+    CK(i_t.set(t, 8 * L * N, s));
+    CK(o_r.set(ranges_out, 4 * T * M * N));
+    CK(o_e.set(err_out, 8 * T * M * N));
+    CK(o_dt.set(dt_out, 8 * T * N));
+    CK(o_n.set(n_epochs, 4 * N));
+    const int fix = (flags & KFPOS_ASM_FIX_ROW_CLEAR) ? 1 : 0;
+    const size_t rows = fix ? 1 : 256;
+    void *tbl_r = nullptr, *tbl_e = nullptr;
+    CK(cudaMalloc(&tbl_r, 4 * rows * M * N));
+    cudaError_t e = cudaMalloc(&tbl_e, 8 * rows * M * N);
+    if (e == cudaSuccess) e = cudaMemsetAsync(tbl_r, 0xff, 4 * rows * M * N, s); // initialiseTagList: -1
+    if (e == cudaSuccess) e = cudaMemsetAsync(tbl_e, 0, 8 * rows * M * N, s);
+    if (e == cudaSuccess) {
+        AssembleParams p;
+        p.N = n_logs; p.L = n_msgs; p.max_epochs = max_epochs;
+        p.M = n_anchors; p.fix_b12 = fix; p.first_dt = first_dt;
+        p.anchor = (const uint8_t *)i_a.d; p.seq = (const uint8_t *)i_s.d;
+        p.range_mm = (const int32_t *)i_r.d; p.err = (const double *)i_e.d; p.t = (const double *)i_t.d;
+        p.tbl_r = (int32_t *)tbl_r; p.tbl_e = (double *)tbl_e;
+        p.ranges_out = (int32_t *)o_r.d; p.err_out = (double *)o_e.d; p.dt_out = (double *)o_dt.d;
+        p.n_epochs = (int32_t *)o_n.d;
+        e = launch_assemble(p, s);
+    }
+    if (e == cudaSuccess) e = o_r.back(s);
+    if (e == cudaSuccess) e = o_e.back(s);
+    if (e == cudaSuccess) e = o_dt.back(s);
+    if (e == cudaSuccess) e = o_n.back(s);
+    // the scratch table and the temporary copies are freed on return: finish the work first
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    cudaFree(tbl_r);
+    cudaFree(tbl_e);
+    if (e != cudaSuccess) return map_cuda_err(e);
+    if (e2 != cudaSuccess) return map_cuda_err(e2);
     return KFPOS_OK;
 }
 

@@ -1,0 +1,106 @@
+// kfpos_assemble.cu -- the "epoch assembler" (SURVEY.md §8f-1): turns raw time-sorted UWB ranging
+// logs into the SoA epoch tensors the replay kernels stream, the batched form of PosGenerator's
+// ranging aggregation (Posgenerator.cpp:143-281, 476-507): rangings are grouped by their sequence
+// number in a 256-row table; a row is sent when the next sequence number starts or when the
+// one-shot 50 ms timer (Posgenerator.h:77) expires after the last ranging.
+//
+// One thread per log, the log index fastest in every tensor, so the 32 lanes of a warp read 32
+// consecutive bytes/words per message field and write 32 consecutive words per output slot.  The
+// work is byte/integer shuffling: the kernel is HBM-bound (roofline = measured copy bandwidth).
+// The 256-row table lives in global memory in the same layout ([row][slot][log]); with the row
+// clearing FIXED a single row is enough.
+#include "kfpos_kernels.cuh"
+
+namespace kfpos {
+
+__global__ void __launch_bounds__(128) assemble_kernel(const AssembleParams p) {
+    const int64_t f = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (f >= p.N) return;
+    const int64_t N = p.N;
+    const int M = p.M;
+    int32_t *tr = p.tbl_r + f;
+    double *te = p.tbl_e + f;
+    int range_seq = -1; // initialiseTagList (Posgenerator.cpp:499-507); the table is pre-set to -1 / 0
+    int64_t n_ep = 0;
+    bool have_last = false, armed = false, flushed_once = false;
+    double t_last = 0.0, t_prev = 0.0;
+
+    auto flush = [&](double tnow) { // sendRangingMeasurementIfAvailable (:155-198)
+        if (range_seq == -1) return;
+        if (n_ep < p.max_epochs) {
+            const int64_t row = (int64_t)(p.fix_b12 ? 0 : range_seq) * M;
+            for (int a = 0; a < M; ++a) {
+                p.ranges_out[(n_ep * M + a) * N + f] = tr[(row + a) * N];
+                if (p.err_out) p.err_out[(n_ep * M + a) * N + f] = te[(row + a) * N];
+            }
+            p.dt_out[n_ep * N + f] = flushed_once ? tnow - t_prev : p.first_dt;
+        }
+        n_ep += 1;
+        t_prev = tnow;
+        flushed_once = true;
+        armed = false; // timerRanging.stop() (:174)
+    };
+
+    // software pipeline: the fields of message i + 1 are in flight while message i is processed
+    int a_n = 0xff, s_n = 0;
+    int32_t r_n = 0;
+    double e_n = 0.0, t_n = 0.0;
+    auto load = [&](int64_t i) {
+        a_n = p.anchor[i * N + f];
+        s_n = p.seq[i * N + f];
+        r_n = p.range_mm[i * N + f];
+        e_n = p.err ? p.err[i * N + f] : 0.0;
+        t_n = p.t[i * N + f];
+    };
+    if (p.L > 0) load(0);
+    for (int64_t i = 0; i < p.L; ++i) {
+        const int a = a_n, s = s_n;
+        const int32_t r = r_n;
+        const double e = e_n, ti = t_n;
+        if (i + 1 < p.L) load(i + 1);
+        if (a == 0xff || a >= M) continue; // padding of a ragged log
+        // the one-shot timer fires 0.05 s after the last ranging if nothing arrived before (:143-152)
+        if (have_last && armed && ti - t_last > 0.05) flush(t_last + 0.05);
+        if (range_seq == s) { // a ranging of the current sequence number (:229-239)
+            const int64_t row = (int64_t)(p.fix_b12 ? 0 : s) * M;
+            tr[(row + a) * N] = r;
+            if (e > 0.0) te[(row + a) * N] = e; // withErrorEstimation (:94,236)
+        } else { // a new sequence number: the previous report is sent first (:240-267)
+            flush(ti);
+            const int64_t row = (int64_t)(p.fix_b12 ? 0 : s) * M;
+            if (p.fix_b12) {
+                for (int k = 0; k < M; ++k) {
+                    tr[(row + k) * N] = -1;
+                    te[(row + k) * N] = 0.0;
+                }
+            } else { // as written: slot 0 only, 64 times (:251-255)
+                tr[row * N] = -1;
+                te[row * N] = 0.0;
+            }
+            range_seq = s;
+            tr[(row + a) * N] = r;
+            te[(row + a) * N] = e;
+        }
+        t_last = ti; // timerRanging.stop(); timerRanging.start() (:270-273)
+        have_last = true;
+        armed = true;
+    }
+    if (have_last && armed) flush(t_last + 0.05); // the timer after the last ranging of the log
+    // epochs this log did not produce: no ranging, dt < 0 = "no step" for the replay
+    for (int64_t k = n_ep; k < p.max_epochs; ++k) {
+        for (int a = 0; a < M; ++a) {
+            p.ranges_out[(k * M + a) * N + f] = -1;
+            if (p.err_out) p.err_out[(k * M + a) * N + f] = 0.0;
+        }
+        p.dt_out[k * N + f] = -1.0;
+    }
+    if (p.n_epochs) p.n_epochs[f] = (int32_t)(n_ep > 0x7fffffff ? 0x7fffffff : n_ep);
+}
+
+cudaError_t launch_assemble(const AssembleParams &p, cudaStream_t s) {
+    if (p.N <= 0) return cudaSuccess;
+    assemble_kernel<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+} // namespace kfpos

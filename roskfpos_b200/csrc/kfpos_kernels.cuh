@@ -29,7 +29,8 @@ struct T6Params {
     int ignore_worst;
     double ignore_thr;
     double accel_noise;
-    const double *dt; // device [T]
+    const double *dt;   // device [T], common to the batch
+    const double *dt_f; // or null: per-filter SoA [T][N]; a value < 0 = this filter has no epoch t
     double *x;        // SoA [6][N]  (rows 3..5 stay 0)
     double *P;        // SoA [21][N] packed lower triangle
     int32_t *status;  // [N], OR-ed
@@ -142,6 +143,22 @@ cudaError_t launch_t6_get_pose(int64_t N, double dt, double accel_noise, const d
 // (position = rows 0,1 and row `zrow`, or the constant `zconst` when zrow < 0)
 cudaError_t launch_error_stats(int64_t N, const double *x, int zrow, double zconst, const int32_t *status,
                                const double *truth, double *partials, double *out4, cudaStream_t s);
+
+// epoch assembler (kfpos_assemble.cu): N logs of L messages, SoA [L][N]
+struct AssembleParams {
+    int64_t N, L, max_epochs;
+    int M, fix_b12;
+    double first_dt;
+    const uint8_t *anchor, *seq;
+    const int32_t *range_mm;
+    const double *err, *t;
+    int32_t *tbl_r; // [rows][M][N], rows = 256 (as written) or 1 (fix_b12), pre-set to -1
+    double *tbl_e;  // same shape, pre-set to 0
+    int32_t *ranges_out;
+    double *err_out, *dt_out;
+    int32_t *n_epochs;
+};
+cudaError_t launch_assemble(const AssembleParams &p, cudaStream_t s);
 
 // DFMA-only microbenchmark on the current device (the FP64 roofline denominator)
 cudaError_t measure_fp64_peak(double *flops_per_s);

@@ -58,8 +58,24 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
         unsigned status_or = 0;
 
         prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, f, N);
+        double dt_next = p.dt_f ? __ldg(p.dt_f + f) : 0.0;
         for (int t = 0; t < p.T; ++t) {
-            const double dt = __ldg(p.dt + t);
+            // per-filter time steps (assembled logs): a negative dt = this filter has no epoch t.
+            // The lanes that do step are the ones that re-converge below.
+            const double dt = p.dt_f ? dt_next : __ldg(p.dt + t);
+            if (p.dt_f && t + 1 < p.T) dt_next = __ldg(p.dt_f + (int64_t)(t + 1) * N + f);
+            const bool stepping = !(dt < 0.0);
+            const unsigned emask = p.dt_f ? __ballot_sync(wmask, stepping) : wmask;
+            if (!stepping) { // keep the landing zone protocol going, touch nothing else
+                cp_async_wait_all();
+                if (t + 1 < p.T) prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, (int64_t)(t + 1) * m * N + f, N);
+                if (p.traj) {
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) p.traj[((int64_t)t * 3 + k) * N + f] = pos[k];
+                }
+                if (p.sel) p.sel[(int64_t)t * N + f] = -1;
+                continue;
+            }
 
             // ---- predict (TOA.cpp:115-123): x^- = F x with v = 0, P^- = F P F^T + Q.
             // The member covariance is overwritten before the try block, so P^-
@@ -82,8 +98,8 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
             T6Result res;
             int rc, ignored = -1;
             if (!LOO) {
-                rc = t6_update<PME, MT>(p.anchors, ep, ep.valid, pos, Pm, res, st, wmask);
-                __syncwarp(wmask);
+                rc = t6_update<PME, MT>(p.anchors, ep, ep.valid, pos, Pm, res, st, emask);
+                __syncwarp(emask);
             } else {
                 // kalmanStep3DCanIgnoreAnAnchor (TOA.cpp:185-238): the all-anchor solve (i = -1),
                 // then -- only with > 4 rangings -- one solve per left-out anchor, all from the same P^-
