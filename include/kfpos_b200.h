@@ -241,6 +241,18 @@ int kfpos_batch_replay_events(kfpos_batch *b, int n_events, const kfpos_event *e
  * [n][N], P_pred SoA [n*n][N] (either may be NULL).                              */
 int kfpos_batch_get_pose(kfpos_batch *b, double dt, double *x_pred, double *P_pred, void *stream);
 
+/* getPose as the publisher consumes it (PosGenerator::publishPositionReport, Posgenerator.cpp:
+ * 385-470, after stateToPose TOA.cpp:159-183 / KF.cpp:324-363 / TOAIMU.cpp:198-241): the batched
+ * output formatter for downstream consumers.  pose13 SoA [13][N]: position x,y,z (K8: z = the
+ * configured tag height), orientation quaternion x,y,z,w (K8: rotation by theta about z; T6/T9:
+ * all 0 as the reference leaves it), linear speed x,y,z, angular speed x,y,z (T9 reports its
+ * ACCELERATION there, TOAIMU.cpp:213-215).  cov36 SoA [36][N]: the 36 values copied into
+ * geometry_msgs/PoseWithCovariance.covariance, cov36[i] = covarianceMatrix(i) in Armadillo's
+ * column-major linear order (T9's matrix is 9x9: its first four columns).  Either output may be
+ * NULL.  Returns KFPOS_ERR_NOT_READY until a measurement has been processed after
+ * set_state(x, NULL) (getPose returns false, KF.cpp:713-717).                           */
+int kfpos_batch_get_pose_msg(kfpos_batch *b, double dt, double *pose13, double *cov36, void *stream);
+
 /* ----------------------------------------------------------------------- ML
  * newTOAMeasurement + getPose of MLLocation (ML.cpp:421-486) for N independent
  * epochs; variant / use2d / num_ignored_rangings / best_mode / ml_start from the

@@ -183,6 +183,8 @@ void ko_t9_events(int64_t N, int n_events, const ko_event *ev, int M, const doub
 int ko_version(void);
 int ko_max_threads(void);
 
+void ko_pose_msg(int model, const double *x, const double *P, double tag_z, double pose13[13], double cov36[36]);
+
 /* ------------------------------------------------------- ranging aggregation (ko_assemble.c) */
 int64_t ko_assemble(int64_t L, int M, int64_t stride, const uint8_t *anchor, const uint8_t *seq,
                     const int32_t *range_mm, const double *err, const double *t, int64_t max_epochs,

@@ -673,3 +673,50 @@ void ko_t9_get_pose(const ko_t9 *f, double dt, double xo[9], double Ppred[81]) {
     memcpy(Ppred, f->P, sizeof(double) * 81);
     predict_cov(9, F, Q, Ppred);
 }
+
+/* ============================================================ pose message
+ * stateToPose of the three filters (TOA.cpp:159-183, KF.cpp:324-363, TOAIMU.cpp:198-241) applied to
+ * the predicted state / covariance of getPose, read the way the publisher reads a report
+ * (Posgenerator.cpp:385-470): pose13 = x, y, z, rotX, rotY, rotZ, rotW, linearSpeed(3),
+ * angularSpeed(3); cov36[i] = covarianceMatrix(i), i < 36, Armadillo's column-major linear index
+ * (for T9 the matrix is 9 x 9, so the message gets its first four columns).
+ * model: 1 = T6, 2 = K8, 3 = T9.  x / P: predicted state and row-major n x n covariance.  The
+ * speed fields stateToPose of T6 never writes are reported as 0. */
+void ko_pose_msg(int model, const double *x, const double *P, double tag_z, double pose13[13], double cov36[36]) {
+    double C[81];
+    int n = 6;
+    for (int i = 0; i < 13; ++i) pose13[i] = 0.0;
+    for (int i = 0; i < 81; ++i) C[i] = 0.0;
+    if (model == 1) {
+        pose13[0] = x[0]; pose13[1] = x[1]; pose13[2] = x[2];
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) C[i * 6 + j] = P[i * 6 + j];
+    } else if (model == 2) {
+        const double half = x[6] * 0.5;
+        pose13[0] = x[0]; pose13[1] = x[1]; pose13[2] = tag_z;
+        pose13[5] = sin(half); pose13[6] = cos(half);
+        pose13[7] = x[2]; pose13[8] = x[3];
+        pose13[12] = x[7];
+        for (int i = 0; i < 6; ++i) C[i * 6 + i] = 0.01;
+        C[0 * 6 + 0] = P[0 * 8 + 0]; C[0 * 6 + 1] = P[0 * 8 + 1];
+        C[1 * 6 + 0] = P[1 * 8 + 0]; C[1 * 6 + 1] = P[1 * 8 + 1];
+        C[0 * 6 + 5] = P[0 * 8 + 6]; C[1 * 6 + 5] = P[1 * 8 + 6];
+        C[5 * 6 + 0] = P[6 * 8 + 0]; C[5 * 6 + 1] = P[6 * 8 + 1];
+        C[5 * 6 + 5] = P[6 * 8 + 6];
+    } else {
+        n = 9;
+        for (int i = 0; i < 3; ++i) {
+            pose13[i] = x[i];
+            pose13[7 + i] = x[3 + i];
+            pose13[10 + i] = x[6 + i]; /* the acceleration, in the angular-speed fields (:213-215) */
+        }
+        for (int i = 0; i < 9; ++i) C[i * 9 + i] = 0.01;
+        for (int i = 0; i < 3; ++i) {
+            for (int j = 0; j < 3; ++j) C[i * 9 + j] = P[i * 9 + j];
+            C[i * 9 + 7] = P[i * 9 + 8];
+            C[7 * 9 + i] = P[8 * 9 + i];
+        }
+        C[7 * 9 + 7] = P[8 * 9 + 8];
+    }
+    for (int i = 0; i < 36; ++i) cov36[i] = C[(i % n) * n + i / n];
+}

@@ -372,6 +372,11 @@ class T9:
     def P(self):
         return np.array(self.f.P).reshape(9, 9)
 
+    def get_pose(self, dt):
+        x = np.zeros(9); P = np.zeros(81)
+        lib().ko_t9_get_pose(C.byref(self.f), C.c_double(dt), _p(x), _p(P))
+        return x, P.reshape(9, 9)
+
 
 # ------------------------------------------------- ranging aggregation (Posgenerator.cpp:143-281)
 def assemble(anchor, seq, range_mm, t, n_anchors, max_epochs, err=None, fix_b12=False, first_dt=0.1):
@@ -392,3 +397,22 @@ def assemble(anchor, seq, range_mm, t, n_anchors, max_epochs, err=None, fix_b12=
                             _p(range_mm, C.c_int32), _p(e), _p(t), C.c_int64(T), int(fix_b12),
                             C.c_double(first_dt), _p(ro, C.c_int32), _p(eo), _p(dt), _p(ne, C.c_int32))
     return dict(ranges=ro, err=eo, dt=dt, n_epochs=ne)
+
+
+# ------------------------------------------------------------------ pose message
+def pose_msg(model, x_pred, P_pred, tag_z=0.0):
+    """stateToPose + the publisher's read-out (see ko_pose_msg).  x_pred [n] or [n][N], P_pred
+    [n][n] or [n*n][N] (row-major).  Returns (pose [13][N], cov [36][N]) (1-D for a single filter)."""
+    x = np.asarray(x_pred, dtype=np.float64)
+    single = x.ndim == 1
+    n = x.shape[0]
+    X = x.reshape(n, -1)
+    Pm = np.asarray(P_pred, dtype=np.float64).reshape(n * n, -1)
+    N = X.shape[1]
+    pose = np.empty((13, N)); cov = np.empty((36, N))
+    for f in range(N):
+        xf = np.ascontiguousarray(X[:, f]); Pf = np.ascontiguousarray(Pm[:, f])
+        po = np.empty(13); co = np.empty(36)
+        lib().ko_pose_msg(int(model), _p(xf), _p(Pf), C.c_double(tag_z), _p(po), _p(co))
+        pose[:, f] = po; cov[:, f] = co
+    return (pose[:, 0], cov[:, 0]) if single else (pose, cov)

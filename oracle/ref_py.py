@@ -179,6 +179,15 @@ class RefT9:
             _LIB.ref_t9_destroy(self.h)
 
 
+def pose_msg(obj, dt):
+    """(rc, pose13, cov36) of getPose `dt` after the last update, read as the publisher reads it
+    (Posgenerator.cpp:385-470)."""
+    kind = {RefT6: 1, RefK8: 2, RefT9: 3}[type(obj)]
+    pose = np.zeros(13); cov = np.zeros(36)
+    rc = lib().ref_get_pose_msg(obj.h, kind, C.c_longlong(ns(dt)), _p(pose), _p(cov))
+    return rc, pose, cov
+
+
 def t6_replay(x0, ranges_m, anchors, dt, err, accel_noise=0.5):
     """Batch driver (single thread): ranges f64 metres [T][M][N], x0 [3][N]."""
     ranges_m = np.ascontiguousarray(ranges_m, dtype=np.float64)

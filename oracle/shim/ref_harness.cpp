@@ -237,6 +237,29 @@ void ref_t9_get(void *h, double *x9, double *P81) {
     copy_mat(f->mEstimationCovariance, 9, P81);
 }
 
+// ------------------------------------------------- pose message (getPose + publisher)
+// getPose of the given filter `dt` after its last update, then the fields exactly as
+// PosGenerator::publishPositionReport reads them (Posgenerator.cpp:385-470): position,
+// orientation quaternion, linear and angular speed, and covariance[i] = covarianceMatrix(i)
+// for i < 36 (Armadillo's column-major linear index, also for T9's 9x9 matrix).
+// kind: 1 = KalmanFilterTOA, 2 = KalmanFilter, 3 = KalmanFilterTOAIMU.
+int ref_get_pose_msg(void *h, int kind, long long dt_ns, double *pose13, double *cov36) {
+    advance(dt_ns);
+    Vector3 p = {};
+    bool ok = false;
+    int rc = guarded([&] {
+        if (kind == 1) ok = ((KalmanFilterTOA *)h)->getPose(p);
+        else if (kind == 2) ok = ((KalmanFilter *)h)->getPose(p);
+        else ok = ((KalmanFilterTOAIMU *)h)->getPose(p);
+    });
+    kfshim::fake_clock::ticks() -= dt_ns; // the poll must not move the filter's clock
+    const double v[13] = {p.x, p.y, p.z, p.rotX, p.rotY, p.rotZ, p.rotW, p.linearSpeedX, p.linearSpeedY,
+                          p.linearSpeedZ, p.angularSpeedX, p.angularSpeedY, p.angularSpeedZ};
+    memcpy(pose13, v, sizeof v);
+    if (rc == 0 && ok) rc = guarded([&] { for (int i = 0; i < 36; ++i) cov36[i] = p.covarianceMatrix(i); });
+    return rc ? rc : (ok ? 0 : 4);
+}
+
 // ------------------------------------------------------- batch timing driver
 // T6 replay of N filters x T steps over the SoA tensors of the C ABI (ranges f64
 // metres [T][M][N]); used by bench.py as the "reference" CPU baseline.  One

@@ -222,6 +222,15 @@ class Batch:
                 "kfpos_batch_get_pose")
         return x, P
 
+    def get_pose_msg(self, dt, stream=None):
+        """getPose in the publisher's layout: (pose [13][N], cov [36][N])."""
+        pose = np.empty((13, self.N))
+        cov = np.empty((36, self.N))
+        L.check(L.lib().kfpos_batch_get_pose_msg(self._h, float(dt), C.c_void_p(pose.ctypes.data),
+                                                 C.c_void_p(cov.ctypes.data), _stream_ptr(stream)),
+                "kfpos_batch_get_pose_msg")
+        return pose, cov
+
     # --------------------------------------------------------------------- ML
     def ml_solve(self, ranges, err=0.01, out=None, stream=None):
         """ranges [M][N].  Returns dict(pos [3][N], cov [9][N], iters, sel [2][N], status)."""

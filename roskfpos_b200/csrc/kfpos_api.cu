@@ -58,6 +58,7 @@ struct kfpos_batch {
     kfpos_config cfg;
     AnchorTable anchors;
     bool have_anchors = false;
+    bool stepped = false; // a measurement has been processed since the (fresh) state was set
     double *d_x = nullptr;      // SoA [n][N]
     double *d_P = nullptr;      // SoA [np][N]
     int32_t *d_status = nullptr;
@@ -293,6 +294,7 @@ extern "C" int kfpos_batch_set_state(kfpos_batch *b, const double *x, const doub
     if (b->d_has) CK(cudaMemsetAsync(b->d_has, 0, sizeof(int32_t) * N, s));
     if (b->d_latch) CK(cudaMemsetAsync(b->d_latch, 0, sizeof(double) * 16 * N, s));
     if (b->d_latch_u) CK(cudaMemsetAsync(b->d_latch_u, 0, sizeof(double) * 16, s));
+    b->stepped = P != nullptr; // a restored checkpoint is a running filter; P0 = 0 is a fresh one
     if (!xd || (P && !on_device(P))) CK(cudaStreamSynchronize(s));
     return KFPOS_OK;
 }
@@ -472,6 +474,7 @@ int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_range
                   double err_scalar, const double *d_err, double *d_traj, int32_t *d_sel, cudaStream_t s,
                   const double *d_dt_f) {
     const RangeStream rs = make_rs(b, d_ranges, fmt, err_scalar, d_err);
+    b->stepped = true;
     switch (b->model) {
     case KFPOS_MODEL_T6: {
         T6Params p;
@@ -526,6 +529,7 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
                const double *d_err, const double *d_sensors, double *d_traj, cudaStream_t s) {
     static_assert(sizeof(kfpos_event) == sizeof(EventDesc), "kfpos_event and EventDesc must have one layout");
     if (n <= 0) return KFPOS_OK;
+    b->stepped = true;
     CK(b->scratch[7].reserve(sizeof(EventDesc) * (size_t)n));
     CK(cudaMemcpyAsync(b->scratch[7].p, events, sizeof(EventDesc) * (size_t)n, cudaMemcpyHostToDevice, s));
     const RangeStream rs = make_rs(b, d_ranges, fmt, err_scalar, d_err);
@@ -727,6 +731,29 @@ extern "C" int kfpos_batch_get_pose(kfpos_batch *b, double dt, double *x_pred, d
     if (cx) CK(cudaMemcpyAsync(x_pred, dx, sizeof(double) * b->n * N, cudaMemcpyDeviceToHost, s));
     if (cP) CK(cudaMemcpyAsync(P_pred, dP, sizeof(double) * b->n * b->n * N, cudaMemcpyDeviceToHost, s));
     if (cx || cP) CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
+extern "C" int kfpos_batch_get_pose_msg(kfpos_batch *b, double dt, double *pose13, double *cov36, void *stream) {
+    if (!b || b->model == KFPOS_MODEL_ML) return KFPOS_ERR_INVALID;
+    if (!b->stepped) return KFPOS_ERR_NOT_READY; // getPose returns false before the first measurement
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N;
+    CK(b->scratch[2].reserve(sizeof(double) * b->n * N));
+    CK(b->scratch[3].reserve(sizeof(double) * b->n * b->n * N));
+    double *dx = (double *)b->scratch[2].p, *dP = (double *)b->scratch[3].p;
+    int rc = kfpos_batch_get_pose(b, dt, dx, dP, stream);
+    if (rc) return rc;
+    void *d_pose = nullptr, *d_cov = nullptr;
+    bool c_pose = false, c_cov = false;
+    if ((rc = stage_out(b, 4, pose13, sizeof(double) * 13 * N, &d_pose, &c_pose))) return rc;
+    if ((rc = stage_out(b, 5, cov36, sizeof(double) * 36 * N, &d_cov, &c_cov))) return rc;
+    const int model = b->model == KFPOS_MODEL_T6 ? 1 : (b->model == KFPOS_MODEL_K8 ? 2 : 3);
+    CK(launch_pose_msg(model, b->N, b->cfg.fixed_height, dx, dP, (double *)d_pose, (double *)d_cov, s));
+    if (c_pose) CK(cudaMemcpyAsync(pose13, d_pose, sizeof(double) * 13 * N, cudaMemcpyDeviceToHost, s));
+    if (c_cov) CK(cudaMemcpyAsync(cov36, d_cov, sizeof(double) * 36 * N, cudaMemcpyDeviceToHost, s));
+    if (c_pose || c_cov) CK(cudaStreamSynchronize(s));
     return KFPOS_OK;
 }
 

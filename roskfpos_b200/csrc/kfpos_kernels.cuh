@@ -144,6 +144,10 @@ cudaError_t launch_t6_get_pose(int64_t N, double dt, double accel_noise, const d
 cudaError_t launch_error_stats(int64_t N, const double *x, int zrow, double zconst, const int32_t *status,
                                const double *truth, double *partials, double *out4, cudaStream_t s);
 
+// getPose report in the publisher's layout (kfpos_misc.cu); model 1 = T6, 2 = K8, 3 = T9
+cudaError_t launch_pose_msg(int model, int64_t N, double tag_z, const double *x_pred, const double *P_pred_full,
+                            double *pose13, double *cov36, cudaStream_t s);
+
 // epoch assembler (kfpos_assemble.cu): N logs of L messages, SoA [L][N]
 struct AssembleParams {
     int64_t N, L, max_epochs;

@@ -167,4 +167,67 @@ cudaError_t measure_fp64_peak(double *flops_per_s) {
     return e;
 }
 
+// stateToPose of the three filters (TOA.cpp:159-183, KF.cpp:324-363, TOAIMU.cpp:198-241) on the
+// predicted state / covariance of getPose, laid out the way the publisher reads a report
+// (Posgenerator.cpp:385-470): pose SoA [13][N] = x, y, z, rotX, rotY, rotZ, rotW, linearSpeed(3),
+// angularSpeed(3); cov SoA [36][N], cov[i] = covarianceMatrix(i), Armadillo's column-major index.
+// x: SoA [n][N] predicted state; Pf: SoA [n*n][N] predicted covariance, row-major.
+__global__ void pose_msg_kernel(int model, int64_t N, double tag_z, const double *x, const double *Pf, double *pose,
+                                double *cov) {
+    const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= N) return;
+    const int n = model == 1 ? 6 : (model == 2 ? 8 : 9);
+    auto X = [&](int i) { return x[(int64_t)i * N + f]; };
+    auto P = [&](int i, int j) { return Pf[(int64_t)(i * n + j) * N + f]; };
+    double v[13];
+#pragma unroll
+    for (int i = 0; i < 13; ++i) v[i] = 0.0;
+    if (model == 1) {
+        v[0] = X(0); v[1] = X(1); v[2] = X(2);
+    } else if (model == 2) {
+        double sn, cs;
+        sincos(X(6) * 0.5, &sn, &cs);
+        v[0] = X(0); v[1] = X(1); v[2] = tag_z;
+        v[5] = sn; v[6] = cs;
+        v[7] = X(2); v[8] = X(3);
+        v[12] = X(7);
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            v[i] = X(i);
+            v[7 + i] = X(3 + i);
+            v[10 + i] = X(6 + i); // the acceleration, in the angular-speed fields (TOAIMU.cpp:213-215)
+        }
+    }
+    if (pose) {
+#pragma unroll
+        for (int i = 0; i < 13; ++i) pose[(int64_t)i * N + f] = v[i];
+    }
+    if (!cov) return;
+    const int nc = model == 3 ? 9 : 6; // dimension of the report's covarianceMatrix
+    for (int i = 0; i < 36; ++i) {
+        const int r = i % nc, c = i / nc; // column-major linear index
+        double val = (r == c && model != 1) ? 0.01 : 0.0;
+        if (model == 1) {
+            if (r < 3 && c < 3) val = P(r, c);
+        } else if (model == 2) {
+            const int pr = r == 5 ? 6 : r, pc = c == 5 ? 6 : c; // theta sits in slot 5 of the report
+            const bool rs = r < 2 || r == 5, cs2 = c < 2 || c == 5;
+            if (rs && cs2) val = P(pr, pc);
+        } else {
+            const int pr = r == 7 ? 8 : r, pc = c == 7 ? 8 : c;
+            const bool rs = r < 3 || r == 7, cs2 = c < 3 || c == 7;
+            if (rs && cs2) val = P(pr, pc);
+        }
+        cov[(int64_t)i * N + f] = val;
+    }
+}
+
+cudaError_t launch_pose_msg(int model, int64_t N, double tag_z, const double *x_pred, const double *P_pred_full,
+                            double *pose13, double *cov36, cudaStream_t s) {
+    if (N <= 0) return cudaSuccess;
+    pose_msg_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(model, N, tag_z, x_pred, P_pred_full, pose13, cov36);
+    return cudaGetLastError();
+}
+
 } // namespace kfpos

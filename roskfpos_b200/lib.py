@@ -71,6 +71,7 @@ SIGNATURES = {
     "kfpos_batch_step_compass": (_I, [_VP, _D, _VP, _VP]),
     "kfpos_batch_replay_events": (_I, [_VP, _I, _VP, _VP, _I, _D, _VP, _VP, _I64, _VP, _VP]),
     "kfpos_batch_get_pose": (_I, [_VP, _D, _VP, _VP, _VP]),
+    "kfpos_batch_get_pose_msg": (_I, [_VP, _D, _VP, _VP, _VP]),
     "kfpos_batch_ml_solve": (_I, [_VP, _VP, _I, _D, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_batch_get_counters": (_I, [_VP, C.POINTER(C.c_double * 8), _I, _VP]),
     "kfpos_batch_error_stats": (_I, [_VP, _VP, C.POINTER(C.c_double * 4), _VP]),

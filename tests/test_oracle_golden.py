@@ -101,3 +101,37 @@ def test_ml_golden(oracle):
         if m < (3 if g["use2d"][i] else 4):
             assert out["rc"] == 1 and np.array_equal(out["pos"], g["start"][i])
     assert n_chaotic <= 4
+
+
+@pytest.mark.parametrize("name", ["t6", "k8", "t9"])
+def test_pose_message_golden(oracle, name):
+    """getPose + the publisher's read-out of the report (Posgenerator.cpp:385-470) produced by the
+    reference's own classes (tests/golden/make_golden_pose.py): the oracle filter replays the same
+    inputs, is polled at the same lags, and its packed message must match field by field."""
+    g = np.load(os.path.join(GOLD, "pose_msg.npz"))
+    anc, m = g["anchors"], g["anchors"].shape[0]
+    if name == "t6":
+        o, model = oracle.T6(0.5, False, 0.5, g["x0"]), 1
+    elif name == "k8":
+        o, model = oracle.K8(0.5, float(g["k8_init_angle"]), 0.5, g["x0"], **CFG_K8), 2
+    else:
+        o, model = oracle.T9(0.5, 0.5, g["x0"]), 3
+    k = 0
+    for t in range(len(g["ranges"])):
+        if name == "k8" and t % 3 == 0:
+            # the reference uses 0.1 s for its very first update whatever the clock says (KF.cpp:238)
+            o.new_compass(float(g["compass_dt"]) if t else 0.1, float(g["compass"][t]))
+        if name == "k8":  # the shim build zero-initialises tentativePos.z (DESIGN.md §2, caveat ii)
+            o.new_toa(float(g["dt"]), g["ranges"][t], anc, 0.01, b1_zero_z=True)
+        else:
+            o.new_toa(float(g["dt"]), g["ranges"][t], anc, 0.01)
+        if t % 4 == 3:
+            for lag in g["lags"]:
+                xp, Pp = o.get_pose(float(lag))
+                if name == "t6":
+                    xp = np.concatenate([xp, np.zeros(3)])
+                pose, cov = oracle.pose_msg(model, xp, Pp, tag_z=CFG_K8["tag_z"])
+                assert np.abs(pose - g[name + "_pose"][k]).max() < TOL, (name, t, lag)
+                assert relP(cov, g[name + "_cov"][k]) < TOL, (name, t, lag)
+                k += 1
+    assert k == len(g[name + "_pose"])
