@@ -92,6 +92,9 @@ typedef struct {
 void ko_t6_init(ko_t6 *f, double accel_noise, int ignore_worst, double thr, const double p0[3]);
 void ko_t6_new_toa(ko_t6 *f, double dt, int n_slots, const double *ranges,
                    const double *anchors, const double *errs, ko_info *info);
+void ko_t6_new_toa_sel(ko_t6 *f, double dt, int n_slots, const double *ranges, const double *anchors,
+                       const double *errs, int variant, int n_ignore, int best_mode, ko_info *info,
+                       uint32_t *mask_out);
 void ko_t6_get_pose(const ko_t6 *f, double dt, double pos[3], double Ppred[36]);
 
 /* ------------------------------------------------------------------- K8 */

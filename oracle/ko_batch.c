@@ -35,10 +35,26 @@ static inline double load_range(const void *ranges, int fmt, int64_t idx) {
     }
 }
 
+void ko_t6_replay_sel(int64_t N, int T, int M, const double *anchors, const double *dt,
+                      const void *ranges, int fmt, double err_scalar, const double *err_arr,
+                      double accel_noise, int ignore_worst, double thr, int variant, int n_ignore, int best_mode,
+                      double *x, double *P, double *traj, int32_t *sel, double *counters, int32_t *status,
+                      int threads);
+
 void ko_t6_replay(int64_t N, int T, int M, const double *anchors, const double *dt,
                   const void *ranges, int fmt, double err_scalar, const double *err_arr,
                   double accel_noise, int ignore_worst, double thr, double *x, double *P,
                   double *traj, int32_t *sel, double *counters, int32_t *status, int threads) {
+    ko_t6_replay_sel(N, T, M, anchors, dt, ranges, fmt, err_scalar, err_arr, accel_noise, ignore_worst, thr, 0, 0, 0,
+                     x, P, traj, sel, counters, status, threads);
+}
+
+/* variant != 0: the EKF-side NLOS variants (ko_t6_new_toa_sel); sel then holds the slot mask used */
+void ko_t6_replay_sel(int64_t N, int T, int M, const double *anchors, const double *dt,
+                      const void *ranges, int fmt, double err_scalar, const double *err_arr,
+                      double accel_noise, int ignore_worst, double thr, int variant, int n_ignore, int best_mode,
+                      double *x, double *P, double *traj, int32_t *sel, double *counters, int32_t *status,
+                      int threads) {
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0;
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
@@ -58,13 +74,15 @@ void ko_t6_replay(int64_t N, int T, int M, const double *anchors, const double *
                 e[a] = err_arr ? err_arr[idx] : err_scalar;
             }
             ko_info info;
-            ko_t6_new_toa(&flt, dt[t], M, r, anchors, e, &info);
+            uint32_t used = 0;
+            if (variant) ko_t6_new_toa_sel(&flt, dt[t], M, r, anchors, e, variant, n_ignore, best_mode, &info, &used);
+            else ko_t6_new_toa(&flt, dt[t], M, r, anchors, e, &info);
             c0 += info.ml_iters; c1 += info.cost_evals; c2 += info.gain_evals;
             if (info.status & ~(KO_ST_MAXITER)) c3 += 1;
             st_or |= info.status;
             if (traj)
                 for (int k = 0; k < 3; ++k) traj[((int64_t)t * 3 + k) * N + f] = flt.pos[k];
-            if (sel) sel[(int64_t)t * N + f] = info.ignored;
+            if (sel) sel[(int64_t)t * N + f] = variant ? (int32_t)used : info.ignored;
         }
         for (int k = 0; k < 3; ++k) x[(int64_t)k * N + f] = flt.pos[k];
         for (int k = 0; k < 36; ++k) P[(int64_t)k * N + f] = flt.P[k];

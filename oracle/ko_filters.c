@@ -302,6 +302,54 @@ void ko_t6_new_toa(ko_t6 *f, double dt, int n_slots, const double *ranges, const
     t6_estimate(f, dt, m, n, info);
 }
 
+/* EKF-side NLOS variants (README.md:85-108, config_pos.xml:5-28).  The reference documents
+ * variant / numIgnoredRangings / bestMode for "type = 1: EKF" but implements the selection only in
+ * MLLocation, so there is no reference behaviour to pin: this is the restatement of north_star (3).
+ * The ML estimator is started at the predicted position (= the stored position: the predicted
+ * velocity is 0) and selects the rangings; the normal update then runs on the survivors, kept in
+ * slot order.  variant 1: solve with all rangings, sort by squared residual at that solution,
+ * drop the last min(n - 4, n_ignore) (ML.cpp:307-347; no selection when that solve fails);
+ * variant 2: the 4-ranging group of ko_ml_best_group (ML.cpp:351-414) when n >= 4.
+ * The Newton iterations of the selection solves are added to info->ml_iters.  *mask_out = slots used. */
+void ko_t6_new_toa_sel(ko_t6 *f, double dt, int n_slots, const double *ranges, const double *anchors,
+                       const double *errs, int variant, int n_ignore, int best_mode, ko_info *info,
+                       uint32_t *mask_out) {
+    ko_meas m[KO_MAX_ANCHORS], sub[KO_MAX_ANCHORS];
+    int n = gather(n_slots, ranges, anchors, errs, m);
+    unsigned char keep[KO_MAX_ANCHORS];
+    for (int i = 0; i < n; ++i) keep[i] = 1;
+    int it_sel = 0, it = 0;
+    const double start[3] = {f->pos[0], f->pos[1], f->pos[2]};
+    if (variant == 1 && n > 0) {
+        double p0[3], c0[9];
+        if (ko_ml3d(m, n, start, p0, c0, &it) == 0) {
+            int order[KO_MAX_ANCHORS];
+            ko_best_rangings(m, n, p0, order);
+            int drop = n - 4 < n_ignore ? n - 4 : n_ignore;
+            if (drop < 0) drop = 0;
+            for (int i = n - drop; i < n; ++i) keep[order[i]] = 0;
+        }
+        it_sel += it;
+    } else if (variant == 2 && n >= 4) {
+        double p0[3], c0[9];
+        int bi, ng;
+        uint32_t bm = 0;
+        ko_ml_best_group(m, n, start, 0, best_mode, 0, p0, c0, &it, &bi, &bm, &ng);
+        it_sel += it;
+        for (int i = 0; i < n; ++i) keep[i] = (bm >> i) & 1u;
+    }
+    int ns = 0;
+    uint32_t mask = 0;
+    for (int i = 0; i < n; ++i)
+        if (keep[i]) {
+            sub[ns++] = m[i];
+            mask |= 1u << m[i].slot;
+        }
+    t6_estimate(f, dt, sub, ns, info);
+    info->ml_iters += it_sel;
+    if (mask_out) *mask_out = mask;
+}
+
 /* getPose, TOA.cpp:438-473: predict only, state untouched */
 void ko_t6_get_pose(const ko_t6 *f, double dt, double pos[3], double Ppred[36]) {
     double F[36], Q[36], x[6], xp[6];

@@ -147,8 +147,8 @@ def ml_batch(ranges, anchors, err, start, use2d=False, variant=0, n_ignore=0, be
 
 
 # ------------------------------------------------------------------- replays
-def t6_replay(x0, P0, ranges, anchors, dt, err, accel_noise=0.5, ignore_worst=False, thr=0.0,
-              want_traj=False, threads=0):
+def t6_replay(x0, P0, ranges, anchors, dt, err, accel_noise=0.5, ignore_worst=False, thr=0.0, variant=0, n_ignore=0,
+              best_mode=0, want_traj=False, threads=0):
     """x0 [3][N], P0 [36][N] or None (zeros); ranges [T][M][N]; dt scalar or [T]."""
     ranges = np.ascontiguousarray(ranges)
     T, M, N = ranges.shape
@@ -161,10 +161,10 @@ def t6_replay(x0, P0, ranges, anchors, dt, err, accel_noise=0.5, ignore_worst=Fa
     sel = np.zeros((T, N), dtype=np.int32)
     counters = np.zeros(4)
     status = np.zeros(N, dtype=np.int32)
-    lib().ko_t6_replay(C.c_int64(N), T, M, _p(anchors), _p(dt), _vp(ranges), FMT[ranges.dtype],
+    lib().ko_t6_replay_sel(C.c_int64(N), T, M, _p(anchors), _p(dt), _vp(ranges), FMT[ranges.dtype],
                        C.c_double(err if err_arr is None else 0.0), _p(err_arr),
-                       C.c_double(accel_noise), int(ignore_worst), C.c_double(thr), _p(x), _p(P),
-                       _p(traj), _p(sel, C.c_int32), _p(counters), _p(status, C.c_int32), int(threads))
+                           C.c_double(accel_noise), int(ignore_worst), C.c_double(thr), int(variant), int(n_ignore),
+                           int(best_mode), _p(x), _p(P), _p(traj), _p(sel, C.c_int32), _p(counters), _p(status, C.c_int32), int(threads))
     return dict(x=x, P=P, traj=traj, sel=sel, counters=counters, status=status)
 
 

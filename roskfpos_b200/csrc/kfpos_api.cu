@@ -483,6 +483,9 @@ int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_range
         p.N = b->N;
         p.T = T;
         p.ignore_worst = b->cfg.ignore_worst_anchor;
+        p.variant = b->cfg.variant;
+        p.n_ignore = b->cfg.num_ignored_rangings;
+        p.best_mode = b->cfg.best_mode;
         p.ignore_thr = b->cfg.ignore_cost_threshold;
         p.accel_noise = b->cfg.accel_noise;
         p.dt = d_dt;

@@ -27,6 +27,7 @@ struct T6Params {
     int64_t N;
     int T;
     int ignore_worst;
+    int variant, n_ignore, best_mode; // EKF-side NLOS variants (config_pos.xml; 0 = normal)
     double ignore_thr;
     double accel_noise;
     const double *dt;   // device [T], common to the batch

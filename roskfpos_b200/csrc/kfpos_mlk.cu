@@ -108,21 +108,7 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
             if (!last && rc != ML_SINGULAR) {
                 // estimatePositionIgnoreN (ML.cpp:307-347): drop the tail of the ascending
                 // residual order; ties keep the lower index (App. B-11); re-solve from the start
-                for (int dcount = 0; dcount < drop; ++dcount) {
-                    double worst = -1.0;
-                    int wi = -1;
-                    for (int i = 0; i < m; ++i) {
-                        if (!((used >> i) & 1u)) continue;
-                        const double ex = p.anchors.x[i] - pos[0], ey = p.anchors.y[i] - pos[1],
-                                     ez = p.anchors.z[i] - pos[2];
-                        const double d = sqrt(ex * ex + ey * ey + ez * ez);
-                        const double zi = ep.z_at(i);
-                        const double q = (d - zi) * (d - zi);
-                        if (q >= worst) { worst = q; wi = i; }
-                    }
-                    if (wi < 0) break; // all residuals NaN
-                    used &= ~(1u << wi);
-                }
+                used = drop_worst<PME, MT>(p.anchors, ep, used, pos, drop);
                 phase = 1;
                 pos[0] = p.start[0]; pos[1] = p.start[1]; pos[2] = p.start[2];
                 rs.iter = 0u;
@@ -133,46 +119,9 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
         if (p.variant == 1 && phase == 1) index = drop;
 
         if (!parked && p.variant == 2 && rc != ML_SINGULAR && n >= k) {
-            // estimatePositionBestGroup (ML.cpp:351-414): all C(n,k) subsets in
-            // prev_permutation (= lexicographic) order; `<=` keeps the last minimum.
-            // App. B-3: subset = measurements with mask true; B-4: 2-D criterion
-            // = cov(0,0)+cov(1,1); best_mode 1 = cov(2,2) (3-D only).
-            unsigned char slot[32];
-            int c = 0;
-            for (int i = 0; i < m; ++i)
-                if ((ep.valid >> i) & 1u) slot[c++] = (unsigned char)i;
-            double minErr = 0.0;
-            int minIdx = -1, gi = 0;
-            int a[4] = {0, 1, 2, 3};
-            while (true) {
-                unsigned gm = 0u;
-                for (int j = 0; j < k; ++j) gm |= 1u << slot[a[j]];
-                double gp[3] = {p.start[0], p.start[1], p.start[2]}, gc[6] = {0, 0, 0, 0, 0, 0}, gs;
-                MlResume grs = {0.0, 0u};
-                const int grc = ml_any<PME, MT>(p.anchors, ep, gm, use2d, gp, gc, gs, iters, 10000u, &grs);
-                double cur;
-                if (use2d) cur = gc[0] + gc[2];
-                else if (p.best_mode == 1) cur = gc[5];
-                else cur = gc[0] + gc[2] + gc[5];
-                if (grc != ML_OK) cur = nan("");
-                if (minIdx == -1 || cur <= minErr) {
-                    minIdx = gi;
-                    minErr = cur;
-                    pos[0] = gp[0]; pos[1] = gp[1]; pos[2] = gp[2];
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) cov[q] = gc[q];
-                    used = gm;
-                    rc = grc;
-                }
-                ++gi;
-                // next combination in lexicographic order
-                int j = k - 1;
-                while (j >= 0 && a[j] == n - k + j) --j;
-                if (j < 0) break;
-                ++a[j];
-                for (int q = j + 1; q < k; ++q) a[q] = a[q - 1] + 1;
-            }
-            index = minIdx;
+            // estimatePositionBestGroup (ML.cpp:351-414)
+            const double start[3] = {p.start[0], p.start[1], p.start[2]};
+            index = best_group<PME, MT>(p.anchors, ep, ep.valid, use2d, p.best_mode, start, iters, pos, cov, used, rc);
         }
 
         if (!parked) {

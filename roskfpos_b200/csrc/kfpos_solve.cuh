@@ -312,6 +312,84 @@ KF_DEV int ml_solve2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
     return ML_OK;
 }
 
+// estimatePositionIgnoreN's selection (ML.cpp:307-347): removes from `used` the `drop` rangings with
+// the largest squared residual at `pos` -- the tail of the ascending std::sort order; ties keep the
+// lower index.
+template <bool PME, int MT>
+KF_DEV unsigned drop_worst(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned used, const double (&pos)[3],
+                           int drop) {
+    for (int dcount = 0; dcount < drop; ++dcount) {
+        double worst = -1.0;
+        int wi = -1;
+        for (int i = 0; i < ep.m_slots; ++i) {
+            if (!((used >> i) & 1u)) continue;
+            const double ex = A.x[i] - pos[0], ey = A.y[i] - pos[1], ez = A.z[i] - pos[2];
+            const double d = sqrt(ex * ex + ey * ey + ez * ez);
+            const double zi = ep.z_at(i);
+            const double q = (d - zi) * (d - zi);
+            if (q >= worst) { worst = q; wi = i; }
+        }
+        if (wi < 0) break; // all residuals NaN
+        used &= ~(1u << wi);
+    }
+    return used;
+}
+
+// estimatePositionBestGroup's scan (ML.cpp:351-414): all C(n,k) subsets of the valid rangings in
+// prev_permutation (= lexicographic) order, each solved from `start`; the subset with the smallest
+// criterion wins, `<=` keeps the LAST minimum.  App. B-3: subset = measurements with mask true;
+// B-4: 2-D criterion = cov(0,0)+cov(1,1); best_mode 1 = cov(2,2) (3-D only).  Returns the subset
+// index (>= 0) and its mask / position / covariance / solver code; -1 when n < k.
+template <bool PME, int MT>
+KF_DEV int best_group(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned valid, bool use2d, int best_mode,
+                      const double (&start)[3], unsigned &iters, double (&pos)[3], double (&cov)[6],
+                      unsigned &used, int &rc) {
+    const int k = use2d ? 3 : 4, n = __popc(valid);
+    if (n < k) return -1;
+    unsigned char slot[32];
+    int c = 0;
+    for (int i = 0; i < ep.m_slots; ++i)
+        if ((valid >> i) & 1u) slot[c++] = (unsigned char)i;
+    double minErr = 0.0;
+    int minIdx = -1, gi = 0;
+    int a[4] = {0, 1, 2, 3};
+    while (true) {
+        unsigned gm = 0u;
+        for (int j = 0; j < k; ++j) gm |= 1u << slot[a[j]];
+        double gp[3] = {start[0], start[1], start[2]}, gc[6] = {0, 0, 0, 0, 0, 0}, gs;
+        int grc;
+        if (use2d) {
+            double c2[3] = {0, 0, 0};
+            grc = ml_solve2<PME, MT>(A, ep, gm, gp, gs, iters, c2);
+            gc[0] = c2[0]; gc[1] = c2[1]; gc[2] = c2[2];
+        } else {
+            grc = ml_solve3<PME, MT>(A, ep, gm, gp, gs, iters, gc);
+        }
+        double cur;
+        if (use2d) cur = gc[0] + gc[2];
+        else if (best_mode == 1) cur = gc[5];
+        else cur = gc[0] + gc[2] + gc[5];
+        if (grc != ML_OK) cur = nan("");
+        if (minIdx == -1 || cur <= minErr) {
+            minIdx = gi;
+            minErr = cur;
+            pos[0] = gp[0]; pos[1] = gp[1]; pos[2] = gp[2];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cov[q] = gc[q];
+            used = gm;
+            rc = grc;
+        }
+        ++gi;
+        // next combination in lexicographic order
+        int j = k - 1;
+        while (j >= 0 && a[j] == n - k + j) --j;
+        if (j < 0) break;
+        ++a[j];
+        for (int q = j + 1; q < k; ++q) a[q] = a[q - 1] + 1;
+    }
+    return minIdx;
+}
+
 // ---- information-form ranging pass of one IEKF iteration at the iterate p = x^- + dx:
 //   c = sum eps_i^2 / R_i,  b = sum h_i y_i / R_i,  G = sum h_i h_i^T / R_i   (packed xx,xy,yy,xz,yz,zz)
 // with h_i = (p - a_i)/d_i, eps_i = r_i - d_i, y_i = eps_i + h_i . dx  (= eps - J delta, delta = -dx)

@@ -21,7 +21,13 @@ __host__ __device__ inline int t6_smem_rows(int m, int fmt, bool pme, bool in_re
 }
 
 // MT > 0: compile-time anchor count (unrolled anchor loops, ranges in registers); MT == 0: run-time.
-template <bool PME, bool LOO, int MT>
+// SEL: EKF-side NLOS variants (README.md:85-108, config_pos.xml:5-28; the reference documents them
+// but only implements them in MLLocation): before the update the ML estimator, started at the
+// predicted position, selects the rangings -- variant 1 drops the numIgnoredRangings with the
+// largest residual at its solution (ML.cpp:307-347), variant 2 keeps the 4-anchor group with the
+// smallest covariance criterion (ML.cpp:351-414, bestMode) -- and the iterated update runs on the
+// survivors.  The mask of the slots used goes to `sel`.
+template <bool PME, bool LOO, int MT, bool SEL = false>
 __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __grid_constant__ T6Params p) {
     extern __shared__ double smem[];
     const int64_t f = (int64_t)blockIdx.x * T6_BLOCK + threadIdx.x;
@@ -97,7 +103,23 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
             if (ep.valid == 0u) st.status |= 1u;
             T6Result res;
             int rc, ignored = -1;
-            if (!LOO) {
+            if (SEL) {
+                unsigned used = ep.valid;
+                const int n = __popc(ep.valid);
+                double p0[3] = {pos[0], pos[1], pos[2]}, sse0, cov0[6];
+                if (p.variant == 1 && n > 0) {
+                    if (ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, nullptr) == ML_OK) {
+                        int drop = min(n - 4, p.n_ignore);
+                        used = drop_worst<PME, MT>(p.anchors, ep, used, p0, drop < 0 ? 0 : drop);
+                    }
+                } else if (p.variant == 2 && n >= 4) {
+                    int grc;
+                    ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, cov0); // the all-ranging solve of :353
+                    best_group<PME, MT>(p.anchors, ep, ep.valid, false, p.best_mode, pos, st.ml_iters, p0, cov0, used, grc);
+                }
+                rc = t6_update<PME, MT>(p.anchors, ep, used, pos, Pm, res, st, 0u);
+                ignored = (int)used;
+            } else if (!LOO) {
                 rc = t6_update<PME, MT>(p.anchors, ep, ep.valid, pos, Pm, res, st, emask);
                 __syncwarp(emask);
             } else {
@@ -167,14 +189,14 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
     warp_accumulate(p.counters + CNT_IGNORED, n_ignored);
 }
 
-template <bool PME, bool LOO, int MT>
+template <bool PME, bool LOO, int MT, bool SEL = false>
 static cudaError_t launch_k(const T6Params &p, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + T6_BLOCK - 1) / T6_BLOCK);
     const size_t smem = (size_t)t6_smem_rows(p.rs.m_slots, p.rs.fmt, PME, MT > 0) * T6_BLOCK * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(t6_replay_kernel<PME, LOO, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(t6_replay_kernel<PME, LOO, MT, SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
-    t6_replay_kernel<PME, LOO, MT><<<grid, T6_BLOCK, smem, s>>>(p);
+    t6_replay_kernel<PME, LOO, MT, SEL><<<grid, T6_BLOCK, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -182,6 +204,10 @@ cudaError_t launch_t6_replay(const T6Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.T <= 0) return cudaSuccess;
     const bool pme = p.rs.err != nullptr;
     const int m = p.rs.m_slots;
+    if (p.variant == 1 || p.variant == 2) {
+        if (p.ignore_worst) return cudaErrorInvalidValue; // the two heuristics are alternatives
+        return pme ? launch_k<true, false, 0, true>(p, s) : launch_k<false, false, 0, true>(p, s);
+    }
     if (p.ignore_worst) {
         if (pme) return launch_k<true, true, 0>(p, s);
         if (m == 8) return launch_k<false, true, 8>(p, s);

@@ -184,3 +184,30 @@ def test_t6_error_stats_and_determinism(kflib):
     e2 = ((outs[0][0][:3] - truth[-1]) ** 2).sum(axis=0)
     s = outs[0][1]
     assert s[2] == N and abs(s[0] - e2.sum()) <= 1e-12 * e2.sum()
+
+
+@pytest.mark.parametrize("variant,m,n_ignore,best_mode", [(1, 16, 2, 0), (1, 8, 3, 0), (2, 8, 0, 0), (2, 6, 0, 1)])
+def test_t6_ekf_side_nlos_variants(kflib, oracle, variant, m, n_ignore, best_mode):
+    """EKF-side variants 1 (drop the N worst rangings) and 2 (best 4-anchor group): the slot mask
+    each update used is bit-exact, state and covariance within 1e-9 on every filter whose oracle
+    result is itself stable (variant 2 solves exactly determined 4-anchor groups, see tests/util.py)."""
+    # a filter is one unit: few steps for variant 2, whose instability compounds along a trajectory
+    N, T = (3000, 2) if variant == 2 else (3000, 20)
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=300 + m)
+    r = synth.ranges_mm(truth[1:], anc, seed=310 + m, p_nlos=0.15)
+    kw = dict(variant=variant, n_ignore=n_ignore, best_mode=best_mode)
+    ref = run_oracle(oracle, truth[0], r, anc, 0.1, 0.01, **kw)
+    per = [run_oracle(oracle, truth[0], p, anc, 0.1, 0.01, **kw) for p in ulp_perturbations(to_metres(r))]
+    got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, want_sel=True, accel_noise=0.5, variant=variant,
+                  num_ignored_rangings=n_ignore, best_mode=best_mode)
+    keys = dict(float_keys=("x",), cov_keys=("P",), int_keys=("status", "sel"))
+    rep = assert_parity(got, ref, per, min_stable=0.93 if variant == 1 else 0.6,
+                        # per selection the same tie allowance as test_ml_best_group_selection (2 steps here)
+                        max_tie_frac=5e-3 if variant == 1 else 4e-2,
+                        what=f"T6 variant {variant} m={m}", **keys)
+    print("parity report variant", variant, m, rep)
+    used = np.array([bin(int(v) & 0xFFFFFFFF).count("1") for v in got["sel"].ravel()])
+    assert np.all(used == (m - min(m - 4, n_ignore) if variant == 1 else 4))
+    c = got["counters"]
+    assert c["updates"] == N * T
