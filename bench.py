@@ -308,11 +308,42 @@ def run_b200(args):
         te = torch.tensor([max(ems, wall if world == 1 else ems)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        h2d = int(h_ranges.numel() * h_ranges.element_size() + 8 * 6 * N + 8 * 3 * N)
         e2e = {"value": world * N * T * Ke / (float(te.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": int(h_ranges.numel() * h_ranges.element_size() + 8 * 6 * N + 8 * 3 * N),
-               "d2h_bytes_per_step": int(8 * 6 * N + 32), "steps": Ke,
-               "ms_per_step": float(te.item()) / Ke}
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * 6 * N + 32), "steps": Ke,
+               "ms_per_step": float(te.item()) / Ke,
+               "h2d_gbs": h2d * Ke / (float(te.item()) * 1e-3) / 1e9,
+               "note": "host range log in the reference's int32-mm table format; the step is bound by the "
+                       "host-to-device copy (h2d_gbs), which the replay kernel overlaps chunk by chunk"}
         del h_ranges, hr
+        # the same step with the host log in the library's uint16-mm wire format (ranges < 65.5 m)
+        try:
+            h16 = torch.empty(ranges.shape, dtype=torch.uint16, pin_memory=True)
+            h16.copy_(ranges.to(torch.uint16))
+            hr16 = h16.numpy()
+
+            def step_e2e16():
+                batch.set_state(hx, None, stream=stream)
+                batch.replay_toa(0.1, hr16, err=0.01, stream=stream)
+                s_ = batch.error_stats(ht, stream=stream)
+                L.check(L.lib().kfpos_batch_get_state(batch._h, C.c_void_p(hp.ctypes.data), None, None,
+                                                      C.c_void_p(stream.cuda_stream)), "get_state")
+                return s_
+            step_e2e16()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(Ke):
+                s3 = step_e2e16()
+            barrier()
+            wall16 = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(wall16, op=dist.ReduceOp.MAX)
+            e2e["uint16_wire_format"] = {"value": world * N * T * Ke / (float(wall16.item()) * 1e-3),
+                                         "h2d_bytes_per_step": int(h16.numel() * 2 + 8 * 9 * N),
+                                         "rmse_equal": bool(abs(s3[0] - s2[0]) <= 1e-12 * abs(s2[0]))}
+            del h16, hr16
+        except Exception as exc:  # an extra, never fatal
+            e2e["uint16_wire_format"] = {"error": repr(exc)}
 
     # ---- roofline of the dominant kernel (t6_replay_kernel): FP64 CUDA-core bound
     upd = max(cnt["updates"], 1.0)
@@ -327,6 +358,9 @@ def run_b200(args):
             "peak_source": "measured live: kfpos_measure_fp64_peak (DFMA-only kernel, best of 5)",
             "kernel": "t6_replay_kernel<8,false,false>", "kernel_ms": kernel_ms,
             "flop_per_update": w_alg, "mean_iters": {"ml": i_ml, "cost": i_c, "gain": i_g},
+            "numerator": "SURVEY.md §8(d) W_alg v1 (sequential-scalar IEKF count) with the measured iteration "
+                         "counters; the kernel's information-form IEKF executes fewer flops than that count "
+                         "(profiles/README.md: executed FP64 instructions per update from ncu)",
             "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                     "peak_source": peak_src, "bytes_per_update": alg_bytes / (N * T)}}
 
@@ -427,7 +461,37 @@ def bench_other_configs(local, dev, args):
         t = timed(run)
     out["config4c_t6_leave_one_out_16anchors"] = {"updates_per_s": Nl * Tl / t, "ms": t * 1e3,
                                                   "filters": Nl, "epochs": Tl, "solves_per_update": 17}
+    # ---- config 4 (EKF side): variant 1, the 2 worst of 16 rangings dropped before the update
+    with Batch(L.MODEL_T6, Nl, device=local, anchors=anc16, accel_noise=0.5, variant=1, num_ignored_rangings=2) as b:
+        def run():
+            b.set_state(x0f, None, stream=stream)
+            b.replay_toa(0.1, rl, err=0.01, stream=stream)
+        t = timed(run)
+    out["config4_t6_variant1_ignore2_16anchors"] = {"updates_per_s": Nl * Tl / t, "ms": t * 1e3, "filters": Nl,
+                                                    "epochs": Tl}
     del rl
+    # ---- epoch assembler: raw ranging logs -> epoch tensors; HBM-bound
+    from roskfpos_b200.batch import assemble_epochs
+    Na, n_seq, Ma = 1 << 19, 32, 8
+    La = n_seq * Ma
+    g = torch.Generator(device=dev); g.manual_seed(11)
+    a_idx = torch.arange(La, device=dev, dtype=torch.int64).remainder(Ma).to(torch.uint8)[:, None].expand(La, Na).contiguous()
+    sq = (torch.arange(La, device=dev) // Ma).to(torch.uint8)[:, None].expand(La, Na).contiguous()
+    rmm = torch.randint(500, 15000, (La, Na), generator=g, device=dev, dtype=torch.int32)
+    tt = (torch.arange(La, device=dev, dtype=torch.float64) * 0.002 + (torch.arange(La, device=dev) // Ma) * 0.084)[:, None] \
+        .expand(La, Na).contiguous()
+    Ta = n_seq + 2
+    oa = dict(ranges=torch.empty((Ta, Ma, Na), dtype=torch.int32, device=dev), err=None,
+              dt=torch.empty((Ta, Na), dtype=torch.float64, device=dev),
+              n_epochs=torch.empty(Na, dtype=torch.int32, device=dev))
+    t = timed(lambda: assemble_epochs(a_idx, sq, rmm, tt, Ma, Ta, fix_row_clear=True, device=local, out=oa, stream=stream))
+    bytes_a = La * Na * (1 + 1 + 4 + 8) + Ta * Ma * Na * 4 + Ta * Na * 8 + Na * 4
+    peaks, _ = load_peaks()
+    out["assembler_fixed_row_clear"] = {"rangings_per_s": La * Na / t, "ms": t * 1e3, "logs": Na, "rangings_per_log": La,
+                                        "algorithmic_gbs": bytes_a / t / 1e9,
+                                        "hbm_frac": bytes_a / t / 1e9 / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
+                                        "note": "includes the call's scratch allocation and stream sync"}
+    del a_idx, sq, rmm, tt, oa
     # ---- configs 3 and 5: K8 multi-sensor event streams, 8 anchors, 1 Mi filters
     for name, full, n_macro in (("config3_k8_imu_mag", False, 5), ("config5_k8_full_multisensor", True, 4)):
         Nk = 1 << 20

@@ -77,6 +77,7 @@ enum kfpos_range_fmt {
 #define KFPOS_ST_ML_NAN 16   /* T6 NaN guard fired (TOA.cpp:270-272)                         */
 #define KFPOS_ST_MAXITER 32  /* IEKF used all iterations without meeting the break test      */
 #define KFPOS_ST_ASYM_R 64   /* K8 IMU covariance block not symmetric (cov[1] != cov[3])     */
+#define KFPOS_ST_Z_GATE 128  /* ML: estimated z outside [min_z, max_z] (config_pos.xml:22-25) */
 
 /* ML variants (MLLocation.h:5-7) and best-group criteria (MLLocation.h:10-11) */
 #define KFPOS_ML_VARIANT_NORMAL 0
@@ -108,7 +109,8 @@ typedef struct kfpos_config {
     int32_t variant;              /* variant                                        */
     int32_t num_ignored_rangings; /* numIgnoredRangings                             */
     int32_t best_mode;            /* bestMode                                       */
-    double min_z, max_z;          /* minZ, maxZ (output gate; documentation only)   */
+    double min_z, max_z;          /* minZ, maxZ: ML output gate, active when max_z >
+                                     min_z: estimates outside get KFPOS_ST_Z_GATE    */
     double ml_start[3];           /* previousEstimation: (1,1,4) by default         */
     /* config_uwb.xml <uwb .../>  (KF.cpp:793-800) */
     int32_t use_fixed_height;     /* useFixedHeight                                 */

@@ -792,6 +792,8 @@ extern "C" int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt,
     p.start[0] = b->cfg.ml_start[0];
     p.start[1] = b->cfg.ml_start[1];
     p.start[2] = b->cfg.ml_start[2];
+    p.min_z = b->cfg.min_z;
+    p.max_z = b->cfg.max_z;
     p.pos = (double *)d_pos;
     p.cov = (double *)d_cov;
     p.iters = (int32_t *)d_it;

@@ -46,6 +46,7 @@ struct MlParams {
     int64_t N;
     int use2d, variant, n_ignore, best_mode;
     double start[3];
+    double min_z, max_z; // output gate (config_pos.xml minZ / maxZ), active when max_z > min_z
     double *pos;     // SoA [3][N] or null
     double *cov;     // SoA [9][N] or null
     int32_t *iters;  // [N] or null

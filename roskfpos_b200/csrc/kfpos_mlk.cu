@@ -143,9 +143,12 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
                 p.sel[f] = (int32_t)used;
                 p.sel[N + f] = index;
             }
-            const int stv = rc == ML_OK ? 0 : (rc == ML_FEW ? 2 : 4);
+            int stv = rc == ML_OK ? 0 : (rc == ML_FEW ? 2 : 4);
+            // minZ / maxZ (config_pos.xml:22-25): "no estimation if the estimated Z is lower / greater" --
+            // the estimate is still written, flagged for the consumer to drop
+            if (p.max_z > p.min_z && (pos[2] < p.min_z || pos[2] > p.max_z)) stv |= 128;
             if (p.status) p.status[f] = stv;
-            bad = stv != 0;
+            bad = (stv & ~128) != 0;
             done = 1u;
         } else {
             iters = 0u; // counted when the epoch completes

@@ -16,6 +16,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "kfpos_b200.h")
 MODEL_ML, MODEL_T6, MODEL_K8, MODEL_T9 = 0, 1, 2, 3
 FMT_F64_M, FMT_I32_MM, FMT_U16_MM = 0, 1, 2
 ST_NO_MEAS, ST_ML_FEW, ST_SINGULAR, ST_NAN, ST_ML_NAN, ST_MAXITER, ST_ASYM_R = 1, 2, 4, 8, 16, 32, 64
+ST_Z_GATE = 128
 
 
 class KfposConfig(C.Structure):

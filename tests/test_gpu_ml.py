@@ -138,3 +138,16 @@ def test_ml_straggler_queue(kflib, oracle, variant):
     rep_slow = assert_parity(sub(got), sub(ref), [sub(p) for p in per], min_stable=0.0, max_tie_frac=0.05,
                              what=f"parked epochs v{variant}", **keys)
     print("parity report stragglers", variant, rep, rep_slow, int(slow.sum()))
+
+
+def test_ml_z_gate(kflib):
+    """minZ / maxZ of config_pos.xml: estimates whose z falls outside are flagged, not altered."""
+    N, m = 5000, 8
+    anc, truth, r = epochs(m, N, seed=950)
+    plain = gpu_ml(kflib, anc, r)
+    gated = gpu_ml(kflib, anc, r, min_z=0.9, max_z=1.1)
+    assert np.array_equal(plain["pos"], gated["pos"]) and not (plain["status"] & kflib.ST_Z_GATE).any()
+    out = (gated["pos"][2] < 0.9) | (gated["pos"][2] > 1.1)
+    assert 0.05 < out.mean() < 0.95
+    assert np.array_equal((gated["status"] & kflib.ST_Z_GATE) != 0, out)
+    assert np.array_equal(gated["status"] & ~kflib.ST_Z_GATE, plain["status"])
