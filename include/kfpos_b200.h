@@ -289,7 +289,9 @@ int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt, double err
  * flags: 0 = as written, the 256-row table whose new row gets only slot 0 cleared (:251-255,
  * slots written 256 sequence numbers earlier survive);
  * KFPOS_ASM_FIX_ROW_CLEAR = clear the whole row.  The outputs feed kfpos_batch_replay_epochs
- * (KFPOS_FMT_I32_MM).  Synchronises `stream` before returning (internal scratch is freed). */
+ * (KFPOS_FMT_I32_MM).  With device pointers the call is asynchronous on `stream`; its table
+ * scratch is per device and reused by the next call, so concurrent calls on one device must use
+ * one stream.  Host pointers are staged and the stream is synchronised before returning.   */
 #define KFPOS_ASM_FIX_ROW_CLEAR 1
 int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs, int n_anchors, const uint8_t *anchor,
                           const uint8_t *seq, const int32_t *range_mm, const double *err, const double *t,

@@ -2,7 +2,7 @@
 """Launches each product kernel a few times at a profiling-friendly size (used under
 `ncu -k regex:<name>`; prints its own CUDA-event times so the plain run is a record too).
 
-    python profiles/run_kernels.py [t6] [k8] [k8full] [t9] [ml3] [ml2] [mlign] [loo]
+    python profiles/run_kernels.py [t6] [k8] [k8full] [t9] [ml3] [ml2] [mlign] [loo] [asm]
 """
 import os
 import sys
@@ -19,7 +19,7 @@ from roskfpos_b200.batch import Batch  # noqa: E402
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 stream = torch.cuda.current_stream()
-which = sys.argv[1:] or ["t6", "k8", "k8full", "t9", "ml3", "ml2", "mlign", "loo"]
+which = sys.argv[1:] or ["t6", "k8", "k8full", "t9", "ml3", "ml2", "mlign", "loo", "asm"]
 REPS = 3
 
 
@@ -100,3 +100,19 @@ if "loo" in which:
             b.set_state(x0f, None, stream=stream)
             b.replay_toa(0.1, rl, err=0.01, stream=stream)
         timed("loo", run, Nl * Tl)
+if "asm" in which:
+    from roskfpos_b200.batch import assemble_epochs
+    Na, n_seq, Ma = 1 << 19, 32, 8
+    La = n_seq * Ma
+    g = torch.Generator(device=dev)
+    g.manual_seed(11)
+    a_idx = torch.arange(La, device=dev).remainder(Ma).to(torch.uint8)[:, None].expand(La, Na).contiguous()
+    sq = (torch.arange(La, device=dev) // Ma).to(torch.uint8)[:, None].expand(La, Na).contiguous()
+    rmm = torch.randint(500, 15000, (La, Na), generator=g, device=dev, dtype=torch.int32)
+    tt = (torch.arange(La, device=dev, dtype=torch.float64) * 0.002
+          + (torch.arange(La, device=dev) // Ma) * 0.084)[:, None].expand(La, Na).contiguous()
+    Ta = n_seq + 2
+    oa = dict(ranges=torch.empty((Ta, Ma, Na), dtype=torch.int32, device=dev), err=None,
+              dt=torch.empty((Ta, Na), dtype=torch.float64, device=dev),
+              n_epochs=torch.empty(Na, dtype=torch.int32, device=dev))
+    timed("asm", lambda: assemble_epochs(a_idx, sq, rmm, tt, Ma, Ta, fix_row_clear=True, out=oa, stream=stream), La * Na)

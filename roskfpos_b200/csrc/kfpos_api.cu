@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -872,32 +873,34 @@ extern "C" int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs,
     CK(o_n.set(n_epochs, 4 * N));
     const int fix = (flags & KFPOS_ASM_FIX_ROW_CLEAR) ? 1 : 0;
     const size_t rows = fix ? 1 : 256;
-    void *tbl_r = nullptr, *tbl_e = nullptr;
-    CK(cudaMalloc(&tbl_r, 4 * rows * M * N));
-    cudaError_t e = cudaMalloc(&tbl_e, 8 * rows * M * N);
-    if (e == cudaSuccess) e = cudaMemsetAsync(tbl_r, 0xff, 4 * rows * M * N, s); // initialiseTagList: -1
-    if (e == cudaSuccess) e = cudaMemsetAsync(tbl_e, 0, 8 * rows * M * N, s);
-    if (e == cudaSuccess) {
-        AssembleParams p;
-        p.N = n_logs; p.L = n_msgs; p.max_epochs = max_epochs;
-        p.M = n_anchors; p.fix_b12 = fix; p.first_dt = first_dt;
-        p.anchor = (const uint8_t *)i_a.d; p.seq = (const uint8_t *)i_s.d;
-        p.range_mm = (const int32_t *)i_r.d; p.err = (const double *)i_e.d; p.t = (const double *)i_t.d;
-        p.tbl_r = (int32_t *)tbl_r; p.tbl_e = (double *)tbl_e;
-        p.ranges_out = (int32_t *)o_r.d; p.err_out = (double *)o_e.d; p.dt_out = (double *)o_dt.d;
-        p.n_epochs = (int32_t *)o_n.d;
-        e = launch_assemble(p, s);
-    }
-    if (e == cudaSuccess) e = o_r.back(s);
-    if (e == cudaSuccess) e = o_e.back(s);
-    if (e == cudaSuccess) e = o_dt.back(s);
-    if (e == cudaSuccess) e = o_n.back(s);
-    // the scratch table and the temporary copies are freed on return: finish the work first
-    cudaError_t e2 = cudaStreamSynchronize(s);
-    cudaFree(tbl_r);
-    cudaFree(tbl_e);
-    if (e != cudaSuccess) return map_cuda_err(e);
-    if (e2 != cudaSuccess) return map_cuda_err(e2);
+    // the sequence-number table: per-device scratch that is kept between calls (grown on demand)
+    static std::mutex mtx;
+    static DevBuf tables[64][2];
+    std::lock_guard<std::mutex> lock(mtx);
+    DevBuf &tr = tables[device & 63][0], &te = tables[device & 63][1];
+    CK(tr.reserve(4 * rows * M * N));
+    CK(te.reserve(8 * rows * M * N));
+    CK(cudaMemsetAsync(tr.p, 0xff, 4 * rows * M * N, s)); // initialiseTagList: -1
+    CK(cudaMemsetAsync(te.p, 0, 8 * rows * M * N, s));
+    AssembleParams p;
+    p.N = n_logs; p.L = n_msgs; p.max_epochs = max_epochs;
+    p.M = n_anchors; p.fix_b12 = fix; p.first_dt = first_dt;
+    p.anchor = (const uint8_t *)i_a.d; p.seq = (const uint8_t *)i_s.d;
+    p.range_mm = (const int32_t *)i_r.d; p.err = (const double *)i_e.d; p.t = (const double *)i_t.d;
+    p.tbl_r = (int32_t *)tr.p; p.tbl_e = (double *)te.p;
+    p.ranges_out = (int32_t *)o_r.d; p.err_out = (double *)o_e.d; p.dt_out = (double *)o_dt.d;
+    p.n_epochs = (int32_t *)o_n.d;
+    CK(launch_assemble(p, s));
+    CK(o_r.back(s));
+    CK(o_e.back(s));
+    CK(o_dt.back(s));
+    CK(o_n.back(s));
+    // temporary copies of host arrays are freed on return: finish the work first.  With device
+    // pointers only, the call is asynchronous on `stream` like the rest of the API (the table
+    // is reused by the next call on the same device, which is ordered behind this one only if it
+    // uses the same stream: callers on different streams must synchronise themselves).
+    if (i_a.own || i_s.own || i_r.own || i_e.own || i_t.own || o_r.own || o_e.own || o_dt.own || o_n.own)
+        CK(cudaStreamSynchronize(s));
     return KFPOS_OK;
 }
 
