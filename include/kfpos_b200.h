@@ -316,6 +316,12 @@ int kfpos_batch_error_stats(kfpos_batch *b, const double *truth, double out[4], 
  * times a DFMA-only kernel on `device` and returns the sustained FLOP/s.        */
 int kfpos_measure_fp64_peak(int device, double *flops_per_s);
 
+/* Accuracy self-test of the kernels' elementary functions (no reference equivalent): evaluates the
+ * MUFU-seeded reciprocal and reciprocal square root and the reduced-range sincos on x[0..n) so that
+ * a test can compare them with IEEE division / sqrt / libm.  Outputs may be NULL.               */
+int kfpos_selftest_math(int device, int64_t n, const double *x, double *rcp, double *rsqrt, double *sn,
+                        double *cs);
+
 #ifdef __cplusplus
 }
 #endif

@@ -944,3 +944,25 @@ extern "C" int kfpos_measure_fp64_peak(int device, double *flops_per_s) {
     CK(measure_fp64_peak(flops_per_s));
     return KFPOS_OK;
 }
+
+extern "C" int kfpos_selftest_math(int device, int64_t n, const double *x, double *rcp, double *rsqrt, double *sn,
+                                   double *cs) {
+    if (n <= 0 || !x) return KFPOS_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return KFPOS_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return KFPOS_ERR_CUDA;
+    TmpIn i_x;
+    TmpOut o[4];
+    double *outs[4] = {rcp, rsqrt, sn, cs};
+    CK(i_x.set(x, 8 * (size_t)n, nullptr));
+    for (int k = 0; k < 4; ++k) CK(o[k].set(outs[k], 8 * (size_t)n));
+    CK(launch_selftest_math(n, (const double *)i_x.d, (double *)o[0].d, (double *)o[1].d, (double *)o[2].d,
+                            (double *)o[3].d, nullptr));
+    for (int k = 0; k < 4; ++k) CK(o[k].back(nullptr));
+    CK(cudaStreamSynchronize(nullptr));
+    return KFPOS_OK;
+}

@@ -88,8 +88,6 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const EpochT<PME, M
 
 #pragma unroll
     for (int k = 0; k < 8; ++k) dx[k] = 0.0;
-#pragma unroll
-    for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k];
     double cost = 1e20, prior = 0.0;
     bool broke = false;
     for (int iter = 0; iter < 20; ++iter) {
@@ -105,10 +103,10 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const EpochT<PME, M
             if (!PME) c *= invR0;
         }
         double sn = 0.0, cs = 1.0, sw = 0.0, cw = 1.0;
-        if (ms.has_px4 || ms.has_imu) sincos(th, &sn, &cs);
+        if (ms.has_px4 || ms.has_imu) fast_sincos(th, &sn, &cs);
         double e_p0 = 0, e_p1 = 0, e_p2 = 0, e_i0 = 0, e_i1 = 0, e_i2 = 0, e_m = 0;
         if (ms.has_px4) { // px4flowOutput (KF.cpp:563-571)
-            sincos(om * dt, &sw, &cw);
+            fast_sincos(om * dt, &sw, &cw);
             const double it = 1.0 / dt;
             e_p0 = ms.latch[0] - (cs * vx + sn * vy + it * ((1.0 - cw) * cfg.arm1 - sw * cfg.arm2));
             e_p1 = ms.latch[1] - (-sn * vx + cs * vy + it * (sw * cfg.arm1 + (1.0 - cw) * cfg.arm2));
@@ -132,10 +130,8 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const EpochT<PME, M
 
         // ---- gain step from (x^-, P^-), rows linearised at the iterate (KF.cpp:472-495)
         st.gain_evals += 1;
-        if (iter > 0) {
 #pragma unroll
-            for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k];
-        }
+        for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k]; // not before: 72 registers less in the first pass
         double dn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (mask) { // ranging rows (KF.cpp:611-625): one 2x2 information-form block
             if (!PME) {

@@ -166,6 +166,9 @@ struct AssembleParams {
 };
 cudaError_t launch_assemble(const AssembleParams &p, cudaStream_t s);
 
+cudaError_t launch_selftest_math(int64_t n, const double *x, double *rcp, double *rsq, double *sn, double *cs,
+                                 cudaStream_t s);
+
 // DFMA-only microbenchmark on the current device (the FP64 roofline denominator)
 cudaError_t measure_fp64_peak(double *flops_per_s);
 

@@ -230,4 +230,26 @@ cudaError_t launch_pose_msg(int model, int64_t N, double tag_z, const double *x_
     return cudaGetLastError();
 }
 
+// the fast elementary functions of kfpos_math.cuh evaluated on caller data (accuracy self-test)
+__global__ void selftest_math_kernel(int64_t n, const double *x, double *rcp, double *rsq, double *sn, double *cs) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double v = x[i];
+    if (rcp) rcp[i] = fast_rcp(v);
+    if (rsq) rsq[i] = fast_rsqrt(v);
+    if (sn || cs) {
+        double s_, c_;
+        fast_sincos(v, &s_, &c_);
+        if (sn) sn[i] = s_;
+        if (cs) cs[i] = c_;
+    }
+}
+
+cudaError_t launch_selftest_math(int64_t n, const double *x, double *rcp, double *rsq, double *sn, double *cs,
+                                 cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    selftest_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(n, x, rcp, rsq, sn, cs);
+    return cudaGetLastError();
+}
+
 } // namespace kfpos

@@ -136,8 +136,6 @@ KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r
         }
         return 1;
     }
-#pragma unroll
-    for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = Pm[k];
     for (int iter = 0; iter < 20; ++iter) {
         double c = 0.0, b[3] = {0.0, 0.0, 0.0}, G[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         if (mask) {
@@ -157,10 +155,8 @@ KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r
         cost = newCost;
 
         st.gain_evals += 1;
-        if (iter > 0) {
 #pragma unroll
-            for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = Pm[k];
-        }
+        for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = Pm[k];
         double dn[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
         if (mask) {
             if (!PME) {

@@ -77,6 +77,7 @@ SIGNATURES = {
     "kfpos_batch_get_counters": (_I, [_VP, C.POINTER(C.c_double * 8), _I, _VP]),
     "kfpos_batch_error_stats": (_I, [_VP, _VP, C.POINTER(C.c_double * 4), _VP]),
     "kfpos_measure_fp64_peak": (_I, [_I, C.POINTER(C.c_double)]),
+    "kfpos_selftest_math": (_I, [_I, _I64, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_assemble_epochs": (_I, [_I, _I64, _I64, _I, _VP, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP, _VP, _VP]),
 }
 ASM_FIX_ROW_CLEAR = 1
