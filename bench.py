@@ -353,8 +353,12 @@ def run_b200(args):
     ach = w_alg * N * T / (kernel_ms * 1e-3)
     peaks, peak_src = load_peaks()
     alg_bytes = N * T * M * ranges.element_size() + N * (3 + 21) * 8 * 2
+    # DRAM bytes of ONE launch of the replay kernel at the default size, from ncu
+    # (dram__bytes_read.sum + dram__bytes_write.sum = 3.56 GB + 201.7 MB; profiles/README.md)
+    traffic = 3.7617e9 if (N, T, M) == (1 << 20, 100, 8) else None
     roof = {"bound": "fp64", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
-            "frac": ach / peak if peak else None, "traffic": None,
+            "frac": ach / peak if peak else None, "traffic": traffic, "traffic_unit": "bytes per launch",
+            "algorithmic_bytes": alg_bytes,
             "peak_source": "measured live: kfpos_measure_fp64_peak (DFMA-only kernel, best of 5)",
             "kernel": "t6_replay_kernel<8,false,false>", "kernel_ms": kernel_ms,
             "flop_per_update": w_alg, "mean_iters": {"ml": i_ml, "cost": i_c, "gain": i_g},
