@@ -60,6 +60,7 @@ struct kfpos_batch {
     AnchorTable anchors;
     bool have_anchors = false;
     bool stepped = false; // a measurement has been processed since the (fresh) state was set
+    bool imu_seen = false; // T9: an IMU sample has been submitted since set_state (it stays latched)
     double *d_x = nullptr;      // SoA [n][N]
     double *d_P = nullptr;      // SoA [np][N]
     int32_t *d_status = nullptr;
@@ -295,6 +296,7 @@ extern "C" int kfpos_batch_set_state(kfpos_batch *b, const double *x, const doub
     if (b->d_has) CK(cudaMemsetAsync(b->d_has, 0, sizeof(int32_t) * N, s));
     if (b->d_latch) CK(cudaMemsetAsync(b->d_latch, 0, sizeof(double) * 16 * N, s));
     if (b->d_latch_u) CK(cudaMemsetAsync(b->d_latch_u, 0, sizeof(double) * 16, s));
+    b->imu_seen = false; // the latches are cleared above
     b->stepped = P != nullptr; // a restored checkpoint is a running filter; P0 = 0 is a fresh one
     if (!xd || (P && !on_device(P))) CK(cudaStreamSynchronize(s));
     return KFPOS_OK;
@@ -574,6 +576,8 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.latch = b->d_latch;
         p.has = b->d_has;
         p.latch_u = b->d_latch_u;
+        for (int i = 0; i < n; ++i) b->imu_seen = b->imu_seen || events[i].kind == KFPOS_EV_IMU;
+        p.no_imu = b->imu_seen ? 0 : 1;
         p.traj = d_traj;
         p.counters = b->d_counters;
         CK(launch_t9_replay(p, s));

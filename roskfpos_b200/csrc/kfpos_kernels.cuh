@@ -124,6 +124,7 @@ struct T9Params {
     double *latch;   // SoA rows 0..2: latched acceleration
     int32_t *has;    // [N] bit1: imu latched
     double *latch_u; // [9] batch-wide latched 3x3 acceleration covariance
+    int no_imu;      // host knowledge: no IMU sample latched and none in this schedule -> lean kernel
     double *traj;    // SoA [n_toa][3][N] or null
     unsigned long long *counters;
 };

@@ -13,6 +13,9 @@
 namespace kfpos {
 
 constexpr int T9_BLOCK = 128;
+#ifndef T9_LEAN_MINB
+#define T9_LEAN_MINB 3
+#endif
 
 // shared-memory rows (doubles) per thread: P^- (45), landing zone (rangings or 3 accelerations),
 // [metres column when MT == 0], [errorEstimation column]
@@ -75,7 +78,7 @@ KF_DEV bool accel_block_update(Sym<9> &P, double (&dn)[9], const double (&y)[3],
 // FACTORED like T6's: P = P^- - B M B^T with M returned (Pw untouched, return value 1); with them
 // the ranging block is applied to a register copy Pw per gain step, followed by one 3x3 block
 // update for the accelerometer rows, and Pw = (I - K J) P^- is returned (return value 0).
-template <bool PME, int MT>
+template <bool PME, int MT, bool IMU>
 KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r, bool has_imu, const double (&za)[3],
                      const double (&Ra)[6], const double (&xp)[9], const Col &Pm, Sym<9> &Pw, double (&dx)[9],
                      double (&M)[6], StepStats &st, unsigned wmask) {
@@ -101,7 +104,7 @@ KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r
     for (int k = 0; k < 6; ++k) M[k] = 0.0;
     double cost = 1e20, prior = 0.0;
     bool broke = false;
-    if (!has_imu) { // ---- ranging rows only: factored form, nothing but 3-vectors and 3x3 matrices in flight
+    if (!IMU || !has_imu) { // ---- ranging rows only: factored form, nothing but 3-vectors and 3x3 matrices in flight
         double a[6], s[3] = {0.0, 0.0, 0.0};
 #pragma unroll
         for (int k = 0; k < 6; ++k) a[k] = Pm[k];
@@ -136,6 +139,7 @@ KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r
         }
         return 1;
     }
+    if (!IMU) return 1; // (unreachable: the lean kernel never has accelerometer rows)
     for (int iter = 0; iter < 20; ++iter) {
         double c = 0.0, b[3] = {0.0, 0.0, 0.0}, G[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         if (mask) {
@@ -185,8 +189,10 @@ KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r
     return 0;
 }
 
-template <bool PME, int MT>
-__global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_constant__ T9Params p) {
+// IMU = false: the lean variant for schedules without accelerometer samples (nothing latched, no
+// IMU event): no register copy of the 9x9 covariance anywhere, 4 blocks per SM like T6.
+template <bool PME, int MT, bool IMU>
+__global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_kernel(const __grid_constant__ T9Params p) {
     extern __shared__ double smem[];
     const int64_t f = (int64_t)blockIdx.x * T9_BLOCK + threadIdx.x;
     const bool active = f < p.N;
@@ -243,6 +249,15 @@ __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_con
         if (p.n_events > 0) prefetch(p.events[0]);
         for (int e = 0; e < p.n_events; ++e) {
             const EventDesc ev = p.events[e];
+            const double dt = ev.dt;
+            // ---- predict (TOAIMU.cpp:165-180): a = 0 at the start of every step.  Done before the
+            // event's payload is unpacked so that the epoch's ranges are not live across it.
+            Sym<9> Pw;
+#pragma unroll
+            for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = Pm[k];
+            t9_predict_cov(Pw, dt, p.jolt);
+#pragma unroll
+            for (int k = 0; k < Sym<9>::SZ; ++k) Pm[k] = Pw.a[k];
             cp_async_wait_all();
             st.status = 0u;
             bool has_r = false, has_imu = false;
@@ -260,19 +275,11 @@ __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_con
             }
             if (e + 1 < p.n_events) prefetch(p.events[e + 1]);
             if (has_imu && asym) st.status |= 64u;
-            const double dt = ev.dt;
-            // ---- predict (TOAIMU.cpp:165-180): a = 0 at the start of every step
-            Sym<9> Pw;
-#pragma unroll
-            for (int k = 0; k < Sym<9>::SZ; ++k) Pw.a[k] = Pm[k];
-            t9_predict_cov(Pw, dt, p.jolt);
-#pragma unroll
-            for (int k = 0; k < Sym<9>::SZ; ++k) Pm[k] = Pw.a[k];
             const double xp[9] = {pos[0] + dt * vel[0], pos[1] + dt * vel[1], pos[2] + dt * vel[2],
                                   vel[0], vel[1], vel[2], 0.0, 0.0, 0.0};
             if (has_r && ep.valid == 0u) st.status |= 1u;
             double dx[9], M[6];
-            const int rc = t9_update<PME, MT>(p.anchors, ep, has_r, has_imu, za, Ra, xp, Pm, Pw, dx, M, st, wmask);
+            const int rc = t9_update<PME, MT, IMU>(p.anchors, ep, has_r, IMU && has_imu, za, Ra, xp, Pm, Pw, dx, M, st, wmask);
             __syncwarp(wmask); // the IEKF trip count differs per lane
             if (rc >= 0) {
 #pragma unroll
@@ -329,21 +336,26 @@ __global__ void __launch_bounds__(T9_BLOCK, 2) t9_replay_kernel(const __grid_con
     warp_accumulate(p.counters + CNT_BAD, n_bad);
 }
 
-template <bool PME, int MT>
+template <bool PME, int MT, bool IMU>
 static cudaError_t launch_k(const T9Params &p, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + T9_BLOCK - 1) / T9_BLOCK);
     const size_t smem = (size_t)t9_smem_rows(p.rs.m_slots, p.rs.fmt, PME, MT > 0) * T9_BLOCK * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(t9_replay_kernel<PME, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(t9_replay_kernel<PME, MT, IMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    t9_replay_kernel<PME, MT><<<grid, T9_BLOCK, smem, s>>>(p);
+    t9_replay_kernel<PME, MT, IMU><<<grid, T9_BLOCK, smem, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_t9_replay(const T9Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
-    if (p.rs.err != nullptr) return launch_k<true, 0>(p, s);
-    if (p.rs.m_slots == 8) return launch_k<false, 8>(p, s);
-    return launch_k<false, 0>(p, s);
+    if (p.no_imu) {
+        if (p.rs.err != nullptr) return launch_k<true, 0, false>(p, s);
+        if (p.rs.m_slots == 8) return launch_k<false, 8, false>(p, s);
+        return launch_k<false, 0, false>(p, s);
+    }
+    if (p.rs.err != nullptr) return launch_k<true, 0, true>(p, s);
+    if (p.rs.m_slots == 8) return launch_k<false, 8, true>(p, s);
+    return launch_k<false, 0, true>(p, s);
 }
 
 // getPose (TOAIMU.cpp:476-510): predict-only, state untouched
