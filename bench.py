@@ -234,7 +234,6 @@ def run_b200(args):
         batch.set_state(x0_full, None, stream=stream)
         batch.replay_toa(0.1, ranges, err=0.01, stream=stream)
         s = batch.error_stats(truth_end, stream=stream)
-        s, _, _ = reduce_stats(s, device=dev)  # the only collective: the final statistics reduction
         return s
 
     # ---- device-resident throughput (`value`)
@@ -255,8 +254,10 @@ def run_b200(args):
         kev[k][0].record(stream)
         batch.replay_toa(0.1, ranges, err=0.01, stream=stream)
         kev[k][1].record(stream)
-        s = batch.error_stats(truth_end, stream=stream)
-        s, _, _ = reduce_stats(s, device=dev)
+        s = batch.error_stats(truth_end, stream=stream)  # this rank's 4 doubles, read back every step
+    # the only collective of the job: the final reduction of the statistics (filters are independent,
+    # so nothing forces the ranks into lock-step between the steps)
+    s, _, _ = reduce_stats(s, device=dev)
     e1.record(stream)
     barrier()
     torch.cuda.cudart().cudaProfilerStop()
@@ -266,7 +267,11 @@ def run_b200(args):
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
     cnt = batch.counters(reset=True)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    rank_ms = [ms]
     if world > 1:
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [float(v.item()) for v in allt]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * N * T * K / (ms_max * 1e-3)
@@ -385,8 +390,8 @@ def run_b200(args):
                                        f"{M} anchors, int32-mm ranges, dt 0.1 s, P0=0, fixed initial position",
                            "filters_per_gpu": N, "epochs_per_step": T, "anchors": M,
                            "l2_policy": f"inputs larger than L2 ({N * T * M * 4 / 1e6:.0f} MB range log per step)",
-                           "parallelism": f"filters sharded by index over {world} GPU(s); one all-reduce of 4 doubles per step"},
-                "rmse_m": rmse, "bad_updates": cnt["bad"],
+                           "parallelism": f"filters sharded by index over {world} GPU(s); one all-reduce of 4 doubles at the end"},
+                "rmse_m": rmse, "bad_updates": cnt["bad"], "rank_ms_per_step": [v / K for v in rank_ms],
                 "e2e": e2e, "gpu_launches": 3 * K, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "other_configs": other}
         print(json.dumps(line))
