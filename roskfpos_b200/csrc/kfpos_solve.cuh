@@ -128,6 +128,54 @@ KF_DEV void ml_pass3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
 #define ML_FEW 1       // fewer than minRangings: position = start (ML.cpp:54-58,158-161)
 #define ML_SINGULAR -1 // arma::solve / inv would throw
 
+// covariance of the 3-D estimate, ML.cpp:229-254: J_i = (p - b_i)/d_i ; W = diag(max(e_i, SSE)) ;
+// cov = inv(J^T W^-1 J), packed Sym<3>
+template <bool PME, int MT>
+KF_DEV int ml_cov3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, const double (&p)[3], double sse,
+                   double *cov) {
+    double M[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < ep.m_slots; ++i) {
+        if (!((mask >> i) & 1u)) continue;
+        const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
+        const double id2 = 1.0 / (dx * dx + dy * dy + dz * dz);
+        const double w = id2 / fmax(ep.err(i), sse);
+        M[0] = fma(w * dx, dx, M[0]);
+        M[1] = fma(w * dx, dy, M[1]);
+        M[2] = fma(w * dy, dy, M[2]);
+        M[3] = fma(w * dx, dz, M[3]);
+        M[4] = fma(w * dy, dz, M[4]);
+        M[5] = fma(w * dz, dz, M[5]);
+    }
+    double I[6];
+    if (!inv_sym3(M, I)) return ML_SINGULAR;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) cov[k] = I[k];
+    return ML_OK;
+}
+
+// covariance of the 2-D estimate, ML.cpp:118-141 (xx, xy, yy)
+template <bool PME, int MT>
+KF_DEV int ml_cov2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, const double (&p)[3], double sse,
+                   double *cov) {
+    double m00 = 0, m01 = 0, m11 = 0;
+    for (int i = 0; i < ep.m_slots; ++i) {
+        if (!((mask >> i) & 1u)) continue;
+        const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
+        const double id2 = 1.0 / (dx * dx + dy * dy + dz * dz);
+        const double w = id2 / fmax(ep.err(i), sse);
+        m00 = fma(w * dx, dx, m00);
+        m01 = fma(w * dx, dy, m01);
+        m11 = fma(w * dy, dy, m11);
+    }
+    const double det = m00 * m11 - m01 * m01;
+    if (!(det != 0.0)) return ML_SINGULAR;
+    const double id = 1.0 / det;
+    cov[0] = m11 * id;
+    cov[1] = -m01 * id;
+    cov[2] = m00 * id;
+    return ML_OK;
+}
+
 // estimatePosition (3-D), ML.cpp:153-257.  p: in = start, out = estimate.
 // sse_out = estimationError at the returned point, sse_start = at the start point.
 // The covariance inv(J^T W^-1 J) (ML.cpp:229-254) is produced only when cov != nullptr.
@@ -179,26 +227,7 @@ KF_DEV int ml_solve3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
     }
     iters += iter;
     sse_out = ps.sse;
-    if (cov) {
-        // J_i = (p - b_i)/d_i ; W = diag(max(e_i, SSE)) ; cov = inv(J^T W^-1 J)
-        double M[6] = {0, 0, 0, 0, 0, 0};
-        for (int i = 0; i < ep.m_slots; ++i) {
-            if (!((mask >> i) & 1u)) continue;
-            const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
-            const double id2 = 1.0 / (dx * dx + dy * dy + dz * dz);
-            const double w = id2 / fmax(ep.err(i), ps.sse);
-            M[0] = fma(w * dx, dx, M[0]);
-            M[1] = fma(w * dx, dy, M[1]);
-            M[2] = fma(w * dy, dy, M[2]);
-            M[3] = fma(w * dx, dz, M[3]);
-            M[4] = fma(w * dy, dz, M[4]);
-            M[5] = fma(w * dz, dz, M[5]);
-        }
-        double I[6];
-        if (!inv_sym3(M, I)) return ML_SINGULAR;
-#pragma unroll
-        for (int k = 0; k < 6; ++k) cov[k] = I[k];
-    }
+    if (cov) return ml_cov3<PME, MT>(A, ep, mask, p, ps.sse, cov);
     return ML_OK;
 }
 
@@ -291,24 +320,7 @@ KF_DEV int ml_solve2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
     }
     iters += iter;
     sse_out = ps.sse;
-    if (cov) {
-        double m00 = 0, m01 = 0, m11 = 0;
-        for (int i = 0; i < ep.m_slots; ++i) {
-            if (!((mask >> i) & 1u)) continue;
-            const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
-            const double id2 = 1.0 / (dx * dx + dy * dy + dz * dz);
-            const double w = id2 / fmax(ep.err(i), ps.sse);
-            m00 = fma(w * dx, dx, m00);
-            m01 = fma(w * dx, dy, m01);
-            m11 = fma(w * dy, dy, m11);
-        }
-        const double det = m00 * m11 - m01 * m01;
-        if (!(det != 0.0)) return ML_SINGULAR;
-        const double id = 1.0 / det;
-        cov[0] = m11 * id;
-        cov[1] = -m01 * id;
-        cov[2] = m00 * id;
-    }
+    if (cov) return ml_cov2<PME, MT>(A, ep, mask, p, ps.sse, cov);
     return ML_OK;
 }
 

@@ -38,6 +38,19 @@ def test_no_cpu_fallback_without_gpu(kflib):
         assert e.code == -2
     else:
         raise AssertionError("Batch() succeeded without a GPU")
+    # the handle-free entry points as well
+    import ctypes as C
+    import numpy as np
+    x = np.ones(4)
+    assert kflib.lib().kfpos_selftest_math(0, 4, C.c_void_p(x.ctypes.data), None, None, None, None) == -2
+    a = np.zeros((2, 1), dtype=np.uint8); r = np.zeros((2, 1), dtype=np.int32); t = np.zeros((2, 1))
+    o = np.zeros((1, 4, 1), dtype=np.int32); dt = np.zeros((1, 1))
+    rc = kflib.lib().kfpos_assemble_epochs(0, 1, 2, 4, C.c_void_p(a.ctypes.data), C.c_void_p(a.ctypes.data),
+                                           C.c_void_p(r.ctypes.data), None, C.c_void_p(t.ctypes.data), 1, 0, 0.1,
+                                           C.c_void_p(o.ctypes.data), None, C.c_void_p(dt.ctypes.data), None, None)
+    assert rc == -2
+    v = C.c_double(0.0)
+    assert kflib.lib().kfpos_measure_fp64_peak(0, C.byref(v)) == -2
 
 
 def test_config_struct_layout(kflib):
