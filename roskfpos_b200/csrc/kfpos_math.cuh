@@ -148,7 +148,7 @@ KF_DEV bool inv_sym3(const double (&H)[6], double (&I)[6]) {
     const double c02 = b * e - c * d;
     const double det = a * c00 + b * c01 + c * c02;
     if (!(det != 0.0)) return false;
-    const double id = 1.0 / det;
+    const double id = fast_rcp(det);
     I[0] = c00 * id;
     I[1] = c01 * id;
     I[2] = (a * f - c * c) * id;
