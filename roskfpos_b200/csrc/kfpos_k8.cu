@@ -8,7 +8,10 @@
 
 namespace kfpos {
 
-constexpr int K8_BLOCK = 128;
+#ifndef K8_BLOCK_SZ
+#define K8_BLOCK_SZ 128
+#endif
+constexpr int K8_BLOCK = K8_BLOCK_SZ;
 #ifndef K8_MINB
 #define K8_MINB 2 // 255 registers: the register copy of P (72) + increments + Jacobian entries
 #endif
