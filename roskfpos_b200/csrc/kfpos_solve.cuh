@@ -75,11 +75,15 @@ struct MlPass3 {
 // gradient / Hessian / costs at p over the slots in `mask` (ML.cpp:171-222).
 // With a scalar errorEstimation the weight 1/e is common to g and H and cancels in
 // the Newton step, so only the stop-test cost carries it.
-template <bool PME, int MT>
+// ACCG (scalar errorEstimation only): also accumulate Gu = sum u u^T of the unit vectors, packed
+// xx, xy, yy, xz, yz, zz -- with sse and g of the same pass that is everything the FIRST iteration of
+// the IEKF needs at this point (cost = sse / R, b = -g / R, G = Gu / R), see t6_update.
+template <bool PME, int MT, bool ACCG = false>
 KF_DEV void ml_pass3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, int nvalid,
-                     const double (&p)[3], MlPass3 &o) {
+                     const double (&p)[3], MlPass3 &o, double *Gu = nullptr) {
     double wc = 0.0, sse = 0.0, g0 = 0.0, g1 = 0.0, g2 = 0.0;
     double h0 = 0.0, h1 = 0.0, h2 = 0.0, h3 = 0.0, h4 = 0.0, h5 = 0.0, c1s = 0.0;
+    double u0 = 0.0, u1 = 0.0, u2 = 0.0, u3 = 0.0, u4 = 0.0, u5 = 0.0;
 #pragma unroll(MT > 0 ? MT : 2)
     for (int i = 0; i < ep.m(); ++i) {
         const bool on = (mask >> i) & 1u;
@@ -110,12 +114,19 @@ KF_DEV void ml_pass3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
             const double t = res * invd;
             g0 = fma(t, dx, g0); g1 = fma(t, dy, g1); g2 = fma(t, dz, g2);
             c1s += rid; // sum of (1 - r/d) = nvalid - sum r/d
-            const double c2 = rid * (invd * invd);
+            const double w2 = invd * invd;
+            const double c2 = rid * w2;
             const double cx = c2 * dx, cy = c2 * dy, cz = c2 * dz;
             h0 = fma(cx, dx, h0); h1 = fma(cx, dy, h1); h2 = fma(cy, dy, h2);
             h3 = fma(cx, dz, h3); h4 = fma(cy, dz, h4); h5 = fma(cz, dz, h5);
+            if (ACCG) {
+                const double wx = w2 * dx, wy = w2 * dy, wz = w2 * dz;
+                u0 = fma(wx, dx, u0); u1 = fma(wx, dy, u1); u2 = fma(wy, dy, u2);
+                u3 = fma(wx, dz, u3); u4 = fma(wy, dz, u4); u5 = fma(wz, dz, u5);
+            }
         }
     }
+    if (ACCG) { Gu[0] = u0; Gu[1] = u1; Gu[2] = u2; Gu[3] = u3; Gu[4] = u4; Gu[5] = u5; }
     if (!PME) c1s = (double)nvalid - c1s;
     o.sse = sse;
     o.wcost = PME ? wc : sse * fast_rcp(ep.e0);
@@ -228,6 +239,37 @@ KF_DEV int ml_solve3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
     iters += iter;
     sse_out = ps.sse;
     if (cov) return ml_cov3<PME, MT>(A, ep, mask, p, ps.sse, cov);
+    return ML_OK;
+}
+
+// The same solver for the EKFs' inner ML (scalar errorEstimation, no covariance, no resume): its
+// pass at the START point -- the predicted position, where the IEKF's first iteration also
+// linearises -- additionally returns g and Gu = sum u u^T, which give that iteration's
+// b = -g / R and G = Gu / R without another pass over the anchors (its cost is sse_start / R).
+template <int MT>
+KF_DEV int ml_solve3_ekf(const AnchorTable &A, const EpochT<false, MT> &ep, unsigned mask, double (&p)[3],
+                         double &sse_out, unsigned &iters, double &sse_start, double (&g_start)[3],
+                         double (&Gu_start)[6]) {
+    const int nvalid = __popc(mask);
+    MlPass3 ps;
+    ml_pass3<false, MT, true>(A, ep, mask, nvalid, p, ps, Gu_start);
+    sse_start = ps.sse;
+    sse_out = ps.sse;
+    g_start[0] = ps.g[0]; g_start[1] = ps.g[1]; g_start[2] = ps.g[2];
+    if (nvalid < 4) return ML_FEW;
+    double cost = 1e20, newCost = 1.0;
+    unsigned iter = 0;
+    while (rel_change_gt(cost, newCost) && iter < 10000u) {
+        iter += 1;
+        cost = newCost;
+        double s[3];
+        if (!solve_sym3(ps.H, ps.g, s)) { iters += iter; return ML_SINGULAR; }
+        p[0] -= s[0]; p[1] -= s[1]; p[2] -= s[2];
+        ml_pass3<false, MT>(A, ep, mask, nvalid, p, ps);
+        newCost = ps.wcost;
+    }
+    iters += iter;
+    sse_out = ps.sse;
     return ML_OK;
 }
 

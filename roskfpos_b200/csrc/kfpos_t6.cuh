@@ -64,8 +64,13 @@ KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
                      const Col &Pm, T6Result &out, StepStats &st, unsigned wmask = 0u) {
     // ---- inner ML solve from the predicted position (TOA.cpp:268-273)
     double pml[3] = {xp[0], xp[1], xp[2]};
-    double sse, sse_xp;
-    const int rc = ml_solve3<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &sse_xp);
+    double sse, sse_xp = 0.0;
+    // scalar errorEstimation: the Newton solver's pass at its start point x^- is also the IEKF's first
+    // pass: cost = sse_xp / R, b = -g_xp / R (eps - J delta = eps at delta = 0), G = Gu_xp / R
+    double g_xp[3] = {0.0, 0.0, 0.0}, Gu_xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    int rc;
+    if constexpr (PME) rc = ml_solve3<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &sse_xp);
+    else rc = ml_solve3_ekf<MT>(A, ep, mask, pml, sse, st.ml_iters, sse_xp, g_xp, Gu_xp);
     if (wmask) __syncwarp(wmask);
     if (rc == ML_FEW) st.status |= 2u;
     if (rc == ML_SINGULAR) return ML_SINGULAR;
@@ -91,7 +96,15 @@ KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
         // ---- one pass: cost at the current iterate (TOA.cpp:297-305) and the
         //      information-form accumulators of the rows linearised there (TOA.cpp:313-320)
         double c, b[3], G[6];
-        iekf_pass<PME, MT, 3>(A, ep, mask, sse, xp[0] + dx[0], xp[1] + dx[1], xp[2] + dx[2], dx, c, b, G);
+        if (!PME && iter == 0) {
+            c = sse_xp;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) b[k] = -g_xp[k];
+#pragma unroll
+            for (int k = 0; k < 6; ++k) G[k] = Gu_xp[k];
+        } else {
+            iekf_pass<PME, MT, 3>(A, ep, mask, sse, xp[0] + dx[0], xp[1] + dx[1], xp[2] + dx[2], dx, c, b, G);
+        }
         const double newCost = (PME ? c : c * invR0) + prior;
         st.cost_evals += 1;
         if (rel_change_lt(cost, newCost, 1e-3)) { broke = true; break; }
