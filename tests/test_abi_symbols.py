@@ -62,3 +62,22 @@ def test_config_struct_layout(kflib):
     assert cfg.mag_angle_offset == 0.25 and cfg.mag_cov == 0.0001
     assert cfg.imu_use_fixed_cov_acc == 1 and cfg.imu_cov_gyro_z == 0.089
     assert list(cfg.ml_start) == [1.0, 1.0, 4.0]
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/kfpos_b200.h must be consumable from C (cgo / JNI / ctypes style bindings), not only C++;
+    a C program links against the library with nothing but the header."""
+    import os
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "kfpos_b200.h"\n#include <stdio.h>\n'
+                   "int main(void) { kfpos_config c; kfpos_config_default(&c);\n"
+                   '  printf("%d %s\\n", kfpos_abi_version(), kfpos_strerror(KFPOS_ERR_CUDA));\n'
+                   "  return kfpos_abi_version() == KFPOS_ABI_VERSION ? 0 : 1; }\n")
+    exe = tmp_path / "abi"
+    inc = os.path.dirname(L.HEADER_PATH)
+    libdir = os.path.dirname(L.SO_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{inc}", str(src), "-o", str(exe),
+                           f"-L{libdir}", "-lkfpos_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("1 "), (out.stdout, out.stderr)
