@@ -517,6 +517,33 @@ def bench_other_configs(local, dev, args):
                      "rmse_xy_m": float(np.sqrt(s4[1] / max(s4[2], 1))), "bad_updates": c["bad"],
                      "input_mb": (w["sensors"].numel() * 8 + w["ranges"].numel() * 4) / 1e6}
         del w
+    # ---- config 5 at scale: 8 Mi filters (the per-GPU share of the 64 M-filter Monte Carlo on 8 GPUs), inputs
+    # synthesised on the device chunk by chunk (kfpos_synth_k8) and replayed; generation is inside the timed region
+    torch.cuda.empty_cache()
+    Nm, n_macro, chunk = 1 << 23, 8, 2
+    with Batch(L.MODEL_K8, Nm, device=local, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5) as b:
+        first = synth.k8_montecarlo_chunk(Nm, 0, chunk, anc, dev, seed=synth.SEED + 9, full=True, want_x0=True, stream=stream)
+        x0m = first["x0"].clone()
+        bufs = first
+
+        def run_mc(replay=True):
+            nonlocal bufs
+            b.set_state(x0m, None, stream=stream)
+            for m0 in range(0, n_macro, chunk):
+                bufs = synth.k8_montecarlo_chunk(Nm, m0, chunk, anc, dev, seed=synth.SEED + 9, full=True, out=bufs, stream=stream)
+                if replay:
+                    b.replay_events(bufs["events"], ranges=bufs["ranges"], sensors=bufs["sensors"], err=0.01, stream=stream)
+        t_all = timed(run_mc, reps=2)
+        s4 = b.error_stats(bufs["truth_end"], stream=stream)
+        c = b.counters()
+        t_gen = timed(lambda: run_mc(False), reps=2)
+    n_ev = n_macro * len(synth.MACRO_FULL)
+    out["config5_k8_montecarlo_8Mi_filters"] = {
+        "all_event_updates_per_s": Nm * n_ev / t_all, "toa_updates_per_s": Nm * n_macro / t_all, "ms": t_all * 1e3,
+        "generation_ms": t_gen * 1e3, "filters": Nm, "events": n_ev, "chunk_macro_steps": chunk,
+        "rmse_xy_m": float(np.sqrt(s4[1] / max(s4[2], 1))), "bad_updates": c["bad"],
+        "note": "inputs generated in-kernel (Philox4x32-10) inside the timed region, never resident as a whole"}
+    del bufs, first, x0m
     return out
 
 

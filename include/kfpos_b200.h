@@ -316,6 +316,29 @@ int kfpos_batch_error_stats(kfpos_batch *b, const double *truth, double out[4], 
  * times a DFMA-only kernel on `device` and returns the sustained FLOP/s.        */
 int kfpos_measure_fp64_peak(int device, double *flops_per_s);
 
+/* Monte Carlo inputs for K8 batches, generated on the device (no reference equivalent; BASELINE
+ * configs 3 and 5 run millions of filters for 1000 steps: their sensor streams do not fit in memory
+ * and are synthesised chunk by chunk into the tensors kfpos_batch_replay_events streams).  Each
+ * value is a pure function of (seed, first_filter + f, event global_index, sample) through the
+ * counter-based Philox4x32-10 generator: independent of sharding and chunking.  Truth: planar
+ * Lissajous x = 5 + 3 sin(0.20 t + a), y = 5 + 3 sin(0.31 t + b), heading th0 + 0.05 t with a, b, th0
+ * per filter.  Payload rows written at `offset` (rows of N values): KFPOS_EV_TOA n_anchors int32 mm
+ * ranges (noise sigma_r m) into `ranges`; KFPOS_EV_IMU gyro z, body accel x, y (variances 0.089,
+ * 0.003); KFPOS_EV_PX4 the five PX4Flow fields (33.333 ms, height 5 m, quality 200);
+ * KFPOS_EV_COMPASS heading + N(0, 0.01^2) -- the payload layouts of kfpos_batch_replay_events.
+ * events: HOST array; x0 (SoA [8][N], state at t = 0) and truth_end (SoA [3][N], position at
+ * t_end) optional.  Synchronises `stream` before returning.                                    */
+typedef struct kfpos_synth_event {
+    int32_t kind;         /* kfpos_event_kind                                   */
+    int32_t global_index; /* index of the event in the whole run (RNG counter)  */
+    double t;             /* time of the event, s                               */
+    int64_t offset;       /* first output row                                   */
+} kfpos_synth_event;
+int kfpos_synth_k8(int device, int64_t n_filters, int64_t first_filter, uint64_t seed, int n_anchors,
+                   const double *anchors_xyz, double tag_z, double sigma_r, int n_events,
+                   const kfpos_synth_event *events, double t_end, int64_t range_rows, int64_t sensor_rows,
+                   int32_t *ranges, double *sensors, double *x0, double *truth_end, void *stream);
+
 /* Accuracy self-test of the kernels' elementary functions (no reference equivalent): evaluates the
  * MUFU-seeded reciprocal and reciprocal square root and the reduced-range sincos on x[0..n) so that
  * a test can compare them with IEEE division / sqrt / libm.  Outputs may be NULL.               */

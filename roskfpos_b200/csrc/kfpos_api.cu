@@ -949,6 +949,66 @@ extern "C" int kfpos_measure_fp64_peak(int device, double *flops_per_s) {
     return KFPOS_OK;
 }
 
+extern "C" int kfpos_synth_k8(int device, int64_t n_filters, int64_t first_filter, uint64_t seed, int n_anchors,
+                              const double *anchors_xyz, double tag_z, double sigma_r, int n_events,
+                              const kfpos_synth_event *events, double t_end, int64_t range_rows, int64_t sensor_rows,
+                              int32_t *ranges, double *sensors, double *x0, double *truth_end, void *stream) {
+    static_assert(sizeof(kfpos_synth_event) == sizeof(SynthEvent), "kfpos_synth_event and SynthEvent must have one layout");
+    if (n_filters <= 0 || n_anchors <= 0 || n_anchors > KFPOS_MAX_ANCHORS || !anchors_xyz || n_events < 0 ||
+        (n_events > 0 && !events) || range_rows < 0 || sensor_rows < 0)
+        return KFPOS_ERR_INVALID;
+    for (int i = 0; i < n_events; ++i) { // every event must write inside the tensors it was given
+        const int rows = events[i].kind == KFPOS_EV_TOA ? n_anchors
+                         : events[i].kind == KFPOS_EV_PX4 ? 5 : events[i].kind == KFPOS_EV_IMU ? 3
+                         : events[i].kind == KFPOS_EV_COMPASS ? 1 : -1;
+        const int64_t lim = events[i].kind == KFPOS_EV_TOA ? range_rows : sensor_rows;
+        if (rows < 0 || events[i].offset < 0 || events[i].offset + rows > lim) return KFPOS_ERR_INVALID;
+        if ((events[i].kind == KFPOS_EV_TOA && !ranges) || (events[i].kind != KFPOS_EV_TOA && !sensors))
+            return KFPOS_ERR_INVALID;
+    }
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return KFPOS_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return KFPOS_ERR_CUDA;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)n_filters;
+    TmpOut o_r, o_s, o_x, o_t;
+    CK(o_r.set(ranges, 4 * (size_t)range_rows * N));
+    CK(o_s.set(sensors, 8 * (size_t)sensor_rows * N));
+    CK(o_x.set(x0, 8 * 8 * N));
+    CK(o_t.set(truth_end, 8 * 3 * N));
+    void *d_ev = nullptr;
+    if (n_events > 0) {
+        CK(cudaMalloc(&d_ev, sizeof(SynthEvent) * (size_t)n_events));
+        cudaError_t e = cudaMemcpyAsync(d_ev, events, sizeof(SynthEvent) * (size_t)n_events, cudaMemcpyHostToDevice, s);
+        if (e != cudaSuccess) { cudaFree(d_ev); return map_cuda_err(e); }
+    }
+    SynthK8Params p;
+    memset(&p.anchors, 0, sizeof p.anchors);
+    p.anchors.n = n_anchors;
+    for (int i = 0; i < n_anchors; ++i) {
+        p.anchors.x[i] = anchors_xyz[3 * i]; p.anchors.y[i] = anchors_xyz[3 * i + 1]; p.anchors.z[i] = anchors_xyz[3 * i + 2];
+    }
+    p.N = n_filters; p.filter0 = first_filter; p.seed = seed; p.M = n_anchors; p.n_events = n_events;
+    p.tag_z = tag_z; p.sigma_r = sigma_r; p.t_end = t_end;
+    p.events = (const SynthEvent *)d_ev;
+    p.ranges = (int32_t *)o_r.d; p.sensors = (double *)o_s.d; p.x0 = (double *)o_x.d; p.truth_end = (double *)o_t.d;
+    cudaError_t e = launch_synth_k8(p, s);
+    if (e == cudaSuccess) e = o_r.back(s);
+    if (e == cudaSuccess) e = o_s.back(s);
+    if (e == cudaSuccess) e = o_x.back(s);
+    if (e == cudaSuccess) e = o_t.back(s);
+    // the schedule copy (and any host staging) is freed on return
+    cudaError_t e2 = cudaStreamSynchronize(s);
+    if (d_ev) cudaFree(d_ev);
+    if (e != cudaSuccess) return map_cuda_err(e);
+    if (e2 != cudaSuccess) return map_cuda_err(e2);
+    return KFPOS_OK;
+}
+
 extern "C" int kfpos_selftest_math(int device, int64_t n, const double *x, double *rcp, double *rsqrt, double *sn,
                                    double *cs) {
     if (n <= 0 || !x) return KFPOS_ERR_INVALID;

@@ -170,6 +170,27 @@ cudaError_t launch_assemble(const AssembleParams &p, cudaStream_t s);
 cudaError_t launch_selftest_math(int64_t n, const double *x, double *rcp, double *rsq, double *sn, double *cs,
                                  cudaStream_t s);
 
+// Monte Carlo input generator for K8 batches (kfpos_synth.cu)
+struct SynthEvent {
+    int32_t kind;
+    int32_t global_index; // index of the event in the whole run (RNG counter)
+    double t;             // time of the event, s
+    int64_t offset;       // first output row (rows of `ranges` for EV_TOA, of `sensors` otherwise)
+};
+struct SynthK8Params {
+    AnchorTable anchors;
+    int64_t N, filter0;
+    uint64_t seed;
+    int M, n_events;
+    double tag_z, sigma_r, t_end;
+    const SynthEvent *events; // device [n_events]
+    int32_t *ranges;          // SoA [rows][N] int32 mm
+    double *sensors;          // SoA [rows][N]
+    double *x0;               // SoA [8][N] or null
+    double *truth_end;        // SoA [3][N] or null: (x, y, tag z) at t_end
+};
+cudaError_t launch_synth_k8(const SynthK8Params &p, cudaStream_t s);
+
 // DFMA-only microbenchmark on the current device (the FP64 roofline denominator)
 cudaError_t measure_fp64_peak(double *flops_per_s);
 

@@ -47,6 +47,10 @@ class KfposEvent(C.Structure):
                 ("aux", C.c_double * 9)]
 
 
+class KfposSynthEvent(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("global_index", C.c_int32), ("t", C.c_double), ("offset", C.c_int64)]
+
+
 _LIB = None
 
 # name -> (restype, argtypes); every symbol include/kfpos_b200.h declares
@@ -77,6 +81,7 @@ SIGNATURES = {
     "kfpos_batch_get_counters": (_I, [_VP, C.POINTER(C.c_double * 8), _I, _VP]),
     "kfpos_batch_error_stats": (_I, [_VP, _VP, C.POINTER(C.c_double * 4), _VP]),
     "kfpos_measure_fp64_peak": (_I, [_I, C.POINTER(C.c_double)]),
+    "kfpos_synth_k8": (_I, [_I, _I64, _I64, C.c_uint64, _I, _VP, _D, _D, _I, _VP, _D, _I64, _I64, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_selftest_math": (_I, [_I, _I64, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_assemble_epochs": (_I, [_I, _I64, _I64, _I, _VP, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP, _VP, _VP]),
 }

@@ -202,3 +202,60 @@ def device_ranges_mm(n_filters: int, n_steps: int, anchors: np.ndarray, dt: floa
         d = d + sigma * torch.randn(d.shape, generator=g, device=device, dtype=torch.float64)
         out[k] = torch.floor(d * 1000.0).clamp_(min=0).to(dtype)
     return out, x0.contiguous(), p.contiguous()
+
+
+def k8_montecarlo_chunk(n_filters, macro0, n_macro, anchors, device, seed=SEED, full=False, sigma_r=0.10,
+                        first_filter=0, want_x0=False, out=None, stream=None):
+    """Macro-steps [macro0, macro0 + n_macro) of the K8 Monte Carlo workload, generated ON THE DEVICE by
+    kfpos_synth_k8 (Philox4x32-10; the stream of a filter depends only on seed, its global index and the
+    global event index).  Returns the dict k8_workload returns (events for replay_events, ranges int32
+    [T][M][N], sensors f64 [R][N], truth_end [3][N], x0 [8][N] if want_x0) with torch tensors on `device`;
+    `out` may hold the tensors of a previous chunk of the same shape to be reused."""
+    import ctypes as C
+    import torch
+    from . import lib as L
+    macro = MACRO_FULL if full else MACRO_IMU_MAG
+    M, N = len(anchors), int(n_filters)
+    rows_of = {EV_IMU: 3, EV_PX4: 5, EV_COMPASS: 1}
+    # event times from integer milliseconds, so that they do not depend on where a chunk starts
+    cum_ms = np.cumsum([int(round(dt * 1000)) for _, dt in macro])
+    macro_ms = int(cum_ms[-1])
+    t = 0.0
+    events, sev = [], []
+    n_rng = n_sens = 0
+    for mstep in range(n_macro):
+        for j, (kind, dt) in enumerate(macro):
+            t = ((macro0 + mstep) * macro_ms + int(cum_ms[j])) / 1000.0
+            g = (macro0 + mstep) * len(macro) + j
+            if kind == EV_TOA:
+                off = n_rng * M; n_rng += 1
+                events.append((kind, dt, off, None))
+            else:
+                off = n_sens; n_sens += rows_of[kind]
+                events.append((kind, dt, off, IMU_AUX if kind == EV_IMU else None))
+            sev.append((kind, g, t, off))
+    dev = torch.device(device)
+    if out is None:
+        out = {}
+    def buf(name, shape, dtype):
+        tns = out.get(name)
+        if tns is None or tuple(tns.shape) != tuple(shape):
+            tns = torch.empty(shape, device=dev, dtype=dtype)
+        return tns
+    ranges = buf("ranges", (n_rng, M, N), torch.int32)
+    sensors = buf("sensors", (n_sens, N), torch.float64)
+    truth_end = buf("truth_end", (3, N), torch.float64)
+    x0 = buf("x0", (8, N), torch.float64) if want_x0 else None
+    arr = (L.KfposSynthEvent * len(sev))()
+    for i, (kind, g, tt, off) in enumerate(sev):
+        arr[i].kind, arr[i].global_index, arr[i].t, arr[i].offset = int(kind), int(g), float(tt), int(off)
+    anc = np.ascontiguousarray(anchors, dtype=np.float64)
+    sp = None if stream is None else C.c_void_p(int(getattr(stream, "cuda_stream", stream)))
+    L.check(L.lib().kfpos_synth_k8(dev.index or 0, N, int(first_filter), C.c_uint64(seed), M,
+                                   C.c_void_p(anc.ctypes.data), 1.049, float(sigma_r), len(sev),
+                                   C.cast(arr, C.c_void_p), float(t), n_rng * M, n_sens,
+                                   C.c_void_p(ranges.data_ptr()), C.c_void_p(sensors.data_ptr()),
+                                   None if x0 is None else C.c_void_p(x0.data_ptr()),
+                                   C.c_void_p(truth_end.data_ptr()), sp), "kfpos_synth_k8")
+    return dict(events=events, ranges=ranges, sensors=sensors, x0=x0, truth_end=truth_end, tag_z=1.049,
+                n_toa=n_rng, n_events=len(events))
