@@ -400,6 +400,77 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_config5(args):
+    """BASELINE config 5: full multi-sensor K8 Monte Carlo, --mc-filters filters sharded by index over the
+    ranks, inputs generated on the device chunk by chunk (never resident), one all-reduce of the error
+    statistics at the end.  Optional mode; prints its own JSON line (metric k8_events_per_sec)."""
+    import torch
+    import torch.distributed as dist
+    from roskfpos_b200 import lib as L, synth
+    from roskfpos_b200.batch import Batch
+    from roskfpos_b200.shard import reduce_stats, shard_bounds
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    stream = torch.cuda.current_stream()
+    lo, hi = shard_bounds(args.mc_filters, rank, world)
+    N, K, W, n_macro, chunk = hi - lo, args.steps, args.warmup, args.mc_macro_steps, 2
+    anc = synth.anchors_for(8)
+    batch = Batch(L.MODEL_K8, N, device=local, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5)
+    bufs = synth.k8_montecarlo_chunk(N, 0, chunk, anc, dev, seed=synth.SEED, full=True, first_filter=lo, want_x0=True,
+                                     stream=stream)
+    x0 = bufs["x0"].clone()
+
+    def step():
+        nonlocal bufs
+        batch.set_state(x0, None, stream=stream)
+        for m0 in range(0, n_macro, chunk):
+            bufs = synth.k8_montecarlo_chunk(N, m0, min(chunk, n_macro - m0), anc, dev, seed=synth.SEED, full=True,
+                                             first_filter=lo, out=bufs, stream=stream)
+            batch.replay_events(bufs["events"], ranges=bufs["ranges"], sensors=bufs["sensors"], err=0.01, stream=stream)
+        return batch.error_stats(bufs["truth_end"], stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(W):
+        step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        s = step()
+    s, _, rmse_xy = reduce_stats(s, device=dev)
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    n_ev = n_macro * len(synth.MACRO_FULL)
+    if rank == 0:
+        print(json.dumps({"metric": "k8_multisensor_events_per_sec", "value": args.mc_filters * n_ev * K / (ms * 1e-3),
+                          "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                          "data": "synthetic, generated on the device inside the timed region",
+                          "config": {"workload": f"BASELINE config 5: K8 (UWB+IMU+mag+PX4Flow) Monte Carlo, {args.mc_filters} "
+                                                 f"filters in total, {n_macro} macro-steps of {len(synth.MACRO_FULL)} events, "
+                                                 f"8 anchors", "filters_per_gpu": N, "parallelism":
+                                     f"filters sharded by index over {world} GPU(s); one all-reduce of 4 doubles at the end"},
+                          "toa_updates_per_s": args.mc_filters * n_macro * K / (ms * 1e-3),
+                          "rmse_xy_m": rmse_xy, "filters_counted": s[2], "bad_filters": s[3]}))
+    batch.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def bench_other_configs(local, dev, args):
     """The remaining BASELINE.json configs as secondary numbers (device-resident inputs, CUDA
     events, 1 warm-up + 3 timed repetitions each).  Not the headline metric."""
@@ -568,11 +639,18 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary BASELINE configs")
+    ap.add_argument("--workload", default="t6", choices=["t6", "config5"],
+                    help="t6 = the headline metric (default); config5 = BASELINE config 5 itself: the K8 multi-sensor "
+                         "Monte Carlo with --mc-filters filters in TOTAL sharded over the ranks (strong scaling)")
+    ap.add_argument("--mc-filters", type=int, default=1 << 26, help="config5: total filters (64 Mi)")
+    ap.add_argument("--mc-macro-steps", type=int, default=4, help="config5: 0.1 s macro-steps per bench step")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "config5":
+        run_config5(args)
     else:
         run_b200(args)
 
