@@ -419,11 +419,18 @@ def run_config5(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     stream = torch.cuda.current_stream()
+    full = args.workload == "config5"
+    if not args.mc_filters:
+        args.mc_filters = (1 << 26) if full else (1 << 20)
+    if not args.mc_macro_steps:
+        args.mc_macro_steps = 4 if full else 1000
+    macro = synth.MACRO_FULL if full else synth.MACRO_IMU_MAG
     lo, hi = shard_bounds(args.mc_filters, rank, world)
-    N, K, W, n_macro, chunk = hi - lo, args.steps, args.warmup, args.mc_macro_steps, 2
+    N, K, W, n_macro = hi - lo, args.steps, args.warmup, args.mc_macro_steps
+    chunk = 2 if full else max(1, min(n_macro, (3 << 30) // (N * 8 * 35)))  # ~3 GB of inputs in flight
     anc = synth.anchors_for(8)
     batch = Batch(L.MODEL_K8, N, device=local, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5)
-    bufs = synth.k8_montecarlo_chunk(N, 0, chunk, anc, dev, seed=synth.SEED, full=True, first_filter=lo, want_x0=True,
+    bufs = synth.k8_montecarlo_chunk(N, 0, chunk, anc, dev, seed=synth.SEED, full=full, first_filter=lo, want_x0=True,
                                      stream=stream)
     x0 = bufs["x0"].clone()
 
@@ -431,7 +438,7 @@ def run_config5(args):
         nonlocal bufs
         batch.set_state(x0, None, stream=stream)
         for m0 in range(0, n_macro, chunk):
-            bufs = synth.k8_montecarlo_chunk(N, m0, min(chunk, n_macro - m0), anc, dev, seed=synth.SEED, full=True,
+            bufs = synth.k8_montecarlo_chunk(N, m0, min(chunk, n_macro - m0), anc, dev, seed=synth.SEED, full=full,
                                              first_filter=lo, out=bufs, stream=stream)
             batch.replay_events(bufs["events"], ranges=bufs["ranges"], sensors=bufs["sensors"], err=0.01, stream=stream)
         return batch.error_stats(bufs["truth_end"], stream=stream)
@@ -454,15 +461,16 @@ def run_config5(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    n_ev = n_macro * len(synth.MACRO_FULL)
+    n_ev = n_macro * len(macro)
     if rank == 0:
         print(json.dumps({"metric": "k8_multisensor_events_per_sec", "value": args.mc_filters * n_ev * K / (ms * 1e-3),
                           "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
                           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
                           "data": "synthetic, generated on the device inside the timed region",
-                          "config": {"workload": f"BASELINE config 5: K8 (UWB+IMU+mag+PX4Flow) Monte Carlo, {args.mc_filters} "
-                                                 f"filters in total, {n_macro} macro-steps of {len(synth.MACRO_FULL)} events, "
-                                                 f"8 anchors", "filters_per_gpu": N, "parallelism":
+                          "config": {"workload": f"BASELINE config {'5: K8 (UWB+IMU+mag+PX4Flow)' if full else '3: K8 (UWB+IMU+compass)'} "
+                                                 f"Monte Carlo, {args.mc_filters} filters in total, {n_macro} macro-steps of "
+                                                 f"{len(macro)} events, 8 anchors", "filters_per_gpu": N,
+                                     "chunk_macro_steps": chunk, "parallelism":
                                      f"filters sharded by index over {world} GPU(s); one all-reduce of 4 doubles at the end"},
                           "toa_updates_per_s": args.mc_filters * n_macro * K / (ms * 1e-3),
                           "rmse_xy_m": rmse_xy, "filters_counted": s[2], "bad_filters": s[3]}))
@@ -639,17 +647,19 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary BASELINE configs")
-    ap.add_argument("--workload", default="t6", choices=["t6", "config5"],
-                    help="t6 = the headline metric (default); config5 = BASELINE config 5 itself: the K8 multi-sensor "
-                         "Monte Carlo with --mc-filters filters in TOTAL sharded over the ranks (strong scaling)")
-    ap.add_argument("--mc-filters", type=int, default=1 << 26, help="config5: total filters (64 Mi)")
-    ap.add_argument("--mc-macro-steps", type=int, default=4, help="config5: 0.1 s macro-steps per bench step")
+    ap.add_argument("--workload", default="t6", choices=["t6", "config3", "config5"],
+                    help="t6 = the headline metric (default); config3 / config5 = those BASELINE configs themselves: the "
+                         "K8 IMU+compass+UWB (1 Mi filters x 1000 steps) / full multi-sensor (64 Mi filters) Monte Carlo "
+                         "with --mc-filters filters in TOTAL sharded over the ranks (strong scaling)")
+    ap.add_argument("--mc-filters", type=int, default=0, help="config3/5: total filters (default 1 Mi / 64 Mi)")
+    ap.add_argument("--mc-macro-steps", type=int, default=0,
+                    help="config3/5: 0.1 s macro-steps per bench step (default 1000 / 4)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "config5":
+    elif args.workload in ("config3", "config5"):
         run_config5(args)
     else:
         run_b200(args)
