@@ -1,8 +1,10 @@
 // kfpos_t6.cu -- persistent replay kernel for KalmanFilterTOA batches (G1+G2+G3+G5
-// of SURVEY.md §2).  One thread per filter; the filter's position and the working
-// covariance stay in registers and its P^- / per-anchor scratch in a private
-// shared-memory column across all T steps.  Per step the only global traffic is
-// the coalesced read of the filter's M rangings (SoA, filter index fastest) and
+// of SURVEY.md §2).  One thread per filter; across all T steps the filter's position
+// (and, for a compile-time anchor count, the epoch's ranges) stay in registers and its
+// packed covariance in a private shared-memory column; the update is computed in
+// factored form (kfpos_t6.cuh), so the covariance is touched twice per step (predict,
+// apply).  Per step the only global traffic is the coalesced read of the filter's M
+// rangings (SoA, filter index fastest), prefetched one epoch ahead with cp.async, and
 // the optional trajectory / selection stores.
 #include "kfpos_kernels.cuh"
 #include "kfpos_t6.cuh"
