@@ -238,8 +238,7 @@ def run_b200(args):
 
     # ---- device-resident throughput (`value`)
     sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
+    sampler.start()  # every rank watches its own GPU
     for _ in range(W):
         step_resident()
     batch.counters(reset=True)
@@ -262,9 +261,15 @@ def run_b200(args):
     barrier()
     torch.cuda.cudart().cudaProfilerStop()
     sampler.window(t_start, time.perf_counter())
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in kev]))
+    per_rank = [{"rank": rank, "kernel_ms": kernel_ms, "sm_mhz": clocks.get("sm_mhz"),
+                 "power_w_max": clocks.get("power_w_max"), "reasons": clocks.get("reasons")}]
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, per_rank[0])
+        per_rank = gathered
     cnt = batch.counters(reset=True)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     rank_ms = [ms]
@@ -391,7 +396,7 @@ def run_b200(args):
                            "filters_per_gpu": N, "epochs_per_step": T, "anchors": M,
                            "l2_policy": f"inputs larger than L2 ({N * T * M * 4 / 1e6:.0f} MB range log per step)",
                            "parallelism": f"filters sharded by index over {world} GPU(s); one all-reduce of 4 doubles at the end"},
-                "rmse_m": rmse, "bad_updates": cnt["bad"], "rank_ms_per_step": [v / K for v in rank_ms],
+                "rmse_m": rmse, "bad_updates": cnt["bad"], "rank_ms_per_step": [v / K for v in rank_ms], "ranks": per_rank,
                 "e2e": e2e, "gpu_launches": 3 * K, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "other_configs": other}
         print(json.dumps(line))

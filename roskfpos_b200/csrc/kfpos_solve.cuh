@@ -66,6 +66,19 @@ KF_DEV bool rel_change_lt(double cost, double newCost, double tol) {
     return q / cost < tol;
 }
 
+// Exact shortcut for Newton iterations that never meet the stop test.  The iteration is a
+// deterministic map p -> F(p) (the stop test is a function of two successive points), and in floating
+// point an oscillating sequence almost always becomes EXACTLY periodic after a few hundred steps.
+// Brent's cycle detection compares the iterate with a reference point that is refreshed at powers of
+// two; a bit-for-bit match after `lam` steps proves that the sequence repeats with period lam and --
+// having just gone once around without stopping -- that it will run to the reference's cap of 10000
+// iterations (ML.cpp:67,165).  The caller then skips whole periods: the remaining
+// (10000 - iter) mod lam iterations end in exactly the state the full run would reach.  Used by the
+// EKFs' inner solver, where one such solve would hold a warp of the persistent replay kernel for
+// milliseconds (the ML kernel parks long solves instead, kfpos_mlk.cu).
+// (implemented inline in ml_solve3_ekf: the reference point lives in three shared-memory words, the
+// iteration counter is the clock, so the common 2-4 step solve pays one load and one compare a step)
+
 struct MlPass3 {
     double wcost, sse;
     double g[3];
@@ -249,7 +262,7 @@ KF_DEV int ml_solve3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
 template <int MT>
 KF_DEV int ml_solve3_ekf(const AnchorTable &A, const EpochT<false, MT> &ep, unsigned mask, double (&p)[3],
                          double &sse_out, unsigned &iters, double &sse_start, double (&g_start)[3],
-                         double (&Gu_start)[6]) {
+                         double (&Gu_start)[6], const Col &cyc_ref) {
     const int nvalid = __popc(mask);
     MlPass3 ps;
     ml_pass3<false, MT, true>(A, ep, mask, nvalid, p, ps, Gu_start);
@@ -267,6 +280,14 @@ KF_DEV int ml_solve3_ekf(const AnchorTable &A, const EpochT<false, MT> &ep, unsi
         p[0] -= s[0]; p[1] -= s[1]; p[2] -= s[2];
         ml_pass3<false, MT>(A, ep, mask, nvalid, p, ps);
         newCost = ps.wcost;
+        // Brent's cycle detection (see CycleDetect) with the reference point in shared memory and the
+        // iteration count as its clock: refreshed when iter is a power of two
+        if ((iter & (iter - 1u)) == 0u) {
+            cyc_ref[0] = p[0]; cyc_ref[1] = p[1]; cyc_ref[2] = p[2];
+        } else if (p[0] == cyc_ref[0] && p[1] == cyc_ref[1] && p[2] == cyc_ref[2]) {
+            const unsigned per = iter - (1u << (31 - __clz(iter)));
+            iter = 10000u - (10000u - iter) % per;
+        }
     }
     iters += iter;
     sse_out = ps.sse;

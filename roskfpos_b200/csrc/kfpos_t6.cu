@@ -17,9 +17,9 @@ constexpr int T6_BLOCK = 128;
 #endif
 
 // shared-memory rows (doubles) per thread: [metres column when MT == 0], [errorEstimation
-// column], P^-, landing zone of the prefetch
+// column], P^-, the reference point of the Newton cycle detector, landing zone of the prefetch
 __host__ __device__ inline int t6_smem_rows(int m, int fmt, bool pme, bool in_regs) {
-    return (in_regs ? 0 : m) + (pme ? m : 0) + 21 + raw_rows(fmt, m);
+    return (in_regs ? 0 : m) + (pme ? m : 0) + 21 + 3 + raw_rows(fmt, m);
 }
 
 // MT > 0: compile-time anchor count (unrolled anchor loops, ranges in registers); MT == 0: run-time.
@@ -51,6 +51,7 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
         };
         EpochT<PME, MT> ep;
         const Col Pm = take(21);
+        const Col cyc = take(3);
         ep.z = MT > 0 ? Pm : take(m);
         ep.e = PME ? take(m) : Pm;
         ep.e0 = p.rs.err_scalar;
@@ -119,10 +120,10 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
                     ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, cov0); // the all-ranging solve of :353
                     best_group<PME, MT>(p.anchors, ep, ep.valid, false, p.best_mode, pos, st.ml_iters, p0, cov0, used, grc);
                 }
-                rc = t6_update<PME, MT>(p.anchors, ep, used, pos, Pm, res, st, 0u);
+                rc = t6_update<PME, MT>(p.anchors, ep, used, pos, Pm, res, st, 0u, &cyc);
                 ignored = (int)used;
             } else if (!LOO) {
-                rc = t6_update<PME, MT>(p.anchors, ep, ep.valid, pos, Pm, res, st, emask);
+                rc = t6_update<PME, MT>(p.anchors, ep, ep.valid, pos, Pm, res, st, emask, &cyc);
                 __syncwarp(emask);
             } else {
                 // kalmanStep3DCanIgnoreAnAnchor (TOA.cpp:185-238): the all-anchor solve (i = -1),
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
                 for (int i = -1; i < n_try && rc == 0; ++i) {
                     if (i >= 0 && !((ep.valid >> i) & 1u)) continue;
                     T6Result ri;
-                    rc = t6_update<PME, MT>(p.anchors, ep, i < 0 ? ep.valid : (ep.valid & ~(1u << i)), pos, Pm, ri, st);
+                    rc = t6_update<PME, MT>(p.anchors, ep, i < 0 ? ep.valid : (ep.valid & ~(1u << i)), pos, Pm, ri, st, 0u, &cyc);
                     if (rc != 0) break;
                     if (i < 0) {
                         res = ri;
