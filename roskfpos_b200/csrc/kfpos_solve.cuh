@@ -216,7 +216,8 @@ struct MlResume {
 template <bool PME, int MT>
 KF_DEV int ml_solve3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, double (&p)[3],
                      double &sse_out, unsigned &iters, double *cov /* packed Sym<3> or null */,
-                     double *sse_start = nullptr, unsigned iter_cap = 10000u, MlResume *rs = nullptr) {
+                     double *sse_start = nullptr, unsigned iter_cap = 10000u, MlResume *rs = nullptr,
+                     const Col *cyc_ref = nullptr /* EKF callers: arms the cycle detection (see below) */) {
     const int nvalid = __popc(mask);
     MlPass3 ps;
     double cost = 1e20, newCost = 1.0;
@@ -248,6 +249,15 @@ KF_DEV int ml_solve3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
         if (!solve_sym3(ps.H, ps.g, s)) { iters += iter; return ML_SINGULAR; }
         // newPos = solve(H, H pos - g)  ==  pos - H^-1 g
         p[0] -= s[0]; p[1] -= s[1]; p[2] -= s[2];
+        if (cyc_ref) { // Brent's cycle detection, as in ml_solve3_ekf
+            const Col &c = *cyc_ref;
+            if ((iter & (iter - 1u)) == 0u) {
+                c[0] = p[0]; c[1] = p[1]; c[2] = p[2];
+            } else if (p[0] == c[0] && p[1] == c[1] && p[2] == c[2]) {
+                const unsigned per = iter - (1u << (31 - __clz(iter)));
+                iter = 10000u - (10000u - iter) % per;
+            }
+        }
     }
     iters += iter;
     sse_out = ps.sse;

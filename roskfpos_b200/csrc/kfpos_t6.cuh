@@ -69,7 +69,7 @@ KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
     // pass: cost = sse_xp / R, b = -g_xp / R (eps - J delta = eps at delta = 0), G = Gu_xp / R
     double g_xp[3] = {0.0, 0.0, 0.0}, Gu_xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     int rc;
-    if constexpr (PME) rc = ml_solve3<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &sse_xp);
+    if constexpr (PME) rc = ml_solve3<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &sse_xp, 10000u, nullptr, cyc_ref);
     else rc = ml_solve3_ekf<MT>(A, ep, mask, pml, sse, st.ml_iters, sse_xp, g_xp, Gu_xp, *cyc_ref);
     if (wmask) __syncwarp(wmask);
     if (rc == ML_FEW) st.status |= 2u;

@@ -21,7 +21,7 @@ constexpr int T9_BLOCK = 128;
 // [metres column when MT == 0], [errorEstimation column]
 __host__ __device__ inline int t9_land_rows(int m, int fmt) { return raw_rows(fmt, m) > 3 ? raw_rows(fmt, m) : 3; }
 __host__ __device__ inline int t9_smem_rows(int m, int fmt, bool pme, bool in_regs) {
-    return 45 + t9_land_rows(m, fmt) + (in_regs ? 0 : m) + (pme ? m : 0);
+    return 45 + 3 + t9_land_rows(m, fmt) + (in_regs ? 0 : m) + (pme ? m : 0); // + cycle-detector reference point
 }
 
 // P^- = F P F^T + Q (TOAIMU.cpp:392-421)
@@ -81,13 +81,13 @@ KF_DEV bool accel_block_update(Sym<9> &P, double (&dn)[9], const double (&y)[3],
 template <bool PME, int MT, bool IMU>
 KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r, bool has_imu, const double (&za)[3],
                      const double (&Ra)[6], const double (&xp)[9], const Col &Pm, Sym<9> &Pw, double (&dx)[9],
-                     double (&M)[6], StepStats &st, unsigned wmask) {
+                     double (&M)[6], StepStats &st, unsigned wmask, const Col &cyc) {
     const unsigned mask = has_r ? ep.valid : 0u;
     double sse = -1.0;
     int rc = ML_OK;
     if (has_r) { // TOAIMU.cpp:268-270 (no NaN guard in this class)
         double pml[3] = {xp[0], xp[1], xp[2]};
-        rc = ml_solve3<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr);
+        rc = ml_solve3<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr, nullptr, 10000u, nullptr, &cyc);
         if (mask == 0u) sse = -1.0;
         // has_r is a property of the event, common to the batch: every lane of wmask is here
         if (wmask) __syncwarp(wmask);
@@ -210,6 +210,7 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
             return c;
         };
         const Col Pm = take(45);
+        const Col cyc = take(3);
         const Col land = take(t9_land_rows(m, p.rs.fmt));
         const RawColPriv raw = {land}; // rangings land in the same private column
         EpochT<PME, MT> ep;
@@ -279,7 +280,7 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
                                   vel[0], vel[1], vel[2], 0.0, 0.0, 0.0};
             if (has_r && ep.valid == 0u) st.status |= 1u;
             double dx[9], M[6];
-            const int rc = t9_update<PME, MT, IMU>(p.anchors, ep, has_r, IMU && has_imu, za, Ra, xp, Pm, Pw, dx, M, st, wmask);
+            const int rc = t9_update<PME, MT, IMU>(p.anchors, ep, has_r, IMU && has_imu, za, Ra, xp, Pm, Pw, dx, M, st, wmask, cyc);
             __syncwarp(wmask); // the IEKF trip count differs per lane
             if (rc >= 0) {
 #pragma unroll
