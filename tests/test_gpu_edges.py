@@ -66,3 +66,37 @@ def test_maximum_anchor_count_and_odd_batch_sizes(kflib, oracle, N):
     ok = mref["iters"] < 100  # epochs whose Newton iteration wanders are compared in test_gpu_ml.py
     assert np.abs(got["pos"][:, ok] - mref["pos"][:, ok]).max() < 1e-9
     assert np.array_equal(got["iters"][ok], mref["iters"][ok])
+
+
+@pytest.mark.parametrize("N", [1, 33, 130])
+def test_event_stream_models_at_odd_batch_sizes(kflib, oracle, N):
+    """K8 (full multi-sensor schedule) and T9 (rangings + accelerometer) with batches that do not fill a
+    warp / a block: the partially filled warp takes part in the warp-level re-convergence."""
+    from roskfpos_b200.batch import Batch
+    anc = synth.anchors_for(8)
+    w = synth.k8_workload(N, 3, anc, seed=70 + N, full=True)
+    cfg = oracle.k8_cfg(0.5, 0.5, **synth.K8_ORACLE_CFG)
+    ref = oracle.k8_replay(w["x0"], None, w["events"], w["ranges"], w["sensors"], anc, 0.01, cfg)
+    with Batch(kflib.MODEL_K8, N, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5) as b:
+        b.set_state(w["x0"])
+        b.replay_events(w["events"], ranges=w["ranges"], sensors=w["sensors"], err=0.01)
+        x, P, st = b.get_state()
+    assert rel_err_state(x, ref["x"]) < REL_TOL and rel_err_cov(P, ref["P"]) < REL_TOL
+    # T9: TOA epochs interleaved with accelerometer samples
+    T = 6
+    truth = synth.truth_lissajous(N, T, 0.1, seed=80 + N)
+    r = synth.ranges_mm(truth[1:], anc, seed=81 + N)
+    rng = np.random.default_rng(N)
+    acc = rng.normal(0, 0.2, size=(3 * T, N))
+    cov = [0.01, 0.001, 0.0, 0.001, 0.02, 0.0, 0.0, 0.0, 0.03]
+    events = []
+    for t in range(T):
+        events.append((kflib.EV_IMU, 0.04, 3 * t, cov))
+        events.append((kflib.EV_TOA, 0.06, t * 8, None))
+    x0 = np.zeros((9, N)); x0[:3] = truth[0]
+    ref9 = oracle.t9_events(x0, None, events, r, acc, anc, 0.01)
+    with Batch(kflib.MODEL_T9, N, anchors=anc, accel_noise=0.5, jolt=0.5) as b:
+        b.set_state(x0)
+        b.replay_events(events, ranges=r, sensors=acc, err=0.01)
+        x9, P9, st9 = b.get_state()
+    assert rel_err_state(x9, ref9["x"]) < REL_TOL and rel_err_cov(P9, ref9["P"]) < REL_TOL
