@@ -65,3 +65,67 @@ def test_t6_random_configuration(kflib, oracle, seed):
     rep = assert_parity(got, ref, per, float_keys=("x",), cov_keys=("P",), int_keys=("status", "sel"),
                         min_stable=0.5 if few else 0.9, max_tie_frac=4e-2 if few else 1e-2, what=str(c))
     print("fuzz", seed, c, rep)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("KF_FUZZ_SEEDS", "16"))))
+def test_k8_random_event_schedule(kflib, oracle, seed):
+    """K8: random schedules of the five event kinds (random order and dt, PX4 frames of quality 0, raw
+    magnetometer samples, missing rangings, per-ranging errors, 4 / 6 / 8 anchors) against the oracle."""
+    from roskfpos_b200.batch import Batch
+    rng = np.random.default_rng(5000 + seed)
+    m = int(rng.choice([4, 6, 8, 8]))
+    N, n_ev = int(rng.integers(1, 400)), int(rng.integers(3, 40))
+    pme = bool(rng.integers(0, 2))
+    anc = synth.anchors_for(m)
+    th = rng.uniform(-3, 3, N)
+    pos = np.stack([rng.uniform(2, 8, N), rng.uniform(2, 8, N)])
+    x0 = np.zeros((8, N)); x0[:2] = pos; x0[2:4] = rng.normal(0, 0.3, (2, N)); x0[6] = th; x0[7] = rng.normal(0, 0.1, N)
+    d = np.sqrt((pos[0][None] - anc[:, 0:1]) ** 2 + (pos[1][None] - anc[:, 1:2]) ** 2 + (1.049 - anc[:, 2:3]) ** 2)
+    events, rows, rng_rows = [], [], []
+    for _ in range(n_ev):
+        kind = int(rng.choice([synth.EV_TOA, synth.EV_PX4, synth.EV_IMU, synth.EV_IMU, synth.EV_MAG, synth.EV_COMPASS]))
+        dt = float(rng.uniform(0.003, 0.12))
+        if kind == synth.EV_TOA:
+            r = np.floor((d + 0.1 * rng.normal(size=d.shape)) * 1000)
+            r[rng.random(r.shape) < 0.15] = 0
+            events.append((kind, dt, len(rng_rows) * m, None)); rng_rows.append(r)
+        elif kind == synth.EV_PX4:
+            q = np.where(rng.random(N) < 0.25, 0.0, 150.0)
+            off = len(rows)
+            rows += [rng.normal(0, 2e-3, N), rng.normal(0, 2e-3, N), rng.normal(0, 1e-3, N), np.full(N, 33333.0), q]
+            events.append((kind, dt, off, None))
+        elif kind == synth.EV_IMU:
+            off = len(rows)
+            rows += [rng.normal(0.05, 0.3, N), rng.normal(0, 0.3, N), rng.normal(0, 0.3, N)]
+            events.append((kind, dt, off, [0.004, 1e-4, 1e-4, 0.005, 0.07]))
+        elif kind == synth.EV_MAG:
+            off = len(rows)
+            a = th + 0.05 * rng.normal(size=N)
+            rows += [np.cos(a), np.sin(a)]
+            events.append((kind, dt, off, None))
+        else:
+            off = len(rows)
+            rows.append(np.arctan2(np.sin(th + 0.02 * rng.normal(size=N)), np.cos(th)))
+            events.append((kind, dt, off, None))
+    ranges = np.ascontiguousarray(np.array(rng_rows).reshape(-1, m, N).astype(np.int32)) if rng_rows else \
+        np.zeros((1, m, N), dtype=np.int32)
+    sensors = np.ascontiguousarray(np.array(rows)) if rows else np.zeros((1, N))
+    err = rng.uniform(0.005, 0.05, size=ranges.shape) if pme else 0.01
+    xml = list(synth.K8_XML)
+    ocfg = dict(synth.K8_ORACLE_CFG)
+    if rng.random() < 0.5:  # covariances from the messages instead of the fixed XML values
+        xml[2] = '<config><imu useFixedCovarianceAcceleration="0" useFixedCovarianceAngularVelocityZ="0"/></config>'
+        ocfg.update(imu_fixed_cov_acc=0, imu_fixed_cov_gyro=0)
+    cfg = oracle.k8_cfg(0.5, 0.5, **ocfg)
+    ref = oracle.k8_replay(x0, None, events, ranges, sensors, anc, err, cfg)
+    with Batch(kflib.MODEL_K8, N, anchors=anc, xml=xml, accel_noise=0.5, jolt=0.5) as b:
+        b.set_state(x0)
+        b.replay_events(events, ranges=ranges, sensors=sensors, err=err)
+        x, P, st = b.get_state()
+    ok = np.isfinite(ref["x"]).all(axis=0)
+    assert ok.mean() > 0.9
+    ex = np.abs(x - ref["x"])[:, ok].max() if ok.any() else 0.0
+    with np.errstate(invalid="ignore", divide="ignore"):
+        eP = (np.abs(P - ref["P"]).max(axis=0) / np.abs(ref["P"]).max(axis=0))[ok].max() if ok.any() else 0.0
+    assert ex < 1e-9 and eP < 1e-9, (m, N, n_ev, pme, ex, eP)
+    assert np.array_equal(st[ok] & ~(32 | 64), ref["status"][ok] & ~(32 | 64))
