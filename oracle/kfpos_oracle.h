@@ -117,6 +117,8 @@ typedef struct {
     double px4_itime, px4_vx, px4_vy, px4_gz, px4_cv, px4_cg; /* lastPX4FlowMeasurement */
     double imu_wz, imu_cwz, imu_ax, imu_ay, imu_cxy[4];       /* lastImuMeasurement     */
     double mag_angle, mag_c;                                  /* lastMagMeasurement     */
+    /* EKF-side NLOS variants (config_pos.xml; see ko_t6_new_toa_sel): 0 = normal */
+    int variant, n_ignore, best_mode;
 } ko_k8;
 void ko_k8_init(ko_k8 *f, double accel_noise, double init_angle, double jolt, const double p0[2]);
 void ko_k8_new_toa(ko_k8 *f, double dt, int n_slots, const double *ranges,

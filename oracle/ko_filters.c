@@ -528,7 +528,42 @@ void ko_k8_new_toa(ko_k8 *f, double dt, int n_slots, const double *ranges, const
                    const double *errs, int b1_zero_z, ko_info *info) {
     ko_meas m[KO_MAX_ANCHORS];
     int n = gather(n_slots, ranges, anchors, errs, m);
-    k8_estimate(f, dt, 1, m, n, f->has_px4, f->has_imu, f->has_mag, b1_zero_z, info);
+    if (f->variant == 0) {
+        k8_estimate(f, dt, 1, m, n, f->has_px4, f->has_imu, f->has_mag, b1_zero_z, info);
+        return;
+    }
+    /* EKF-side NLOS variants, the 2-D counterpart of ko_t6_new_toa_sel: the ML estimator, started at the
+     * predicted position (p + dt v, tag height), selects the rangings -- variant 1 drops the
+     * min(n - 3, n_ignore) with the largest residual, variant 2 keeps the best 3-anchor group
+     * (ML.cpp:351-414 with the 2-D criterion of App. B-4) -- and the update runs on the survivors. */
+    ko_meas sub[KO_MAX_ANCHORS];
+    unsigned char keep[KO_MAX_ANCHORS];
+    for (int i = 0; i < n; ++i) keep[i] = 1;
+    int it_sel = 0, it = 0;
+    const double start[3] = {f->pos[0] + dt * f->vel[0], f->pos[1] + dt * f->vel[1], f->tag_z};
+    if (f->variant == 1 && n > 0) {
+        double p0[3], c0[4];
+        if (ko_ml2d(m, n, start, b1_zero_z, p0, c0, &it) == 0) {
+            int order[KO_MAX_ANCHORS];
+            ko_best_rangings(m, n, p0, order);
+            int drop = n - 3 < f->n_ignore ? n - 3 : f->n_ignore;
+            if (drop < 0) drop = 0;
+            for (int i = n - drop; i < n; ++i) keep[order[i]] = 0;
+        }
+        it_sel += it;
+    } else if (f->variant == 2 && n >= 3) {
+        double p0[3], c0[9];
+        int bi, ng;
+        uint32_t bm = 0;
+        ko_ml_best_group(m, n, start, 1, f->best_mode, b1_zero_z, p0, c0, &it, &bi, &bm, &ng);
+        it_sel += it;
+        for (int i = 0; i < n; ++i) keep[i] = (bm >> i) & 1u;
+    }
+    int ns = 0;
+    for (int i = 0; i < n; ++i)
+        if (keep[i]) sub[ns++] = m[i];
+    k8_estimate(f, dt, 1, sub, ns, f->has_px4, f->has_imu, f->has_mag, b1_zero_z, info);
+    info->ml_iters += it_sel;
 }
 
 /* newPX4FlowMeasurement KF.cpp:100-133 */

@@ -42,7 +42,8 @@ class KoK8(C.Structure):
                 ("px4_gz", C.c_double), ("px4_cv", C.c_double), ("px4_cg", C.c_double),
                 ("imu_wz", C.c_double), ("imu_cwz", C.c_double), ("imu_ax", C.c_double),
                 ("imu_ay", C.c_double), ("imu_cxy", C.c_double * 4),
-                ("mag_angle", C.c_double), ("mag_c", C.c_double)]
+                ("mag_angle", C.c_double), ("mag_c", C.c_double),
+                ("variant", C.c_int), ("n_ignore", C.c_int), ("best_mode", C.c_int)]
 
 
 class KoT9(C.Structure):

@@ -527,6 +527,10 @@ K8Cfg make_k8cfg(const kfpos_batch *b) {
     c.mag_cov = b->cfg.mag_cov;
     c.imu_fix_acc = b->cfg.imu_use_fixed_cov_acc;
     c.imu_fix_gyro = b->cfg.imu_use_fixed_cov_gyro_z;
+    c.variant = b->cfg.variant;
+    c.n_ignore = b->cfg.num_ignored_rangings;
+    c.best_mode = b->cfg.best_mode;
+    c._pad = 0;
     return c;
 }
 

@@ -44,7 +44,11 @@ KF_DEV void prefetch_event(const RawColPriv &raw, const Col &land, const EventDe
     }
 }
 
-template <bool PME, int MT>
+// SEL: EKF-side NLOS variants (config_pos.xml variant / numIgnoredRangings / bestMode, see kfpos_t6.cu):
+// at a TOA event the 2-D ML estimator, started at the predicted position, selects the rangings --
+// variant 1 drops the N with the largest residual, variant 2 keeps the best THREE anchors -- and the
+// update runs on the survivors.
+template <bool PME, int MT, bool SEL = false>
 __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __grid_constant__ K8Params p) {
     extern __shared__ double smem[];
     const int64_t f = (int64_t)blockIdx.x * K8_BLOCK + threadIdx.x;
@@ -170,7 +174,26 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
 
                 if (has_r && ep.valid == 0u) st.status |= 1u;
                 double dx[8];
-                const int rc = k8_update<PME, MT>(p.anchors, p.cfg, ep, has_r, ms, dt, xp, Pm, Pw, dx, st, wmask);
+                unsigned used = ep.valid;
+                if (SEL && has_r) {
+                    const int n = __popc(ep.valid);
+                    const double start[3] = {xp[0], xp[1], p.cfg.tag_z};
+                    double p0[3] = {start[0], start[1], start[2]}, sse0, cov0[6];
+                    if (p.cfg.variant == 1 && n > 0) {
+                        if (ml_solve2<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, nullptr) == ML_OK) {
+                            const int drop = min(n - 3, p.cfg.n_ignore);
+                            used = drop_worst<PME, MT>(p.anchors, ep, used, p0, drop < 0 ? 0 : drop);
+                        }
+                    } else if (p.cfg.variant == 2 && n >= 3) {
+                        int grc;
+                        double c2[3];
+                        ml_solve2<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, c2); // the all-ranging solve
+                        best_group<PME, MT>(p.anchors, ep, ep.valid, true, p.cfg.best_mode, start, st.ml_iters, p0, cov0,
+                                            used, grc);
+                    }
+                }
+                const int rc = k8_update<PME, MT>(p.anchors, p.cfg, ep, has_r, used, ms, dt, xp, Pm, Pw, dx, st,
+                                                  SEL ? 0u : wmask);
                 if (rc == 0) {
                     px = xp[0] + dx[0]; py = xp[1] + dx[1];
                     vx = xp[2] + dx[2]; vy = xp[3] + dx[3];
@@ -217,18 +240,20 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
     warp_accumulate(p.counters + CNT_BAD, n_bad);
 }
 
-template <bool PME, int MT>
+template <bool PME, int MT, bool SEL = false>
 static cudaError_t launch_k(const K8Params &p, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + K8_BLOCK - 1) / K8_BLOCK);
     const size_t smem = (size_t)k8_smem_rows(p.rs.m_slots, p.rs.fmt, PME, MT > 0) * K8_BLOCK * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(k8_replay_kernel<PME, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k8_replay_kernel<PME, MT, SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k8_replay_kernel<PME, MT><<<grid, K8_BLOCK, smem, s>>>(p);
+    k8_replay_kernel<PME, MT, SEL><<<grid, K8_BLOCK, smem, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_k8_replay(const K8Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
+    if (p.cfg.variant == 1 || p.cfg.variant == 2)
+        return p.rs.err != nullptr ? launch_k<true, 0, true>(p, s) : launch_k<false, 0, true>(p, s);
     if (p.rs.err != nullptr) return launch_k<true, 0>(p, s);
     if (p.rs.m_slots == 8) return launch_k<false, 8>(p, s);
     return launch_k<false, 0>(p, s);

@@ -62,10 +62,10 @@ struct K8Meas {
 // accelerometer pair as a 2x2 block: its covariance may carry off-diagonals, KF.cpp:431-434).
 // wmask: lanes that run this event together, re-converged after the Newton loop (0 = none).
 template <bool PME, int MT>
-KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const EpochT<PME, MT> &ep, bool has_r, const K8Meas &ms,
-                     double dt, const double (&xp)[8], const Col &Pm, Sym<8> &Pw, double (&dx)[8], StepStats &st,
-                     unsigned wmask) {
-    const unsigned mask = has_r ? ep.valid : 0u;
+KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const EpochT<PME, MT> &ep, bool has_r, unsigned used,
+                     const K8Meas &ms, double dt, const double (&xp)[8], const Col &Pm, Sym<8> &Pw, double (&dx)[8],
+                     StepStats &st, unsigned wmask) {
+    const unsigned mask = has_r ? used : 0u; // used = ep.valid, or the EKF-side variant's selection
     double sse = -1.0;
     int rc = ML_OK;
     if (has_r) { // inner ML 2-D solve from (x^-_0, x^-_1, tagZ) (KF.cpp:403-405)

@@ -84,6 +84,8 @@ struct K8Cfg {
     double imu_cov_acc, imu_cov_gyro;
     double mag_offset, mag_cov;
     int imu_fix_acc, imu_fix_gyro;
+    int variant, n_ignore, best_mode; // EKF-side NLOS variants (config_pos.xml; 0 = normal)
+    int _pad;
 };
 
 struct K8Params {

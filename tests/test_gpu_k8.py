@@ -131,3 +131,43 @@ def test_k8_toa_only_replay_and_get_pose(kflib, oracle):
         xr, Pr = o.get_pose(0.04)
         assert np.abs(xp[:, f] - xr).max() < 1e-12
         assert np.abs(Pp[:, f].reshape(8, 8) - Pr).max() <= 1e-12 * np.abs(Pr).max()
+
+
+@pytest.mark.parametrize("variant,n_ignore", [(1, 2), (2, 0)])
+def test_k8_ekf_side_nlos_variants(kflib, oracle, variant, n_ignore):
+    """EKF-side variants for the planar filter: variant 1 drops the N worst rangings, variant 2 keeps the
+    best THREE anchors (the 2-D best group), selected by the 2-D ML estimator from the predicted position;
+    compass events in between so that the latched sensor rows take part in the update."""
+    from roskfpos_b200.batch import Batch
+    from tests.util import to_metres, ulp_perturbations
+    N, T, m = 2500, 4, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=401, z=1.049)
+    r = synth.ranges_mm(truth[1:], anc, seed=402, p_nlos=0.15)
+    rng = np.random.default_rng(403)
+    comp = rng.uniform(-3, 3, size=(T, N))
+    events = []
+    for t in range(T):
+        events.append((synth.EV_COMPASS, 0.03, t, None))
+        events.append((synth.EV_TOA, 0.07, t * m, None))
+    x0 = np.zeros((8, N)); x0[:2] = truth[0][:2]; x0[6] = comp[0]
+    cfg = oracle.k8_cfg(0.5, 0.5, variant=variant, n_ignore=n_ignore, **synth.K8_ORACLE_CFG)
+    run = lambda rr: oracle.k8_replay(x0, None, events, rr, comp, anc, 0.01, cfg)
+    ref = run(r)
+    per = [run(p) for p in ulp_perturbations(to_metres(r))]
+    with Batch(kflib.MODEL_K8, N, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5, variant=variant,
+               num_ignored_rangings=n_ignore) as b:
+        b.set_state(x0)
+        b.replay_events(events, ranges=r, sensors=comp, err=0.01)
+        x, P, st = b.get_state()
+        cnt = b.counters()
+    plain = oracle.k8_replay(x0, None, events, r, comp, anc, 0.01, oracle.k8_cfg(0.5, 0.5, **synth.K8_ORACLE_CFG))
+    assert np.abs(plain["x"] - ref["x"]).max() > 1e-3  # the selection does change the estimate
+    got = dict(x=x, P=P, status=st & ~32)
+    for d in [ref] + per:
+        d["status"] = d["status"] & ~32
+    rep = assert_parity(got, ref, per, float_keys=("x",), cov_keys=("P",), int_keys=("status",),
+                        min_stable=0.9 if variant == 1 else 0.6, max_tie_frac=1e-2 if variant == 1 else 6e-2,
+                        what=f"K8 variant {variant}")
+    print("parity report K8 variant", variant, rep, cnt)
+    assert cnt["updates"] == N * len(events)
