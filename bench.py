@@ -140,7 +140,12 @@ def cpu_reference(n_anchors, tsteps, seconds, threads=0):
             res = pool.map(_ref_worker, [(synth.SEED + 100 + i, nf, tsteps, n_anchors) for i in range(cores)])
         tt = max(t for t, _, _ in res)
         upd = sum(u for _, u, _ in res)
-        return {"value": upd / tt, "unit": UNIT, "cores": cores, "kind": "reference",
+        # the reference's native mode: ONE filter, one thread, BASELINE config 1 (4 anchors,
+        # 10 000 steps at 10 Hz)
+        t1, u1, _ = _ref_worker((synth.SEED + 1, 1, 10000, 4))
+        native = {"updates_per_s": u1 / t1, "us_per_update": 1e6 * t1 / u1,
+                  "sample": "1 filter x 10000 steps, 4 anchors (BASELINE config 1a), one thread"}
+        return {"value": upd / tt, "unit": UNIT, "cores": cores, "kind": "reference", "single_filter": native,
                 "sample": f"{nf * cores} filters x {tsteps} steps, {n_anchors} anchors, the reference's own "
                           f"KalmanFilterTOA.cpp + MLLocation.cpp (g++ -O2, shim Armadillo over OpenBLAS LAPACK), "
                           f"{cores} single-threaded processes, {tt:.1f} s",
