@@ -99,12 +99,12 @@ typedef struct kfpos_config {
     int32_t ignore_worst_anchor;  /* ignoreWorstAnchorMode (T6)                     */
     int32_t _pad0;
     double ignore_cost_threshold; /* ignoreCostThreshold (T6)                       */
-    /* MLLocation ctor (ML.h:30) + config_pos.xml <algorithm .../>.  For T6 and K8 batches variant /
+    /* MLLocation ctor (ML.h:30) + config_pos.xml <algorithm .../>.  For T6, K8 and T9 batches variant /
      * num_ignored_rangings / best_mode select the EKF-side NLOS variants that README.md:85-108
      * documents (the reference implements them only in MLLocation): the ML estimator, started at
      * the predicted position, picks the rangings (variant 1: drop the N with the largest residual,
-     * ML.cpp:307-347; variant 2: keep the best group, ML.cpp:351-414 -- 4 anchors for T6's 3-D
-     * solve, the "best 3 anchors" of the documentation for K8's 2-D solve) and the iterated update
+     * ML.cpp:307-347; variant 2: keep the best group, ML.cpp:351-414 -- 4 anchors for the 3-D
+     * solves of T6 / T9, the "best 3 anchors" of the documentation for K8's 2-D solve) and the iterated update
      * runs on the survivors; for T6 `sel` of kfpos_batch_replay_toa holds the slot mask used.     */
     int32_t use2d;                /* use2d                                          */
     int32_t variant;              /* variant                                        */

@@ -138,6 +138,7 @@ typedef struct {
     double P[81];
     int has_imu;
     double imu_a[3], imu_cov[9];
+    int variant, n_ignore, best_mode; /* EKF-side NLOS variants (see ko_t6_new_toa_sel); 0 = normal */
 } ko_t9;
 void ko_t9_init(ko_t9 *f, double accel_noise, double jolt, const double p0[3]);
 void ko_t9_new_toa(ko_t9 *f, double dt, int n_slots, const double *ranges,
@@ -180,6 +181,10 @@ void ko_k8_replay(int64_t N, int n_events, const ko_event *ev, int M, const doub
                   int fmt, double err_scalar, const double *err_arr, const double *sensors, const ko_k8 *cfg,
                   int b1_zero_z, double *x /*[8][N]*/, double *P /*[64][N]*/, double *traj, double *counters /*[5]*/,
                   int32_t *status, int threads);
+void ko_t9_events_sel(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
+                      int fmt, double err_scalar, const double *err_arr, const double *sensors, double accel_noise,
+                      double jolt, int variant, int n_ignore, int best_mode, double *x, double *P, double *traj,
+                      double *counters, int32_t *status, int threads);
 void ko_t9_events(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
                   int fmt, double err_scalar, const double *err_arr, const double *sensors, double accel_noise,
                   double jolt, double *x /*[9][N]*/, double *P /*[81][N]*/, double *traj, double *counters /*[5]*/,

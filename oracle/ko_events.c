@@ -113,6 +113,15 @@ void ko_k8_replay(int64_t N, int n_events, const ko_event *ev, int M, const doub
 void ko_t9_events(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
                   int fmt, double err_scalar, const double *err_arr, const double *sensors, double accel_noise,
                   double jolt, double *x, double *P, double *traj, double *counters, int32_t *status, int threads) {
+    ko_t9_events_sel(N, n_events, ev, M, anchors, ranges, fmt, err_scalar, err_arr, sensors, accel_noise, jolt, 0, 0, 0,
+                     x, P, traj, counters, status, threads);
+}
+
+/* variant != 0: the EKF-side NLOS variants (ko_t9_new_toa selects the rangings first) */
+void ko_t9_events_sel(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
+                      int fmt, double err_scalar, const double *err_arr, const double *sensors, double accel_noise,
+                      double jolt, int variant, int n_ignore, int best_mode, double *x, double *P, double *traj,
+                      double *counters, int32_t *status, int threads) {
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
@@ -122,6 +131,7 @@ void ko_t9_events(int64_t N, int n_events, const ko_event *ev, int M, const doub
         ko_t9 flt;
         double p0[3] = {x[0 * N + f], x[1 * N + f], x[2 * N + f]};
         ko_t9_init(&flt, accel_noise, jolt, p0);
+        flt.variant = variant; flt.n_ignore = n_ignore; flt.best_mode = best_mode;
         for (int k = 0; k < 3; ++k) flt.vel[k] = x[(int64_t)(3 + k) * N + f];
         for (int k = 0; k < 81; ++k) flt.P[k] = P[(int64_t)k * N + f];
         int st_or = 0, n_toa = 0;

@@ -737,7 +737,43 @@ void ko_t9_new_toa(ko_t9 *f, double dt, int n_slots, const double *ranges, const
                    const double *errs, ko_info *info) {
     ko_meas m[KO_MAX_ANCHORS];
     int n = gather(n_slots, ranges, anchors, errs, m);
-    t9_estimate(f, dt, 1, m, n, f->has_imu, info);
+    if (f->variant == 0) {
+        t9_estimate(f, dt, 1, m, n, f->has_imu, info);
+        return;
+    }
+    /* EKF-side NLOS variants, as ko_t6_new_toa_sel: 3-D ML selection from the predicted position (F x)[0:3] */
+    ko_meas sub[KO_MAX_ANCHORS];
+    unsigned char keep[KO_MAX_ANCHORS];
+    for (int i = 0; i < n; ++i) keep[i] = 1;
+    int it_sel = 0, it = 0;
+    double Fs[81], Qs[81], xs0[9], xps[9];
+    for (int i = 0; i < 3; ++i) { xs0[i] = f->pos[i]; xs0[3 + i] = f->vel[i]; xs0[6 + i] = f->acc[i]; }
+    t9_FQ(f->jolt, dt, Fs, Qs);
+    matvec(9, Fs, xs0, xps);
+    const double start[3] = {xps[0], xps[1], xps[2]};
+    if (f->variant == 1 && n > 0) {
+        double p0[3], c0[9];
+        if (ko_ml3d(m, n, start, p0, c0, &it) == 0) {
+            int order[KO_MAX_ANCHORS];
+            ko_best_rangings(m, n, p0, order);
+            int drop = n - 4 < f->n_ignore ? n - 4 : f->n_ignore;
+            if (drop < 0) drop = 0;
+            for (int i = n - drop; i < n; ++i) keep[order[i]] = 0;
+        }
+        it_sel += it;
+    } else if (f->variant == 2 && n >= 4) {
+        double p0[3], c0[9];
+        int bi, ng;
+        uint32_t bm = 0;
+        ko_ml_best_group(m, n, start, 0, f->best_mode, 0, p0, c0, &it, &bi, &bm, &ng);
+        it_sel += it;
+        for (int i = 0; i < n; ++i) keep[i] = (bm >> i) & 1u;
+    }
+    int ns = 0;
+    for (int i = 0; i < n; ++i)
+        if (keep[i]) sub[ns++] = m[i];
+    t9_estimate(f, dt, 1, sub, ns, f->has_imu, info);
+    info->ml_iters += it_sel;
 }
 
 void ko_t9_new_imu(ko_t9 *f, double dt, const double acc[3], const double cov_acc[9],

@@ -49,7 +49,8 @@ class KoK8(C.Structure):
 class KoT9(C.Structure):
     _fields_ = [("accel_noise", C.c_double), ("jolt", C.c_double), ("pos", C.c_double * 3),
                 ("vel", C.c_double * 3), ("acc", C.c_double * 3), ("P", C.c_double * 81),
-                ("has_imu", C.c_int), ("imu_a", C.c_double * 3), ("imu_cov", C.c_double * 9)]
+                ("has_imu", C.c_int), ("imu_a", C.c_double * 3), ("imu_cov", C.c_double * 9),
+                ("variant", C.c_int), ("n_ignore", C.c_int), ("best_mode", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -235,7 +236,7 @@ def k8_replay(x0, P0, events, ranges, sensors, anchors, err, cfg, b1_zero_z=Fals
 
 
 def t9_events(x0, P0, events, ranges, sensors, anchors, err, accel_noise=0.5, jolt=0.5, want_traj=False,
-              threads=0):
+              threads=0, variant=0, n_ignore=0, best_mode=0):
     anchors = np.ascontiguousarray(anchors, dtype=np.float64)
     M = len(anchors)
     x = np.array(x0, dtype=np.float64, order="C", copy=True)
@@ -250,11 +251,11 @@ def t9_events(x0, P0, events, ranges, sensors, anchors, err, accel_noise=0.5, jo
     counters = np.zeros(5)
     status = np.zeros(N, dtype=np.int32)
     arr = _events(events)
-    lib().ko_t9_events(C.c_int64(N), len(events), arr, M, _p(anchors), _vp(ranges),
-                       FMT[ranges.dtype] if ranges is not None else 0,
-                       C.c_double(err if err_arr is None else 0.0), _p(err_arr), _p(sensors),
-                       C.c_double(accel_noise), C.c_double(jolt), _p(x), _p(P), _p(traj), _p(counters),
-                       _p(status, C.c_int32), int(threads))
+    lib().ko_t9_events_sel(C.c_int64(N), len(events), arr, M, _p(anchors), _vp(ranges),
+                           FMT[ranges.dtype] if ranges is not None else 0,
+                           C.c_double(err if err_arr is None else 0.0), _p(err_arr), _p(sensors),
+                           C.c_double(accel_noise), C.c_double(jolt), int(variant), int(n_ignore), int(best_mode),
+                           _p(x), _p(P), _p(traj), _p(counters), _p(status, C.c_int32), int(threads))
     return dict(x=x, P=P, traj=traj, counters=counters, status=status)
 
 

@@ -582,6 +582,9 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.latch_u = b->d_latch_u;
         for (int i = 0; i < n; ++i) b->imu_seen = b->imu_seen || events[i].kind == KFPOS_EV_IMU;
         p.no_imu = b->imu_seen ? 0 : 1;
+        p.variant = b->cfg.variant;
+        p.n_ignore = b->cfg.num_ignored_rangings;
+        p.best_mode = b->cfg.best_mode;
         p.traj = d_traj;
         p.counters = b->d_counters;
         CK(launch_t9_replay(p, s));

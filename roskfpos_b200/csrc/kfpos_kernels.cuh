@@ -127,6 +127,7 @@ struct T9Params {
     int32_t *has;    // [N] bit1: imu latched
     double *latch_u; // [9] batch-wide latched 3x3 acceleration covariance
     int no_imu;      // host knowledge: no IMU sample latched and none in this schedule -> lean kernel
+    int variant, n_ignore, best_mode; // EKF-side NLOS variants (config_pos.xml; 0 = normal)
     double *traj;    // SoA [n_toa][3][N] or null
     unsigned long long *counters;
 };

@@ -79,10 +79,10 @@ KF_DEV bool accel_block_update(Sym<9> &P, double (&dn)[9], const double (&y)[3],
 // the ranging block is applied to a register copy Pw per gain step, followed by one 3x3 block
 // update for the accelerometer rows, and Pw = (I - K J) P^- is returned (return value 0).
 template <bool PME, int MT, bool IMU>
-KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r, bool has_imu, const double (&za)[3],
+KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r, unsigned used, bool has_imu, const double (&za)[3],
                      const double (&Ra)[6], const double (&xp)[9], const Col &Pm, Sym<9> &Pw, double (&dx)[9],
                      double (&M)[6], StepStats &st, unsigned wmask, const Col &cyc) {
-    const unsigned mask = has_r ? ep.valid : 0u;
+    const unsigned mask = has_r ? used : 0u; // used = ep.valid, or the EKF-side variant's selection
     double sse = -1.0;
     int rc = ML_OK;
     if (has_r) { // TOAIMU.cpp:268-270 (no NaN guard in this class)
@@ -191,7 +191,8 @@ KF_DEV int t9_update(const AnchorTable &A, const EpochT<PME, MT> &ep, bool has_r
 
 // IMU = false: the lean variant for schedules without accelerometer samples (nothing latched, no
 // IMU event): no register copy of the 9x9 covariance anywhere, 4 blocks per SM like T6.
-template <bool PME, int MT, bool IMU>
+// SEL: the EKF-side NLOS variants (see kfpos_t6.cu), 3-D selection from the predicted position.
+template <bool PME, int MT, bool IMU, bool SEL = false>
 __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_kernel(const __grid_constant__ T9Params p) {
     extern __shared__ double smem[];
     const int64_t f = (int64_t)blockIdx.x * T9_BLOCK + threadIdx.x;
@@ -280,7 +281,24 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
                                   vel[0], vel[1], vel[2], 0.0, 0.0, 0.0};
             if (has_r && ep.valid == 0u) st.status |= 1u;
             double dx[9], M[6];
-            const int rc = t9_update<PME, MT, IMU>(p.anchors, ep, has_r, IMU && has_imu, za, Ra, xp, Pm, Pw, dx, M, st, wmask, cyc);
+            unsigned used = ep.valid;
+            if (SEL && has_r) {
+                const int n = __popc(ep.valid);
+                const double start[3] = {xp[0], xp[1], xp[2]};
+                double p0[3] = {xp[0], xp[1], xp[2]}, sse0, cov0[6];
+                if (p.variant == 1 && n > 0) {
+                    if (ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, nullptr) == ML_OK) {
+                        const int drop = min(n - 4, p.n_ignore);
+                        used = drop_worst<PME, MT>(p.anchors, ep, used, p0, drop < 0 ? 0 : drop);
+                    }
+                } else if (p.variant == 2 && n >= 4) {
+                    int grc;
+                    ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, cov0); // the all-ranging solve
+                    best_group<PME, MT>(p.anchors, ep, ep.valid, false, p.best_mode, start, st.ml_iters, p0, cov0, used, grc);
+                }
+            }
+            const int rc = t9_update<PME, MT, IMU>(p.anchors, ep, has_r, used, IMU && has_imu, za, Ra, xp, Pm, Pw, dx, M, st,
+                                                   SEL ? 0u : wmask, cyc);
             __syncwarp(wmask); // the IEKF trip count differs per lane
             if (rc >= 0) {
 #pragma unroll
@@ -337,18 +355,20 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
     warp_accumulate(p.counters + CNT_BAD, n_bad);
 }
 
-template <bool PME, int MT, bool IMU>
+template <bool PME, int MT, bool IMU, bool SEL = false>
 static cudaError_t launch_k(const T9Params &p, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + T9_BLOCK - 1) / T9_BLOCK);
     const size_t smem = (size_t)t9_smem_rows(p.rs.m_slots, p.rs.fmt, PME, MT > 0) * T9_BLOCK * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(t9_replay_kernel<PME, MT, IMU>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(t9_replay_kernel<PME, MT, IMU, SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    t9_replay_kernel<PME, MT, IMU><<<grid, T9_BLOCK, smem, s>>>(p);
+    t9_replay_kernel<PME, MT, IMU, SEL><<<grid, T9_BLOCK, smem, s>>>(p);
     return cudaGetLastError();
 }
 
 cudaError_t launch_t9_replay(const T9Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
+    if (p.variant == 1 || p.variant == 2)
+        return p.rs.err != nullptr ? launch_k<true, 0, true, true>(p, s) : launch_k<false, 0, true, true>(p, s);
     if (p.no_imu) {
         if (p.rs.err != nullptr) return launch_k<true, 0, false>(p, s);
         if (p.rs.m_slots == 8) return launch_k<false, 8, false>(p, s);

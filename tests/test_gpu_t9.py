@@ -72,3 +72,41 @@ def test_t9_imu_events_and_step_api(kflib, oracle):
     oracle.lib().ko_t9_get_pose(C.byref(o.f), C.c_double(0.02), xr.ctypes.data_as(C.POINTER(C.c_double)),
                                 Pr.ctypes.data_as(C.POINTER(C.c_double)))
     assert np.abs(xp[:, 7] - xr).max() < 1e-12 and np.abs(Pp[:, 7] - Pr).max() <= 1e-12 * np.abs(Pr).max()
+
+
+@pytest.mark.parametrize("variant,n_ignore", [(1, 2), (2, 0)])
+def test_t9_ekf_side_nlos_variants(kflib, oracle, variant, n_ignore):
+    """EKF-side variants for the 9-state filter (as T6: 3-D ML selection from the predicted position,
+    variant 1 drops the N worst rangings, variant 2 keeps the best four anchors), with accelerometer
+    events in between so that ranging and accelerometer rows are both exercised."""
+    from roskfpos_b200.batch import Batch
+    from tests.util import assert_parity, to_metres, ulp_perturbations
+    N, T, m = 2500, 4, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=501)
+    r = synth.ranges_mm(truth[1:], anc, seed=502, p_nlos=0.15)
+    rng = np.random.default_rng(503)
+    cov = np.array([[0.02, 0.002, 0.0], [0.002, 0.03, 0.001], [0.0, 0.001, 0.05]]).ravel()
+    sens = rng.normal(0, 0.2, size=(3 * T, N))
+    events = []
+    for t in range(T):
+        events.append((2, 0.04, 3 * t, cov))
+        events.append((0, 0.06, t * m, None))
+    x0 = np.zeros((9, N)); x0[:3] = truth[0]
+    run = lambda rr, v=variant: oracle.t9_events(x0, None, events, rr, sens, anc, 0.01, variant=v, n_ignore=n_ignore)
+    ref = run(r)
+    per = [run(p) for p in ulp_perturbations(to_metres(r))]
+    with Batch(kflib.MODEL_T9, N, anchors=anc, accel_noise=0.5, jolt=0.5, variant=variant,
+               num_ignored_rangings=n_ignore) as b:
+        b.set_state(x0)
+        b.replay_events(events, ranges=r, sensors=sens, err=0.01)
+        x, P, st = b.get_state()
+        cnt = b.counters()
+    plain = run(r, 0)
+    assert np.abs(plain["x"] - ref["x"]).max() > 1e-3  # the selection does change the estimate
+    got = dict(x=x, P=P, status=st)
+    rep = assert_parity(got, ref, per, float_keys=("x",), cov_keys=("P",), int_keys=("status",),
+                        min_stable=0.9 if variant == 1 else 0.45, max_tie_frac=1e-2 if variant == 1 else 6e-2,
+                        what=f"T9 variant {variant}")  # best-group ties compound along the trajectory
+    print("parity report T9 variant", variant, rep, cnt)
+    assert cnt["updates"] == N * len(events)
