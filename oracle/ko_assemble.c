@@ -10,10 +10,16 @@
  *   initialiseTagList                    :499-507   (table = -1, errorEstimation = 0)
  *   calculateTagLocationWithRangings     :476-496   (a slot is used when its value is > 0)
  *
- * PINNING: parity unpinned.  Posgenerator.cpp needs ROS, tf and four message packages and cannot be
- * compiled here; this restatement is pinned only by the hand-computed cases of
- * tests/test_oracle_assemble.py.  The wall clock of the reference (steady_clock at the moment a
- * report is sent) is replaced by the arrival time stamps of the log.
+ * PINNING: pinned against the reference's own source.  Posgenerator.cpp is compiled UNMODIFIED into
+ * oracle/_ref/libkfref.so against stand-ins for ROS, tf and the message packages (oracle/shim/ros,
+ * kfshim_msgs.h); oracle/shim/posgen_harness.cpp plays ROS's event loop on the fake clock (the
+ * one-shot timer fires when it is due before the next ranging arrives) and records every epoch
+ * handed to newTOAMeasurement.  Evidence: tests/golden/posgen.npz (tests/golden/make_golden_posgen.py)
+ * replayed by tests/test_oracle_golden.py -- epochs bit-equal, timeLag to 1e-12, and the whole
+ * log -> report chain -- and tests/test_oracle_vs_ref.py on fresh random logs; plus the hand-computed
+ * cases of tests/test_oracle_assemble.py.  The wall clock of the reference (steady_clock at the
+ * moment a report is sent) is the arrival time stamp of the log here; gtec_msgs/Ranging itself is
+ * an un-vendored dependency (field list restated in kfshim_msgs.h).
  *
  * One call = one tag's time-sorted stream.  A message with anchor == 0xFF (or >= M) is padding.
  * The reference keeps 256 rows indexed by seq and, when a new seq starts, clears only slot 0 of the

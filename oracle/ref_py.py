@@ -198,3 +198,57 @@ def t6_replay(x0, ranges_m, anchors, dt, err, accel_noise=0.5):
     rc = lib().ref_t6_replay(C.c_longlong(N), T, M, _p(anchors), C.c_longlong(ns(dt)), _p(ranges_m),
                              C.c_double(err), C.c_double(accel_noise), _p(x0), _p(x), _p(P))
     return dict(rc=rc, x=x, P=P)
+
+
+class RefPosGenerator:
+    """The reference's PosGenerator (publishers/Posgenerator.cpp, unmodified) behind a recording
+    algorithm: feed a ranging log, read back the epochs it hands to newTOAMeasurement and the
+    report the node would publish.  algorithm: -1 = record only, 2 = ML, 5 = KalmanFilterTOA,
+    6 = KalmanFilterTOAIMU (Posgenerator.h:62-68)."""
+
+    def __init__(self, anchors, algorithm=-1, tag_id=0, anchor_ids=None, accel_noise=0.5, jolt=0.5,
+                 use_start=False, start=(0.0, 0.0, 0.0), ignore_worst=False, cost_threshold=0.0,
+                 use2d=False, variant=0, n_ignore=0):
+        anchors = _arr(anchors)
+        self.M = anchors.shape[0]
+        ids = np.arange(self.M, dtype=np.int32) if anchor_ids is None else np.ascontiguousarray(anchor_ids, np.int32)
+        l = lib()
+        l.ref_pg_create.restype = C.c_void_p
+        l.ref_pg_feed.restype = C.c_longlong
+        l.ref_pg_epochs.restype = C.c_longlong
+        self.h = C.c_void_p(l.ref_pg_create(int(algorithm), int(tag_id), self.M, _p(anchors),
+                                            ids.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(accel_noise),
+                                            C.c_double(jolt), int(use_start), _p(_arr(start)), int(ignore_worst),
+                                            C.c_double(cost_threshold), int(use2d), int(variant), int(n_ignore)))
+
+    def close(self):
+        if self.h:
+            lib().ref_pg_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def feed(self, anchor_id, range_mm, seq, t, err=None, tag_id=None, flush_tail=True):
+        ip = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        a, r, s = ip(anchor_id), ip(range_mm), ip(seq)
+        tg = np.zeros_like(a) if tag_id is None else ip(tag_id)
+        t = _arr(t)
+        e = None if err is None else _arr(err)
+        i32 = lambda x: x.ctypes.data_as(C.POINTER(C.c_int))
+        return int(lib().ref_pg_feed(self.h, C.c_longlong(len(a)), i32(a), i32(tg), i32(r), i32(s),
+                                     _p(e) if e is not None else None, _p(t), int(flush_tail)))
+
+    def epochs(self, max_epochs):
+        r = np.zeros((max_epochs, self.M)); e = np.zeros((max_epochs, self.M)); lag = np.zeros(max_epochs)
+        n = int(lib().ref_pg_epochs(self.h, C.c_longlong(max_epochs), self.M, _p(r), _p(e), _p(lag)))
+        k = min(n, max_epochs)
+        return dict(n=n, ranges=r[:k], err=e[:k], time_lag=lag[:k])
+
+    def report(self, t):
+        pose = np.zeros(13); cov = np.zeros(36)
+        rc = lib().ref_pg_report(self.h, C.c_double(t), _p(pose), _p(cov))
+        return rc, pose, cov
+
+    def errors(self):
+        return int(lib().ref_pg_errors(self.h))

@@ -120,8 +120,16 @@ KF_DEV double wrap_angle(double a) {
     return a;
 }
 
+// A determinant the dense solvers of the reference accept: non-zero and finite.  An error estimate
+// of 0 (a ranging without errorEstimation in per-measurement mode) puts 1/0 into the normal matrix;
+// arma::solve / inv reject that like an exactly singular matrix (update skipped, status SINGULAR).
+KF_DEV bool usable_det(double det) {
+    const double a = fabs(det);
+    return a > 0.0 && a <= 1.7976931348623157e308;
+}
+
 // Symmetric 3x3 solve H s = g by cofactors.  H packed [xx, xy, yy, xz, yz, zz]
-// (Sym<3> order).  Returns false when det is 0 or NaN.
+// (Sym<3> order).  Returns false when det is 0, infinite or NaN.
 KF_DEV bool solve_sym3(const double (&H)[6], const double (&g)[3], double (&s)[3]) {
     const double a = H[0], b = H[1], c = H[3], d = H[2], e = H[4], f = H[5];
     // [a b c; b d e; c e f]
@@ -129,7 +137,7 @@ KF_DEV bool solve_sym3(const double (&H)[6], const double (&g)[3], double (&s)[3
     const double c01 = c * e - b * f;
     const double c02 = b * e - c * d;
     const double det = a * c00 + b * c01 + c * c02;
-    if (!(det != 0.0)) return false;
+    if (!usable_det(det)) return false;
     const double c11 = a * f - c * c;
     const double c12 = b * c - a * e;
     const double c22 = a * d - b * b;
@@ -147,7 +155,7 @@ KF_DEV bool inv_sym3(const double (&H)[6], double (&I)[6]) {
     const double c01 = c * e - b * f;
     const double c02 = b * e - c * d;
     const double det = a * c00 + b * c01 + c * c02;
-    if (!(det != 0.0)) return false;
+    if (!usable_det(det)) return false;
     const double id = fast_rcp(det);
     I[0] = c00 * id;
     I[1] = c01 * id;
@@ -161,7 +169,7 @@ KF_DEV bool inv_sym3(const double (&H)[6], double (&I)[6]) {
 // Symmetric 2x2 solve [a b; b d] s = g
 KF_DEV bool solve_sym2(double a, double b, double d, double g0, double g1, double &s0, double &s1) {
     const double det = a * d - b * b;
-    if (!(det != 0.0)) return false;
+    if (!usable_det(det)) return false;
     const double id = fast_rcp(det);
     s0 = (d * g0 - b * g1) * id;
     s1 = (a * g1 - b * g0) * id;

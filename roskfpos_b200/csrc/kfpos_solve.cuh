@@ -192,7 +192,7 @@ KF_DEV int ml_cov2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mas
         m11 = fma(w * dy, dy, m11);
     }
     const double det = m00 * m11 - m01 * m01;
-    if (!(det != 0.0)) return ML_SINGULAR;
+    if (!usable_det(det)) return ML_SINGULAR;
     const double id = 1.0 / det;
     cov[0] = m11 * id;
     cov[1] = -m01 * id;

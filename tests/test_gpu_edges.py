@@ -100,3 +100,74 @@ def test_event_stream_models_at_odd_batch_sizes(kflib, oracle, N):
         b.replay_events(events, ranges=r, sensors=acc, err=0.01)
         x9, P9, st9 = b.get_state()
     assert rel_err_state(x9, ref9["x"]) < REL_TOL and rel_err_cov(P9, ref9["P"]) < REL_TOL
+
+
+def test_rangings_without_error_estimate(kflib, oracle):
+    """Per-measurement mode with errorEstimation == 0 on some rangings (what PosGenerator stores for
+    a ranging that carried none, Posgenerator.cpp:94,236): the ML weights 1/e are infinite, the
+    reference's dense solver rejects the normal matrix and the epoch is skipped (covariance stays
+    predicted, status SINGULAR).  Epochs of the same filter with estimates everywhere update normally."""
+    from roskfpos_b200.batch import Batch
+    N, T, m = 1024, 8, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=71)
+    r = synth.ranges_mm(truth[1:], anc, seed=72, p_missing=0.1)
+    rng = np.random.default_rng(73)
+    e = rng.uniform(0.005, 0.05, size=(T, m, N))
+    hit = rng.random((T, 1, N)) < 0.4  # 40 % of the epochs have some rangings without an estimate
+    e[np.broadcast_to(hit, e.shape) & (rng.random(e.shape) < 0.3)] = 0.0
+    ref = oracle.t6_replay(truth[0], None, r, anc, 0.1, e)
+    with Batch(kflib.MODEL_T6, N, anchors=anc, accel_noise=0.5) as b:
+        b.set_state(truth[0])
+        b.replay_toa(0.1, r, err=e)
+        x, P, st = b.get_state()
+    assert np.isfinite(x).all() and np.isfinite(P).all()
+    from tests.util import assert_parity, to_metres, ulp_perturbations
+    per = [oracle.t6_replay(truth[0], None, pr, anc, 0.1, e) for pr in ulp_perturbations(to_metres(r))]
+    for d in [ref] + per:
+        d["status"] = d["status"] & 4
+    # units that are not stable under 1-ulp input changes (an ill-conditioned 6-ranging epoch) are exempt
+    assert_parity(dict(x=x[:3], P=P, status=st & 4), ref, per, float_keys=("x",), cov_keys=("P",),
+                  int_keys=("status",), min_stable=0.99, what="T6 with missing error estimates")
+    assert (st & 4).any() and not (st & 4).all()
+    x0 = np.zeros((9, N)); x0[:3] = truth[0]
+    ref9 = oracle.t9_replay(x0, None, r, anc, 0.1, e)
+    with Batch(kflib.MODEL_T9, N, anchors=anc, accel_noise=0.5, jolt=0.5) as b:
+        b.set_state(x0)
+        b.replay_toa(0.1, r, err=e)
+        x, P, st = b.get_state()
+    assert np.isfinite(x).all() and np.isfinite(P).all()
+    per = [oracle.t9_replay(x0, None, pr, anc, 0.1, e) for pr in ulp_perturbations(to_metres(r))]
+    for d in [ref9] + per:
+        d["status"] = d["status"] & 4
+    assert_parity(dict(x=x, P=P, status=st & 4), ref9, per, float_keys=("x",), cov_keys=("P",),
+                  int_keys=("status",), min_stable=0.99, what="T9 with missing error estimates")
+    assert (st & 4).any()
+    # K8: compass events between the ranging epochs, 2-D inner ML (solve_sym2)
+    comp = rng.uniform(-3, 3, size=(T, N))
+    events = []
+    for t in range(T):
+        events.append((synth.EV_COMPASS, 0.03, t, None))
+        events.append((synth.EV_TOA, 0.07, t * m, None))
+    x8 = np.zeros((8, N)); x8[:2] = truth[0][:2]; x8[6] = comp[0]
+    cfg = oracle.k8_cfg(0.5, 0.5, **synth.K8_ORACLE_CFG)
+    ref8 = oracle.k8_replay(x8, None, events, r, comp, anc, e, cfg)
+    per = [oracle.k8_replay(x8, None, events, pr, comp, anc, e, cfg) for pr in ulp_perturbations(to_metres(r))]
+    with Batch(kflib.MODEL_K8, N, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5) as b:
+        b.set_state(x8)
+        b.replay_events(events, ranges=r, sensors=comp, err=e)
+        x, P, st = b.get_state()
+    assert np.isfinite(x).all() and np.isfinite(P).all()
+    for d in [ref8] + per:
+        d["status"] = d["status"] & 4
+    assert_parity(dict(x=x, P=P, status=st & 4), ref8, per, float_keys=("x",), cov_keys=("P",),
+                  int_keys=("status",), min_stable=0.99, what="K8 with missing error estimates")
+    assert (st & 4).any()
+    for use2d in (False, True):
+        mref = oracle.ml_batch(r[0], anc, e[0], [1.0, 1.0, 4.0], use2d=use2d)
+        with Batch(kflib.MODEL_ML, N, anchors=anc, use2d=int(use2d)) as b:
+            got = b.ml_solve(r[0], err=e[0])
+        assert np.array_equal(got["status"] & 4, mref["status"] & 4) and (mref["status"] & 4).any()
+        ok = (mref["status"] == 0) & (mref["iters"] < 100)
+        assert ok.sum() > N // 3
+        assert np.abs(got["pos"][:, ok] - mref["pos"][:, ok]).max() < 1e-9

@@ -1,6 +1,6 @@
 """Oracle of the ranging aggregation (PosGenerator, Posgenerator.cpp:143-281) against hand-computed
-cases.  The reference's publisher cannot be compiled here (ROS): this oracle is pinned by these
-known-answer tests only ("parity unpinned")."""
+cases (the pinning against the reference's own PosGenerator is in test_oracle_golden.py and
+test_oracle_vs_ref.py)."""
 import numpy as np
 
 from oracle import oracle_py as O

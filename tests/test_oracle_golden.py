@@ -135,3 +135,56 @@ def test_pose_message_golden(oracle, name):
                 assert relP(cov, g[name + "_cov"][k]) < TOL, (name, t, lag)
                 k += 1
     assert k == len(g[name + "_pose"])
+
+
+def _posgen_logs():
+    g = np.load(os.path.join(GOLD, "posgen.npz"))
+    return g, g["anchors"].shape[0], g["anchor"].shape[1]
+
+
+def test_posgen_epochs_golden(oracle):
+    """ko_assemble against the epochs the reference's own PosGenerator (Posgenerator.cpp compiled
+    unmodified, tests/golden/make_golden_posgen.py) handed to newTOAMeasurement: same number of
+    epochs, the same slots in each, ranges and error estimates bit-equal, timeLag to 1e-12 (the
+    reference differences integer nanoseconds, the oracle doubles)."""
+    g, M, N = _posgen_logs()
+    T = int(g["n_epochs"].max())
+    o = oracle.assemble(g["anchor"], g["seq"], g["range_mm"], g["t"], M, T + 3, err=g["err"])
+    assert np.array_equal(o["n_epochs"], g["n_epochs"])
+    for j in range(N):
+        n = int(g["n_epochs"][j])
+        raw = o["ranges"][:n, :, j]
+        used = raw > 0  # calculateTagLocationWithRangings (Posgenerator.cpp:483)
+        assert np.array_equal(np.where(used, raw / 1000.0, 0.0), g["ep_ranges"][:n, :, j]), j
+        assert np.array_equal(np.where(used, o["err"][:n, :, j], 0.0), g["ep_err"][:n, :, j]), j
+        assert g["ep_lag"][0, j] == 0.0  # "first estimation": the filters substitute 0.1 s themselves
+        assert np.abs(o["dt"][1:n, j] - g["ep_lag"][1:n, j]).max(initial=0.0) < 1e-12, j
+        assert np.all(o["dt"][n:, j] == -1.0)
+
+
+@pytest.mark.parametrize("name", ["t6", "t9"])
+def test_posgen_pipeline_golden(oracle, name):
+    """log -> report: the reference node (PosGenerator + filter + publisher, all unmodified) against
+    the oracle pieces chained the same way (assemble -> new_toa per epoch -> getPose -> message).
+    Log 2 (311 sparse, partly junk epochs) is looser: T6 accumulates 1.3e-11 through its
+    ill-conditioned updates, and T9's epoch 302 contains a 96-iteration Newton run whose
+    relative-change stop amplifies the rounding difference between LAPACK and the oracle's solver to
+    2.6e-7 (the "chaotic" class of test_t6_golden); every other epoch and log agrees to 1e-11."""
+    g, M, N = _posgen_logs()
+    anc = g["anchors"]
+    T = int(g["n_epochs"].max())
+    o = oracle.assemble(g["anchor"], g["seq"], g["range_mm"], g["t"], M, T, err=g["err"])
+    for j in range(N):
+        p0 = g["x0"][:, j]
+        f = oracle.T6(0.5, False, 0.0, p0) if name == "t6" else oracle.T9(0.5, 0.5, p0)
+        for k in range(int(g["n_epochs"][j])):
+            r = o["ranges"][k, :, j] / 1000.0
+            f.new_toa(float(o["dt"][k, j]), np.where(r > 0, r, 0.0), anc, o["err"][k, :, j])
+        for i, lag in enumerate(g["lags"]):
+            xp, Pp = f.get_pose(float(lag))
+            if name == "t6":
+                xp = np.concatenate([xp, np.zeros(3)])
+            pose, cov = oracle.pose_msg(1 if name == "t6" else 3, xp, Pp)
+            tol = (1e-9 if name == "t6" else 1e-6) if j == 2 else TOL
+            assert np.abs(pose - g[name + "_pose"][j, i]).max() < tol, (name, j, lag)
+            assert relP(cov, g[name + "_cov"][j, i]) < tol, (name, j, lag)

@@ -79,3 +79,39 @@ def test_ml_random_epochs(oracle, use2d, variant, n_ign, m):
             assert b["iters"] > 50  # Newton wandered: rounding-chaotic in the reference itself
             n_unstable += 1
     assert n_unstable <= 10
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13, 14])
+def test_assembler_vs_live_posgenerator(oracle, seed):
+    """ko_assemble against the reference's PosGenerator on fresh random logs: out-of-order anchors,
+    dropped rangings, sequence numbers wrapping past 255 (stale table slots, App. B-12), silences
+    longer than the 50 ms timer, non-positive ranges, rangings for another tag, missing error
+    estimates."""
+    rng = np.random.default_rng(seed)
+    M = int(rng.integers(4, 17))
+    anc = synth.anchors_for(M)
+    a, s, r, t, e, tag = [], [], [], [], [], []
+    tt = 0.0
+    for q in range(int(rng.integers(300, 700))):
+        if rng.random() < 0.08:
+            tt += 0.08
+        for k in rng.permutation(M):
+            if rng.random() < 0.25:
+                continue
+            tt += 0.001 * int(rng.integers(1, 4))
+            a.append(k); s.append(q % 256); r.append(int(rng.integers(-2, 9000))); t.append(round(tt, 3))
+            e.append(float(np.float32(rng.random() * 0.2)) if rng.random() < 0.7 else 0.0)
+            tag.append(0 if rng.random() < 0.9 else 3)
+        tt += 0.01 * int(rng.integers(0, 4))
+    a, s, r, t, e, tag = (np.array(v) for v in (a, s, r, t, e, tag))
+    pg = R.RefPosGenerator(anc, tag_id=0)
+    n = pg.feed(a, r, s, t, err=e, tag_id=tag)
+    ep = pg.epochs(n)
+    mine = tag == 0  # one oracle call = one tag's stream (Posgenerator.cpp:203-205 drops the others)
+    o = oracle.assemble(a[mine], s[mine], r[mine], t[mine], M, n + 4, err=e[mine])
+    assert int(o["n_epochs"][0]) == n and n > 300
+    raw = o["ranges"][:n, :, 0]
+    assert np.array_equal(np.where(raw > 0, raw / 1000.0, 0.0), ep["ranges"])
+    assert np.array_equal(np.where(raw > 0, o["err"][:n, :, 0], 0.0), ep["err"])
+    assert ep["time_lag"][0] == 0.0
+    assert np.abs(o["dt"][1:n, 0] - ep["time_lag"][1:]).max() < 1e-12
