@@ -207,18 +207,25 @@ class RefPosGenerator:
     6 = KalmanFilterTOAIMU (Posgenerator.h:62-68)."""
 
     def __init__(self, anchors, algorithm=-1, tag_id=0, anchor_ids=None, accel_noise=0.5, jolt=0.5,
-                 use_start=False, start=(0.0, 0.0, 0.0), ignore_worst=False, cost_threshold=0.0,
-                 use2d=False, variant=0, n_ignore=0):
+                 use_start=False, start=(0.0, 0.0, 0.0), start_angle=0.0, ignore_worst=False, cost_threshold=0.0,
+                 use2d=False, variant=0, n_ignore=0, xml=None):
         anchors = _arr(anchors)
         self.M = anchors.shape[0]
         ids = np.arange(self.M, dtype=np.int32) if anchor_ids is None else np.ascontiguousarray(anchor_ids, np.int32)
         l = lib()
+        if algorithm == 4:  # KalmanFilter reads its XML documents from the parameter server
+            params = dict(XML_DEFAULT)
+            params.update(xml or {})
+            for k, v in params.items():
+                l.ref_set_param(k.encode(), v.encode())
         l.ref_pg_create.restype = C.c_void_p
+        l.ref_pg_epoch_times.restype = C.c_longlong
         l.ref_pg_feed.restype = C.c_longlong
         l.ref_pg_epochs.restype = C.c_longlong
         self.h = C.c_void_p(l.ref_pg_create(int(algorithm), int(tag_id), self.M, _p(anchors),
                                             ids.ctypes.data_as(C.POINTER(C.c_int)), C.c_double(accel_noise),
-                                            C.c_double(jolt), int(use_start), _p(_arr(start)), int(ignore_worst),
+                                            C.c_double(jolt), int(use_start), _p(_arr(start)),
+                                            C.c_double(start_angle), int(ignore_worst),
                                             C.c_double(cost_threshold), int(use2d), int(variant), int(n_ignore)))
 
     def close(self):
@@ -238,6 +245,15 @@ class RefPosGenerator:
         i32 = lambda x: x.ctypes.data_as(C.POINTER(C.c_int))
         return int(lib().ref_pg_feed(self.h, C.c_longlong(len(a)), i32(a), i32(tg), i32(r), i32(s),
                                      _p(e) if e is not None else None, _p(t), int(flush_tail)))
+
+    def sensor(self, kind, t, values):
+        """kind 1 px4 / 2 imu / 3 mag / 4 compass (see ref_pg_sensor)."""
+        return int(lib().ref_pg_sensor(self.h, int(kind), C.c_double(t), _p(_arr(values))))
+
+    def epoch_times(self, max_epochs):
+        t = np.zeros(max_epochs)
+        n = int(lib().ref_pg_epoch_times(self.h, C.c_longlong(max_epochs), _p(t)))
+        return t[:min(n, max_epochs)]
 
     def epochs(self, max_epochs):
         r = np.zeros((max_epochs, self.M)); e = np.zeros((max_epochs, self.M)); lag = np.zeros(max_epochs)

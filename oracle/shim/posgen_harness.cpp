@@ -20,6 +20,7 @@ struct Epoch {
     std::vector<double> r, e;
     std::vector<int> index, id;
     double time_lag;
+    long long t_ns;
 };
 
 class Recorder : public PositionEstimationAlgorithm {
@@ -30,6 +31,18 @@ public:
     std::string last_error;
     bool init() override { return inner ? inner->init() : true; }
     bool getPose(Vector3 &pose) override { return inner ? inner->getPose(pose) : false; }
+    void newPX4FlowMeasurement(double ix, double iy, double irz, double itime, int quality) override {
+        if (inner) inner->newPX4FlowMeasurement(ix, iy, irz, itime, quality);
+    }
+    void newIMUMeasurement(VectorDim3 w, double cw[9], VectorDim3 a, double ca[9]) override {
+        if (inner) inner->newIMUMeasurement(w, cw, a, ca);
+    }
+    void newMAGMeasurement(VectorDim3 mag, double cm[9]) override {
+        if (inner) inner->newMAGMeasurement(mag, cm);
+    }
+    void newCompassMeasurement(double compass) override {
+        if (inner) inner->newCompassMeasurement(compass);
+    }
     void newTOAMeasurement(const std::vector<double> &rangings, const std::vector<Beacon> &beacons,
                            const std::vector<double> &errorEstimations, double timeLag) override {
         Epoch ep;
@@ -40,6 +53,7 @@ public:
             ep.id.push_back(beacons[i].id);
         }
         ep.time_lag = timeLag;
+        ep.t_ns = kfshim::fake_clock::ticks();
         epochs.push_back(ep);
         if (inner) {
             try {
@@ -77,15 +91,18 @@ extern "C" {
 
 // algorithm: -1 = recorder only, else ALGORITHM_* of Posgenerator.h:62-68 (2 = ML, 5 = KF_TOA, 6 = KF_TOA_IMU).
 // anchors: n x (x, y, z); anchor_ids: the marker ids (the anchorId of the rangings).
+// ALGORITHM_KF (4) reads its five XML documents from the parameters "kfpos_pos", "kfpos_px4",
+// "kfpos_tag", "kfpos_imu", "kfpos_mag" (ref_set_param).
 void *ref_pg_create(int algorithm, int tag_id, int n_anchors, const double *anchors, const int *anchor_ids,
-                    double accel_noise, double jolt, int use_start, const double *start_xyz, int ignore_worst,
-                    double cost_threshold, int use2d, int variant, int n_ignore) {
+                    double accel_noise, double jolt, int use_start, const double *start_xyz, double start_angle,
+                    int ignore_worst, double cost_threshold, int use2d, int variant, int n_ignore) {
     Handle *h = new Handle();
     h->t0_ns = kfshim::fake_clock::ticks();
     PosGenerator &g = h->gen;
     g.setPublishers(h->pub, h->pub_path, h->pub_odom);
     g.setDynamicParameters(accel_noise, jolt);
-    g.setStartParameters(use_start != 0, start_xyz[0], start_xyz[1], start_xyz[2], 0.0);
+    g.setStartParameters(use_start != 0, start_xyz[0], start_xyz[1], start_xyz[2], start_angle);
+    g.setExternalFilesParameters("kfpos_pos", "kfpos_px4", "kfpos_tag", "kfpos_imu", "kfpos_mag");
     g.setHeuristicIgnore(ignore_worst != 0, cost_threshold);
     g.setDeviceIdentifiers(tag_id);
     g.setHeuristicML(use2d != 0, variant, n_ignore);
@@ -129,6 +146,59 @@ long long ref_pg_feed(void *hv, long long L, const int *anchor_id, const int *ta
     }
     if (flush_tail) fire_due_timer(h, (long long)1 << 62);
     return (long long)h->rec->epochs.size();
+}
+
+// One sensor message at time t (seconds since create), through PosGenerator's own callbacks
+// (Posgenerator.cpp:100-140).  kind 1: PX4Flow v = {integrated_x, integrated_y, integrated_zgyro,
+// integration_time_us, quality}; 2: IMU v = {angular_velocity[3], its covariance[9],
+// linear_acceleration[3], its covariance[9]}; 3: magnetometer v = {field[3], covariance[9]};
+// 4: compass v = {heading}.  Returns 0, or 1/2/3 when the algorithm threw.
+int ref_pg_sensor(void *hv, int kind, double t, const double *v) {
+    Handle *h = (Handle *)hv;
+    const long long t_ns = h->t0_ns + (long long)(t * 1e9 + 0.5);
+    fire_due_timer(h, t_ns);
+    kfshim::fake_clock::ticks() = t_ns;
+    try {
+        if (kind == 1) {
+            mavros_msgs::OpticalFlowRad *m = new mavros_msgs::OpticalFlowRad();
+            m->integrated_x = (float)v[0]; m->integrated_y = (float)v[1]; m->integrated_zgyro = (float)v[2];
+            m->integration_time_us = (uint32_t)v[3]; m->quality = (uint8_t)v[4];
+            h->gen.newPX4FlowMeasurement(mavros_msgs::OpticalFlowRad::ConstPtr(m));
+        } else if (kind == 2) {
+            sensor_msgs::Imu *m = new sensor_msgs::Imu();
+            m->angular_velocity.x = v[0]; m->angular_velocity.y = v[1]; m->angular_velocity.z = v[2];
+            for (int i = 0; i < 9; ++i) m->angular_velocity_covariance[i] = v[3 + i];
+            m->linear_acceleration.x = v[12]; m->linear_acceleration.y = v[13]; m->linear_acceleration.z = v[14];
+            for (int i = 0; i < 9; ++i) m->linear_acceleration_covariance[i] = v[15 + i];
+            h->gen.newIMUMeasurement(sensor_msgs::Imu::ConstPtr(m));
+        } else if (kind == 3) {
+            sensor_msgs::MagneticField *m = new sensor_msgs::MagneticField();
+            m->magnetic_field.x = v[0]; m->magnetic_field.y = v[1]; m->magnetic_field.z = v[2];
+            for (int i = 0; i < 9; ++i) m->magnetic_field_covariance[i] = v[3 + i];
+            h->gen.newMAGMeasurement(sensor_msgs::MagneticField::ConstPtr(m));
+        } else if (kind == 4) {
+            std_msgs::Float64 m;
+            m.data = v[0];
+            h->gen.newCompassMeasurement(m);
+        } else {
+            return -1;
+        }
+    } catch (const std::runtime_error &) {
+        return 1;
+    } catch (const std::logic_error &) {
+        return 2;
+    } catch (...) {
+        return 3;
+    }
+    return 0;
+}
+
+// Times (seconds since create) at which the recorded epochs reached the algorithm.
+long long ref_pg_epoch_times(void *hv, long long max_epochs, double *t) {
+    Handle *h = (Handle *)hv;
+    const std::vector<Epoch> &ep = h->rec->epochs;
+    for (long long k = 0; k < (long long)ep.size() && k < max_epochs; ++k) t[k] = (ep[k].t_ns - h->t0_ns) * 1e-9;
+    return (long long)ep.size();
 }
 
 // Dense copy of the recorded epochs: ranges [max][M] in metres by beacon INDEX (0 = slot not in

@@ -115,3 +115,82 @@ def test_assembler_vs_live_posgenerator(oracle, seed):
     assert np.array_equal(np.where(raw > 0, o["err"][:n, :, 0], 0.0), ep["err"])
     assert ep["time_lag"][0] == 0.0
     assert np.abs(o["dt"][1:n, 0] - ep["time_lag"][1:]).max() < 1e-12
+
+
+def test_k8_node_with_all_sensors(oracle):
+    """The whole reference node for the 8-state filter: rangings through PosGenerator's aggregation
+    (the 75 ms of sensor traffic between two ranging bursts lets the 50 ms timer send every epoch,
+    and the next burst sends it again), IMU / PX4Flow / magnetometer / compass through its callbacks
+    (Posgenerator.cpp:92-140), the report through publishPositionReport -- against the oracle pieces
+    chained the same way.  (The reference build reads ML.cpp:64's uninitialised z as 0, App. B-1:
+    b1_zero_z.)"""
+    from tests.test_oracle_golden import CFG_K8
+    M, T = 8, 25
+    anc = synth.anchors_for(M)
+    rng = np.random.default_rng(21)
+    truth = synth.truth_lissajous(1, T, 0.1, seed=22)
+    p0 = truth[0][:, 0]
+    pg = R.RefPosGenerator(anc, algorithm=4, start=[p0[0], p0[1], 0.0], use_start=True, start_angle=0.3)
+    o = oracle.K8(0.5, 0.3, 0.5, p0[:2], **CFG_K8)
+    cav = np.diag([1e-3, 1e-3, 2e-3]).ravel()
+    cac = np.array([[4e-3, 1e-4, 0], [1e-4, 5e-3, 0], [0, 0, 6e-3]]).ravel()
+    log = dict(a=[], s=[], r=[], t=[], e=[])
+    state = dict(t_last=None, done=0)
+
+    def dt_to(t):  # the filter's own clock: 0.1 s for its first update (KF.cpp:238), else since the last callback
+        d = 0.1 if state["t_last"] is None else t - state["t_last"]
+        state["t_last"] = t
+        return d
+
+    def sync():  # epochs the node handed to the filter since the last look, at the times it did
+        times = pg.epoch_times(4 * T)
+        if len(times) > state["done"]:
+            ep = oracle.assemble(log["a"], log["s"], log["r"], log["t"], M, len(times), err=log["e"])
+            assert int(ep["n_epochs"][0]) >= len(times)
+            for k in range(state["done"], len(times)):
+                rr = ep["ranges"][k, :, 0] / 1000.0
+                o.new_toa(dt_to(times[k]), np.where(rr > 0, rr, 0.0), anc, ep["err"][k, :, 0], b1_zero_z=True)
+            state["done"] = len(times)
+
+    tt = 0.0
+    for q in range(T):
+        for k in range(3):  # three IMU samples, one PX4Flow, one heading source, then the ranging burst
+            tt = round(tt + 0.02, 3)
+            w, a = [0.0, 0.0, rng.normal(0.1, 0.05)], [rng.normal(0, 0.3), rng.normal(0, 0.3), 9.8]
+            assert pg.sensor(2, tt, np.concatenate([w, cav, a, cac])) == 0
+            sync()
+            o.new_imu(dt_to(tt), w, cav, a, cac)
+        tt = round(tt + 0.01, 3)
+        px = np.array([np.float32(rng.normal(0, 0.002)), np.float32(rng.normal(0, 0.002)),
+                       np.float32(rng.normal(0, 0.001)), 33333.0, 200.0], dtype=np.float64)
+        assert pg.sensor(1, tt, px) == 0
+        sync()
+        o.new_px4(dt_to(tt), px[0], px[1], px[2], px[3], int(px[4]))
+        tt = round(tt + 0.005, 3)
+        if q % 2:
+            c = rng.uniform(-3, 3)
+            assert pg.sensor(4, tt, [c]) == 0
+            sync()
+            o.new_compass(dt_to(tt), c)
+        else:
+            mg = np.array([np.cos(0.3 + 0.01 * q), np.sin(0.3 + 0.01 * q), 0.1])
+            assert pg.sensor(3, tt, np.concatenate([mg, np.zeros(9)])) == 0
+            sync()
+            o.new_mag(dt_to(tt), mg)
+        for k in range(M):
+            if rng.random() < 0.1:
+                continue
+            tt = round(tt + 0.001, 3)
+            d = np.linalg.norm(anc[k] - truth[q + 1][:, 0]) + rng.normal(0, 0.05)
+            msg = (k, q, int(d * 1000), tt, float(np.float32(0.01 + 0.02 * rng.random())))
+            for key, v in zip("asrte", msg):
+                log[key].append(v)
+            pg.feed([msg[0]], [msg[2]], [msg[1]], [msg[3]], err=[msg[4]], flush_tail=False)
+            sync()
+    assert state["done"] == 2 * (T - 1) and pg.errors() == 0
+    rc, pose, cov = pg.report(tt + 0.013)
+    assert rc == 0
+    xp, Pp = o.get_pose(tt + 0.013 - state["t_last"])
+    po, co = oracle.pose_msg(2, xp, Pp, tag_z=CFG_K8["tag_z"])
+    assert np.abs(po - pose).max() < TOL
+    assert relP(co, cov) < TOL
