@@ -97,7 +97,10 @@ typedef struct kfpos_config {
     double jolt;                  /* jolt (K8, T9)                                  */
     double initial_angle;         /* initialAngle (K8)                              */
     int32_t ignore_worst_anchor;  /* ignoreWorstAnchorMode (T6)                     */
-    int32_t _pad0;
+    int32_t ml2d_zero_tentative_z; /* 0 (default): the 2-D ML solver's tentative cost uses z = start z
+                                      (the evident intent of ML.cpp:64,102-106);
+                                      1: z = 0, what a build of the reference that zero-initialises
+                                      the uninitialised `tentativePos` computes (K8, 2-D ML)        */
     double ignore_cost_threshold; /* ignoreCostThreshold (T6)                       */
     /* MLLocation ctor (ML.h:30) + config_pos.xml <algorithm .../>.  For T6, K8 and T9 batches variant /
      * num_ignored_rangings / best_mode select the EKF-side NLOS variants that README.md:85-108

@@ -530,7 +530,7 @@ K8Cfg make_k8cfg(const kfpos_batch *b) {
     c.variant = b->cfg.variant;
     c.n_ignore = b->cfg.num_ignored_rangings;
     c.best_mode = b->cfg.best_mode;
-    c._pad = 0;
+    c.zero_tz = b->cfg.ml2d_zero_tentative_z != 0;
     return c;
 }
 
@@ -798,6 +798,8 @@ extern "C" int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt,
     p.rs = make_rs(b, d_r, fmt, err_scalar, (const double *)d_e);
     p.N = b->N;
     p.use2d = b->cfg.use2d;
+    p.zero_tz = b->cfg.ml2d_zero_tentative_z != 0;
+    p._pad = 0;
     p.variant = b->cfg.variant;
     p.n_ignore = b->cfg.num_ignored_rangings;
     p.best_mode = b->cfg.best_mode;

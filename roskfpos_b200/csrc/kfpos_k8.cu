@@ -180,16 +180,18 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                     const double start[3] = {xp[0], xp[1], p.cfg.tag_z};
                     double p0[3] = {start[0], start[1], start[2]}, sse0, cov0[6];
                     if (p.cfg.variant == 1 && n > 0) {
-                        if (ml_solve2<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, nullptr) == ML_OK) {
+                        if (ml_solve2<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, nullptr, nullptr,
+                                               p.cfg.zero_tz != 0) == ML_OK) {
                             const int drop = min(n - 3, p.cfg.n_ignore);
                             used = drop_worst<PME, MT>(p.anchors, ep, used, p0, drop < 0 ? 0 : drop);
                         }
                     } else if (p.cfg.variant == 2 && n >= 3) {
                         int grc;
                         double c2[3];
-                        ml_solve2<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, c2); // the all-ranging solve
+                        ml_solve2<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, c2, nullptr,
+                                           p.cfg.zero_tz != 0); // the all-ranging solve
                         best_group<PME, MT>(p.anchors, ep, ep.valid, true, p.cfg.best_mode, start, st.ml_iters, p0, cov0,
-                                            used, grc);
+                                            used, grc, p.cfg.zero_tz != 0);
                     }
                 }
                 const int rc = k8_update<PME, MT>(p.anchors, p.cfg, ep, has_r, used, ms, dt, xp, Pm, Pw, dx, st,
@@ -255,7 +257,7 @@ cudaError_t launch_k8_replay(const K8Params &p, cudaStream_t s) {
     if (p.cfg.variant == 1 || p.cfg.variant == 2)
         return p.rs.err != nullptr ? launch_k<true, 0, true>(p, s) : launch_k<false, 0, true>(p, s);
     if (p.rs.err != nullptr) return launch_k<true, 0>(p, s);
-    if (p.rs.m_slots == 8) return launch_k<false, 8>(p, s);
+    if (p.rs.m_slots == 8 && !p.cfg.zero_tz) return launch_k<false, 8>(p, s);
     return launch_k<false, 0>(p, s);
 }
 

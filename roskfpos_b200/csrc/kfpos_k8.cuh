@@ -70,7 +70,7 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const EpochT<PME, M
     int rc = ML_OK;
     if (has_r) { // inner ML 2-D solve from (x^-_0, x^-_1, tagZ) (KF.cpp:403-405)
         double pml[3] = {xp[0], xp[1], cfg.tag_z};
-        rc = ml_solve2<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr);
+        rc = ml_solve2<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr, nullptr, cfg.zero_tz != 0);
         if (mask == 0u) sse = -1.0; // estimationError of an empty list
         // has_r is a property of the event, common to the batch: every lane of wmask is here
         if (wmask) __syncwarp(wmask);

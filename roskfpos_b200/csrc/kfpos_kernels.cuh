@@ -45,6 +45,7 @@ struct MlParams {
     RangeStream rs;
     int64_t N;
     int use2d, variant, n_ignore, best_mode;
+    int zero_tz, _pad; // ml2d_zero_tentative_z
     double start[3];
     double min_z, max_z; // output gate (config_pos.xml minZ / maxZ), active when max_z > min_z
     double *pos;     // SoA [3][N] or null
@@ -85,7 +86,7 @@ struct K8Cfg {
     double mag_offset, mag_cov;
     int imu_fix_acc, imu_fix_gyro;
     int variant, n_ignore, best_mode; // EKF-side NLOS variants (config_pos.xml; 0 = normal)
-    int _pad;
+    int zero_tz;                      // ml2d_zero_tentative_z (App. B-1 as a zero-initialising build computes it)
 };
 
 struct K8Params {

@@ -33,11 +33,12 @@ struct MlParked {
 static_assert(sizeof(MlParked) == 64, "queue record layout");
 
 template <bool PME, int MT>
-KF_DEV int ml_any(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, bool use2d, double (&pos)[3],
-                  double *cov /* [6] or null */, double &sse, unsigned &iters, unsigned cap, MlResume *rs) {
+KF_DEV int ml_any(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, bool use2d, bool zero_tz,
+                  double (&pos)[3], double *cov /* [6] or null */, double &sse, unsigned &iters, unsigned cap,
+                  MlResume *rs) {
     if (use2d) {
         double c2[3] = {0, 0, 0};
-        const int rc = ml_solve2<PME, MT>(A, ep, mask, pos, sse, iters, cov ? c2 : nullptr);
+        const int rc = ml_solve2<PME, MT>(A, ep, mask, pos, sse, iters, cov ? c2 : nullptr, nullptr, zero_tz);
         if (cov) {
             cov[0] = c2[0]; cov[1] = c2[1]; cov[2] = c2[2];
             cov[3] = cov[4] = cov[5] = 0.0;
@@ -91,7 +92,8 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
         bool parked = false;
         for (;;) {
             const bool last = !(p.variant == 1 && phase == 0);
-            rc = ml_any<PME, MT>(p.anchors, ep, used, use2d, pos, last ? cov : nullptr, sse, iters, cap, &rs);
+            rc = ml_any<PME, MT>(p.anchors, ep, used, use2d, p.zero_tz != 0, pos, last ? cov : nullptr, sse, iters, cap,
+                                 &rs);
             if (rc == ML_MORE) {
                 const int slot = atomicAdd(p.queue_count, 1);
                 if (slot < p.queue_cap) {
@@ -121,7 +123,8 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
         if (!parked && p.variant == 2 && rc != ML_SINGULAR && n >= k) {
             // estimatePositionBestGroup (ML.cpp:351-414)
             const double start[3] = {p.start[0], p.start[1], p.start[2]};
-            index = best_group<PME, MT>(p.anchors, ep, ep.valid, use2d, p.best_mode, start, iters, pos, cov, used, rc);
+            index = best_group<PME, MT>(p.anchors, ep, ep.valid, use2d, p.best_mode, start, iters, pos, cov, used, rc,
+                                        p.zero_tz != 0);
         }
 
         if (!parked) {
@@ -182,8 +185,8 @@ cudaError_t launch_ml_solve(const MlParams &p, cudaStream_t s) {
     if (p.N <= 0) return cudaSuccess;
     if (p.rs.err != nullptr) return launch_k<true, 0>(p, s);
     // BEST solves k-anchor subsets: the branch-skipping rolled loops do k, not m, anchors of work
-    if (p.variant != 2 && p.rs.m_slots == 8) return launch_k<false, 8>(p, s);
-    if (p.variant != 2 && p.rs.m_slots == 16) return launch_k<false, 16>(p, s);
+    if (p.variant != 2 && !p.zero_tz && p.rs.m_slots == 8) return launch_k<false, 8>(p, s);
+    if (p.variant != 2 && !p.zero_tz && p.rs.m_slots == 16) return launch_k<false, 16>(p, s);
     return launch_k<false, 0>(p, s);
 }
 

@@ -356,11 +356,26 @@ KF_DEV void ml_pass2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
 // estimatePosition2D, ML.cpp:48-143.  z stays at its start value.  The damping
 // `step` of the reference never takes effect: a rejected step leaves
 // newCost == cost, so the while-test fails on the next evaluation (ML.cpp:109-116).
-// B-1: the tentative cost is evaluated at z = start z.
+// B-1: the tentative cost is evaluated at z = start z (the evident intent);
+// zero_tz = true evaluates it at z = 0 instead, which is what a build of the reference that
+// zero-initialises ML.cpp:64's `tentativePos` computes (used to replay the reference's golden vectors).
+template <bool PME, int MT>
+KF_DEV double sse_at(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, double px, double py, double pz) {
+    double sse = 0.0;
+    for (int i = 0; i < ep.m_slots; ++i) {
+        if (!((mask >> i) & 1u)) continue;
+        const double dx = A.x[i] - px, dy = A.y[i] - py, dz = A.z[i] - pz;
+        const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+        const double res = fma(-d2, fast_rsqrt(d2), ep.z_at(i));
+        sse = fma(res, res, sse);
+    }
+    return sse;
+}
+
 template <bool PME, int MT>
 KF_DEV int ml_solve2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, double (&p)[3],
                      double &sse_out, unsigned &iters, double *cov /* xx, xy, yy or null */,
-                     double *sse_start = nullptr) {
+                     double *sse_start = nullptr, bool zero_tz = false) {
     const int nvalid = __popc(mask);
     MlPass2 ps, pt;
     double cost = 1e20, newCost = 0.0;
@@ -376,8 +391,10 @@ KF_DEV int ml_solve2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
             if (sse_start) *sse_start = pt.sse;
             if (nvalid < 3) { sse_out = pt.sse; return ML_FEW; }
         } else {
-            if (pt.sse > cost) break; // step /= 2; position kept; the while-test then fails
-            newCost = pt.sse;
+            // only the generic (MT = 0) instantiations carry the test mode; the launchers route it there
+            const double tc = (MT == 0 && zero_tz) ? sse_at<PME, MT>(A, ep, mask, nx, ny, 0.0) : pt.sse;
+            if (tc > cost) break; // step /= 2; position kept; the while-test then fails
+            newCost = tc;
             p[0] = nx; p[1] = ny;
             ps = pt;
         }
@@ -428,7 +445,7 @@ KF_DEV unsigned drop_worst(const AnchorTable &A, const EpochT<PME, MT> &ep, unsi
 template <bool PME, int MT>
 KF_DEV int best_group(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned valid, bool use2d, int best_mode,
                       const double (&start)[3], unsigned &iters, double (&pos)[3], double (&cov)[6],
-                      unsigned &used, int &rc) {
+                      unsigned &used, int &rc, bool zero_tz = false) {
     const int k = use2d ? 3 : 4, n = __popc(valid);
     if (n < k) return -1;
     unsigned char slot[32];
@@ -445,7 +462,7 @@ KF_DEV int best_group(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned 
         int grc;
         if (use2d) {
             double c2[3] = {0, 0, 0};
-            grc = ml_solve2<PME, MT>(A, ep, gm, gp, gs, iters, c2);
+            grc = ml_solve2<PME, MT>(A, ep, gm, gp, gs, iters, c2, nullptr, zero_tz);
             gc[0] = c2[0]; gc[1] = c2[1]; gc[2] = c2[2];
         } else {
             grc = ml_solve3<PME, MT>(A, ep, gm, gp, gs, iters, gc);

@@ -22,7 +22,7 @@ ST_Z_GATE = 128
 class KfposConfig(C.Structure):
     _fields_ = [
         ("accel_noise", C.c_double), ("jolt", C.c_double), ("initial_angle", C.c_double),
-        ("ignore_worst_anchor", C.c_int32), ("_pad0", C.c_int32),
+        ("ignore_worst_anchor", C.c_int32), ("ml2d_zero_tentative_z", C.c_int32),
         ("ignore_cost_threshold", C.c_double),
         ("use2d", C.c_int32), ("variant", C.c_int32), ("num_ignored_rangings", C.c_int32),
         ("best_mode", C.c_int32),
