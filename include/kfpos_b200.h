@@ -283,7 +283,8 @@ int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt, double err
  * starts and when the one-shot 50 ms timer (Posgenerator.h:77) expires after the last ranging
  * of a sequence (the row stays open: late rangings of the same seq are added and the row is
  * emitted again, as the reference does).
- *   inputs, SoA [L][N]: anchor (index into the anchor table; 0xFF or >= n_anchors = padding of
+ *   inputs, SoA [L][N]: anchor (index into the anchor table, i.e. _anchorIndexById[anchorId] of
+ *     :226 -- which yields index 0 for an id it does not know; 0xFF or >= n_anchors = padding of
  *     a ragged log), seq (0..255), range_mm (gtec_msgs/Ranging.range), err (errorEstimation,
  *     NULL = none; only values > 0 overwrite within a sequence, :94,236), t (arrival time, s);
  *   outputs: ranges_out int32 SoA [max_epochs][n_anchors][N] (-1 = no ranging, the table's
