@@ -192,10 +192,12 @@ int kfpos_batch_replay_toa(kfpos_batch *b, int n_steps, const double *dt, const 
                            int fmt, double err_scalar, const double *err_var, double *traj,
                            int32_t *sel, void *stream);
 
-/* T6 only: the same persistent replay with PER-FILTER time steps, for logs assembled by
+/* The same persistent replay with PER-FILTER time steps, for logs assembled by
  * kfpos_assemble_epochs (every tag has its own report times).  dt_per_filter: SoA [T][N];
  * a value < 0 means "filter f has no epoch t": neither predict nor update, its trajectory row
- * repeats the current position.                                                     */
+ * repeats the current position.  T6, and K8 / T9 as ranging-only schedules (their general
+ * kernel instantiation; latched sensor samples of earlier event calls take part as usual);
+ * traj rows as in kfpos_batch_replay_toa / kfpos_batch_replay_events.                  */
 int kfpos_batch_replay_epochs(kfpos_batch *b, int n_steps, const double *dt_per_filter, const void *ranges,
                               int fmt, double err_scalar, const double *err_var, double *traj, void *stream);
 

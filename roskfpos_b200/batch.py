@@ -156,8 +156,8 @@ class Batch:
         return traj, sel
 
     def replay_epochs(self, dt_per_filter, ranges, err=0.01, traj=None, want_traj=False, stream=None):
-        """T6: ranges [T][M][N] with per-filter time steps dt_per_filter [T][N] (< 0 = no epoch), the
-        output of assemble_epochs()."""
+        """T6 / K8 / T9: ranges [T][M][N] with per-filter time steps dt_per_filter [T][N] (< 0 = no
+        epoch), the output of assemble_epochs()."""
         T = int(ranges.shape[0])
         es, ep, keep = self._err(err)
         pr, kr = _ptr(ranges)

@@ -343,7 +343,8 @@ int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_range
                   double err_scalar, const double *d_err, double *d_traj, int32_t *d_sel, cudaStream_t s,
                   const double *d_dt_f = nullptr);
 int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_ranges, int fmt, double err_scalar,
-               const double *d_err, const double *d_sensors, double *d_traj, cudaStream_t s);
+               const double *d_err, const double *d_sensors, double *d_traj, cudaStream_t s,
+               const double *d_dt_f = nullptr);
 
 } // namespace
 
@@ -442,7 +443,8 @@ extern "C" int kfpos_batch_replay_toa(kfpos_batch *b, int n_steps, const double 
 extern "C" int kfpos_batch_replay_epochs(kfpos_batch *b, int n_steps, const double *dt_per_filter, const void *ranges,
                                          int fmt, double err_scalar, const double *err_var, double *traj,
                                          void *stream) {
-    if (!b || b->model != KFPOS_MODEL_T6 || n_steps < 0 || !dt_per_filter || !ranges) return KFPOS_ERR_INVALID;
+    if (!b || n_steps < 0 || !dt_per_filter || !ranges) return KFPOS_ERR_INVALID;
+    if (b->model != KFPOS_MODEL_T6 && b->model != KFPOS_MODEL_K8 && b->model != KFPOS_MODEL_T9) return KFPOS_ERR_INVALID;
     if (fmt < 0 || fmt > 2) return KFPOS_ERR_INVALID;
     if (!b->have_anchors) return KFPOS_ERR_NOT_READY;
     if (n_steps == 0) return KFPOS_OK;
@@ -457,8 +459,19 @@ extern "C" int kfpos_batch_replay_epochs(kfpos_batch *b, int n_steps, const doub
     void *d_traj = nullptr;
     bool copy_traj = false;
     if ((rc = stage_out(b, 2, traj, sizeof(double) * 3 * N * T, &d_traj, &copy_traj))) return rc;
-    rc = launch_replay(b, n_steps, nullptr, d_r, fmt, err_scalar, (const double *)d_e, (double *)d_traj, nullptr, s,
-                       (const double *)d_dtf);
+    if (b->model == KFPOS_MODEL_T6) {
+        rc = launch_replay(b, n_steps, nullptr, d_r, fmt, err_scalar, (const double *)d_e, (double *)d_traj, nullptr, s,
+                           (const double *)d_dtf);
+    } else { // K8 / T9: the epochs as a schedule of ranging events whose time steps are per filter
+        std::vector<kfpos_event> evs(T);
+        for (size_t t = 0; t < T; ++t) {
+            memset(&evs[t], 0, sizeof(kfpos_event));
+            evs[t].kind = KFPOS_EV_TOA;
+            evs[t].offset = (int64_t)t * (int64_t)M;
+        }
+        rc = run_events(b, n_steps, evs.data(), d_r, fmt, err_scalar, (const double *)d_e, nullptr, (double *)d_traj, s,
+                        (const double *)d_dtf);
+    }
     if (rc) return rc;
     if (copy_traj) CK(cudaMemcpyAsync(traj, d_traj, sizeof(double) * 3 * N * T, cudaMemcpyDeviceToHost, s));
     if (copy_traj || !on_device(ranges) || !on_device(dt_per_filter) || (err_var && !on_device(err_var)))
@@ -536,7 +549,7 @@ K8Cfg make_k8cfg(const kfpos_batch *b) {
 
 // events: HOST array; every data pointer already on the device
 int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_ranges, int fmt, double err_scalar,
-               const double *d_err, const double *d_sensors, double *d_traj, cudaStream_t s) {
+               const double *d_err, const double *d_sensors, double *d_traj, cudaStream_t s, const double *d_dt_f) {
     static_assert(sizeof(kfpos_event) == sizeof(EventDesc), "kfpos_event and EventDesc must have one layout");
     if (n <= 0) return KFPOS_OK;
     b->stepped = true;
@@ -559,6 +572,7 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.latch = b->d_latch;
         p.has = b->d_has;
         p.latch_u = b->d_latch_u;
+        p.dt_f = d_dt_f;
         p.traj = d_traj;
         p.counters = b->d_counters;
         CK(launch_k8_replay(p, s));
@@ -585,6 +599,7 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.variant = b->cfg.variant;
         p.n_ignore = b->cfg.num_ignored_rangings;
         p.best_mode = b->cfg.best_mode;
+        p.dt_f = d_dt_f;
         p.traj = d_traj;
         p.counters = b->d_counters;
         CK(launch_t9_replay(p, s));

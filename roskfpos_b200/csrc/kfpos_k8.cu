@@ -99,6 +99,22 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
         for (int e = 0; e < p.n_events; ++e) {
             const EventDesc ev = p.events[e];
             cp_async_wait_all();
+            double dt_ev = ev.dt;
+            if (SEL && p.dt_f) { // ragged replay: every filter has its own time steps
+                dt_ev = p.dt_f[(int64_t)e * N + f];
+                if (dt_ev < 0.0) { // this filter has no such event
+                    if (e + 1 < p.n_events) prefetch_event(raw, land, p.events[e + 1], m, p.rs, p.sensors, N, f);
+                    if (ev.kind == EV_TOA) { // its trajectory row repeats the current state
+                        if (p.traj) {
+                            p.traj[((int64_t)n_toa * 3 + 0) * N + f] = px;
+                            p.traj[((int64_t)n_toa * 3 + 1) * N + f] = py;
+                            p.traj[((int64_t)n_toa * 3 + 2) * N + f] = th;
+                        }
+                        ++n_toa;
+                    }
+                    continue;
+                }
+            }
             st.status = 0u;
             K8Meas ms;
             ms.has_px4 = ms.has_imu = ms.has_mag = false;
@@ -154,9 +170,9 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
             }
             if (e + 1 < p.n_events) prefetch_event(raw, land, p.events[e + 1], m, p.rs, p.sensors, N, f);
             if (skip) {
-                carry += ev.dt;
+                carry += dt_ev;
             } else {
-                const double dt = ev.dt + carry;
+                const double dt = dt_ev + carry;
                 carry = 0.0;
 
                 // ---- predict (KF.cpp:287-305): a = 0 at the start of every step
@@ -220,7 +236,7 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                 }
 
             }
-            __syncwarp(wmask); // the IEKF trip count differs per lane
+            if (!SEL) __syncwarp(wmask); // the IEKF trip count differs per lane
         }
         p.x[0 * N + f] = px; p.x[1 * N + f] = py; p.x[2 * N + f] = vx; p.x[3 * N + f] = vy;
         p.x[4 * N + f] = 0.0; p.x[5 * N + f] = 0.0; p.x[6 * N + f] = th; p.x[7 * N + f] = om;
@@ -254,7 +270,7 @@ static cudaError_t launch_k(const K8Params &p, cudaStream_t s) {
 
 cudaError_t launch_k8_replay(const K8Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
-    if (p.cfg.variant == 1 || p.cfg.variant == 2)
+    if (p.cfg.variant == 1 || p.cfg.variant == 2 || p.dt_f != nullptr) // the general instantiation
         return p.rs.err != nullptr ? launch_k<true, 0, true>(p, s) : launch_k<false, 0, true>(p, s);
     if (p.rs.err != nullptr) return launch_k<true, 0>(p, s);
     if (p.rs.m_slots == 8 && !p.cfg.zero_tz) return launch_k<false, 8>(p, s);

@@ -103,6 +103,7 @@ struct K8Params {
     double *latch;   // SoA [8][N]: px4 vx,vy,gz,cv | imu ax,ay,wz | mag angle
     int32_t *has;    // [N] bit0 px4, bit1 imu, bit2 mag latched
     double *latch_u; // [4] batch-wide latched IMU covariances c00,c01,c11,cw
+    const double *dt_f; // null, or per-filter time steps SoA [n_events][N] (see T9Params)
     double *traj;    // SoA [n_toa][3][N] (px, py, theta) after each TOA event, or null
     unsigned long long *counters;
 };
@@ -127,6 +128,8 @@ struct T9Params {
     double *latch;   // SoA rows 0..2: latched acceleration
     int32_t *has;    // [N] bit1: imu latched
     double *latch_u; // [9] batch-wide latched 3x3 acceleration covariance
+    const double *dt_f; // null, or per-filter time steps SoA [n_events][N] replacing EventDesc::dt (< 0: the
+                        // filter has no such event) -- the ragged epochs of kfpos_batch_replay_epochs
     int no_imu;      // host knowledge: no IMU sample latched and none in this schedule -> lean kernel
     int variant, n_ignore, best_mode; // EKF-side NLOS variants (config_pos.xml; 0 = normal)
     double *traj;    // SoA [n_toa][3][N] or null

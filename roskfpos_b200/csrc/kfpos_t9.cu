@@ -251,7 +251,22 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
         if (p.n_events > 0) prefetch(p.events[0]);
         for (int e = 0; e < p.n_events; ++e) {
             const EventDesc ev = p.events[e];
-            const double dt = ev.dt;
+            double dt = ev.dt;
+            if (SEL && p.dt_f) { // ragged replay: every filter has its own time steps
+                dt = p.dt_f[(int64_t)e * N + f];
+                if (dt < 0.0) { // this filter has no such event
+                    cp_async_wait_all();
+                    if (e + 1 < p.n_events) prefetch(p.events[e + 1]);
+                    if (ev.kind == EV_TOA) { // its trajectory row repeats the current position
+                        if (p.traj) {
+#pragma unroll
+                            for (int k = 0; k < 3; ++k) p.traj[((int64_t)n_toa * 3 + k) * N + f] = pos[k];
+                        }
+                        ++n_toa;
+                    }
+                    continue;
+                }
+            }
             // ---- predict (TOAIMU.cpp:165-180): a = 0 at the start of every step.  Done before the
             // event's payload is unpacked so that the epoch's ranges are not live across it.
             Sym<9> Pw;
@@ -299,7 +314,7 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
             }
             const int rc = t9_update<PME, MT, IMU>(p.anchors, ep, has_r, used, IMU && has_imu, za, Ra, xp, Pm, Pw, dx, M, st,
                                                    SEL ? 0u : wmask, cyc);
-            __syncwarp(wmask); // the IEKF trip count differs per lane
+            if (!SEL) __syncwarp(wmask); // the IEKF trip count differs per lane
             if (rc >= 0) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k) { // velocity and position kept, acceleration dropped (:189-194)
@@ -367,7 +382,7 @@ static cudaError_t launch_k(const T9Params &p, cudaStream_t s) {
 
 cudaError_t launch_t9_replay(const T9Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
-    if (p.variant == 1 || p.variant == 2)
+    if (p.variant == 1 || p.variant == 2 || p.dt_f != nullptr) // the general instantiation
         return p.rs.err != nullptr ? launch_k<true, 0, true, true>(p, s) : launch_k<false, 0, true, true>(p, s);
     if (p.no_imu) {
         if (p.rs.err != nullptr) return launch_k<true, 0, false>(p, s);

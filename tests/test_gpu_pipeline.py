@@ -55,24 +55,63 @@ def test_t6_log_to_report(kflib):
 
 
 def test_t9_log_to_report(kflib):
-    """T9 has no per-filter-dt replay: one single-filter batch per log, the epochs as an event list.
-    Log 2 is left out (its 96-iteration Newton run is a rounding amplifier, see test_oracle_golden);
-    log 4 has rangings without an error estimate, whose epochs the reference rejects (singular)."""
-    from roskfpos_b200 import synth
+    """As test_t6_log_to_report for the 9-state filter (one batch, per-filter time steps).  Log 2 is
+    left out (its 96-iteration Newton run is a rounding amplifier, see test_oracle_golden); log 4
+    has rangings without an error estimate, whose epochs the reference rejects (singular)."""
     from roskfpos_b200.batch import Batch
     g = np.load(GOLD)
-    M = g["anchors"].shape[0]
+    N = len(g["n_epochs"])
     o = _assembled(g)
-    for j in (0, 1, 3, 4, 5):
-        n = int(g["n_epochs"][j])
-        r = np.ascontiguousarray(o["ranges"][:n, :, j:j + 1])
-        e = np.ascontiguousarray(o["err"][:n, :, j:j + 1])
-        x0 = np.zeros((9, 1)); x0[:3, 0] = g["x0"][:, j]
-        events = [(synth.EV_TOA, float(o["dt"][k, j]), k * M, None) for k in range(n)]
-        with Batch(kflib.MODEL_T9, 1, anchors=g["anchors"], accel_noise=0.5, jolt=0.5) as b:
+    x0 = np.zeros((9, N)); x0[:3] = g["x0"]
+    with Batch(kflib.MODEL_T9, N, anchors=g["anchors"], accel_noise=0.5, jolt=0.5) as b:
+        b.set_state(x0)
+        traj = b.replay_epochs(o["dt"], o["ranges"], err=o["err"], want_traj=True)
+        x, P, st = b.get_state()
+        assert np.array_equal(traj[-1], x[:3])  # shorter logs repeat their last position
+        for i, lag in enumerate(g["lags"]):
+            pose, cov = b.get_pose_msg(float(lag))
+            for j in (0, 1, 3, 4, 5):
+                assert np.abs(pose[:, j] - g["t9_pose"][j, i]).max() < 1e-9, (j, lag)
+                assert relP(cov[:, j], g["t9_cov"][j, i]) < 1e-9, (j, lag)
+
+
+def test_k8_t9_ragged_epochs_match_per_filter_replays(kflib, oracle):
+    """kfpos_batch_replay_epochs for K8 and T9: every filter has its own time steps and its own
+    number of epochs; the result equals the oracle run filter by filter on its own schedule."""
+    from roskfpos_b200 import synth
+    from roskfpos_b200.batch import Batch
+    from tests.util import rel_err_cov, rel_err_state
+    N, T, m = 70, 12, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=91)
+    r = synth.ranges_mm(truth[1:], anc, seed=92, p_missing=0.1)
+    rng = np.random.default_rng(93)
+    dt = rng.integers(20, 200, size=(T, N)) / 1000.0
+    dt[rng.random((T, N)) < 0.25] = -1.0  # this filter has no such epoch
+    dt[0] = 0.1
+    e = rng.uniform(0.005, 0.05, size=(T, m, N))
+    for model, n in ((kflib.MODEL_T9, 9), (kflib.MODEL_K8, 8)):
+        x0 = np.zeros((n, N))
+        if n == 9:
+            x0[:3] = truth[0]
+        else:
+            x0[:2] = truth[0][:2]; x0[6] = 0.3
+        kw = dict(xml=synth.K8_XML) if n == 8 else {}
+        with Batch(model, N, anchors=anc, accel_noise=0.5, jolt=0.5, **kw) as b:
             b.set_state(x0)
-            b.replay_events(events, ranges=r, err=e)
-            for i, lag in enumerate(g["lags"]):
-                pose, cov = b.get_pose_msg(float(lag))
-                assert np.abs(pose[:, 0] - g["t9_pose"][j, i]).max() < 1e-9, (j, lag)
-                assert relP(cov[:, 0], g["t9_cov"][j, i]) < 1e-9, (j, lag)
+            b.replay_epochs(dt, r, err=e)
+            x, P, st = b.get_state()
+            cnt = b.counters()
+        assert cnt["updates"] == (dt >= 0).sum()
+        xr = np.zeros_like(x); Pr = np.zeros_like(P)
+        for f in range(N):
+            keep = np.nonzero(dt[:, f] >= 0)[0]
+            ev = [(synth.EV_TOA, float(dt[t, f]), k * m, None) for k, t in enumerate(keep)]
+            rf = np.ascontiguousarray(r[keep][:, :, f:f + 1]); ef = np.ascontiguousarray(e[keep][:, :, f:f + 1])
+            if n == 9:
+                ref = oracle.t9_events(x0[:, f:f + 1], None, ev, rf, None, anc, ef)
+            else:
+                ref = oracle.k8_replay(x0[:, f:f + 1], None, ev, rf, None, anc, ef,
+                                       oracle.k8_cfg(0.5, 0.5, **synth.K8_ORACLE_CFG))
+            xr[:, f] = ref["x"][:, 0]; Pr[:, f] = ref["P"][:, 0]
+        assert rel_err_state(x, xr) < 1e-9 and rel_err_cov(P, Pr) < 1e-9, n
