@@ -129,18 +129,26 @@ KF_DEV void ml_pass3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
             c1s += rid; // sum of (1 - r/d) = nvalid - sum r/d
             const double w2 = invd * invd;
             const double c2 = rid * w2;
-            const double cx = c2 * dx, cy = c2 * dy, cz = c2 * dz;
+            const double cx = c2 * dx, cy = c2 * dy;
             h0 = fma(cx, dx, h0); h1 = fma(cx, dy, h1); h2 = fma(cy, dy, h2);
-            h3 = fma(cx, dz, h3); h4 = fma(cy, dz, h4); h5 = fma(cz, dz, h5);
+            h3 = fma(cx, dz, h3); h4 = fma(cy, dz, h4);
+            // the zz sums follow from the unit length of (dx, dy, dz) / d after the loop
             if (ACCG) {
-                const double wx = w2 * dx, wy = w2 * dy, wz = w2 * dz;
+                const double wx = w2 * dx, wy = w2 * dy;
                 u0 = fma(wx, dx, u0); u1 = fma(wx, dy, u1); u2 = fma(wy, dy, u2);
-                u3 = fma(wx, dz, u3); u4 = fma(wy, dz, u4); u5 = fma(wz, dz, u5);
+                u3 = fma(wx, dz, u3); u4 = fma(wy, dz, u4);
             }
         }
     }
+    if (!PME) {
+        // sum_i (r_i/d_i) u_i u_i^T has trace sum_i r_i/d_i and sum_i u_i u_i^T has trace nvalid (u_i = unit
+        // vector, 0 for a missing ranging): the zz entries cost two subtractions instead of a
+        // multiply and an FMA per anchor
+        h5 = (c1s - h0) - h2;
+        if (ACCG) u5 = ((double)nvalid - u0) - u2;
+        c1s = (double)nvalid - c1s;
+    }
     if (ACCG) { Gu[0] = u0; Gu[1] = u1; Gu[2] = u2; Gu[3] = u3; Gu[4] = u4; Gu[5] = u5; }
-    if (!PME) c1s = (double)nvalid - c1s;
     o.sse = sse;
     o.wcost = PME ? wc : sse * fast_rcp(ep.e0);
     o.g[0] = g0; o.g[1] = g1; o.g[2] = g2;
@@ -535,10 +543,12 @@ KF_DEV void iekf_pass(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned 
             G0 = fma(h0, h0, G0); G1 = fma(h0, h1, G1); G2 = fma(h1, h1, G2);
             if (D == 3) {
                 b2 = fma(h2, y, b2);
-                G3 = fma(h0, h2, G3); G4 = fma(h1, h2, G4); G5 = fma(h2, h2, G5);
+                G3 = fma(h0, h2, G3); G4 = fma(h1, h2, G4);
             }
         }
     }
+    // unit rows: trace(sum h h^T) = number of rangings (a missing one has h = 0)
+    if (!PME && D == 3) G5 = ((double)__popc(mask) - G0) - G2;
     c_out = c;
     b[0] = b0; b[1] = b1; b[2] = b2;
     G[0] = G0; G[1] = G1; G[2] = G2; G[3] = G3; G[4] = G4; G[5] = G5;
