@@ -525,7 +525,8 @@ KF_DEV void iekf_pass(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned 
         }
         const double e = fma(-d2, id, r);
         const double h0 = ex * id, h1 = ey * id, h2 = D == 3 ? ez * id : 0.0;
-        const double y = D == 3 ? fma(h0, dx[0], fma(h1, dx[1], fma(h2, dx[2], e))) : fma(h0, dx[0], fma(h1, dx[1], e));
+        // b = sum h (eps + h . dx) / R = sum h eps / R + G dx: the second term is added after the loop
+        const double y = e;
         if (PME) {
             const double iR = fast_rcp(fmax(sse, ep.e[i]));
             c = fma(e * e, iR, c);
@@ -550,6 +551,14 @@ KF_DEV void iekf_pass(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned 
     // unit rows: trace(sum h h^T) = number of rangings (a missing one has h = 0)
     if (!PME && D == 3) G5 = ((double)__popc(mask) - G0) - G2;
     c_out = c;
+    if (D == 3) {
+        b0 = fma(G0, dx[0], fma(G1, dx[1], fma(G3, dx[2], b0)));
+        b1 = fma(G1, dx[0], fma(G2, dx[1], fma(G4, dx[2], b1)));
+        b2 = fma(G3, dx[0], fma(G4, dx[1], fma(G5, dx[2], b2)));
+    } else {
+        b0 = fma(G0, dx[0], fma(G1, dx[1], b0));
+        b1 = fma(G1, dx[0], fma(G2, dx[1], b1));
+    }
     b[0] = b0; b[1] = b1; b[2] = b2;
     G[0] = G0; G[1] = G1; G[2] = G2; G[3] = G3; G[4] = G4; G[5] = G5;
 }
