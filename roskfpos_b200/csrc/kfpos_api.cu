@@ -212,8 +212,8 @@ extern "C" int kfpos_batch_create(kfpos_batch **out, int device, int model, int6
             return KFPOS_ERR_UNSUPPORTED;
         }
         b->mlq_cap = (int)(N / 8 + 4096);
-        alloc(&b->d_mlq, (size_t)b->mlq_cap * 64);
-        alloc((void **)&b->d_mlq_count, sizeof(int));
+        alloc(&b->d_mlq, (size_t)b->mlq_cap * 64 * 2);
+        alloc((void **)&b->d_mlq_count, sizeof(int) * 2);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -829,9 +829,13 @@ extern "C" int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt,
     p.sel = (int32_t *)d_sel;
     p.status = (int32_t *)d_st;
     p.counters = b->d_counters;
-    p.queue = b->d_mlq;
+    p.queue[0] = b->d_mlq;
+    p.queue[1] = (char *)b->d_mlq + (size_t)b->mlq_cap * 64;
     p.queue_count = b->d_mlq_count;
     p.queue_cap = b->mlq_cap;
+    p.q_in = nullptr; p.q_in_count = nullptr; p.q_out = nullptr; p.q_out_count = nullptr;
+    p.first_cap = 10000u;
+    p.coop_min = 0; p.coop_max = 0;
     CK(launch_ml_solve(p, s));
     if (c_pos) CK(cudaMemcpyAsync(pos, d_pos, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, s));
     if (c_cov) CK(cudaMemcpyAsync(cov, d_cov, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, s));

@@ -54,9 +54,17 @@ struct MlParams {
     int32_t *sel;    // SoA [2][N] or null
     int32_t *status; // [N] or null
     unsigned long long *counters;
-    void *queue;      // straggler queue: queue_cap records of 64 bytes (kfpos_mlk.cu)
-    int *queue_count; // device counter
+    // straggler queues (kfpos_mlk.cu): two buffers of queue_cap 64-byte records + their counters;
+    // launch_ml_solve points q_in / q_out at them launch by launch
+    void *queue[2];
+    int *queue_count; // device int[2]
     int queue_cap;
+    const void *q_in;      // records this launch resumes / advances (RESUME and cooperative kernels)
+    const int *q_in_count;
+    void *q_out;           // where this launch parks; null = finish in place
+    int *q_out_count;
+    unsigned first_cap;    // Newton iterations a solve gets in this launch before it is parked
+    int coop_min, coop_max; // queue lengths [min, max) for which a cooperative launch does its work
 };
 
 // ---- sensor event streams (K8, T9).  The schedule (kind, dt) is common to the batch;

@@ -10,6 +10,22 @@
 // phase) in a queue, and a second launch resumes the parked epochs 32 to a warp.  The resumed
 // iteration sequence is the same arithmetic in the same order, so results do not depend on
 // where an epoch was parked.
+//
+// Cooperative advance.  Most parked epochs run to the 10000-iteration cap, one dependent Newton
+// iteration after the other: ~950 instructions per iteration issued by a single warp, 18 ms
+// whatever the batch size.  Between the main launch and the resume launch a third kernel therefore
+// ADVANCES every parked epoch with a GROUP of lanes per epoch (16 or 32 lanes, one per anchor, when
+// the queue is short; 4 or 8 lanes with four anchors each when it is long): each lane forms its
+// anchors' terms of the cost, gradient and Hessian, the group sums them through shared memory,
+// every lane of the group solves the same 3x3 system.  It stops where the epoch's own stop test
+// is met (or at the cap) and leaves (point, cost, iteration count) in the record; the resume
+// launch then needs one pass to finish the solve.  The sums are associated differently here and
+// in the one-thread solver: parked epochs (1.5 in a thousand) see a rounding-level different --
+// equally valid -- iteration sequence.  With variant IGNORE_N the re-solve on the reduced set can
+// be slow as well: the first resume launch parks those into the second queue, which gets the same
+// treatment.  Measured (16 anchors, variant 1): 1 Mi epochs 19.8 -> 11.9 ms, 4 Mi 24.4 -> 21.0 ms.
+#include <algorithm>
+
 #include "kfpos_kernels.cuh"
 #include "kfpos_solve.cuh"
 
@@ -17,6 +33,9 @@ namespace kfpos {
 
 constexpr int ML_BLOCK = 128;
 constexpr unsigned ML_FIRST_CAP = 32u;
+// queue length up to which the one-lane-per-anchor form is used (measured on 16 anchors: 6.4 ms flat up
+// to ~2700 records, then 2.3 us per record; the 4-lanes-per-record form: 11 ms at 7800 records)
+constexpr int COOP_WIDE_MAX = 4000;
 
 // parked Newton state of one epoch (one 64-byte record)
 struct MlParked {
@@ -48,19 +67,162 @@ KF_DEV int ml_any(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask
     return ml_solve3<PME, MT>(A, ep, mask, pos, sse, iters, cov, nullptr, cap, rs);
 }
 
+// Group sums through the warp's shared-memory tile.  A warp holds 32 / L groups of L lanes; lane
+// `lane` contributes K values; afterwards every lane holds the K sums over ITS group.  Lane gl of
+// a group adds up rows gl, gl + L, ... of its group's L columns (16-byte loads), the totals go back
+// through the tile.  (Shuffles cost more here: in this data-dependent loop every *_sync shuffle
+// is wrapped in a WARPSYNC.COLLECTIVE sequence, ~20 cycles each.)  Two tiles alternate between
+// iterations so that one __syncwarp per hand-over is enough.
+constexpr int COOP_STRIDE = 34;                       // doubles per row: rows 16-byte aligned, four banks apart
+constexpr int COOP_TOT = 12 * COOP_STRIDE;            // totals: [group][12]
+constexpr int COOP_TILE = COOP_TOT + 8 * 12;          // doubles per tile
+template <int K, int L>
+KF_DEV void group_sum(double *tile, int lane, double (&v)[K]) {
+    const int grp = lane / L, gl = lane % L;
+#pragma unroll
+    for (int j = 0; j < K; ++j) tile[j * COOP_STRIDE + lane] = v[j];
+    __syncwarp();
+#pragma unroll
+    for (int j0 = 0; j0 < K; j0 += L) {
+        const int j = j0 + gl;
+        if (j < K) {
+            const double2 *row = reinterpret_cast<const double2 *>(tile + j * COOP_STRIDE + grp * L);
+            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll
+            for (int i = 0; i < L / 4; ++i) {
+                const double2 lo = row[2 * i], hi = row[2 * i + 1];
+                a0 += lo.x; a1 += lo.y; a2 += hi.x; a3 += hi.y;
+            }
+            tile[COOP_TOT + grp * 12 + j] = (a0 + a1) + (a2 + a3);
+        }
+    }
+    __syncwarp();
+    const double2 *tot = reinterpret_cast<const double2 *>(tile + COOP_TOT + grp * 12);
+#pragma unroll
+    for (int j = 0; j < K / 2; ++j) {
+        const double2 t = tot[j];
+        v[2 * j] = t.x; v[2 * j + 1] = t.y;
+    }
+    if (K & 1) v[K - 1] = tile[COOP_TOT + grp * 12 + K - 1];
+}
+
+// L lanes per parked record (32 / L records per warp), A anchor slots per lane (slot = gl + L a):
+// advances each record's 3-D Newton solve (the loop of ml_solve3, ML.cpp:165-222) to its stop
+// test or the iteration cap.  Warps stride over the queue; a warp leaves when all its records are done.
+template <bool PME, int L, int A>
+__global__ void __launch_bounds__(ML_BLOCK) ml_coop_kernel(const __grid_constant__ MlParams p) {
+    __shared__ __align__(16) double tiles[ML_BLOCK / 32][2 * COOP_TILE];
+    constexpr int G = 32 / L;
+    const int lane = threadIdx.x & 31, grp = lane / L, gl = lane % L;
+    double *tile = tiles[threadIdx.x >> 5];
+    const int count = min(*p.q_in_count, p.queue_cap);
+    // two instantiations are launched back to back and the queue length picks one: many lanes per
+    // record give the shortest iteration (few records: latency-bound), few lanes per record the
+    // least work per record (many records: the wide form would be throughput-bound)
+    if (count < p.coop_min || count >= p.coop_max) return;
+    const int n_warps = (int)(gridDim.x * (ML_BLOCK / 32));
+    const int64_t N = p.N;
+    const int m = p.rs.m_slots;
+    const double inv_e0 = fast_rcp(p.rs.err_scalar);
+    for (int wbase = (int)(blockIdx.x * (ML_BLOCK / 32) + (threadIdx.x >> 5)) * G; wbase < count; wbase += n_warps * G) {
+        const bool live = wbase + grp < count;
+        MlParked *rec = reinterpret_cast<MlParked *>(const_cast<void *>(p.q_in)) + (live ? wbase + grp : wbase);
+        const int64_t f = rec->idx;
+        const unsigned used = live ? rec->used : 0u;
+        double ax[A], ay[A], az[A], r[A], w[A];
+        bool on[A];
+#pragma unroll
+        for (int a = 0; a < A; ++a) {
+            const int slot = gl + L * a;
+            on[a] = slot < m && ((used >> slot) & 1u);
+            const int li = slot < m ? slot : 0;
+            ax[a] = p.anchors.x[li]; ay[a] = p.anchors.y[li]; az[a] = p.anchors.z[li];
+            r[a] = 0.0; w[a] = 1.0;
+            if (on[a]) {
+                const int64_t at = (int64_t)li * N + f;
+                if (p.rs.fmt == 0) r[a] = reinterpret_cast<const double *>(p.rs.ranges)[at];
+                else if (p.rs.fmt == 1) r[a] = mm_to_m((double)reinterpret_cast<const int32_t *>(p.rs.ranges)[at]);
+                else r[a] = mm_to_m((double)reinterpret_cast<const uint16_t *>(p.rs.ranges)[at]);
+                if (PME) w[a] = fast_rcp(p.rs.err[at]);
+            }
+        }
+        const double nvalid = (double)__popc(used);
+        double px = rec->p[0], py = rec->p[1], pz = rec->p[2], cost = rec->cost;
+        unsigned iter = rec->iter;
+        bool done = !live;
+        for (unsigned round = 0;; ++round) {
+            constexpr int K = PME ? 11 : 10;
+            double v[K];
+#pragma unroll
+            for (int j = 0; j < K; ++j) v[j] = 0.0;
+#pragma unroll
+            for (int a = 0; a < A; ++a) {
+                const double dx = ax[a] - px, dy = ay[a] - py, dz = az[a] - pz;
+                const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+                const double invd = on[a] ? fast_rsqrt(d2) : 0.0;
+                const double res = fma(-d2, invd, r[a]);
+                const double rid = r[a] * invd;
+                const double t = res * invd * w[a];
+                const double c2 = rid * invd * invd * w[a];
+                const double cx = c2 * dx, cy = c2 * dy;
+                v[0] = fma(res * res, w[a], v[0]);
+                v[1] = fma(t, dx, v[1]); v[2] = fma(t, dy, v[2]); v[3] = fma(t, dz, v[3]);
+                v[4] += PME ? (on[a] ? (1.0 - rid) * w[a] : 0.0) : rid;
+                v[5] = fma(cx, dx, v[5]); v[6] = fma(cx, dy, v[6]); v[7] = fma(cy, dy, v[7]);
+                v[8] = fma(cx, dz, v[8]); v[9] = fma(cy, dz, v[9]);
+                if (PME) v[K - 1] = fma(c2 * dz, dz, v[K - 1]);
+            }
+            group_sum<K, L>(tile + (round & 1u) * COOP_TILE, lane, v);
+            if (!done) {
+                const double wcost = v[0];
+                double c1s = v[4], h5;
+                if (PME) {
+                    h5 = v[K - 1];
+                } else { // unit direction vectors: see ml_pass3
+                    h5 = (c1s - v[5]) - v[7];
+                    c1s = nvalid - c1s;
+                }
+                const double newCost = PME ? wcost : wcost * inv_e0;
+                if (!(rel_change_gt(cost, newCost) && iter < 10000u)) {
+                    done = true;
+                } else {
+                    const double H[6] = {v[5] + c1s, v[6], v[7] + c1s, v[8], v[9], h5 + c1s};
+                    const double g[3] = {v[1], v[2], v[3]};
+                    double s[3];
+                    if (!solve_sym3(H, g, s)) {
+                        done = true; // left to the one-thread solver, which reports it
+                    } else {
+                        iter += 1;
+                        cost = newCost;
+                        px -= s[0]; py -= s[1]; pz -= s[2];
+                    }
+                }
+            }
+            if (__all_sync(0xffffffffu, done)) break;
+        }
+        if (gl == 0 && live) {
+            rec->p[0] = px; rec->p[1] = py; rec->p[2] = pz;
+            rec->cost = cost;
+            rec->iter = iter;
+        }
+        __syncwarp();
+    }
+}
+
 // RESUME = false: thread f owns epoch f;  true: thread q owns parked record q.
 template <bool PME, int MT, bool RESUME>
 __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constant__ MlParams p) {
     extern __shared__ double smem[];
     const int64_t t = (int64_t)blockIdx.x * ML_BLOCK + threadIdx.x;
-    MlParked *queue = reinterpret_cast<MlParked *>(p.queue);
-    const bool active = RESUME ? t < min(*p.queue_count, p.queue_cap) : t < p.N;
+    const MlParked *queue_in = reinterpret_cast<const MlParked *>(p.q_in);
+    MlParked *queue = reinterpret_cast<MlParked *>(p.q_out);
+    const bool active = RESUME ? t < min(*p.q_in_count, p.queue_cap) : t < p.N;
     unsigned iters = 0, bad = 0, done = 0;
     if (active) {
         const int64_t N = p.N;
         const int m = MT > 0 ? MT : p.rs.m_slots;
         MlParked rec;
-        if (RESUME) rec = queue[t];
+        if (RESUME) rec = queue_in[t];
         const int64_t f = RESUME ? (int64_t)rec.idx : t;
         EpochT<PME, MT> ep;
         ep.z = Col{smem + threadIdx.x, ML_BLOCK};
@@ -87,7 +249,7 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
             pos[0] = rec.p[0]; pos[1] = rec.p[1]; pos[2] = rec.p[2];
             rs.cost = rec.cost; rs.iter = rec.iter;
         }
-        unsigned cap = (RESUME || p.variant == 2) ? 10000u : ML_FIRST_CAP; // BEST does not park
+        unsigned cap = p.variant == 2 ? 10000u : p.first_cap; // BEST does not park
         int rc;
         bool parked = false;
         for (;;) {
@@ -95,7 +257,7 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
             rc = ml_any<PME, MT>(p.anchors, ep, used, use2d, p.zero_tz != 0, pos, last ? cov : nullptr, sse, iters, cap,
                                  &rs);
             if (rc == ML_MORE) {
-                const int slot = atomicAdd(p.queue_count, 1);
+                const int slot = queue ? atomicAdd(p.q_out_count, 1) : p.queue_cap;
                 if (slot < p.queue_cap) {
                     rec.idx = (int32_t)f; rec.phase = phase; rec.used = used; rec.iter = rs.iter; rec.iters = iters;
                     rec._pad = 0u; rec.cost = rs.cost; rec.p[0] = pos[0]; rec.p[1] = pos[1]; rec.p[2] = pos[2];
@@ -163,22 +325,48 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
 }
 
 template <bool PME, int MT>
-static cudaError_t launch_k(const MlParams &p, cudaStream_t s) {
+static cudaError_t launch_k(const MlParams &p0, cudaStream_t s) {
+    MlParams p = p0;
     const int m = p.rs.m_slots;
     const size_t smem = (size_t)((MT > 0 ? 0 : m) + (PME ? m : 0) + raw_rows(p.rs.fmt, m)) * ML_BLOCK * sizeof(double);
     cudaError_t e = cudaFuncSetAttribute(ml_solve_kernel<PME, MT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(ml_solve_kernel<PME, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    e = cudaMemsetAsync(p.queue_count, 0, sizeof(int), s);
+    e = cudaMemsetAsync(p.queue_count, 0, 2 * sizeof(int), s);
     if (e != cudaSuccess) return e;
+    const bool parks = !p.use2d && p.variant != 2;
+    p.q_in = nullptr; p.q_in_count = nullptr;
+    p.q_out = parks ? p.queue[0] : nullptr; p.q_out_count = p.queue_count;
+    p.first_cap = parks ? ML_FIRST_CAP : 10000u;
     ml_solve_kernel<PME, MT, false><<<(unsigned)((p.N + ML_BLOCK - 1) / ML_BLOCK), ML_BLOCK, smem, s>>>(p);
     e = cudaGetLastError();
-    if (e != cudaSuccess) return e;
-    // the parked epochs, densely packed; sized for the whole queue (blocks beyond the count exit at once)
-    if (!p.use2d && p.variant != 2)
-        ml_solve_kernel<PME, MT, true><<<(unsigned)((p.queue_cap + ML_BLOCK - 1) / ML_BLOCK), ML_BLOCK, smem, s>>>(p);
-    return cudaGetLastError();
+    if (e != cudaSuccess || !parks) return e;
+    // the parked epochs: grids sized for the whole queue (warps / blocks beyond the count exit at once)
+    const unsigned coop_grid = (unsigned)std::min<int64_t>(((int64_t)p.queue_cap * 32 + ML_BLOCK - 1) / ML_BLOCK, 148 * 8);
+    const unsigned res_grid = (unsigned)((p.queue_cap + ML_BLOCK - 1) / ML_BLOCK);
+    const int rounds = p.variant == 1 ? 2 : 1; // IGNORE_N solves twice
+    for (int q = 0; q < rounds; ++q) {
+        p.q_in = p.queue[q]; p.q_in_count = p.queue_count + q;
+        if (m <= 16) {
+            p.coop_min = 0; p.coop_max = COOP_WIDE_MAX;
+            ml_coop_kernel<PME, 16, 1><<<coop_grid, ML_BLOCK, 0, s>>>(p);
+            p.coop_min = COOP_WIDE_MAX; p.coop_max = 0x7fffffff;
+            ml_coop_kernel<PME, 4, 4><<<coop_grid, ML_BLOCK, 0, s>>>(p);
+        } else {
+            p.coop_min = 0; p.coop_max = COOP_WIDE_MAX;
+            ml_coop_kernel<PME, 32, 1><<<coop_grid, ML_BLOCK, 0, s>>>(p);
+            p.coop_min = COOP_WIDE_MAX; p.coop_max = 0x7fffffff;
+            ml_coop_kernel<PME, 8, 4><<<coop_grid, ML_BLOCK, 0, s>>>(p);
+        }
+        const bool last = q + 1 == rounds;
+        p.q_out = last ? nullptr : p.queue[q + 1]; p.q_out_count = p.queue_count + q + 1;
+        p.first_cap = last ? 10000u : ML_FIRST_CAP;
+        ml_solve_kernel<PME, MT, true><<<res_grid, ML_BLOCK, smem, s>>>(p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t launch_ml_solve(const MlParams &p, cudaStream_t s) {
