@@ -107,7 +107,15 @@ void *ref_pg_create(int algorithm, int tag_id, int n_anchors, const double *anch
     g.setDeviceIdentifiers(tag_id);
     g.setHeuristicML(use2d != 0, variant, n_ignore);
     h->rec = new Recorder();
-    if (algorithm >= 0) {
+    if (algorithm == ALGORITHM_ML) {
+        // PosGenerator::setAlgorithm (Posgenerator.cpp:530-537) minus its init() call: MLLocation::init()
+        // flows off the end of a bool function (MLLocation.cpp:415-417), which g++ -O2 compiles to a fall
+        // through into the next function
+        Vector3 s0 = {};
+        if (use_start) { s0.x = start_xyz[0]; s0.y = start_xyz[1]; s0.z = start_xyz[2]; }
+        else { s0.x = 1; s0.y = 1; s0.z = 4; }
+        h->rec->inner.reset(new MLLocation(use2d != 0, variant, n_ignore, s0));
+    } else if (algorithm >= 0) {
         g.setAlgorithm(algorithm);
         h->rec->inner.reset(g.mPositionAlgorithm.release());
     }

@@ -6,7 +6,8 @@ fake clock).  For a handful of ranging logs it stores
   * every epoch PosGenerator handed to newTOAMeasurement (ranges in metres by beacon index, 0 = slot
     not in the epoch; error estimates; timeLag),
   * the report the node publishes (PoseWithCovarianceStamped + Odometry twist) when polled at
-    several lags after the last epoch, with KalmanFilterTOA and with KalmanFilterTOAIMU behind it.
+    several lags after the last epoch, with KalmanFilterTOA and with KalmanFilterTOAIMU behind it,
+    and with MLLocation (variants 0 and 1) behind it.
 Run:  python tests/golden/make_golden_posgen.py
 """
 import os
@@ -90,6 +91,15 @@ def main():
                 out.setdefault(name + "_pose", np.zeros((N, len(LAGS), 13)))[j, k] = pose
                 out.setdefault(name + "_cov", np.zeros((N, len(LAGS), 36)))[j, k] = cov
             out.setdefault(name + "_failed", np.zeros(N, np.int32))[j] = pg.errors()
+        # ALGORITHM_ML: the report is MLLocation::getPose on the LAST epoch (stateless, start (1,1,4));
+        # variant 0 and variant 1 ignoring 2.  rc != 0: getPose threw (an error estimate of 0)
+        for v, (variant, n_ign) in enumerate(((0, 0), (1, 2))):
+            pg = R.RefPosGenerator(anc, algorithm=2, variant=variant, n_ignore=n_ign)
+            assert pg.feed(a, r, s, t, err=e) == ne
+            rc, pose, cov = pg.report(t[-1] + 0.06)
+            out.setdefault("ml_rc", np.zeros((N, 2), np.int32))[j, v] = rc
+            out.setdefault("ml_pose", np.zeros((N, 2, 13)))[j, v] = pose
+            out.setdefault("ml_cov", np.zeros((N, 2, 36)))[j, v] = cov
     T = int(out["n_epochs"].max())
     out["ep_ranges"] = np.zeros((T, M, N)); out["ep_err"] = np.zeros((T, M, N)); out["ep_lag"] = np.full((T, N), -1.0)
     for j, ep in enumerate(eps):

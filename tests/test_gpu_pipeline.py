@@ -115,3 +115,26 @@ def test_k8_t9_ragged_epochs_match_per_filter_replays(kflib, oracle):
                                        oracle.k8_cfg(0.5, 0.5, **synth.K8_ORACLE_CFG))
             xr[:, f] = ref["x"][:, 0]; Pr[:, f] = ref["P"][:, 0]
         assert rel_err_state(x, xr) < 1e-9 and rel_err_cov(P, Pr) < 1e-9, n
+
+
+def test_ml_log_to_report(kflib):
+    """ALGORITHM_ML behind the reference node: its report is MLLocation::getPose on the last epoch of
+    the log.  All logs as one batch of stateless epochs (each log's last epoch), variants 0 and 1."""
+    from roskfpos_b200.batch import Batch
+    g = np.load(GOLD)
+    N, M = len(g["n_epochs"]), g["anchors"].shape[0]
+    o = _assembled(g)
+    last = g["n_epochs"] - 1
+    r = np.ascontiguousarray(np.stack([o["ranges"][last[j], :, j] for j in range(N)], axis=1))  # [M][N]
+    e = np.ascontiguousarray(np.stack([o["err"][last[j], :, j] for j in range(N)], axis=1))
+    for v, (variant, n_ign) in enumerate(((0, 0), (1, 2))):
+        with Batch(kflib.MODEL_ML, N, anchors=g["anchors"], variant=variant, num_ignored_rangings=n_ign,
+                   ml_start=[1.0, 1.0, 4.0]) as b:
+            out = b.ml_solve(r, err=e)
+        for j in range(N):
+            if g["ml_rc"][j, v] != 0:
+                assert out["status"][j] & 4, (j, v)  # the reference throws, the library flags SINGULAR
+                continue
+            assert out["status"][j] == 0
+            assert np.abs(out["pos"][:, j] - g["ml_pose"][j, v, :3]).max() < 1e-9, (j, v)
+            assert relP(out["cov"][:, j].reshape(3, 3), g["ml_cov"][j, v].reshape(6, 6)[:3, :3]) < 1e-9, (j, v)

@@ -188,3 +188,22 @@ def test_posgen_pipeline_golden(oracle, name):
             tol = (1e-9 if name == "t6" else 1e-6) if j == 2 else TOL
             assert np.abs(pose - g[name + "_pose"][j, i]).max() < tol, (name, j, lag)
             assert relP(cov, g[name + "_cov"][j, i]) < tol, (name, j, lag)
+
+
+def test_posgen_ml_node_golden(oracle):
+    """ALGORITHM_ML behind the reference node: the report is the ML estimate of the last epoch."""
+    g, M, N = _posgen_logs()
+    T = int(g["n_epochs"].max())
+    o = oracle.assemble(g["anchor"], g["seq"], g["range_mm"], g["t"], M, T, err=g["err"])
+    for j in range(N):
+        k = int(g["n_epochs"][j]) - 1
+        r = o["ranges"][k, :, j] / 1000.0
+        for v, (variant, n_ign) in enumerate(((0, 0), (1, 2))):
+            m = oracle.ml_epoch(np.where(r > 0, r, 0.0), g["anchors"], o["err"][k, :, j], [1.0, 1.0, 4.0],
+                                variant=variant, n_ignore=n_ign)
+            if g["ml_rc"][j, v] != 0:
+                assert m["rc"] < 0, (j, v)  # both reject the epoch (singular)
+                continue
+            assert np.abs(m["pos"] - g["ml_pose"][j, v, :3]).max() < TOL, (j, v)
+            assert relP(np.asarray(m["cov"])[:3, :3], g["ml_cov"][j, v].reshape(6, 6)[:3, :3]) < TOL, (j, v)
+            assert np.all(g["ml_pose"][j, v, 3:] == 0.0)
