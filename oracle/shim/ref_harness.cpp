@@ -286,3 +286,20 @@ int ref_t6_replay(long long N, int T, int M, const double *anchors, long long dt
 }
 
 } // extern "C"
+
+extern "C" {
+
+// What KalmanFilter::init() parsed out of its five XML documents (KF.cpp:752-880), in the order
+// of the kfpos_config fields they correspond to.
+void ref_k8_config(void *h, double *out /* [15] */) {
+    KalmanFilter *f = (KalmanFilter *)h;
+    const double v[15] = {(double)f->mUseFixedHeight, f->mUWBtagZ, (double)f->mTagIdUWB,
+                          (double)f->mUseFixedHeightPX4Flow, f->mPX4flowHeight, f->mPX4FlowArmP1, f->mPX4FlowArmP2,
+                          f->mInitAnglePX4Flow, f->mCovarianceVelocityPX4Flow, f->mCovarianceGyroZPX4Flow,
+                          (double)f->mUseImuFixedCovarianceAcceleration, f->mImuCovarianceAcceleration,
+                          (double)f->mUseImuFixedCovarianceAngularVelocityZ, f->mUmuCovarianceAngularVelocityZ,
+                          f->mMagAngleOffset};
+    memcpy(out, v, sizeof v);
+}
+double ref_k8_config_mag_cov(void *h) { return ((KalmanFilter *)h)->mCovarianceMag; }
+} // extern "C"

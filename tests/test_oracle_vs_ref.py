@@ -194,3 +194,44 @@ def test_k8_node_with_all_sensors(oracle):
     po, co = oracle.pose_msg(2, xp, Pp, tag_z=CFG_K8["tag_z"])
     assert np.abs(po - pose).max() < TOL
     assert relP(co, cov) < TOL
+
+
+def test_xml_config_semantics_match_the_reference(kflib):
+    """kfpos_config_load_xml against what the reference's KalmanFilter::init() (KF.cpp:752-880) parses
+    out of the same five XML documents: random values, missing attributes (default 0), flags that are
+    only true for the value 1, the armP0 -> arm1 / armP1 -> arm2 naming."""
+    import ctypes as C
+    from roskfpos_b200.batch import make_config
+    rng = np.random.default_rng(31)
+    R.lib().ref_k8_config_mag_cov.restype = C.c_double
+    for trial in range(40):
+        def attr(name, kind):
+            if rng.random() < 0.15:
+                return "", 0.0  # attribute missing -> the reference's default 0
+            v = int(rng.integers(0, 3)) if kind == "flag" else (int(rng.integers(0, 9)) if kind == "int"
+                                                                else round(float(rng.uniform(-3, 9)), 6))
+            return f' {name}="{v}"', float(v)
+        spec = {
+            "kfpos_tag": ("uwb", [("useFixedHeight", "flag"), ("fixedHeight", "d"), ("tagId", "int")]),
+            "kfpos_px4": ("px4flow", [("useFixedSensorHeight", "flag"), ("sensorHeight", "d"), ("armP0", "d"),
+                                      ("armP1", "d"), ("sensorInitAngle", "d"), ("covarianceVelocity", "d"),
+                                      ("covarianceGyroZ", "d")]),
+            "kfpos_imu": ("imu", [("useFixedCovarianceAcceleration", "flag"), ("covarianceAcceleration", "d"),
+                                  ("useFixedCovarianceAngularVelocityZ", "flag"),
+                                  ("covarianceAngularVelocityZ", "d")]),
+            "kfpos_mag": ("mag", [("angleOffset", "d"), ("covarianceMag", "d")]),
+        }
+        xml = {}
+        for key, (tag, attrs) in spec.items():
+            xml[key] = "<config><" + tag + "".join(attr(n, k)[0] for n, k in attrs) + "/></config>"
+        f = R.RefK8(0.5, 0.0, 0.5, [1.0, 1.0, 0.0], xml=xml)
+        ref = np.zeros(15)
+        R.lib().ref_k8_config(f.h, ref.ctypes.data_as(C.POINTER(C.c_double)))
+        mag_cov = R.lib().ref_k8_config_mag_cov(f.h)
+        cfg = make_config(xml=[xml[k] for k in ("kfpos_tag", "kfpos_px4", "kfpos_imu", "kfpos_mag")])
+        got = [cfg.use_fixed_height, cfg.fixed_height, cfg.tag_id, cfg.px4_use_fixed_sensor_height,
+               cfg.px4_sensor_height, cfg.px4_arm_p0, cfg.px4_arm_p1, cfg.px4_sensor_init_angle,
+               cfg.px4_cov_velocity, cfg.px4_cov_gyro_z, cfg.imu_use_fixed_cov_acc, cfg.imu_cov_acc,
+               cfg.imu_use_fixed_cov_gyro_z, cfg.imu_cov_gyro_z, cfg.mag_angle_offset]
+        assert np.array_equal(np.array(got, dtype=np.float64), ref), (trial, xml, got, ref)
+        assert cfg.mag_cov == mag_cov
