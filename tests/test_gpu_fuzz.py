@@ -67,7 +67,8 @@ def test_t6_random_configuration(kflib, oracle, seed):
     # sums are associated -- so the small batches of this test need room for one or two of them
     few = m <= 5 or c["p_missing"] >= 0.4 or c["mode"] in ("v1", "v2", "loo")
     rep = assert_parity(got, ref, per, float_keys=("x",), cov_keys=("P",), int_keys=("status", "sel"),
-                        min_stable=0.5 if few else 0.9, max_tie_frac=4e-2 if few else 1e-2, what=str(c))
+                        min_stable=0.5 if few else 0.9, max_tie_frac=4e-2 if few else 1e-2,
+                        min_allowed=1 if few else 0, what=str(c))  # a batch of a dozen filters: room for one tie
     print("fuzz", seed, c, rep)
 
 

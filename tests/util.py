@@ -67,7 +67,7 @@ def stable_units(ref, perturbed, float_keys=(), cov_keys=(), int_keys=()):
 
 
 def assert_parity(got, ref, perturbed, float_keys=(), cov_keys=(), int_keys=(), tol=REL_TOL,
-                  min_stable=1.0, max_tie_frac=0.0, tie_tol=np.inf, what=""):
+                  min_stable=1.0, max_tie_frac=0.0, tie_tol=np.inf, what="", min_allowed=0):
     """Every stable unit must meet the parity bar; at most `max_tie_frac` of them may instead be
     a rounding-level tie of a discrete decision (error <= tie_tol / an integer flip)."""
     fe, im = unit_errors(got, ref, float_keys, cov_keys, int_keys)
@@ -77,7 +77,7 @@ def assert_parity(got, ref, perturbed, float_keys=(), cov_keys=(), int_keys=(), 
     ok = (fe <= tol) & ~im
     viol = stable & ~ok
     n_viol = int(viol.sum())
-    allowed = int(np.floor(max_tie_frac * stable.sum()))
+    allowed = max(int(min_allowed), int(np.floor(max_tie_frac * stable.sum())))
     worst = float(fe[stable].max()) if stable.any() else 0.0
     assert n_viol <= allowed, (f"{what}: {n_viol} stable units miss the parity bar (allowed {allowed}); "
                                f"worst float err {worst:.3e}, int mismatches {int((im & stable).sum())}")
