@@ -122,7 +122,13 @@ typedef struct kfpos_config {
     double fixed_height;          /* fixedHeight -> mUWBtagZ                        */
     /* config_px4flow.xml <px4flow .../>  (KF.cpp:766-779) */
     int32_t px4_use_fixed_sensor_height; /* useFixedSensorHeight (never read)       */
-    int32_t _pad1;
+    int32_t ml_exact_order;       /* ML batches: 0 (default) BestGroup epochs are solved in the reference's
+                                     exact operation order (IEEE division / square root, no fused
+                                     multiply-adds: selection indices, iteration counts and values are bit-
+                                     identical to a CPU build of MLLocation.cpp's arithmetic), IgnoreN
+                                     epochs whose residual order is within 1e-6 of a tie are re-decided
+                                     the same way; 1: every epoch of every variant in exact order;
+                                     -1: fast formulation only (selection may flip on rounding-level ties) */
     double px4_sensor_height;     /* sensorHeight -> mPX4flowHeight                 */
     double px4_arm_p0;            /* armP0 -> mPX4FlowArmP1                         */
     double px4_arm_p1;            /* armP1 -> mPX4FlowArmP2                         */

@@ -336,7 +336,8 @@ void ko_t6_new_toa_sel(ko_t6 *f, double dt, int n_slots, const double *ranges, c
         uint32_t bm = 0;
         ko_ml_best_group(m, n, start, 0, best_mode, 0, p0, c0, &it, &bi, &bm, &ng);
         it_sel += it;
-        for (int i = 0; i < n; ++i) keep[i] = (bm >> i) & 1u;
+        if (bi >= 0) /* a failed solve selects nothing: the update then runs on all rangings */
+            for (int i = 0; i < n; ++i) keep[i] = (bm >> i) & 1u;
     }
     int ns = 0;
     uint32_t mask = 0;
@@ -557,7 +558,8 @@ void ko_k8_new_toa(ko_k8 *f, double dt, int n_slots, const double *ranges, const
         uint32_t bm = 0;
         ko_ml_best_group(m, n, start, 1, f->best_mode, b1_zero_z, p0, c0, &it, &bi, &bm, &ng);
         it_sel += it;
-        for (int i = 0; i < n; ++i) keep[i] = (bm >> i) & 1u;
+        if (bi >= 0) /* a failed solve selects nothing: the update then runs on all rangings */
+            for (int i = 0; i < n; ++i) keep[i] = (bm >> i) & 1u;
     }
     int ns = 0;
     for (int i = 0; i < n; ++i)
@@ -767,7 +769,8 @@ void ko_t9_new_toa(ko_t9 *f, double dt, int n_slots, const double *ranges, const
         uint32_t bm = 0;
         ko_ml_best_group(m, n, start, 0, f->best_mode, 0, p0, c0, &it, &bi, &bm, &ng);
         it_sel += it;
-        for (int i = 0; i < n; ++i) keep[i] = (bm >> i) & 1u;
+        if (bi >= 0) /* a failed solve selects nothing: the update then runs on all rangings */
+            for (int i = 0; i < n; ++i) keep[i] = (bm >> i) & 1u;
     }
     int ns = 0;
     for (int i = 0; i < n; ++i)

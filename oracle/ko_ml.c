@@ -167,7 +167,14 @@ int ko_ml_ignore_n(const ko_meas *m, int n, const double start[3], int use2d, in
     double p0[3], cov0[9];
     int it0 = 0, it1 = 0;
     int min_r = use2d ? 3 : 4;
-    ml_any(m, n, start, use2d, b1_zero_z, p0, cov0, &it0);
+    if (ml_any(m, n, start, use2d, b1_zero_z, p0, cov0, &it0) < 0) {
+        /* the first solve throws out of estimatePositionIgnoreN (ML.cpp:315-320): nothing is selected */
+        for (int i = 0; i < n; ++i) order[i] = i;
+        pos[0] = p0[0]; pos[1] = p0[1]; pos[2] = p0[2];
+        if (n_dropped) *n_dropped = -1;
+        if (iters) *iters = it0;
+        return -1;
+    }
     ko_best_rangings(m, n, p0, order);
     ko_meas sorted[KO_MAX_ANCHORS];
     for (int i = 0; i < n; ++i) sorted[i] = m[order[i]];
@@ -206,10 +213,12 @@ int ko_ml_best_group(const ko_meas *m, int n, const double start[3], int use2d, 
     if (best_index) *best_index = -1;
     if (best_mask) *best_mask = 0;
     if (n_groups) *n_groups = 0;
-    if (n < k) {
+    if (n < k || rc < 0) { /* a failed solve throws out of estimatePositionBestGroup (ML.cpp:353-358) */
         if (iters) *iters = it_total;
         return rc;
     }
+    double pos_all[3] = {pos[0], pos[1], pos[2]}, cov_all[9];
+    memcpy(cov_all, cov, sizeof(double) * d * d);
     unsigned char v[KO_MAX_ANCHORS];
     for (int i = 0; i < n; ++i) v[i] = i < k;
     double minErr = 0;
@@ -230,7 +239,17 @@ int ko_ml_best_group(const ko_meas *m, int n, const double start[3], int use2d, 
         if (use2d) cur = gc[0] + gc[3];
         else if (best_mode == 1) cur = gc[8];
         else cur = gc[0] + gc[4] + gc[8];
-        if (grc != 0) cur = NAN; /* no defined reference result: never selected unless first */
+        if (grc != 0) {
+            /* arma::solve / inv throws inside the subset loop (ML.cpp:384-389): the reference never
+             * reaches the selection.  Restated as: the epoch reports SINGULAR, keeps the all-ranging
+             * estimate and selects no group -- whichever subset failed, first or not. */
+            pos[0] = pos_all[0]; pos[1] = pos_all[1]; pos[2] = pos_all[2];
+            memcpy(cov, cov_all, sizeof(double) * d * d);
+            if (best_mask) *best_mask = 0;
+            if (n_groups) *n_groups = idx + 1;
+            if (iters) *iters = it_total;
+            return -1;
+        }
         if (minIdx == -1 || cur <= minErr) { /* ML.cpp:402-410: first seeds, then <= */
             minIdx = idx;
             minErr = cur;
@@ -275,7 +294,7 @@ int ko_ml_epoch(int n_slots, const double *ranges, const double *anchors, const 
     } else if (variant == 1) {
         int order[KO_MAX_ANCHORS], drop = 0;
         rc = ko_ml_ignore_n(m, n, start, use2d, n_ignore, b1_zero_z, pos, cov, iters, order, &drop);
-        for (int i = n - drop; i < n; ++i) used &= ~(1u << slot_of[order[i]]);
+        for (int i = n - (drop > 0 ? drop : 0); i < n; ++i) used &= ~(1u << slot_of[order[i]]);
         idx = drop;
     } else {
         uint32_t mask = 0;

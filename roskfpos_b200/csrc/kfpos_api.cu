@@ -73,6 +73,8 @@ struct kfpos_batch {
     void *d_mlq = nullptr;
     int *d_mlq_count = nullptr;
     int mlq_cap = 0;
+    int32_t *d_xq = nullptr; // epochs handed to the exact-order solver (kfpos_exact.cu)
+    int xq_cap = 0;
     int32_t *d_has = nullptr;
     DevBuf scratch[N_SCRATCH];
     DevBuf stage[2];
@@ -213,7 +215,9 @@ extern "C" int kfpos_batch_create(kfpos_batch **out, int device, int model, int6
         }
         b->mlq_cap = (int)(N / 8 + 4096);
         alloc(&b->d_mlq, (size_t)b->mlq_cap * 64 * 2);
-        alloc((void **)&b->d_mlq_count, sizeof(int) * 2);
+        alloc((void **)&b->d_mlq_count, sizeof(int) * 4); // [0..1] straggler queues, [2] exact-order queue
+        b->xq_cap = (int)(N / 16 + 1024);
+        alloc((void **)&b->d_xq, sizeof(int32_t) * (size_t)b->xq_cap);
     }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->copy_stream, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
@@ -243,6 +247,7 @@ extern "C" void kfpos_batch_destroy(kfpos_batch *b) {
     cudaFree(b->d_latch_u);
     cudaFree(b->d_mlq);
     cudaFree(b->d_mlq_count);
+    cudaFree(b->d_xq);
     for (auto &s : b->scratch) s.release();
     for (auto &s : b->stage) s.release();
     for (int i = 0; i < 2; ++i) {
@@ -836,6 +841,10 @@ extern "C" int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt,
     p.q_in = nullptr; p.q_in_count = nullptr; p.q_out = nullptr; p.q_out_count = nullptr;
     p.first_cap = 10000u;
     p.coop_min = 0; p.coop_max = 0;
+    p.exact_mode = b->cfg.ml_exact_order;
+    p.xq = b->d_xq;
+    p.xq_count = b->d_mlq_count + 2;
+    p.xq_cap = b->xq_cap;
     CK(launch_ml_solve(p, s));
     if (c_pos) CK(cudaMemcpyAsync(pos, d_pos, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, s));
     if (c_cov) CK(cudaMemcpyAsync(cov, d_cov, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, s));

@@ -204,10 +204,11 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                     } else if (p.cfg.variant == 2 && n >= 3) {
                         int grc;
                         double c2[3];
-                        ml_solve2<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, c2, nullptr,
-                                           p.cfg.zero_tz != 0); // the all-ranging solve
-                        best_group<PME, MT>(p.anchors, ep, ep.valid, true, p.cfg.best_mode, start, st.ml_iters, p0, cov0,
-                                            used, grc, p.cfg.zero_tz != 0);
+                        // the all-ranging solve; a failed solve (there or in a subset) selects nothing
+                        if (ml_solve2<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, c2, nullptr,
+                                               p.cfg.zero_tz != 0) != ML_SINGULAR)
+                            best_group<PME, MT>(p.anchors, ep, ep.valid, true, p.cfg.best_mode, start, st.ml_iters, p0,
+                                                cov0, used, grc, p.cfg.zero_tz != 0);
                     }
                 }
                 const int rc = k8_update<PME, MT>(p.anchors, p.cfg, ep, has_r, used, ms, dt, xp, Pm, Pw, dx, st,

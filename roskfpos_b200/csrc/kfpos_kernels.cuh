@@ -65,7 +65,17 @@ struct MlParams {
     int *q_out_count;
     unsigned first_cap;    // Newton iterations a solve gets in this launch before it is parked
     int coop_min, coop_max; // queue lengths [min, max) for which a cooperative launch does its work
+    // exact-order solver (kfpos_exact.cu): kfpos_config.ml_exact_order, and the queue of epoch indices
+    // whose residual order the fast solver found too close to a tie to decide (variant 1)
+    int exact_mode;
+    int xq_cap;
+    int32_t *xq;
+    int *xq_count;
 };
+constexpr int KFPOS_MAX_ANCHORS_DEV = 32;
+// relative margin below which the fast solver does not trust its own order of two squared residuals
+// (its positions agree with the reference's to ~1e-11: four orders of magnitude of room)
+constexpr double ML_TIE_MARGIN = 1e-6;
 
 // ---- sensor event streams (K8, T9).  The schedule (kind, dt) is common to the batch;
 // `offset` is the first ROW (units of N elements) of the event's payload: rows of the
@@ -121,6 +131,7 @@ cudaError_t launch_k8_replay(const K8Params &p, cudaStream_t s);
 cudaError_t launch_k8_get_pose(int64_t N, double dt, double accel_noise, double jolt, const double *x,
                                const double *P, double *x_pred, double *P_pred_full, cudaStream_t s);
 cudaError_t launch_ml_solve(const MlParams &p, cudaStream_t s);
+cudaError_t launch_ml_exact(const MlParams &p, bool queued, cudaStream_t s); // kfpos_exact.cu
 
 struct T9Params {
     AnchorTable anchors;

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
         }
         unsigned cap = p.variant == 2 ? 10000u : p.first_cap; // BEST does not park
         int rc;
-        bool parked = false;
+        bool parked = false, near_tie = false;
         for (;;) {
             const bool last = !(p.variant == 1 && phase == 0);
             rc = ml_any<PME, MT>(p.anchors, ep, used, use2d, p.zero_tz != 0, pos, last ? cov : nullptr, sse, iters, cap,
@@ -272,7 +272,15 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
             if (!last && rc != ML_SINGULAR) {
                 // estimatePositionIgnoreN (ML.cpp:307-347): drop the tail of the ascending
                 // residual order; ties keep the lower index (App. B-11); re-solve from the start
-                used = drop_worst<PME, MT>(p.anchors, ep, used, pos, drop);
+                used = drop_worst<PME, MT>(p.anchors, ep, used, pos, drop, p.xq ? &near_tie : nullptr);
+                if (near_tie) { // too close to call with this arithmetic: the exact-order solver decides
+                    const int slot = atomicAdd(p.xq_count, 1);
+                    if (slot < p.xq_cap) {
+                        p.xq[slot] = (int32_t)f;
+                        parked = true; // nothing is written or counted here
+                        break;
+                    }
+                }
                 phase = 1;
                 pos[0] = p.start[0]; pos[1] = p.start[1]; pos[2] = p.start[2];
                 rs.iter = 0u;
@@ -369,13 +377,30 @@ static cudaError_t launch_k(const MlParams &p0, cudaStream_t s) {
     return cudaSuccess;
 }
 
-cudaError_t launch_ml_solve(const MlParams &p, cudaStream_t s) {
-    if (p.N <= 0) return cudaSuccess;
+static cudaError_t launch_fast(const MlParams &p, cudaStream_t s) {
     if (p.rs.err != nullptr) return launch_k<true, 0>(p, s);
     // BEST solves k-anchor subsets: the branch-skipping rolled loops do k, not m, anchors of work
     if (p.variant != 2 && !p.zero_tz && p.rs.m_slots == 8) return launch_k<false, 8>(p, s);
     if (p.variant != 2 && !p.zero_tz && p.rs.m_slots == 16) return launch_k<false, 16>(p, s);
     return launch_k<false, 0>(p, s);
+}
+
+// kfpos_config.ml_exact_order: 1 = every epoch in exact order; 0 = BestGroup in exact order, IgnoreN with
+// the fast solver + an exact re-decision of the near-ties, NORMAL with the fast solver; -1 = fast only
+cudaError_t launch_ml_solve(const MlParams &p0, cudaStream_t s) {
+    if (p0.N <= 0) return cudaSuccess;
+    MlParams p = p0;
+    if (p.exact_mode > 0 || (p.exact_mode == 0 && p.variant == 2)) return launch_ml_exact(p, false, s);
+    const bool recheck = p.exact_mode == 0 && p.variant == 1 && p.xq != nullptr && p.xq_cap > 0;
+    if (!recheck) {
+        p.xq = nullptr;
+        return launch_fast(p, s);
+    }
+    cudaError_t e = cudaMemsetAsync(p.xq_count, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    e = launch_fast(p, s);
+    if (e != cudaSuccess) return e;
+    return launch_ml_exact(p, true, s);
 }
 
 } // namespace kfpos

@@ -242,6 +242,9 @@ KF_DEV int ml_solve3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
             first = false;
             if (sse_start) *sse_start = ps.sse;
             if (nvalid < 4) { sse_out = ps.sse; return ML_FEW; }
+            // scalar errorEstimation == 0: the reference divides gradient and Hessian by it, its solver
+            // rejects the non-finite normal matrix (here the weight cancels, so say so explicitly)
+            if (!PME && ep.e0 == 0.0) { sse_out = ps.sse; return ML_SINGULAR; }
         } else {
             newCost = ps.wcost;
         }
@@ -288,6 +291,7 @@ KF_DEV int ml_solve3_ekf(const AnchorTable &A, const EpochT<false, MT> &ep, unsi
     sse_out = ps.sse;
     g_start[0] = ps.g[0]; g_start[1] = ps.g[1]; g_start[2] = ps.g[2];
     if (nvalid < 4) return ML_FEW;
+    if (ep.e0 == 0.0) return ML_SINGULAR; // see ml_solve3
     double cost = 1e20, newCost = 1.0;
     unsigned iter = 0;
     while (rel_change_gt(cost, newCost) && iter < 10000u) {
@@ -398,6 +402,7 @@ KF_DEV int ml_solve2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
             newCost = pt.sse;
             if (sse_start) *sse_start = pt.sse;
             if (nvalid < 3) { sse_out = pt.sse; return ML_FEW; }
+            if (!PME && ep.e0 == 0.0) { sse_out = pt.sse; return ML_SINGULAR; } // see ml_solve3
         } else {
             // only the generic (MT = 0) instantiations carry the test mode; the launchers route it there
             const double tc = (MT == 0 && zero_tz) ? sse_at<PME, MT>(A, ep, mask, nx, ny, 0.0) : pt.sse;
@@ -425,11 +430,15 @@ KF_DEV int ml_solve2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
 // estimatePositionIgnoreN's selection (ML.cpp:307-347): removes from `used` the `drop` rangings with
 // the largest squared residual at `pos` -- the tail of the ascending std::sort order; ties keep the
 // lower index.
+// near_tie (optional): set when the smallest dropped and the largest kept squared residual are within
+// ML_TIE_MARGIN of each other (or not comparable) -- the decision then belongs to the exact-order solver.
 template <bool PME, int MT>
 KF_DEV unsigned drop_worst(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned used, const double (&pos)[3],
-                           int drop) {
-    for (int dcount = 0; dcount < drop; ++dcount) {
-        double worst = -1.0;
+                           int drop, bool *near_tie = nullptr) {
+    double worst = -1.0;
+    int dcount = 0;
+    for (; dcount < drop; ++dcount) {
+        worst = -1.0;
         int wi = -1;
         for (int i = 0; i < ep.m_slots; ++i) {
             if (!((used >> i) & 1u)) continue;
@@ -441,6 +450,21 @@ KF_DEV unsigned drop_worst(const AnchorTable &A, const EpochT<PME, MT> &ep, unsi
         }
         if (wi < 0) break; // all residuals NaN
         used &= ~(1u << wi);
+    }
+    if (near_tie && drop > 0) {
+        // `worst` = the smallest dropped residual (each round removed the largest one left)
+        double kept = -1.0;
+        bool odd = dcount < drop;
+        for (int i = 0; i < ep.m_slots; ++i) {
+            if (!((used >> i) & 1u)) continue;
+            const double ex = A.x[i] - pos[0], ey = A.y[i] - pos[1], ez = A.z[i] - pos[2];
+            const double d = sqrt(ex * ex + ey * ey + ez * ez);
+            const double zi = ep.z_at(i);
+            const double q = (d - zi) * (d - zi);
+            if (!(q == q)) odd = true;
+            kept = fmax(kept, q);
+        }
+        *near_tie = odd || !(worst - kept > ML_TIE_MARGIN * worst);
     }
     return used;
 }
@@ -456,6 +480,12 @@ KF_DEV int best_group(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned 
                       unsigned &used, int &rc, bool zero_tz = false) {
     const int k = use2d ? 3 : 4, n = __popc(valid);
     if (n < k) return -1;
+    // on entry pos / cov hold the all-ranging estimate (ML.cpp:353-358); it is what remains when a
+    // subset's solve fails -- the reference's solver then throws out of the scan, nothing is selected
+    const double pos_all[3] = {pos[0], pos[1], pos[2]};
+    double cov_all[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) cov_all[q] = cov[q];
     unsigned char slot[32];
     int c = 0;
     for (int i = 0; i < ep.m_slots; ++i)
@@ -479,7 +509,14 @@ KF_DEV int best_group(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned 
         if (use2d) cur = gc[0] + gc[2];
         else if (best_mode == 1) cur = gc[5];
         else cur = gc[0] + gc[2] + gc[5];
-        if (grc != ML_OK) cur = nan("");
+        if (grc != ML_OK) {
+            pos[0] = pos_all[0]; pos[1] = pos_all[1]; pos[2] = pos_all[2];
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cov[q] = cov_all[q];
+            used = valid;
+            rc = ML_SINGULAR;
+            return -1;
+        }
         if (minIdx == -1 || cur <= minErr) {
             minIdx = gi;
             minErr = cur;

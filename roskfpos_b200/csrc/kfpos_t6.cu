@@ -117,8 +117,9 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
                     }
                 } else if (p.variant == 2 && n >= 4) {
                     int grc;
-                    ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, cov0); // the all-ranging solve of :353
-                    best_group<PME, MT>(p.anchors, ep, ep.valid, false, p.best_mode, pos, st.ml_iters, p0, cov0, used, grc);
+                    // the all-ranging solve of :353; a failed solve (there or in a subset) selects nothing
+                    if (ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, cov0) != ML_SINGULAR)
+                        best_group<PME, MT>(p.anchors, ep, ep.valid, false, p.best_mode, pos, st.ml_iters, p0, cov0, used, grc);
                 }
                 rc = t6_update<PME, MT>(p.anchors, ep, used, pos, Pm, res, st, 0u, &cyc);
                 ignored = (int)used;

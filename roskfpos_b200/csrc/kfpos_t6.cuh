@@ -80,8 +80,10 @@ KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
     }
     if (mask == 0u) sse = -1.0; // estimationError of an empty list (ML.cpp:265-267)
 
-    // R_ii = max(mlRangingError, errorEstimation_i) (TOA.cpp:281)
-    const double invR0 = fast_rcp(fmax(sse, ep.e0));
+    // R_ii = max(mlRangingError, errorEstimation_i) (TOA.cpp:281).  An epoch without rangings has no
+    // rows at all: the reference's update is then x = x^-, P = P^- (K empty), whatever errorEstimation is
+    // (the C++ mirror forwards such epochs with err_scalar = 0) -- the weight must be an exact 0, not 1/0.
+    const double invR0 = mask ? fast_rcp(fmax(sse, ep.e0)) : 0.0;
     double a[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k) a[k] = Pm[k]; // position block of P^-

@@ -308,8 +308,9 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
                     }
                 } else if (p.variant == 2 && n >= 4) {
                     int grc;
-                    ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, cov0); // the all-ranging solve
-                    best_group<PME, MT>(p.anchors, ep, ep.valid, false, p.best_mode, start, st.ml_iters, p0, cov0, used, grc);
+                    // the all-ranging solve; a failed solve (there or in a subset) selects nothing
+                    if (ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, cov0) != ML_SINGULAR)
+                        best_group<PME, MT>(p.anchors, ep, ep.valid, false, p.best_mode, start, st.ml_iters, p0, cov0, used, grc);
                 }
             }
             const int rc = t9_update<PME, MT, IMU>(p.anchors, ep, has_r, used, IMU && has_imu, za, Ra, xp, Pm, Pw, dx, M, st,

@@ -28,7 +28,7 @@ class KfposConfig(C.Structure):
         ("best_mode", C.c_int32),
         ("min_z", C.c_double), ("max_z", C.c_double), ("ml_start", C.c_double * 3),
         ("use_fixed_height", C.c_int32), ("tag_id", C.c_int32), ("fixed_height", C.c_double),
-        ("px4_use_fixed_sensor_height", C.c_int32), ("_pad1", C.c_int32),
+        ("px4_use_fixed_sensor_height", C.c_int32), ("ml_exact_order", C.c_int32),
         ("px4_sensor_height", C.c_double), ("px4_arm_p0", C.c_double), ("px4_arm_p1", C.c_double),
         ("px4_sensor_init_angle", C.c_double), ("px4_cov_velocity", C.c_double),
         ("px4_cov_gyro_z", C.c_double),

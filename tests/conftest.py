@@ -24,3 +24,10 @@ def kflib():
     from roskfpos_b200 import lib
     lib.lib()
     return lib
+
+
+def pytest_sessionfinish(session, exitstatus):
+    """Leave the observed parity numbers (stable fraction, tie count, worst error per test) on disk."""
+    from tests import util
+    out = os.environ.get("KFPOS_PARITY_REPORT", os.path.join(ROOT, "gpurun_out", "parity_report.json"))
+    util.write_parity_report(out)

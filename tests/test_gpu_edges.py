@@ -171,3 +171,71 @@ def test_rangings_without_error_estimate(kflib, oracle):
         ok = (mref["status"] == 0) & (mref["iters"] < 100)
         assert ok.sum() > N // 3
         assert np.abs(got["pos"][:, ok] - mref["pos"][:, ok]).max() < 1e-9
+
+
+@pytest.mark.parametrize("err", [0.0, 0.01])
+def test_empty_epochs_and_zero_scalar_error_estimate(kflib, oracle, err):
+    """Epochs without any ranging (PosGenerator forwards them when every range is <= 0) leave the
+    predicted state and covariance untouched, also with errorEstimation == 0 (what the C++ mirror of
+    KalmanFilterTOA passes for an empty call).  With rangings AND a scalar errorEstimation of exactly 0
+    the reference's Newton solve divides by it and its solver throws: update skipped, status SINGULAR
+    (with fewer than 4 / 3 rangings the Newton solve is never entered and the update is a normal one)."""
+    from roskfpos_b200.batch import Batch
+    from tests.util import assert_parity, to_metres, ulp_perturbations
+    N, T, m = 512, 6, 8
+    anc = synth.anchors_for(m)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=91)
+    r = synth.ranges_mm(truth[1:], anc, seed=92, p_missing=0.15)
+    r[1, :, : N // 2] = 0   # an empty epoch for half of the filters
+    r[3, :, ::3] = 0
+    r[2, 3:, 5::7] = 0      # three rangings only
+    pers = ulp_perturbations(to_metres(r))
+    keys = dict(float_keys=("x",), cov_keys=("P",), int_keys=("status",), min_stable=0.9)
+
+    def st5(d):
+        return dict(x=d["x"], P=d["P"], status=d["status"] & 5)
+
+    ref = st5(oracle.t6_replay(truth[0], None, r, anc, 0.1, err))
+    per = [st5(oracle.t6_replay(truth[0], None, q, anc, 0.1, err)) for q in pers]
+    with Batch(kflib.MODEL_T6, N, anchors=anc, accel_noise=0.5) as b:
+        b.set_state(truth[0])
+        b.replay_toa(0.1, r, err=err)
+        x, P, st = b.get_state()
+    assert np.isfinite(x).all() and np.isfinite(P).all()
+    assert (ref["status"] & 1).any() and ((ref["status"] & 4) != 0).any() == (err == 0.0)
+    assert_parity(dict(x=x[:3], P=P, status=st & 5), ref, per, what=f"T6 empty epochs err={err}", **keys)
+    # step API, one filter, an empty epoch first (the path of the C++ mirror)
+    with Batch(kflib.MODEL_T6, 1, anchors=anc, accel_noise=0.5) as b:
+        b.set_state(truth[0][:, :1])
+        b.step_toa(0.1, np.zeros((m, 1)), err=0.0)
+        b.step_toa(0.1, np.ascontiguousarray(r[0][:, :1]), err=0.01)
+        x1, P1, st1 = b.get_state()
+    r2 = np.stack([np.zeros((m, 1), dtype=r.dtype), r[0][:, :1]])
+    ref1 = oracle.t6_replay(truth[0][:, :1], None, r2, anc, 0.1, 0.01)
+    assert np.isfinite(x1).all() and rel_err_state(x1[:3], ref1["x"]) < REL_TOL and rel_err_cov(P1, ref1["P"]) < REL_TOL
+    # T9 and K8 (ranging-only schedules) and the ML solver
+    x0 = np.zeros((9, N)); x0[:3] = truth[0]
+    ref9 = st5(oracle.t9_replay(x0, None, r, anc, 0.1, err))
+    per = [st5(oracle.t9_replay(x0, None, q, anc, 0.1, err)) for q in pers]
+    with Batch(kflib.MODEL_T9, N, anchors=anc, accel_noise=0.5, jolt=0.5) as b:
+        b.set_state(x0)
+        b.replay_toa(0.1, r, err=err)
+        x, P, st = b.get_state()
+    assert np.isfinite(x).all()
+    assert_parity(dict(x=x, P=P, status=st & 5), ref9, per, what=f"T9 empty epochs err={err}", **keys)
+    events = [(synth.EV_TOA, 0.1, t * m, None) for t in range(T)]
+    x8 = np.zeros((8, N)); x8[:2] = truth[0][:2]
+    cfg = oracle.k8_cfg(0.5, 0.5, **synth.K8_ORACLE_CFG)
+    ref8 = st5(oracle.k8_replay(x8, None, events, r, np.zeros((1, N)), anc, err, cfg))
+    per = [st5(oracle.k8_replay(x8, None, events, q, np.zeros((1, N)), anc, err, cfg)) for q in pers]
+    with Batch(kflib.MODEL_K8, N, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5) as b:
+        b.set_state(x8)
+        b.replay_events(events, ranges=r, sensors=np.zeros((1, N)), err=err)
+        x, P, st = b.get_state()
+    assert np.isfinite(x).all()
+    assert_parity(dict(x=x, P=P, status=st & 5), ref8, per, what=f"K8 empty epochs err={err}", **keys)
+    for use2d in (False, True):
+        mref = oracle.ml_batch(r[0], anc, err, [1.0, 1.0, 4.0], use2d=use2d)
+        with Batch(kflib.MODEL_ML, N, anchors=anc, use2d=int(use2d)) as b:
+            got = b.ml_solve(r[0], err=err)
+        assert np.array_equal(got["status"] & 6, mref["status"] & 6)
