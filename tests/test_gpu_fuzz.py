@@ -52,7 +52,7 @@ def test_t6_random_configuration(kflib, oracle, seed):
         kw_o.update(variant=v, n_ignore=2); kw_g.update(variant=v, num_ignored_rangings=2)
     run = lambda rr: oracle.t6_replay(truth[0], P0, rr, anc, dt, err, **kw_o)
     ref = run(r)
-    per = [run(p) for p in ulp_perturbations(to_metres(r))]
+    per = [run(p) for p in ulp_perturbations(to_metres(r), n_random=32 if c["mode"] in ("v1", "v2") else 8)]
     with Batch(kflib.MODEL_T6, N, anchors=anc, **kw_g) as b:
         x0 = np.zeros((6, N)); x0[:3] = truth[0]
         b.set_state(x0, P0)
@@ -67,8 +67,7 @@ def test_t6_random_configuration(kflib, oracle, seed):
     # sums are associated -- so the small batches of this test need room for one or two of them
     few = m <= 5 or c["p_missing"] >= 0.4 or c["mode"] in ("v1", "v2", "loo")
     rep = assert_parity(got, ref, per, float_keys=("x",), cov_keys=("P",), int_keys=("status", "sel"),
-                        min_stable=0.5 if few else 0.9, max_tie_frac=4e-2 if few else 1e-2,
-                        min_allowed=1 if few else 0, what=str(c))  # a batch of a dozen filters: room for one tie
+                        min_stable=0.4 if few else 0.85, max_tie_frac=1e-3, what=str(c))
     print("fuzz", seed, c, rep)
 
 

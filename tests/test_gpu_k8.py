@@ -154,7 +154,7 @@ def test_k8_ekf_side_nlos_variants(kflib, oracle, variant, n_ignore):
     cfg = oracle.k8_cfg(0.5, 0.5, variant=variant, n_ignore=n_ignore, **synth.K8_ORACLE_CFG)
     run = lambda rr: oracle.k8_replay(x0, None, events, rr, comp, anc, 0.01, cfg)
     ref = run(r)
-    per = [run(p) for p in ulp_perturbations(to_metres(r))]
+    per = [run(p) for p in ulp_perturbations(to_metres(r), n_random=12)]
     with Batch(kflib.MODEL_K8, N, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5, variant=variant,
                num_ignored_rangings=n_ignore) as b:
         b.set_state(x0)
@@ -167,7 +167,7 @@ def test_k8_ekf_side_nlos_variants(kflib, oracle, variant, n_ignore):
     for d in [ref] + per:
         d["status"] = d["status"] & ~32
     rep = assert_parity(got, ref, per, float_keys=("x",), cov_keys=("P",), int_keys=("status",),
-                        min_stable=0.9 if variant == 1 else 0.6, max_tie_frac=1e-2 if variant == 1 else 6e-2,
+                        min_stable=0.9 if variant == 1 else 0.6, max_tie_frac=1e-3,
                         what=f"K8 variant {variant}")
     print("parity report K8 variant", variant, rep, cnt)
     assert cnt["updates"] == N * len(events)

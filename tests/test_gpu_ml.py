@@ -21,9 +21,9 @@ def gpu_ml(kflib, anc, r, err=0.01, **cfg):
         return b.ml_solve(r, err=err)
 
 
-def oracle_ml(oracle, r, anc, err, start, **kw):
+def oracle_ml(oracle, r, anc, err, start, n_random=4, **kw):
     ref = oracle.ml_batch(r, anc, err, start, **kw)
-    per = [oracle.ml_batch(p, anc, err, start, **kw) for p in ulp_perturbations(to_metres(r))]
+    per = [oracle.ml_batch(p, anc, err, start, **kw) for p in ulp_perturbations(to_metres(r), n_random=n_random)]
     return ref, per
 
 
@@ -68,7 +68,7 @@ def test_ml_ragged_and_too_few(kflib, oracle, use2d):
     few = ref["status"] == 2
     assert np.array_equal(got["pos"][:, few], ref["pos"][:, few])  # start returned untouched
     rep = assert_parity(got, ref, per, float_keys=("pos",), int_keys=("status", "iters"),
-                        min_stable=0.85, max_tie_frac=2e-3, what=f"ML ragged 2d={use2d}")
+                        min_stable=0.85, max_tie_frac=1e-3, what=f"ML ragged 2d={use2d}")
     print("parity report ragged", use2d, rep)
 
 
@@ -126,11 +126,12 @@ def test_ml_best_group_fast_formulation(kflib, oracle, use2d, m, best_mode):
     if m == 16:  # the exact grid is singular for collinear triples (see above): jitter it
         anc = anc + np.random.default_rng(5).uniform(-0.4, 0.4, size=anc.shape) * [1, 1, 0]
         r = synth.ranges_mm(truth, anc, seed=617, p_nlos=0.15)
-    ref, per = oracle_ml(oracle, r, anc, 0.01, start_for(use2d), use2d=use2d, variant=2, best_mode=best_mode)
+    ref, per = oracle_ml(oracle, r, anc, 0.01, start_for(use2d), use2d=use2d, variant=2, best_mode=best_mode,
+                         n_random=16 if use2d else 48)
     got = gpu_ml(kflib, anc, r, use2d=use2d, variant=2, best_mode=best_mode, ml_start=start_for(use2d),
                  ml_exact_order=-1)
     rep = assert_parity(got, ref, per, float_keys=("pos",), int_keys=("status", "sel"),
-                        min_stable=0.85, max_tie_frac=1e-2, what=f"BestGroup fast 2d={use2d} m={m}")
+                        min_stable=0.8, max_tie_frac=1e-3, what=f"BestGroup fast 2d={use2d} m={m}")
     print("parity report best (fast)", use2d, m, best_mode, rep)
 
 
@@ -209,7 +210,7 @@ def test_ml_straggler_queue(kflib, oracle, variant):
     rep = assert_parity(got, ref, per, min_stable=0.99, max_tie_frac=1e-3, what=f"stragglers v{variant}", **keys)
     # the parked epochs on their own: those the oracle calls stable must all agree
     sub = lambda d: {k: np.asarray(v)[..., slow] for k, v in d.items()}
-    rep_slow = assert_parity(sub(got), sub(ref), [sub(p) for p in per], min_stable=0.0, max_tie_frac=0.05,
+    rep_slow = assert_parity(sub(got), sub(ref), [sub(p) for p in per], min_stable=0.0, max_tie_frac=0.0,
                              what=f"parked epochs v{variant}", **keys)
     print("parity report stragglers", variant, rep, rep_slow, int(slow.sum()))
 

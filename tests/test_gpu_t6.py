@@ -28,10 +28,10 @@ def run_oracle(oracle, x0, r, anc, dt, err, P0=None, **kw):
     return out
 
 
-def oracle_with_perturbations(oracle, x0, r, anc, dt, err, **kw):
+def oracle_with_perturbations(oracle, x0, r, anc, dt, err, n_random=4, **kw):
     rm = to_metres(r)
     ref = run_oracle(oracle, x0, r, anc, dt, err, **kw)
-    per = [run_oracle(oracle, x0, p, anc, dt, err, **kw) for p in ulp_perturbations(rm)]
+    per = [run_oracle(oracle, x0, p, anc, dt, err, **kw) for p in ulp_perturbations(rm, n_random=n_random)]
     return ref, per
 
 
@@ -62,7 +62,7 @@ def test_t6_replay_parity_few_anchors(kflib, oracle, m, N, T):
     r = synth.ranges_mm(truth[1:], anc, seed=200 + m)
     ref, per = oracle_with_perturbations(oracle, truth[0], r, anc, 0.1, 0.01)
     got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, accel_noise=0.5)
-    rep = assert_parity(got, ref, per, min_stable=0.97, max_tie_frac=3e-3, what=f"T6 m={m}", **KEYS)
+    rep = assert_parity(got, ref, per, min_stable=0.95, max_tie_frac=1e-3, what=f"T6 m={m}", **KEYS)
     print("parity report", m, rep)
     assert np.isfinite(got["x"]).all()
 
@@ -94,7 +94,7 @@ def test_t6_missing_rangings_and_variable_dt(kflib, oracle):
     err = rng.uniform(0.005, 0.05, size=r.shape)
     ref, per = oracle_with_perturbations(oracle, truth[0], r, anc, dt, err)
     got = run_gpu(kflib, truth[0], r, anc, dt, err, accel_noise=0.5)
-    rep = assert_parity(got, ref, per, min_stable=0.9, max_tie_frac=3e-3, what="T6 ragged", **KEYS)
+    rep = assert_parity(got, ref, per, min_stable=0.9, max_tie_frac=1e-3, what="T6 ragged", **KEYS)
     print("parity report ragged", rep)
     assert (ref["status"] & 1).any() and (ref["status"] & 2).any()
 
@@ -139,7 +139,7 @@ def test_t6_leave_one_out_selection(kflib, oracle, thr):
     got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, want_sel=True, accel_noise=0.5,
                   ignore_worst_anchor=1, ignore_cost_threshold=thr)
     rep = assert_parity(got, ref, per, float_keys=("x",), cov_keys=("P",), int_keys=("status", "sel"),
-                        min_stable=0.95, max_tie_frac=3e-3, what=f"T6 leave-one-out thr={thr}")
+                        min_stable=0.93, max_tie_frac=1e-3, what=f"T6 leave-one-out thr={thr}")
     print("parity report loo", thr, rep)
     assert (ref["sel"] >= 0).any()
 
@@ -198,13 +198,13 @@ def test_t6_ekf_side_nlos_variants(kflib, oracle, variant, m, n_ignore, best_mod
     r = synth.ranges_mm(truth[1:], anc, seed=310 + m, p_nlos=0.15)
     kw = dict(variant=variant, n_ignore=n_ignore, best_mode=best_mode)
     ref = run_oracle(oracle, truth[0], r, anc, 0.1, 0.01, **kw)
-    per = [run_oracle(oracle, truth[0], p, anc, 0.1, 0.01, **kw) for p in ulp_perturbations(to_metres(r))]
+    # variant 2 is chaotic (tests/util.py ulp_perturbations): 48 perturbed oracle runs define "stable"
+    per = [run_oracle(oracle, truth[0], p, anc, 0.1, 0.01, **kw)
+           for p in ulp_perturbations(to_metres(r), n_random=48 if variant == 2 else 12)]
     got = run_gpu(kflib, truth[0], r, anc, 0.1, 0.01, want_sel=True, accel_noise=0.5, variant=variant,
                   num_ignored_rangings=n_ignore, best_mode=best_mode)
     keys = dict(float_keys=("x",), cov_keys=("P",), int_keys=("status", "sel"))
-    rep = assert_parity(got, ref, per, min_stable=0.93 if variant == 1 else 0.6,
-                        # per selection the same tie allowance as test_ml_best_group_selection (2 steps here)
-                        max_tie_frac=5e-3 if variant == 1 else 4e-2,
+    rep = assert_parity(got, ref, per, min_stable=0.9 if variant == 1 else 0.55, max_tie_frac=1e-3,
                         what=f"T6 variant {variant} m={m}", **keys)
     print("parity report variant", variant, m, rep)
     used = np.array([bin(int(v) & 0xFFFFFFFF).count("1") for v in got["sel"].ravel()])

@@ -95,7 +95,7 @@ def test_t9_ekf_side_nlos_variants(kflib, oracle, variant, n_ignore):
     x0 = np.zeros((9, N)); x0[:3] = truth[0]
     run = lambda rr, v=variant: oracle.t9_events(x0, None, events, rr, sens, anc, 0.01, variant=v, n_ignore=n_ignore)
     ref = run(r)
-    per = [run(p) for p in ulp_perturbations(to_metres(r))]
+    per = [run(p) for p in ulp_perturbations(to_metres(r), n_random=48 if variant == 2 else 12)]
     with Batch(kflib.MODEL_T9, N, anchors=anc, accel_noise=0.5, jolt=0.5, variant=variant,
                num_ignored_rangings=n_ignore) as b:
         b.set_state(x0)
@@ -106,7 +106,7 @@ def test_t9_ekf_side_nlos_variants(kflib, oracle, variant, n_ignore):
     assert np.abs(plain["x"] - ref["x"]).max() > 1e-3  # the selection does change the estimate
     got = dict(x=x, P=P, status=st)
     rep = assert_parity(got, ref, per, float_keys=("x",), cov_keys=("P",), int_keys=("status",),
-                        min_stable=0.9 if variant == 1 else 0.45, max_tie_frac=1e-2 if variant == 1 else 6e-2,
+                        min_stable=0.9 if variant == 1 else 0.4, max_tie_frac=1e-3,
                         what=f"T9 variant {variant}")  # best-group ties compound along the trajectory
     print("parity report T9 variant", variant, rep, cnt)
     assert cnt["updates"] == N * len(events)

@@ -116,13 +116,25 @@ def assert_parity(got, ref, perturbed, float_keys=(), cov_keys=(), int_keys=(), 
     return dict(stable=float(frac_stable), worst=worst, ties=n_viol)
 
 
-def ulp_perturbations(r_m):
-    """+-1 and +-2 ulp copies of an f64 range tensor (missing rangings, <= 0, untouched)."""
+def ulp_perturbations(r_m, n_random=4, rel=1e-13, seed=20190816):
+    """Perturbed copies of an f64 range tensor that define "stable" (missing rangings, <= 0, untouched):
+    +-1 and +-2 ulp on every range, plus `n_random` copies with every range moved by +-rel (random sign
+    per element).  rel = 1e-13 is the size of the differences between two correct implementations of
+    this arithmetic (re-association, FMA contraction, another LAPACK): a unit whose oracle result
+    survives them is one whose result is a property of the algorithm and not of a rounding mode.
+    The chaotic selections (4-ranging 3-D subsets) flip under ANY such perturbation with the same
+    probability whatever its size (measured: 13 % per perturbation); for those tests n_random is raised
+    until one further perturbation flips < 1e-3 of the units that survived (24 is enough, 48 used)."""
     up = np.where(r_m > 0, np.nextafter(r_m, np.inf), r_m)
     dn = np.where(r_m > 0, np.nextafter(r_m, -np.inf), r_m)
     up2 = np.where(r_m > 0, np.nextafter(up, np.inf), r_m)
     dn2 = np.where(r_m > 0, np.nextafter(dn, -np.inf), r_m)
-    return [up, dn, up2, dn2]
+    out = [up, dn, up2, dn2]
+    rng = np.random.default_rng(seed)
+    for _ in range(n_random):
+        sgn = rng.choice([-1.0, 1.0], size=r_m.shape)
+        out.append(np.where(r_m > 0, r_m * (1.0 + rel * sgn), r_m))
+    return out
 
 
 def to_metres(r):
