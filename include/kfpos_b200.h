@@ -320,10 +320,35 @@ int kfpos_batch_get_counters(kfpos_batch *b, double out[8], int reset, void *str
 
 /* Error statistics against a truth position SoA [3][N] (host or device):
  * out[0] = sum |p - truth|^2, out[1] = same over x,y only, out[2] = filters
- * counted (finite), out[3] = filters with status != OK.  The sum is a
- * fixed-shape tree over fixed 1024-filter chunks, so it does not depend on the
- * launch geometry; multi-GPU callers add the per-rank vectors (one all-reduce). */
+ * counted (finite), out[3] = filters with status != OK.  Summation order: a fixed
+ * 128-leaf tree per 128-filter chunk (one replay block), then a pairwise tree over
+ * the chunk index -- it depends on the filter index only, not on launch geometry.
+ *   truth == NULL : the ground truth registered with kfpos_batch_set_truth is used;
+ *                   if a replay has run since, only the final tree is launched
+ *                   (the chunk partials were left behind by the replay kernel).
+ *   out == NULL   : enqueue only; the result stays on the device for
+ *                   kfpos_stats_allreduce (no host synchronisation).              */
 int kfpos_batch_error_stats(kfpos_batch *b, const double *truth, double out[4], void *stream);
+
+/* Registers the ground truth (SoA [3][N]; a device pointer is borrowed, a host array
+ * is copied) for the Monte Carlo statistics: from now on every replay launch ends with
+ * the block-level reduction of |p - truth|^2 of its final state (the
+ * reduction is fused into the last replay step).  NULL unregisters.                */
+int kfpos_batch_set_truth(kfpos_batch *b, const double *truth, void *stream);
+
+/* The one collective of a sharded run (no reference equivalent -- the
+ * reference runs one filter): reduces the error statistics of the batches of all ranks
+ * of `comm` (an NCCL communicator with one rank per GPU; NULL = this batch alone).
+ *   out[0..3] as kfpos_batch_error_stats, summed over all ranks;
+ *   out[4] = RMSE = sqrt(out[0] / out[2]);  out[5] = RMSE over x,y.
+ * One ncclAllGather of 4 doubles per rank, then the pairwise tree over the rank index on
+ * every rank: with shards that are aligned powers of two (N_total / n_ranks filters, a
+ * multiple of 128) the result is BIT-IDENTICAL to the single-GPU result.  truth as above
+ * (NULL with nothing registered: reduces what the last kfpos_batch_error_stats left on
+ * the device).  NCCL is bound with dlopen("libnccl.so.2") at the first call:
+ * KFPOS_ERR_UNSUPPORTED when it cannot be found.  Synchronises `stream`.            */
+struct ncclComm;
+int kfpos_stats_allreduce(kfpos_batch *b, struct ncclComm *comm, const double *truth, double out[6], void *stream);
 
 /* Roofline denominator for this FP64 CUDA-core path (no reference equivalent):
  * times a DFMA-only kernel on `device` and returns the sustained FLOP/s.        */

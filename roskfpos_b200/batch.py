@@ -255,11 +255,30 @@ class Batch:
         v = list(buf)
         return dict(updates=v[0], ml_iters=v[1], cost_evals=v[2], gain_evals=v[3], bad=v[4], ignored=v[5])
 
-    def error_stats(self, truth, stream=None):
+    def set_truth(self, truth, stream=None):
+        """Registers the ground truth SoA [3][N]: replay launches then end with the block-level reduction of the
+        error statistics (kfpos_batch_set_truth).  A device tensor is borrowed -- keep it alive."""
+        p, k = _ptr(truth, np.float64)
+        self._truth_keep = k
+        L.check(L.lib().kfpos_batch_set_truth(self._h, p, _stream_ptr(stream)), "kfpos_batch_set_truth")
+
+    def error_stats(self, truth=None, stream=None, readback=True):
+        """[sum |e|^2, sum |e_xy|^2, n, n_bad]; truth None = the registered one; readback False = enqueue only
+        (the result stays on the device for stats_allreduce, no host synchronisation)."""
         buf = (C.c_double * 4)()
         p, k = _ptr(truth, np.float64)
-        L.check(L.lib().kfpos_batch_error_stats(self._h, p, C.byref(buf), _stream_ptr(stream)),
+        L.check(L.lib().kfpos_batch_error_stats(self._h, p, C.byref(buf) if readback else None, _stream_ptr(stream)),
                 "kfpos_batch_error_stats")
+        return np.array(list(buf)) if readback else None
+
+    def stats_allreduce(self, comm=None, truth=None, stream=None):
+        """kfpos_stats_allreduce: the statistics of the batches of all ranks of the NCCL communicator `comm`
+        (a raw ncclComm_t as an int / c_void_p, see shard.nccl_comm; None = this batch alone).
+        Returns [sum |e|^2, sum |e_xy|^2, n, n_bad, rmse, rmse_xy]."""
+        buf = (C.c_double * 6)()
+        p, k = _ptr(truth, np.float64)
+        c = C.c_void_p(int(comm)) if comm else None
+        L.check(L.lib().kfpos_stats_allreduce(self._h, c, p, C.byref(buf), _stream_ptr(stream)), "kfpos_stats_allreduce")
         return np.array(list(buf))
 
 

@@ -10,6 +10,8 @@
 #include <vector>
 
 #include "../../include/kfpos_b200.h"
+#include <dlfcn.h>
+
 #include "kfpos_kernels.cuh"
 
 using namespace kfpos;
@@ -66,6 +68,12 @@ struct kfpos_batch {
     int32_t *d_status = nullptr;
     unsigned long long *d_counters = nullptr;
     double *d_partials = nullptr, *d_out4 = nullptr;
+    // ground truth registered with kfpos_batch_set_truth: the replay kernels then leave the error
+    // partials of their final state in d_partials (the reduction fused into the last replay step)
+    const double *d_truth = nullptr;
+    double *d_truth_own = nullptr;
+    bool partials_fresh = false;
+    double *d_gather = nullptr; // [n_ranks][4] of kfpos_stats_allreduce
     // K8 / T9 latched sensor samples, SoA rows (see kfpos_k8.cuh)
     double *d_latch = nullptr;
     double *d_latch_u = nullptr; // batch-wide latched IMU covariances
@@ -200,8 +208,9 @@ extern "C" int kfpos_batch_create(kfpos_batch **out, int device, int model, int6
         alloc((void **)&b->d_x, sizeof(double) * b->n * N);
         alloc((void **)&b->d_P, sizeof(double) * b->np * N);
         alloc((void **)&b->d_status, sizeof(int32_t) * N);
-        alloc((void **)&b->d_partials, sizeof(double) * 4 * ((N + 1023) / 1024));
+        alloc((void **)&b->d_partials, sizeof(double) * 4 * ((N + STATS_CHUNK - 1) / STATS_CHUNK));
         alloc((void **)&b->d_out4, sizeof(double) * 4);
+        alloc((void **)&b->d_gather, sizeof(double) * 4 * 1024);
     }
     if (model == KFPOS_MODEL_K8 || model == KFPOS_MODEL_T9) {
         alloc((void **)&b->d_latch, sizeof(double) * 16 * N);
@@ -242,6 +251,8 @@ extern "C" void kfpos_batch_destroy(kfpos_batch *b) {
     cudaFree(b->d_counters);
     cudaFree(b->d_partials);
     cudaFree(b->d_out4);
+    cudaFree(b->d_truth_own);
+    cudaFree(b->d_gather);
     cudaFree(b->d_latch);
     cudaFree(b->d_has);
     cudaFree(b->d_latch_u);
@@ -302,6 +313,7 @@ extern "C" int kfpos_batch_set_state(kfpos_batch *b, const double *x, const doub
     if (b->d_latch) CK(cudaMemsetAsync(b->d_latch, 0, sizeof(double) * 16 * N, s));
     if (b->d_latch_u) CK(cudaMemsetAsync(b->d_latch_u, 0, sizeof(double) * 16, s));
     b->imu_seen = false; // the latches are cleared above
+    b->partials_fresh = false;
     b->stepped = P != nullptr; // a restored checkpoint is a running filter; P0 = 0 is a fresh one
     if (!xd || (P && !on_device(P))) CK(cudaStreamSynchronize(s));
     return KFPOS_OK;
@@ -517,7 +529,10 @@ int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_range
         p.traj = d_traj;
         p.sel = d_sel;
         p.counters = b->d_counters;
+        p.truth = b->d_truth;
+        p.partials = b->d_partials;
         CK(launch_t6_replay(p, s));
+        b->partials_fresh = b->d_truth != nullptr;
         return KFPOS_OK;
     }
     default: return KFPOS_ERR_UNSUPPORTED;
@@ -580,7 +595,10 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.dt_f = d_dt_f;
         p.traj = d_traj;
         p.counters = b->d_counters;
+        p.truth = b->d_truth;
+        p.partials = b->d_partials;
         CK(launch_k8_replay(p, s));
+        b->partials_fresh = b->d_truth != nullptr;
         break;
     }
     case KFPOS_MODEL_T9: {
@@ -607,13 +625,16 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.dt_f = d_dt_f;
         p.traj = d_traj;
         p.counters = b->d_counters;
+        p.truth = b->d_truth;
+        p.partials = b->d_partials;
         CK(launch_t9_replay(p, s));
+        b->partials_fresh = b->d_truth != nullptr;
         break;
     }
     default: return KFPOS_ERR_INVALID;
     }
-    // the host event array may be a temporary of the caller
-    CK(cudaStreamSynchronize(s));
+    // (the host event array may be a temporary of the caller: a copy from pageable memory has left the
+    // caller's buffer when cudaMemcpyAsync returns, so no synchronisation is needed here)
     return KFPOS_OK;
 }
 
@@ -958,18 +979,111 @@ extern "C" int kfpos_batch_get_counters(kfpos_batch *b, double out[8], int reset
     return KFPOS_OK;
 }
 
-extern "C" int kfpos_batch_error_stats(kfpos_batch *b, const double *truth, double out[4], void *stream) {
-    if (!b || b->model == KFPOS_MODEL_ML || !truth || !out) return KFPOS_ERR_INVALID;
+extern "C" int kfpos_batch_set_truth(kfpos_batch *b, const double *truth, void *stream) {
+    if (!b || b->model == KFPOS_MODEL_ML) return KFPOS_ERR_INVALID;
     DeviceGuard g(b->device);
     cudaStream_t s = (cudaStream_t)stream;
+    b->partials_fresh = false;
+    if (!truth) {
+        b->d_truth = nullptr;
+        return KFPOS_OK;
+    }
+    if (on_device(truth)) { // borrowed: the caller keeps it alive while it is registered
+        b->d_truth = truth;
+        return KFPOS_OK;
+    }
+    const size_t bytes = sizeof(double) * 3 * (size_t)b->N;
+    if (!b->d_truth_own) CK(cudaMalloc((void **)&b->d_truth_own, bytes));
+    CK(cudaMemcpyAsync(b->d_truth_own, truth, bytes, cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s));
+    b->d_truth = b->d_truth_own;
+    return KFPOS_OK;
+}
+
+namespace {
+// leaves [sum |e|^2, sum |e_xy|^2, n, n_bad] of this batch in d_out4.  truth == null: the partials the last
+// replay launch left behind (kfpos_batch_set_truth) are folded; otherwise they are computed first.
+int enqueue_error_stats(kfpos_batch *b, const double *truth, cudaStream_t s) {
     const void *d_truth = nullptr;
-    int rc = stage_in(b, 0, truth, sizeof(double) * 3 * (size_t)b->N, s, &d_truth);
-    if (rc) return rc;
+    if (truth) {
+        int rc = stage_in(b, 0, truth, sizeof(double) * 3 * (size_t)b->N, s, &d_truth);
+        if (rc) return rc;
+    } else if (!b->partials_fresh) {
+        if (!b->d_truth) return KFPOS_ERR_NOT_READY;
+        d_truth = b->d_truth; // registered, but the state changed since the last replay (single steps, set_state)
+    }
     // K8 is planar: z is the configured tag height (KF.cpp:328-332)
     CK(launch_error_stats(b->N, b->d_x, b->model == KFPOS_MODEL_K8 ? -1 : 2, b->cfg.fixed_height, b->d_status,
                           (const double *)d_truth, b->d_partials, b->d_out4, s));
-    CK(cudaMemcpyAsync(out, b->d_out4, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+    b->partials_fresh = false; // the tree folds the partials in place
+    return KFPOS_OK;
+}
+
+// NCCL is bound at run time (dlopen): the library loads and every other entry point works on a machine
+// without it, and inside a process that already holds a copy (PyTorch's) that copy is the one used.
+typedef int (*nccl_allgather_fn)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef int (*nccl_count_fn)(void *, int *);
+struct NcclApi {
+    nccl_allgather_fn all_gather = nullptr;
+    nccl_count_fn count = nullptr, user_rank = nullptr;
+    bool tried = false;
+};
+NcclApi &nccl_api() {
+    static NcclApi api;
+    if (!api.tried) {
+        api.tried = true;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.all_gather = (nccl_allgather_fn)dlsym(h, "ncclAllGather");
+            api.count = (nccl_count_fn)dlsym(h, "ncclCommCount");
+            api.user_rank = (nccl_count_fn)dlsym(h, "ncclCommUserRank");
+        }
+    }
+    return api;
+}
+} // namespace
+
+extern "C" int kfpos_batch_error_stats(kfpos_batch *b, const double *truth, double out[4], void *stream) {
+    if (!b || b->model == KFPOS_MODEL_ML) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = enqueue_error_stats(b, truth, s);
+    if (rc) return rc;
+    if (out) { // out == null: enqueue only, the result stays on the device (kfpos_stats_allreduce reads it)
+        CK(cudaMemcpyAsync(out, b->d_out4, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+    }
+    return KFPOS_OK;
+}
+
+extern "C" int kfpos_stats_allreduce(kfpos_batch *b, struct ncclComm *comm, const double *truth, double out[6],
+                                     void *stream) {
+    if (!b || b->model == KFPOS_MODEL_ML || !out) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    // truth == null and nothing registered: d_out4 holds what the last kfpos_batch_error_stats left there
+    if (truth || b->d_truth) {
+        int rc = enqueue_error_stats(b, truth, s);
+        if (rc) return rc;
+    }
+    const double *d_res = b->d_out4;
+    if (comm) {
+        NcclApi &api = nccl_api();
+        if (!api.all_gather || !api.count) return KFPOS_ERR_UNSUPPORTED;
+        int n_ranks = 0;
+        if (api.count(comm, &n_ranks) != 0 || n_ranks < 1 || n_ranks > 1024) return KFPOS_ERR_INVALID;
+        // ONE collective: every rank's 4 doubles to every rank (ncclDouble = 8), then the same pairwise
+        // tree over the rank index on every rank -- the top levels of the global tree, in a fixed order
+        if (api.all_gather(b->d_out4, b->d_gather, 4, 8, comm, s) != 0) return KFPOS_ERR_CUDA;
+        CK(launch_error_stats_tree(n_ranks, b->d_gather, b->d_gather, s));
+        d_res = b->d_gather;
+    }
+    CK(cudaMemcpyAsync(out, d_res, sizeof(double) * 4, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    const double n = out[2] > 1.0 ? out[2] : 1.0;
+    out[4] = sqrt(out[0] / n);
+    out[5] = sqrt(out[1] / n);
     return KFPOS_OK;
 }
 

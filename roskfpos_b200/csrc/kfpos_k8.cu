@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
     const unsigned wmask = __ballot_sync(0xffffffffu, active);
     StepStats st = {0u, 0u, 0u, 0u};
     unsigned n_updates = 0, n_bad = 0;
+    double errv[4] = {0.0, 0.0, 0.0, 0.0}; // error terms of the final state (fused statistics)
 
     if (active) {
         const int64_t N = p.N;
@@ -247,7 +248,13 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
         for (int k = 0; k < 8; ++k) p.latch[(int64_t)k * N + f] = latch[k];
         p.has[f] = (int32_t)has;
         p.latch[8 * N + f] = carry;
-        if (p.status) p.status[f] |= (int32_t)status_or;
+        int32_t st_all = (int32_t)status_or;
+        if (p.status) {
+            st_all |= p.status[f];
+            p.status[f] = st_all;
+        }
+        // planar filter: z is the configured tag height (KF.cpp:328-332)
+        if (p.truth) filter_error_terms(px, py, p.cfg.tag_z, p.truth, N, f, st_all != 0, errv);
         if (f == 0) {
             p.latch_u[0] = ic00; p.latch_u[1] = ic01; p.latch_u[2] = ic11; p.latch_u[3] = icw;
         }
@@ -257,6 +264,8 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
     warp_accumulate(p.counters + CNT_COST_EVALS, st.cost_evals);
     warp_accumulate(p.counters + CNT_GAIN_EVALS, st.gain_evals);
     warp_accumulate(p.counters + CNT_BAD, n_bad);
+    static_assert(K8_BLOCK == STATS_CHUNK, "one statistics partial per replay block");
+    if (p.truth) block_stats_partial(errv, smem, p.partials + (int64_t)blockIdx.x * 4);
 }
 
 template <bool PME, int MT, bool SEL = false>

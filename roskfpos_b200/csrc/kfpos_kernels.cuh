@@ -21,6 +21,44 @@ struct RangeStream {
     int m_slots;
 };
 
+// ---- error statistics with a summation order that depends on nothing but the filter index:
+// partial c covers filters [128c, 128c + 128) -- one replay block -- summed by a fixed 128-leaf binary
+// tree in shared memory; the partials are then folded by a pairwise tree over the partial index
+// (launch_error_stats_tree).  Every replay kernel can leave the partials of its final state behind
+// (params.truth / params.partials): the reduction is fused into the last step of the replay, and a
+// shard that starts at a multiple of its power-of-two size is a complete subtree of the global tree, so
+// the reduced result is BIT-IDENTICAL for 1, 2, 4 or 8 GPUs (kfpos_stats_allreduce).
+constexpr int STATS_CHUNK = 128;
+// v = {|e|^2, |e_xy|^2, 1, bad} of this thread's filter (zeros for a thread without one); `sh` = at least
+// 4 * 128 doubles of shared memory nobody else is using any more; every thread of the block calls it
+KF_DEV void block_stats_partial(const double (&v)[4], double *sh, double *partial_out) {
+    const int t = threadIdx.x;
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) sh[q * STATS_CHUNK + t] = v[q];
+    __syncthreads();
+    for (int s = STATS_CHUNK / 2; s > 0; s >>= 1) {
+        if (t < s) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) sh[q * STATS_CHUNK + t] += sh[q * STATS_CHUNK + t + s];
+        }
+        __syncthreads();
+    }
+    if (t < 4) partial_out[t] = sh[t * STATS_CHUNK];
+}
+KF_DEV void filter_error_terms(double px, double py, double pz, const double *truth, int64_t N, int64_t f, bool bad,
+                               double (&v)[4]) {
+    const double ex = px - truth[f], ey = py - truth[N + f], ez = pz - truth[2 * N + f];
+    const double e2 = ex * ex + ey * ey + ez * ez;
+    v[0] = v[1] = v[2] = 0.0;
+    if (isfinite(e2)) {
+        v[0] = e2;
+        v[1] = ex * ex + ey * ey;
+        v[2] = 1.0;
+    }
+    v[3] = bad ? 1.0 : 0.0;
+}
+
 struct T6Params {
     AnchorTable anchors;
     RangeStream rs;
@@ -38,6 +76,8 @@ struct T6Params {
     double *traj;     // SoA [T][3][N] or null
     int32_t *sel;     // SoA [T][N] or null
     unsigned long long *counters;
+    const double *truth; // SoA [3][N] or null: leave the error partials of the final state in `partials`
+    double *partials;    // [ceil(N / 128)][4]
 };
 
 struct MlParams {
@@ -124,6 +164,8 @@ struct K8Params {
     const double *dt_f; // null, or per-filter time steps SoA [n_events][N] (see T9Params)
     double *traj;    // SoA [n_toa][3][N] (px, py, theta) after each TOA event, or null
     unsigned long long *counters;
+    const double *truth; // see T6Params
+    double *partials;
 };
 
 cudaError_t launch_t6_replay(const T6Params &p, cudaStream_t s);
@@ -153,6 +195,8 @@ struct T9Params {
     int variant, n_ignore, best_mode; // EKF-side NLOS variants (config_pos.xml; 0 = normal)
     double *traj;    // SoA [n_toa][3][N] or null
     unsigned long long *counters;
+    const double *truth; // see T6Params
+    double *partials;
 };
 cudaError_t launch_t9_replay(const T9Params &p, cudaStream_t s);
 cudaError_t launch_t9_get_pose(int64_t N, double dt, double jolt, const double *x, const double *P, double *x_pred,
@@ -167,11 +211,13 @@ cudaError_t launch_unpack_cov(int n, int64_t N, const double *packed, double *fu
 cudaError_t launch_t6_get_pose(int64_t N, double dt, double accel_noise, const double *x,
                                const double *P, double *x_pred, double *P_pred_full, cudaStream_t s);
 
-// error statistics: partial[chunk][4] over fixed 1024-filter chunks, then a
-// fixed-shape tree in the second kernel -> out[4]
+// error statistics (see block_stats_partial): partial[c][4] over the 128-filter chunks -- skipped when
+// `truth` is null, i.e. when a replay kernel has already left them -- then the pairwise tree -> out[4]
 // (position = rows 0,1 and row `zrow`, or the constant `zconst` when zrow < 0)
 cudaError_t launch_error_stats(int64_t N, const double *x, int zrow, double zconst, const int32_t *status,
                                const double *truth, double *partials, double *out4, cudaStream_t s);
+// pairwise tree over n vectors of 4 doubles (IN PLACE on `part`): level by level part[i] += part[i + stride]
+cudaError_t launch_error_stats_tree(int64_t n, double *part, double *out4, cudaStream_t s);
 
 // getPose report in the publisher's layout (kfpos_misc.cu); model 1 = T6, 2 = K8, 3 = T9
 cudaError_t launch_pose_msg(int model, int64_t N, double tag_z, const double *x_pred, const double *P_pred_full,

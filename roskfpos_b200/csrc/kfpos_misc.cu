@@ -37,68 +37,30 @@ cudaError_t launch_unpack_cov(int n, int64_t N, const double *packed, double *fu
     return cudaGetLastError();
 }
 
-// ---- error statistics with a launch-geometry-independent summation order:
-// chunk c covers filters [1024c, 1024c+1024); inside a chunk thread i sums the 4
-// filters {i, i+256, i+512, i+768} in that order, then a fixed 256-leaf binary
-// tree in shared memory.  Chunk partials are then folded by ONE block in a fixed
-// order (thread i takes chunks i, i+256, ... ; same tree).
-constexpr int ST_CHUNK = 1024, ST_THREADS = 256;
+// ---- error statistics (summation order: kfpos_kernels.cuh, block_stats_partial)
+__global__ void __launch_bounds__(STATS_CHUNK)
+error_stats_chunks(int64_t N, const double *x, int zrow, double zconst, const int32_t *status, const double *truth,
+                   double *partials) {
+    __shared__ double sh[4 * STATS_CHUNK];
+    double v[4] = {0, 0, 0, 0};
+    const int64_t f = (int64_t)blockIdx.x * STATS_CHUNK + threadIdx.x;
+    if (f < N) {
+        const double pz = zrow >= 0 ? x[(int64_t)zrow * N + f] : zconst;
+        filter_error_terms(x[f], x[N + f], pz, truth, N, f, status && status[f] != 0, v);
+    }
+    block_stats_partial(v, sh, partials + (int64_t)blockIdx.x * 4);
+}
 
-__device__ void tree_reduce4(double (&v)[4], double (*sh)[ST_THREADS]) {
-    const int t = threadIdx.x;
+// pairwise tree over the partial index, one block: the same shape whatever produced the partials
+__global__ void __launch_bounds__(1024) error_stats_tree(int64_t n, double *part, double *out4) {
+    for (int64_t stride = 1; stride < n; stride <<= 1) {
+        for (int64_t i = (int64_t)threadIdx.x * 2 * stride; i + stride < n; i += (int64_t)blockDim.x * 2 * stride) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) sh[q][t] = v[q];
-    __syncthreads();
-    for (int s = ST_THREADS / 2; s > 0; s >>= 1) {
-        if (t < s) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) sh[q][t] += sh[q][t + s];
+            for (int q = 0; q < 4; ++q) part[i * 4 + q] += part[(i + stride) * 4 + q];
         }
         __syncthreads();
     }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) v[q] = sh[q][0];
-}
-
-__global__ void __launch_bounds__(ST_THREADS)
-error_stats_chunks(int64_t N, const double *x, int zrow, double zconst, const int32_t *status, const double *truth,
-                   double *partials) {
-    __shared__ double sh[4][ST_THREADS];
-    double v[4] = {0, 0, 0, 0};
-    const int64_t base = (int64_t)blockIdx.x * ST_CHUNK;
-    for (int r = 0; r < ST_CHUNK / ST_THREADS; ++r) {
-        const int64_t f = base + threadIdx.x + (int64_t)r * ST_THREADS;
-        if (f < N) {
-            const double pz = zrow >= 0 ? x[(int64_t)zrow * N + f] : zconst;
-            const double ex = x[f] - truth[f], ey = x[N + f] - truth[N + f], ez = pz - truth[2 * N + f];
-            const double e2 = ex * ex + ey * ey + ez * ez;
-            if (isfinite(e2)) {
-                v[0] += e2;
-                v[1] += ex * ex + ey * ey;
-                v[2] += 1.0;
-            }
-            if (status && status[f] != 0) v[3] += 1.0;
-        }
-    }
-    tree_reduce4(v, sh);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) partials[(int64_t)blockIdx.x * 4 + q] = v[q];
-    }
-}
-
-__global__ void __launch_bounds__(ST_THREADS) error_stats_final(int64_t n_chunks, const double *partials, double *out4) {
-    __shared__ double sh[4][ST_THREADS];
-    double v[4] = {0, 0, 0, 0};
-    for (int64_t c = threadIdx.x; c < n_chunks; c += ST_THREADS) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] += partials[c * 4 + q];
-    }
-    tree_reduce4(v, sh);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) out4[q] = v[q];
-    }
+    if (threadIdx.x < 4) out4[threadIdx.x] = n > 0 ? part[threadIdx.x] : 0.0;
 }
 
 __global__ void i32_to_f64_kernel(int64_t N, const int32_t *in, double *out) {
@@ -114,10 +76,14 @@ cudaError_t launch_i32_to_f64(int64_t N, const int32_t *in, double *out, cudaStr
 
 cudaError_t launch_error_stats(int64_t N, const double *x, int zrow, double zconst, const int32_t *status,
                                const double *truth, double *partials, double *out4, cudaStream_t s) {
-    const int64_t n_chunks = (N + ST_CHUNK - 1) / ST_CHUNK;
-    if (n_chunks > 0)
-        error_stats_chunks<<<(unsigned)n_chunks, ST_THREADS, 0, s>>>(N, x, zrow, zconst, status, truth, partials);
-    error_stats_final<<<1, ST_THREADS, 0, s>>>(n_chunks, partials, out4);
+    const int64_t n_chunks = (N + STATS_CHUNK - 1) / STATS_CHUNK;
+    if (n_chunks > 0 && truth)
+        error_stats_chunks<<<(unsigned)n_chunks, STATS_CHUNK, 0, s>>>(N, x, zrow, zconst, status, truth, partials);
+    return launch_error_stats_tree(n_chunks, partials, out4, s);
+}
+
+cudaError_t launch_error_stats_tree(int64_t n, double *part, double *out4, cudaStream_t s) {
+    error_stats_tree<<<1, 1024, 0, s>>>(n, part, out4);
     return cudaGetLastError();
 }
 

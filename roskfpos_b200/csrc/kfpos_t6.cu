@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
     const unsigned wmask = __ballot_sync(0xffffffffu, active);
     StepStats st = {0u, 0u, 0u, 0u};
     unsigned n_updates = 0, n_bad = 0, n_ignored = 0;
+    double errv[4] = {0.0, 0.0, 0.0, 0.0}; // error terms of the final state (fused statistics)
 
     if (active) {
         const int64_t N = p.N;
@@ -183,7 +184,12 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
         for (int k = 0; k < 3; ++k) p.x[(int64_t)k * N + f] = pos[k];
 #pragma unroll
         for (int k = 0; k < Sym<6>::SZ; ++k) p.P[(int64_t)k * N + f] = Pm[k];
-        if (p.status) p.status[f] |= (int32_t)status_or;
+        int32_t st_all = (int32_t)status_or;
+        if (p.status) {
+            st_all |= p.status[f];
+            p.status[f] = st_all;
+        }
+        if (p.truth) filter_error_terms(pos[0], pos[1], pos[2], p.truth, N, f, st_all != 0, errv);
     }
     warp_accumulate(p.counters + CNT_UPDATES, n_updates);
     warp_accumulate(p.counters + CNT_ML_ITERS, st.ml_iters);
@@ -191,6 +197,9 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
     warp_accumulate(p.counters + CNT_GAIN_EVALS, st.gain_evals);
     warp_accumulate(p.counters + CNT_BAD, n_bad);
     warp_accumulate(p.counters + CNT_IGNORED, n_ignored);
+    // the block-level reduction of the error statistics, fused into the last step of the replay
+    static_assert(T6_BLOCK == STATS_CHUNK, "one statistics partial per replay block");
+    if (p.truth) block_stats_partial(errv, smem, p.partials + (int64_t)blockIdx.x * 4);
 }
 
 template <bool PME, bool LOO, int MT, bool SEL = false>

@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
     const unsigned wmask = __ballot_sync(0xffffffffu, active);
     StepStats st = {0u, 0u, 0u, 0u};
     unsigned n_updates = 0, n_bad = 0;
+    double errv[4] = {0.0, 0.0, 0.0, 0.0}; // error terms of the final state (fused statistics)
     if (active) {
         const int64_t N = p.N;
         const int m = MT > 0 ? MT : p.rs.m_slots;
@@ -356,7 +357,12 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
 #pragma unroll
         for (int k = 0; k < Sym<9>::SZ; ++k) p.P[(int64_t)k * N + f] = Pm[k];
         p.has[f] = (int32_t)has;
-        if (p.status) p.status[f] |= (int32_t)status_or;
+        int32_t st_all = (int32_t)status_or;
+        if (p.status) {
+            st_all |= p.status[f];
+            p.status[f] = st_all;
+        }
+        if (p.truth) filter_error_terms(pos[0], pos[1], pos[2], p.truth, N, f, st_all != 0, errv);
         if (f == 0 && (has & 2u)) {
             // keep the symmetric part as the latched covariance
             p.latch_u[0] = Ra[0]; p.latch_u[1] = Ra[1]; p.latch_u[2] = Ra[3];
@@ -369,6 +375,8 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
     warp_accumulate(p.counters + CNT_COST_EVALS, st.cost_evals);
     warp_accumulate(p.counters + CNT_GAIN_EVALS, st.gain_evals);
     warp_accumulate(p.counters + CNT_BAD, n_bad);
+    static_assert(T9_BLOCK == STATS_CHUNK, "one statistics partial per replay block");
+    if (p.truth) block_stats_partial(errv, smem, p.partials + (int64_t)blockIdx.x * 4);
 }
 
 template <bool PME, int MT, bool IMU, bool SEL = false>

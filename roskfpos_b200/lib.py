@@ -80,6 +80,8 @@ SIGNATURES = {
     "kfpos_batch_ml_solve": (_I, [_VP, _VP, _I, _D, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_batch_get_counters": (_I, [_VP, C.POINTER(C.c_double * 8), _I, _VP]),
     "kfpos_batch_error_stats": (_I, [_VP, _VP, C.POINTER(C.c_double * 4), _VP]),
+    "kfpos_batch_set_truth": (_I, [_VP, _VP, _VP]),
+    "kfpos_stats_allreduce": (_I, [_VP, _VP, _VP, C.POINTER(C.c_double * 6), _VP]),
     "kfpos_measure_fp64_peak": (_I, [_I, C.POINTER(C.c_double)]),
     "kfpos_synth_k8": (_I, [_I, _I64, _I64, C.c_uint64, _I, _VP, _D, _D, _I, _VP, _D, _I64, _I64, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_selftest_math": (_I, [_I, _I64, _VP, _VP, _VP, _VP, _VP]),
