@@ -97,6 +97,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def load_t6_counters():
+    """ncu counters of ONE launch of the headline kernel, committed under profiles/ (per update, so that they
+    scale to any batch size): executed FP64 instruction mix and DRAM bytes.  profiles/r02_t6_counters.json is
+    written by profiles/extract_counters.py from the .ncu-rep of the same bench command."""
+    p = os.path.join(ROOT, "profiles", "r02_t6_counters.json")
+    if os.path.exists(p):
+        return json.load(open(p))
+    return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -229,6 +239,14 @@ def run_b200(args):
     x0_full[:3] = x0
     batch = Batch(L.MODEL_T6, N, device=local, anchors=anc, accel_noise=0.5)
     stream = torch.cuda.current_stream()
+    # the ground truth is registered once: every replay launch then ends with the block-level reduction of the
+    # error statistics, a step only adds the final tree (no host synchronisation inside the timed loop)
+    batch.set_truth(truth_end, stream=stream)
+    # the job's one collective goes through the C ABI (kfpos_stats_allreduce) on a raw NCCL communicator
+    comm = None
+    if world > 1:
+        from roskfpos_b200.shard import nccl_comm
+        comm = nccl_comm(rank, world, local)
 
     def barrier():
         if world > 1:
@@ -238,8 +256,7 @@ def run_b200(args):
     def step_resident():
         batch.set_state(x0_full, None, stream=stream)
         batch.replay_toa(0.1, ranges, err=0.01, stream=stream)
-        s = batch.error_stats(truth_end, stream=stream)
-        return s
+        batch.error_stats(stream=stream, readback=False)
 
     # ---- device-resident throughput (`value`)
     sampler = ClockSampler(local)
@@ -258,10 +275,10 @@ def run_b200(args):
         kev[k][0].record(stream)
         batch.replay_toa(0.1, ranges, err=0.01, stream=stream)
         kev[k][1].record(stream)
-        s = batch.error_stats(truth_end, stream=stream)  # this rank's 4 doubles, read back every step
+        batch.error_stats(stream=stream, readback=False)  # the final tree over the block partials; stays on the device
     # the only collective of the job: the final reduction of the statistics (filters are independent,
-    # so nothing forces the ranks into lock-step between the steps)
-    s, _, _ = reduce_stats(s, device=dev)
+    # so nothing forces the ranks into lock-step between the steps); one ncclAllGather of 4 doubles + D2H
+    s = batch.stats_allreduce(comm, stream=stream)
     e1.record(stream)
     barrier()
     torch.cuda.cudart().cudaProfilerStop()
@@ -285,13 +302,16 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = world * N * T * K / (ms_max * 1e-3)
-    rmse = float(np.sqrt(s[0] / max(s[2], 1)))
+    rmse = float(s[4])
 
     # ---- end to end through the C ABI with HOST (pinned) buffers
     e2e = None
     if not args.no_e2e:
-        h_ranges = torch.empty(ranges.shape, dtype=ranges.dtype, pin_memory=True)
-        h_ranges.copy_(ranges)
+        # the host log holds the first Te epochs of the same workload (pinned host memory is bounded: 1000
+        # epochs would be 33.5 GB per rank); the per-update rate is what is compared
+        Te = min(T, args.e2e_tsteps)
+        h_ranges = torch.empty((Te,) + tuple(ranges.shape[1:]), dtype=ranges.dtype, pin_memory=True)
+        h_ranges.copy_(ranges[:Te])
         h_x0 = torch.empty(x0_full.shape, dtype=torch.float64, pin_memory=True)
         h_x0.copy_(x0_full)
         h_truth = torch.empty(truth_end.shape, dtype=torch.float64, pin_memory=True)
@@ -324,17 +344,19 @@ def run_b200(args):
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         h2d = int(h_ranges.numel() * h_ranges.element_size() + 8 * 6 * N + 8 * 3 * N)
-        e2e = {"value": world * N * T * Ke / (float(te.item()) * 1e-3), "unit": UNIT,
+        e2e = {"value": world * N * Te * Ke / (float(te.item()) * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * 6 * N + 32), "steps": Ke,
+               "epochs_per_step": Te,
                "ms_per_step": float(te.item()) / Ke,
                "h2d_gbs": h2d * Ke / (float(te.item()) * 1e-3) / 1e9,
                "note": "host range log in the reference's int32-mm table format; the step is bound by the "
                        "host-to-device copy (h2d_gbs), which the replay kernel overlaps chunk by chunk"}
+        h_shape = tuple(h_ranges.shape)
         del h_ranges, hr
         # the same step with the host log in the library's uint16-mm wire format (ranges < 65.5 m)
         try:
-            h16 = torch.empty(ranges.shape, dtype=torch.uint16, pin_memory=True)
-            h16.copy_(ranges.to(torch.uint16))
+            h16 = torch.empty(h_shape, dtype=torch.uint16, pin_memory=True)
+            h16.copy_(ranges[:Te].to(torch.uint16))
             hr16 = h16.numpy()
 
             def step_e2e16():
@@ -353,7 +375,7 @@ def run_b200(args):
             wall16 = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
             if world > 1:
                 dist.all_reduce(wall16, op=dist.ReduceOp.MAX)
-            e2e["uint16_wire_format"] = {"value": world * N * T * Ke / (float(wall16.item()) * 1e-3),
+            e2e["uint16_wire_format"] = {"value": world * N * Te * Ke / (float(wall16.item()) * 1e-3),
                                          "h2d_bytes_per_step": int(h16.numel() * 2 + 8 * 9 * N),
                                          "rmse_equal": bool(abs(s3[0] - s2[0]) <= 1e-12 * abs(s2[0]))}
             del h16, hr16
@@ -368,11 +390,19 @@ def run_b200(args):
     ach = w_alg * N * T / (kernel_ms * 1e-3)
     peaks, peak_src = load_peaks()
     alg_bytes = N * T * M * ranges.element_size() + N * (3 + 21) * 8 * 2
-    # DRAM bytes of ONE launch of the replay kernel at the default size, from ncu
-    # (dram__bytes_read.sum + dram__bytes_write.sum = 3.56 GB + 201.7 MB; profiles/README.md)
-    traffic = 3.7617e9 if (N, T, M) == (1 << 20, 100, 8) else None
+    # executed work and DRAM traffic of ONE launch, from the committed ncu capture of this kernel (per update)
+    ctr = load_t6_counters() if M == 8 else None
+    traffic = frac_exec = exec_flop = None
+    if ctr:
+        traffic = ctr["dram_bytes_per_update"] * N * T
+        exec_flop = ctr["executed_flop_per_update"]
+        frac_exec = exec_flop * N * T / (kernel_ms * 1e-3) / peak if peak else None
     roof = {"bound": "fp64", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
             "frac": ach / peak if peak else None, "traffic": traffic, "traffic_unit": "bytes per launch",
+            "traffic_source": ctr and ctr.get("source"),
+            "frac_executed": frac_exec, "executed_flop_per_update": exec_flop,
+            "executed_note": "2*DFMA + DMUL + DADD thread instructions (smsp__sass_thread_inst_executed_op_d*_pred_on) "
+                             "of the committed ncu capture / updates of that launch, times this run's update rate",
             "algorithmic_bytes": alg_bytes,
             "peak_source": "measured live: kfpos_measure_fp64_peak (DFMA-only kernel, best of 5)",
             "kernel": "t6_replay_kernel<8,false,false>", "kernel_ms": kernel_ms,
@@ -383,10 +413,19 @@ def run_b200(args):
             "hbm": {"achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                     "peak_source": peak_src, "bytes_per_update": alg_bytes / (N * T)}}
 
+    # ---- BASELINE config 5 (64 Mi K8 filters in TOTAL over the ranks: strong scaling), every world size
+    del ranges
+    torch.cuda.empty_cache()
+    config5 = None
+    if not args.no_config5:
+        try:
+            config5 = config5_leg(local, dev, world, rank, comm, args.config5_filters, 2, 2, 1, full=True)
+        except Exception as exc:  # a secondary number must never take the headline line down
+            config5 = {"error": repr(exc)}
+            if world > 1:
+                raise
     other = None
     if rank == 0 and world == 1 and not args.no_extra:
-        del ranges
-        torch.cuda.empty_cache()
         try:
             other = bench_other_configs(local, dev, args)
         except Exception as exc:  # secondary numbers must never take the headline line down
@@ -402,23 +441,89 @@ def run_b200(args):
                            "l2_policy": f"inputs larger than L2 ({N * T * M * 4 / 1e6:.0f} MB range log per step)",
                            "parallelism": f"filters sharded by index over {world} GPU(s); one all-reduce of 4 doubles at the end"},
                 "rmse_m": rmse, "bad_updates": cnt["bad"], "rank_ms_per_step": [v / K for v in rank_ms], "ranks": per_rank,
-                "e2e": e2e, "gpu_launches": 3 * K, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
-                "other_configs": other}
+                "e2e": e2e, "gpu_launches": 2 * K + 1 + (1 if world > 1 else 0), "roofline": roof, "cpu_baseline": cpu,
+                "clocks": clocks, "timed_region_s": ms_max * 1e-3,
+                "config5": config5, "other_configs": other}
         print(json.dumps(line))
     batch.close()
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_config5(args):
-    """BASELINE config 5: full multi-sensor K8 Monte Carlo, --mc-filters filters sharded by index over the
-    ranks, inputs generated on the device chunk by chunk (never resident), one all-reduce of the error
-    statistics at the end.  Optional mode; prints its own JSON line (metric k8_events_per_sec)."""
+def config5_leg(local, dev, world, rank, comm, total_filters, n_macro, K, W, full=True, chunk=None):
+    """BASELINE config 5 (full=False: config 3) as a STRONG-scaling leg: `total_filters` K8 filters in total,
+    sharded by index over the ranks, inputs generated on the device chunk by chunk inside the timed region
+    (never resident), statistics fused into the replay, ONE collective at the end (kfpos_stats_allreduce).
+    Generator and summation tree depend on the global filter index only, so the reduced statistics are
+    bit-identical for any number of GPUs: the hex strings of the returned dict are there to be compared."""
     import torch
     import torch.distributed as dist
     from roskfpos_b200 import lib as L, synth
     from roskfpos_b200.batch import Batch
-    from roskfpos_b200.shard import reduce_stats, shard_bounds
+    from roskfpos_b200.shard import shard_bounds
+    stream = torch.cuda.current_stream()
+    macro = synth.MACRO_FULL if full else synth.MACRO_IMU_MAG
+    lo, hi = shard_bounds(total_filters, rank, world)
+    N = hi - lo
+    if chunk is None:
+        chunk = 2 if full else max(1, min(n_macro, (3 << 30) // (N * 8 * 35)))  # a few GB of inputs in flight
+    anc = synth.anchors_for(8)
+    batch = Batch(L.MODEL_K8, N, device=local, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5)
+    bufs = synth.k8_montecarlo_chunk(N, 0, chunk, anc, dev, seed=synth.SEED, full=full, first_filter=lo, want_x0=True,
+                                     stream=stream)
+    x0 = bufs["x0"].clone()
+    batch.set_truth(bufs["truth_end"], stream=stream)  # rewritten in place by every chunk: the last one counts
+
+    def step():
+        nonlocal bufs
+        batch.set_state(x0, None, stream=stream)
+        for m0 in range(0, n_macro, chunk):
+            bufs = synth.k8_montecarlo_chunk(N, m0, min(chunk, n_macro - m0), anc, dev, seed=synth.SEED, full=full,
+                                             first_filter=lo, out=bufs, stream=stream)
+            batch.replay_events(bufs["events"], ranges=bufs["ranges"], sensors=bufs["sensors"], err=0.01, stream=stream)
+        batch.error_stats(stream=stream, readback=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(W):
+        step()
+    batch.counters(reset=True)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(K):
+        step()
+    s = batch.stats_allreduce(comm, stream=stream)
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    cnt = batch.counters(reset=True)
+    batch.close()
+    del bufs, x0
+    torch.cuda.empty_cache()
+    n_ev = n_macro * len(macro)
+    return {"events_per_s": total_filters * n_ev * K / (ms * 1e-3), "toa_updates_per_s": total_filters * n_macro * K / (ms * 1e-3),
+            "ms_per_step": ms / K, "steps": K, "warmup": W, "total_filters": total_filters, "filters_per_gpu": N,
+            "n_gpus": world, "macro_steps": n_macro, "events_per_macro_step": len(macro), "chunk_macro_steps": chunk,
+            "scaling": "strong", "rmse_xy_m": float(s[5]), "rmse_xy_hex": float(s[5]).hex(),
+            "sum_e2_hex": float(s[0]).hex(), "filters_counted": float(s[2]), "bad_filters": float(s[3]),
+            "bad_updates_this_rank": cnt["bad"],
+            "data": "synthetic, generated on the device (Philox4x32-10) inside the timed region",
+            "collective": "kfpos_stats_allreduce: one ncclAllGather of 4 doubles per rank + pairwise rank tree"}
+
+
+def run_config5(args):
+    """--workload config3 / config5: those BASELINE configs themselves as the whole job; prints its own JSON
+    line (metric k8_multisensor_events_per_sec)."""
+    import torch
+    import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -428,63 +533,29 @@ def run_config5(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    stream = torch.cuda.current_stream()
     full = args.workload == "config5"
     if not args.mc_filters:
         args.mc_filters = (1 << 26) if full else (1 << 20)
     if not args.mc_macro_steps:
         args.mc_macro_steps = 4 if full else 1000
-    macro = synth.MACRO_FULL if full else synth.MACRO_IMU_MAG
-    lo, hi = shard_bounds(args.mc_filters, rank, world)
-    N, K, W, n_macro = hi - lo, args.steps, args.warmup, args.mc_macro_steps
-    chunk = 2 if full else max(1, min(n_macro, (3 << 30) // (N * 8 * 35)))  # ~3 GB of inputs in flight
-    anc = synth.anchors_for(8)
-    batch = Batch(L.MODEL_K8, N, device=local, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5)
-    bufs = synth.k8_montecarlo_chunk(N, 0, chunk, anc, dev, seed=synth.SEED, full=full, first_filter=lo, want_x0=True,
-                                     stream=stream)
-    x0 = bufs["x0"].clone()
-
-    def step():
-        nonlocal bufs
-        batch.set_state(x0, None, stream=stream)
-        for m0 in range(0, n_macro, chunk):
-            bufs = synth.k8_montecarlo_chunk(N, m0, min(chunk, n_macro - m0), anc, dev, seed=synth.SEED, full=full,
-                                             first_filter=lo, out=bufs, stream=stream)
-            batch.replay_events(bufs["events"], ranges=bufs["ranges"], sensors=bufs["sensors"], err=0.01, stream=stream)
-        return batch.error_stats(bufs["truth_end"], stream=stream)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    for _ in range(W):
-        step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(K):
-        s = step()
-    s, _, rmse_xy = reduce_stats(s, device=dev)
-    e1.record(stream)
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    comm = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
-    n_ev = n_macro * len(macro)
+        from roskfpos_b200.shard import nccl_comm
+        comm = nccl_comm(rank, world, local)
+    r = config5_leg(local, dev, world, rank, comm, args.mc_filters, args.mc_macro_steps, args.steps, args.warmup, full=full)
     if rank == 0:
-        print(json.dumps({"metric": "k8_multisensor_events_per_sec", "value": args.mc_filters * n_ev * K / (ms * 1e-3),
-                          "unit": "events/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K,
-                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
-                          "data": "synthetic, generated on the device inside the timed region",
+        print(json.dumps({"metric": "k8_multisensor_events_per_sec", "value": r["events_per_s"],
+                          "unit": "events/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f64", "data": r["data"],
                           "config": {"workload": f"BASELINE config {'5: K8 (UWB+IMU+mag+PX4Flow)' if full else '3: K8 (UWB+IMU+compass)'} "
-                                                 f"Monte Carlo, {args.mc_filters} filters in total, {n_macro} macro-steps of "
-                                                 f"{len(macro)} events, 8 anchors", "filters_per_gpu": N,
-                                     "chunk_macro_steps": chunk, "parallelism":
-                                     f"filters sharded by index over {world} GPU(s); one all-reduce of 4 doubles at the end"},
-                          "toa_updates_per_s": args.mc_filters * n_macro * K / (ms * 1e-3),
-                          "rmse_xy_m": rmse_xy, "filters_counted": s[2], "bad_filters": s[3]}))
-    batch.close()
+                                                 f"Monte Carlo, {args.mc_filters} filters in total, {args.mc_macro_steps} macro-steps of "
+                                                 f"{r['events_per_macro_step']} events, 8 anchors",
+                                     "filters_per_gpu": r["filters_per_gpu"], "chunk_macro_steps": r["chunk_macro_steps"],
+                                     "parallelism": f"filters sharded by index over {world} GPU(s); {r['collective']}"},
+                          "detail": r}))
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -651,12 +722,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--filters", type=int, default=1 << 20, help="filters per GPU")
-    ap.add_argument("--tsteps", type=int, default=100, help="ranging epochs per bench step")
+    ap.add_argument("--tsteps", type=int, default=1000,
+                    help="ranging epochs per bench step (1000: the 33.5 GB range log stays resident in HBM and a "
+                         "20-step timed region lasts seconds, i.e. the number is a sustained one)")
+    ap.add_argument("--e2e-tsteps", type=int, default=100, help="epochs of the pinned HOST log of the e2e leg")
     ap.add_argument("--anchors", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary BASELINE configs")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 64 Mi-filter strong-scaling leg")
+    ap.add_argument("--config5-filters", type=int, default=1 << 26, help="TOTAL K8 filters of the config-5 leg")
     ap.add_argument("--workload", default="t6", choices=["t6", "config3", "config5"],
                     help="t6 = the headline metric (default); config3 / config5 = those BASELINE configs themselves: the "
                          "K8 IMU+compass+UWB (1 Mi filters x 1000 steps) / full multi-sensor (64 Mi filters) Monte Carlo "

@@ -73,6 +73,7 @@ struct kfpos_batch {
     const double *d_truth = nullptr;
     double *d_truth_own = nullptr;
     bool partials_fresh = false;
+    bool out4_valid = false; // d_out4 holds the statistics of the current state
     double *d_gather = nullptr; // [n_ranks][4] of kfpos_stats_allreduce
     // K8 / T9 latched sensor samples, SoA rows (see kfpos_k8.cuh)
     double *d_latch = nullptr;
@@ -314,6 +315,7 @@ extern "C" int kfpos_batch_set_state(kfpos_batch *b, const double *x, const doub
     if (b->d_latch_u) CK(cudaMemsetAsync(b->d_latch_u, 0, sizeof(double) * 16, s));
     b->imu_seen = false; // the latches are cleared above
     b->partials_fresh = false;
+    b->out4_valid = false;
     b->stepped = P != nullptr; // a restored checkpoint is a running filter; P0 = 0 is a fresh one
     if (!xd || (P && !on_device(P))) CK(cudaStreamSynchronize(s));
     return KFPOS_OK;
@@ -533,6 +535,7 @@ int launch_replay(kfpos_batch *b, int T, const double *d_dt, const void *d_range
         p.partials = b->d_partials;
         CK(launch_t6_replay(p, s));
         b->partials_fresh = b->d_truth != nullptr;
+        b->out4_valid = false;
         return KFPOS_OK;
     }
     default: return KFPOS_ERR_UNSUPPORTED;
@@ -599,6 +602,7 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.partials = b->d_partials;
         CK(launch_k8_replay(p, s));
         b->partials_fresh = b->d_truth != nullptr;
+        b->out4_valid = false;
         break;
     }
     case KFPOS_MODEL_T9: {
@@ -629,6 +633,7 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.partials = b->d_partials;
         CK(launch_t9_replay(p, s));
         b->partials_fresh = b->d_truth != nullptr;
+        b->out4_valid = false;
         break;
     }
     default: return KFPOS_ERR_INVALID;
@@ -984,6 +989,7 @@ extern "C" int kfpos_batch_set_truth(kfpos_batch *b, const double *truth, void *
     DeviceGuard g(b->device);
     cudaStream_t s = (cudaStream_t)stream;
     b->partials_fresh = false;
+    b->out4_valid = false;
     if (!truth) {
         b->d_truth = nullptr;
         return KFPOS_OK;
@@ -1016,6 +1022,7 @@ int enqueue_error_stats(kfpos_batch *b, const double *truth, cudaStream_t s) {
     CK(launch_error_stats(b->N, b->d_x, b->model == KFPOS_MODEL_K8 ? -1 : 2, b->cfg.fixed_height, b->d_status,
                           (const double *)d_truth, b->d_partials, b->d_out4, s));
     b->partials_fresh = false; // the tree folds the partials in place
+    b->out4_valid = true;
     return KFPOS_OK;
 }
 
@@ -1062,8 +1069,8 @@ extern "C" int kfpos_stats_allreduce(kfpos_batch *b, struct ncclComm *comm, cons
     if (!b || b->model == KFPOS_MODEL_ML || !out) return KFPOS_ERR_INVALID;
     DeviceGuard g(b->device);
     cudaStream_t s = (cudaStream_t)stream;
-    // truth == null and nothing registered: d_out4 holds what the last kfpos_batch_error_stats left there
-    if (truth || b->d_truth) {
+    // truth == null: what the last kfpos_batch_error_stats left on the device, if the state has not changed since
+    if (truth || !b->out4_valid) {
         int rc = enqueue_error_stats(b, truth, s);
         if (rc) return rc;
     }
