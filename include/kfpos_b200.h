@@ -315,7 +315,9 @@ int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs, int n_anch
  * Work counters accumulated on the device since the last reset, as doubles:
  * [0] updates, [1] inner-ML Newton iterations, [2] IEKF cost evaluations,
  * [3] IEKF gain computations, [4] updates with status != OK, [5] anchors
- * ignored by leave-one-out, [6..7] reserved.                                    */
+ * ignored by leave-one-out, [6] T6 inner-ML solves that ended at the reference's
+ * 10000-iteration cap (ML.cpp:165), [7] of those, the ones whose tail the exact cycle
+ * detection skipped (both counted by the tuned T6 replay only).                  */
 int kfpos_batch_get_counters(kfpos_batch *b, double out[8], int reset, void *stream);
 
 /* Error statistics against a truth position SoA [3][N] (host or device):

@@ -19,7 +19,7 @@ METRICS = ("smsp__sass_thread_inst_executed_op_dfma_pred_on.sum,smsp__sass_threa
 def to_base(value, unit):
     v = float(str(value).replace(",", ""))
     u = (unit or "").lower()
-    scale = {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9,
+    scale = {"kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3,
              "second": 1.0}
     return v * scale.get(u, 1.0)
 

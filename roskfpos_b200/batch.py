@@ -253,7 +253,8 @@ class Batch:
         L.check(L.lib().kfpos_batch_get_counters(self._h, C.byref(buf), int(reset), _stream_ptr(stream)),
                 "kfpos_batch_get_counters")
         v = list(buf)
-        return dict(updates=v[0], ml_iters=v[1], cost_evals=v[2], gain_evals=v[3], bad=v[4], ignored=v[5])
+        return dict(updates=v[0], ml_iters=v[1], cost_evals=v[2], gain_evals=v[3], bad=v[4], ignored=v[5],
+                    ml_capped=v[6], ml_cycles=v[7])
 
     def set_truth(self, truth, stream=None):
         """Registers the ground truth SoA [3][N]: replay launches then end with the block-level reduction of the

@@ -8,8 +8,6 @@
 
 namespace kfpos {
 
-// device counters (unsigned long long each)
-enum { CNT_UPDATES = 0, CNT_ML_ITERS, CNT_COST_EVALS, CNT_GAIN_EVALS, CNT_BAD, CNT_IGNORED, CNT_N = 8 };
 
 // Range stream of a replay: SoA [T][M][N] in `fmt`, optional per-ranging
 // errorEstimation of the same shape.

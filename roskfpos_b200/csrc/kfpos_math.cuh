@@ -260,6 +260,9 @@ KF_DEV void block2_update(Sym<N> &P, double (&dx)[N], const double (&h0)[N], con
 }
 
 // per-thread work counters of one replay (summed into the device counters at the end)
+// device counters (unsigned long long each)
+enum { CNT_UPDATES = 0, CNT_ML_ITERS, CNT_COST_EVALS, CNT_GAIN_EVALS, CNT_BAD, CNT_IGNORED, CNT_ML_CAPPED, CNT_ML_CYCLES, CNT_N = 8 };
+
 struct StepStats {
     unsigned ml_iters, cost_evals, gain_evals, status;
 };

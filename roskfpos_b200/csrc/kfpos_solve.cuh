@@ -283,7 +283,7 @@ KF_DEV int ml_solve3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
 template <int MT>
 KF_DEV int ml_solve3_ekf(const AnchorTable &A, const EpochT<false, MT> &ep, unsigned mask, double (&p)[3],
                          double &sse_out, unsigned &iters, double &sse_start, double (&g_start)[3],
-                         double (&Gu_start)[6], const Col &cyc_ref) {
+                         double (&Gu_start)[6], const Col &cyc_ref, unsigned long long *cnt = nullptr) {
     const int nvalid = __popc(mask);
     MlPass3 ps;
     ml_pass3<false, MT, true>(A, ep, mask, nvalid, p, ps, Gu_start);
@@ -309,8 +309,10 @@ KF_DEV int ml_solve3_ekf(const AnchorTable &A, const EpochT<false, MT> &ep, unsi
         } else if (p[0] == cyc_ref[0] && p[1] == cyc_ref[1] && p[2] == cyc_ref[2]) {
             const unsigned per = iter - (1u << (31 - __clz(iter)));
             iter = 10000u - (10000u - iter) % per;
+            if (cnt) atomicAdd(cnt + CNT_ML_CYCLES, 1ull);
         }
     }
+    if (cnt && iter >= 10000u) atomicAdd(cnt + CNT_ML_CAPPED, 1ull);
     iters += iter;
     sse_out = ps.sse;
     return ML_OK;

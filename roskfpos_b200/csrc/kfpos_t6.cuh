@@ -61,7 +61,8 @@ struct T6Result {
 // once per warp and not once per group of lanes that left the Newton loop together.
 template <bool PME, int MT>
 KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, const double (&xp)[3],
-                     const Col &Pm, T6Result &out, StepStats &st, unsigned wmask = 0u, const Col *cyc_ref = nullptr) {
+                     const Col &Pm, T6Result &out, StepStats &st, unsigned wmask = 0u, const Col *cyc_ref = nullptr,
+                     unsigned long long *cnt = nullptr) {
     // ---- inner ML solve from the predicted position (TOA.cpp:268-273)
     double pml[3] = {xp[0], xp[1], xp[2]};
     double sse, sse_xp = 0.0;
@@ -70,7 +71,7 @@ KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
     double g_xp[3] = {0.0, 0.0, 0.0}, Gu_xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     int rc;
     if constexpr (PME) rc = ml_solve3<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &sse_xp, 10000u, nullptr, cyc_ref);
-    else rc = ml_solve3_ekf<MT>(A, ep, mask, pml, sse, st.ml_iters, sse_xp, g_xp, Gu_xp, *cyc_ref);
+    else rc = ml_solve3_ekf<MT>(A, ep, mask, pml, sse, st.ml_iters, sse_xp, g_xp, Gu_xp, *cyc_ref, cnt);
     if (wmask) __syncwarp(wmask);
     if (rc == ML_FEW) st.status |= 2u;
     if (rc == ML_SINGULAR) return ML_SINGULAR;
