@@ -14,6 +14,7 @@
 #include <cstring>
 #include <stdexcept>
 #include <string>
+#include <limits>
 #include <vector>
 
 #include "../kfpos_b200.h"
@@ -222,6 +223,24 @@ public:
         const double x[8] = {initialPosition.x, initialPosition.y, 0, 0, 0, 0, initialAngle, 0};
         check(kfpos_batch_set_state(b_, x, nullptr, nullptr), "kfpos_batch_set_state");
     }
+    // KF.cpp:6-32: no initial position -- the first epoch with rangings initialises the filter through
+    // MLLocation (KF.cpp:244-285); what PosGenerator constructs with useStartPosition = 0 (PG.cpp:519-528)
+    KalmanFilter(double accelerationNoise, double initialAngle, double jolt, std::string xmlPos,
+                 std::string xmlPX4Flow, std::string xmlTag, std::string xmlImu, std::string xmlMag)
+        : ok_(true) {
+        kfpos_config_default(&cfg_);
+        cfg_.accel_noise = accelerationNoise;
+        cfg_.jolt = jolt;
+        cfg_.initial_angle = initialAngle;
+        const std::string *xml[5] = {&xmlPX4Flow, &xmlTag, &xmlImu, &xmlMag, &xmlPos};
+        for (int i = 0; i < 5; ++i)
+            if (kfpos_config_load_xml(&cfg_, xml[i]->c_str()) != KFPOS_OK) ok_ = false;
+        cfg_.ml_initial_position = 1;
+        create(KFPOS_MODEL_K8, cfg_);
+        const double nan = std::numeric_limits<double>::quiet_NaN();
+        const double x[8] = {nan, nan, 0, 0, 0, 0, initialAngle, 0};
+        check(kfpos_batch_set_state(b_, x, nullptr, nullptr), "kfpos_batch_set_state");
+    }
     bool init() override { return ok_; } // loadConfigurationFiles (KF.cpp:749-893)
     void newTOAMeasurement(const std::vector<double> &rangings, const std::vector<Beacon> &beacons,
                            const std::vector<double> &errorEstimations, double) override {
@@ -253,6 +272,11 @@ public:
         double x[8], P[64];
         check(kfpos_batch_get_pose(b_, sinceLast(), x, P, nullptr), "kfpos_batch_get_pose");
         pose.x = x[0]; pose.y = x[1]; pose.z = cfg_.fixed_height;
+        if (cfg_.ml_initial_position && !cfg_.use_fixed_height) { // mUWBtagZ = the ML estimate's z (KF.cpp:257)
+            double pose13[13];
+            check(kfpos_batch_get_pose_msg(b_, 0.0, pose13, nullptr, nullptr), "kfpos_batch_get_pose_msg");
+            pose.z = pose13[2];
+        }
         const double half = x[6] * 0.5;
         pose.rotX = 0.0; pose.rotY = 0.0; pose.rotZ = std::sin(half); pose.rotW = std::cos(half);
         pose.linearSpeedX = x[2]; pose.linearSpeedY = x[3]; pose.linearSpeedZ = 0.0;
@@ -281,6 +305,18 @@ public:
         c.jolt = jolt;
         create(KFPOS_MODEL_T9, c);
         const double x[9] = {initialPosition.x, initialPosition.y, initialPosition.z, 0, 0, 0, 0, 0, 0};
+        check(kfpos_batch_set_state(b_, x, nullptr, nullptr), "kfpos_batch_set_state");
+    }
+    // TOAIMU.cpp:6-24: no initial position -- ML initialisation from the first epoch with rangings (:118-162)
+    KalmanFilterTOAIMU(double accelerationNoise, double jolt) {
+        kfpos_config c;
+        kfpos_config_default(&c);
+        c.accel_noise = accelerationNoise;
+        c.jolt = jolt;
+        c.ml_initial_position = 1;
+        create(KFPOS_MODEL_T9, c);
+        const double nan = std::numeric_limits<double>::quiet_NaN();
+        const double x[9] = {nan, nan, nan, 0, 0, 0, 0, 0, 0};
         check(kfpos_batch_set_state(b_, x, nullptr, nullptr), "kfpos_batch_set_state");
     }
     void newTOAMeasurement(const std::vector<double> &rangings, const std::vector<Beacon> &beacons,

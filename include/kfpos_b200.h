@@ -78,6 +78,9 @@ enum kfpos_range_fmt {
 #define KFPOS_ST_MAXITER 32  /* IEKF used all iterations without meeting the break test      */
 #define KFPOS_ST_ASYM_R 64   /* K8 IMU covariance block not symmetric (cov[1] != cov[3])     */
 #define KFPOS_ST_Z_GATE 128  /* ML: estimated z outside [min_z, max_z] (config_pos.xml:22-25) */
+#define KFPOS_ST_UNINIT 256  /* K8 / T9 with ml_initial_position: an event met the filter while its position
+                                was still NaN and ended in the ML-initialisation branch (KF.cpp:244-285,
+                                TOAIMU.cpp:118-162): no predict, no update                        */
 
 /* ML variants (MLLocation.h:5-7) and best-group criteria (MLLocation.h:10-11) */
 #define KFPOS_ML_VARIANT_NORMAL 0
@@ -143,6 +146,20 @@ typedef struct kfpos_config {
     /* config_mag.xml <mag .../>  (KF.cpp:839-844) */
     double mag_angle_offset;      /* angleOffset                                    */
     double mag_cov;               /* covarianceMag                                  */
+    /* The constructors WITHOUT initialPosition (KF.cpp:6-32, TOAIMU.cpp:6-24; what PosGenerator builds
+     * when the launch file leaves useStartPosition at 0, PG.cpp:519-528).  0 (default): fixed initial
+     * position, x0 of kfpos_batch_set_state is the state.  1 (K8, T9): a filter whose x0 position is
+     * NaN is UNINITIALISED -- every event updates the sensor latches and the filter's clock only,
+     * until an epoch with rangings arrives: its position then comes from MLLocation (K8: 2-D from
+     * (1, 1, fixedHeight) when use_fixed_height, else 3-D from (1, 1, 4) and the estimated z becomes
+     * THIS filter's tag height; T9: 3-D from (1, 1, 4)) and the 2x2 x-y block of the all-zero
+     * covariance from the ML covariance (KF.cpp:244-285, TOAIMU.cpp:118-162); the epoch performs no
+     * update.  As written: fewer than 3 / 4 rangings initialise the filter AT the start point with
+     * P = 0 (KFPOS_ST_ML_FEW; the reference then throws on the empty covariance matrix); a failed
+     * solve leaves the filter uninitialised (KFPOS_ST_SINGULAR).  T6's branch (TOA.cpp:90-108) is not
+     * offered: it leaves a NON-symmetric covariance behind.                      */
+    int32_t ml_initial_position;
+    int32_t _reserved0;
 } kfpos_config;
 
 /* Fills the defaults the reference uses when an attribute/param is absent (all 0;

@@ -42,6 +42,9 @@ typedef struct {
 #define KO_ST_NAN 8          /* non-finite state after the update                */
 #define KO_ST_ML_NAN 16      /* T6 NaN guard fired (TOA.cpp:270-272)             */
 #define KO_ST_MAXITER 32     /* IEKF ran out of iterations without the break     */
+#define KO_ST_UNINIT 256     /* K8/T9 without a fixed initial position: the event met a filter whose
+                                position was still NaN and ended in the ML-initialisation branch
+                                (KF.cpp:244-285, TOAIMU.cpp:118-162): no predict, no update        */
 
 typedef struct {
     int status;
@@ -119,6 +122,9 @@ typedef struct {
     double mag_angle, mag_c;                                  /* lastMagMeasurement     */
     /* EKF-side NLOS variants (config_pos.xml; see ko_t6_new_toa_sel): 0 = normal */
     int variant, n_ignore, best_mode;
+    /* 1 = the constructor WITHOUT initialPosition (KF.cpp:6-32, mUseFixedInitialPosition = false): while
+     * pos is NaN every event ends in the ML-initialisation branch (KF.cpp:244-285) */
+    int ml_init;
 } ko_k8;
 void ko_k8_init(ko_k8 *f, double accel_noise, double init_angle, double jolt, const double p0[2]);
 void ko_k8_new_toa(ko_k8 *f, double dt, int n_slots, const double *ranges,
@@ -139,6 +145,7 @@ typedef struct {
     int has_imu;
     double imu_a[3], imu_cov[9];
     int variant, n_ignore, best_mode; /* EKF-side NLOS variants (see ko_t6_new_toa_sel); 0 = normal */
+    int ml_init; /* 1 = the constructor without initialPosition (TOAIMU.cpp:6-24): see ko_k8.ml_init */
 } ko_t9;
 void ko_t9_init(ko_t9 *f, double accel_noise, double jolt, const double p0[3]);
 void ko_t9_new_toa(ko_t9 *f, double dt, int n_slots, const double *ranges,
@@ -180,11 +187,11 @@ typedef struct {
 void ko_k8_replay(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
                   int fmt, double err_scalar, const double *err_arr, const double *sensors, const ko_k8 *cfg,
                   int b1_zero_z, double *x /*[8][N]*/, double *P /*[64][N]*/, double *traj, double *counters /*[5]*/,
-                  int32_t *status, int threads);
+                  int32_t *status, int threads, double *tagz /*[N] in/out or NULL*/);
 void ko_t9_events_sel(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
                       int fmt, double err_scalar, const double *err_arr, const double *sensors, double accel_noise,
                       double jolt, int variant, int n_ignore, int best_mode, double *x, double *P, double *traj,
-                      double *counters, int32_t *status, int threads);
+                      double *counters, int32_t *status, int threads, int ml_init);
 void ko_t9_events(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
                   int fmt, double err_scalar, const double *err_arr, const double *sensors, double accel_noise,
                   double jolt, double *x /*[9][N]*/, double *P /*[81][N]*/, double *traj, double *counters /*[5]*/,

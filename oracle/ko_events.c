@@ -28,7 +28,7 @@ static inline double load_range(const void *ranges, int fmt, int64_t idx) {
 void ko_k8_replay(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
                   int fmt, double err_scalar, const double *err_arr, const double *sensors, const ko_k8 *cfg,
                   int b1_zero_z, double *x, double *P, double *traj, double *counters, int32_t *status,
-                  int threads) {
+                  int threads, double *tagz /* [N] in/out or NULL: per-filter tag height (cfg->ml_init, 3-D) */) {
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
@@ -42,6 +42,7 @@ void ko_k8_replay(int64_t N, int n_events, const ko_event *ev, int M, const doub
         flt.angle = x[6 * N + f]; flt.omega = x[7 * N + f];
         for (int k = 0; k < 64; ++k) flt.P[k] = P[(int64_t)k * N + f];
         flt.has_mag = flt.has_px4 = flt.has_imu = 0;
+        if (tagz) flt.tag_z = tagz[f];
         int st_or = 0, n_toa = 0;
         double carry = 0.0;
         for (int e = 0; e < n_events; ++e) {
@@ -92,10 +93,12 @@ void ko_k8_replay(int64_t N, int n_events, const ko_event *ev, int M, const doub
             }
             if (skipped) { carry = dt; continue; }
             carry = 0.0;
-            c0 += info.ml_iters; c1 += info.cost_evals; c2 += info.gain_evals; c4 += 1;
-            if (info.status & ~(KO_ST_MAXITER)) c3 += 1;
+            c0 += info.ml_iters; c1 += info.cost_evals; c2 += info.gain_evals;
+            if (!(info.status & KO_ST_UNINIT)) c4 += 1; /* an update is an event that reaches the predict / update */
+            if (info.status & ~(KO_ST_MAXITER | KO_ST_UNINIT)) c3 += 1;
             st_or |= info.status;
         }
+        if (tagz) tagz[f] = flt.tag_z;
         x[0 * N + f] = flt.pos[0]; x[1 * N + f] = flt.pos[1];
         x[2 * N + f] = flt.vel[0]; x[3 * N + f] = flt.vel[1];
         x[4 * N + f] = 0.0; x[5 * N + f] = 0.0;
@@ -114,14 +117,14 @@ void ko_t9_events(int64_t N, int n_events, const ko_event *ev, int M, const doub
                   int fmt, double err_scalar, const double *err_arr, const double *sensors, double accel_noise,
                   double jolt, double *x, double *P, double *traj, double *counters, int32_t *status, int threads) {
     ko_t9_events_sel(N, n_events, ev, M, anchors, ranges, fmt, err_scalar, err_arr, sensors, accel_noise, jolt, 0, 0, 0,
-                     x, P, traj, counters, status, threads);
+                     x, P, traj, counters, status, threads, 0);
 }
 
 /* variant != 0: the EKF-side NLOS variants (ko_t9_new_toa selects the rangings first) */
 void ko_t9_events_sel(int64_t N, int n_events, const ko_event *ev, int M, const double *anchors, const void *ranges,
                       int fmt, double err_scalar, const double *err_arr, const double *sensors, double accel_noise,
                       double jolt, int variant, int n_ignore, int best_mode, double *x, double *P, double *traj,
-                      double *counters, int32_t *status, int threads) {
+                      double *counters, int32_t *status, int threads, int ml_init) {
     double c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
 #ifdef _OPENMP
     if (threads > 0) omp_set_num_threads(threads);
@@ -132,6 +135,7 @@ void ko_t9_events_sel(int64_t N, int n_events, const ko_event *ev, int M, const 
         double p0[3] = {x[0 * N + f], x[1 * N + f], x[2 * N + f]};
         ko_t9_init(&flt, accel_noise, jolt, p0);
         flt.variant = variant; flt.n_ignore = n_ignore; flt.best_mode = best_mode;
+        flt.ml_init = ml_init;
         for (int k = 0; k < 3; ++k) flt.vel[k] = x[(int64_t)(3 + k) * N + f];
         for (int k = 0; k < 81; ++k) flt.P[k] = P[(int64_t)k * N + f];
         int st_or = 0, n_toa = 0;
@@ -153,8 +157,9 @@ void ko_t9_events_sel(int64_t N, int n_events, const ko_event *ev, int M, const 
                 double a[3] = {sensors[o * N + f], sensors[(o + 1) * N + f], sensors[(o + 2) * N + f]};
                 ko_t9_new_imu(&flt, ev[e].dt, a, ev[e].aux, &info);
             }
-            c0 += info.ml_iters; c1 += info.cost_evals; c2 += info.gain_evals; c4 += 1;
-            if (info.status & ~(KO_ST_MAXITER)) c3 += 1;
+            c0 += info.ml_iters; c1 += info.cost_evals; c2 += info.gain_evals;
+            if (!(info.status & KO_ST_UNINIT)) c4 += 1;
+            if (info.status & ~(KO_ST_MAXITER | KO_ST_UNINIT)) c3 += 1;
             st_or |= info.status;
         }
         for (int k = 0; k < 3; ++k) {

@@ -462,6 +462,35 @@ static void k8_estimate(ko_k8 *f, double dt, int has_r, const ko_meas *m, int n,
     double F[64], Q[64], x[8], xp[8];
     memset(info, 0, sizeof *info);
     info->ignored = -1;
+    if (f->ml_init && (isnan(f->pos[0]) || isnan(f->pos[1]))) {
+        /* KF.cpp:244-285: the first position comes from ML, started at (1, 1, tag height) in 2-D or (1, 1, 4)
+         * in 3-D (then the tag height becomes the estimated z); the 2x2 position block of the ML covariance
+         * goes into the all-zero estimation covariance; nothing else happens in this call. */
+        info->status |= KO_ST_UNINIT;
+        if (has_r) {
+            double p[3], c[9];
+            int it = 0, rc, d;
+            if (f->use_fixed_height) {
+                const double start[3] = {1.0, 1.0, f->tag_z};
+                rc = ko_ml2d(m, n, start, b1_zero_z, p, c, &it);
+                d = 2;
+            } else {
+                const double start[3] = {1.0, 1.0, 4.0};
+                rc = ko_ml3d(m, n, start, p, c, &it);
+                d = 3;
+            }
+            info->ml_iters += it;
+            if (rc < 0) { info->status |= KO_ST_SINGULAR; return; } /* throws before mPosition is assigned */
+            f->pos[0] = p[0]; f->pos[1] = p[1];
+            if (!f->use_fixed_height) f->tag_z = p[2];
+            /* too few rangings: the solver returns its start point with an EMPTY covariance matrix; the
+             * position (and tag height) are assigned, then covarianceMatrix(0,0) throws (KF.cpp:267) */
+            if (rc == 1) { info->status |= KO_ST_ML_FEW; return; }
+            f->P[0 * 8 + 0] = c[0 * d + 0]; f->P[1 * 8 + 0] = c[1 * d + 0];
+            f->P[0 * 8 + 1] = c[0 * d + 1]; f->P[1 * 8 + 1] = c[1 * d + 1];
+        }
+        return;
+    }
     x[0] = f->pos[0]; x[1] = f->pos[1];
     x[2] = f->vel[0]; x[3] = f->vel[1];
     x[4] = f->acc[0]; x[5] = f->acc[1]; /* always 0: never written back (B-9) */
@@ -529,7 +558,7 @@ void ko_k8_new_toa(ko_k8 *f, double dt, int n_slots, const double *ranges, const
                    const double *errs, int b1_zero_z, ko_info *info) {
     ko_meas m[KO_MAX_ANCHORS];
     int n = gather(n_slots, ranges, anchors, errs, m);
-    if (f->variant == 0) {
+    if (f->variant == 0 || (f->ml_init && (isnan(f->pos[0]) || isnan(f->pos[1])))) {
         k8_estimate(f, dt, 1, m, n, f->has_px4, f->has_imu, f->has_mag, b1_zero_z, info);
         return;
     }
@@ -696,6 +725,23 @@ static void t9_estimate(ko_t9 *f, double dt, int has_r, const ko_meas *m, int n,
     double F[81], Q[81], x[9], xp[9];
     memset(info, 0, sizeof *info);
     info->ignored = -1;
+    if (f->ml_init && (isnan(f->pos[0]) || isnan(f->pos[1]))) {
+        /* TOAIMU.cpp:118-162: 3-D ML from (1, 1, 4); only the 2x2 x-y block of its covariance is copied */
+        info->status |= KO_ST_UNINIT;
+        if (has_r) {
+            const double start[3] = {1.0, 1.0, 4.0};
+            double p[3], c[9];
+            int it = 0;
+            int rc = ko_ml3d(m, n, start, p, c, &it);
+            info->ml_iters += it;
+            if (rc < 0) { info->status |= KO_ST_SINGULAR; return; }
+            f->pos[0] = p[0]; f->pos[1] = p[1]; f->pos[2] = p[2];
+            if (rc == 1) { info->status |= KO_ST_ML_FEW; return; } /* empty covariance: (0,0) throws (:133) */
+            f->P[0 * 9 + 0] = c[0]; f->P[1 * 9 + 0] = c[3];
+            f->P[0 * 9 + 1] = c[1]; f->P[1 * 9 + 1] = c[4];
+        }
+        return;
+    }
     for (int i = 0; i < 3; ++i) { x[i] = f->pos[i]; x[3 + i] = f->vel[i]; x[6 + i] = f->acc[i]; }
     t9_FQ(f->jolt, dt, F, Q);
     matvec(9, F, x, xp);
@@ -739,7 +785,7 @@ void ko_t9_new_toa(ko_t9 *f, double dt, int n_slots, const double *ranges, const
                    const double *errs, ko_info *info) {
     ko_meas m[KO_MAX_ANCHORS];
     int n = gather(n_slots, ranges, anchors, errs, m);
-    if (f->variant == 0) {
+    if (f->variant == 0 || (f->ml_init && (isnan(f->pos[0]) || isnan(f->pos[1])))) {
         t9_estimate(f, dt, 1, m, n, f->has_imu, info);
         return;
     }

@@ -43,14 +43,14 @@ class KoK8(C.Structure):
                 ("imu_wz", C.c_double), ("imu_cwz", C.c_double), ("imu_ax", C.c_double),
                 ("imu_ay", C.c_double), ("imu_cxy", C.c_double * 4),
                 ("mag_angle", C.c_double), ("mag_c", C.c_double),
-                ("variant", C.c_int), ("n_ignore", C.c_int), ("best_mode", C.c_int)]
+                ("variant", C.c_int), ("n_ignore", C.c_int), ("best_mode", C.c_int), ("ml_init", C.c_int)]
 
 
 class KoT9(C.Structure):
     _fields_ = [("accel_noise", C.c_double), ("jolt", C.c_double), ("pos", C.c_double * 3),
                 ("vel", C.c_double * 3), ("acc", C.c_double * 3), ("P", C.c_double * 81),
                 ("has_imu", C.c_int), ("imu_a", C.c_double * 3), ("imu_cov", C.c_double * 9),
-                ("variant", C.c_int), ("n_ignore", C.c_int), ("best_mode", C.c_int)]
+                ("variant", C.c_int), ("n_ignore", C.c_int), ("best_mode", C.c_int), ("ml_init", C.c_int)]
 
 
 def build(force: bool = False) -> str:
@@ -212,8 +212,11 @@ def k8_cfg(accel_noise=0.5, jolt=0.5, **cfg):
     return c
 
 
-def k8_replay(x0, P0, events, ranges, sensors, anchors, err, cfg, b1_zero_z=False, want_traj=False, threads=0):
-    """x0 [8][N]; ranges [T][M][N] or None; sensors [R][N] or None; events: (kind, dt, offset_row[, aux])."""
+def k8_replay(x0, P0, events, ranges, sensors, anchors, err, cfg, b1_zero_z=False, want_traj=False, threads=0,
+              tagz=None):
+    """x0 [8][N]; ranges [T][M][N] or None; sensors [R][N] or None; events: (kind, dt, offset_row[, aux]).
+    cfg.ml_init = 1: filters whose x0 position is NaN initialise themselves from their first epoch with
+    rangings (KF.cpp:244-285); `tagz` [N] then carries the per-filter tag height in and out."""
     anchors = np.ascontiguousarray(anchors, dtype=np.float64)
     M = len(anchors)
     x = np.array(x0, dtype=np.float64, order="C", copy=True)
@@ -228,15 +231,19 @@ def k8_replay(x0, P0, events, ranges, sensors, anchors, err, cfg, b1_zero_z=Fals
     counters = np.zeros(5)
     status = np.zeros(N, dtype=np.int32)
     arr = _events(events)
+    tz = None
+    if cfg.ml_init:
+        tz = np.full(N, cfg.tag_z) if tagz is None else np.array(tagz, dtype=np.float64, copy=True)
     lib().ko_k8_replay(C.c_int64(N), len(events), arr, M, _p(anchors), _vp(ranges),
                        FMT[ranges.dtype] if ranges is not None else 0,
                        C.c_double(err if err_arr is None else 0.0), _p(err_arr), _p(sensors), C.byref(cfg),
-                       int(b1_zero_z), _p(x), _p(P), _p(traj), _p(counters), _p(status, C.c_int32), int(threads))
-    return dict(x=x, P=P, traj=traj, counters=counters, status=status)
+                       int(b1_zero_z), _p(x), _p(P), _p(traj), _p(counters), _p(status, C.c_int32), int(threads),
+                       _p(tz))
+    return dict(x=x, P=P, traj=traj, counters=counters, status=status, tagz=tz)
 
 
 def t9_events(x0, P0, events, ranges, sensors, anchors, err, accel_noise=0.5, jolt=0.5, want_traj=False,
-              threads=0, variant=0, n_ignore=0, best_mode=0):
+              threads=0, variant=0, n_ignore=0, best_mode=0, ml_init=0):
     anchors = np.ascontiguousarray(anchors, dtype=np.float64)
     M = len(anchors)
     x = np.array(x0, dtype=np.float64, order="C", copy=True)
@@ -255,7 +262,7 @@ def t9_events(x0, P0, events, ranges, sensors, anchors, err, accel_noise=0.5, jo
                            FMT[ranges.dtype] if ranges is not None else 0,
                            C.c_double(err if err_arr is None else 0.0), _p(err_arr), _p(sensors),
                            C.c_double(accel_noise), C.c_double(jolt), int(variant), int(n_ignore), int(best_mode),
-                           _p(x), _p(P), _p(traj), _p(counters), _p(status, C.c_int32), int(threads))
+                           _p(x), _p(P), _p(traj), _p(counters), _p(status, C.c_int32), int(threads), int(ml_init))
     return dict(x=x, P=P, traj=traj, counters=counters, status=status)
 
 
@@ -345,10 +352,12 @@ class K8:
 
 
 class T9:
-    def __init__(self, accel_noise, jolt, p0):
+    def __init__(self, accel_noise, jolt, p0, **cfg):
         self.f = KoT9()
         p0 = np.ascontiguousarray(p0, dtype=np.float64)
         lib().ko_t9_init(C.byref(self.f), C.c_double(accel_noise), C.c_double(jolt), _p(p0))
+        for k, v in cfg.items():
+            setattr(self.f, k, v)
         self.info = KoInfo()
 
     def new_toa(self, dt, ranges, anchors, errs):

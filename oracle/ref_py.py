@@ -44,8 +44,10 @@ def lib():
     global _LIB
     if _LIB is None:
         l = C.CDLL(SO)
-        for n in ("ref_ml_create", "ref_t6_create", "ref_k8_create", "ref_t9_create"):
+        for n in ("ref_ml_create", "ref_t6_create", "ref_k8_create", "ref_t9_create", "ref_k8_create_nofix",
+                  "ref_t9_create_nofix"):
             getattr(l, n).restype = C.c_void_p
+        l.ref_k8_tag_z.restype = C.c_double
         if l.ref_init(find_lapack().encode()) != 0:
             raise RuntimeError("libkfref: cannot load LAPACK from scipy's OpenBLAS")
         _LIB = l
@@ -121,8 +123,11 @@ class RefK8:
         params.update(xml or {})
         for k, v in params.items():
             lib().ref_set_param(k.encode(), v.encode())
-        h = lib().ref_k8_create(C.c_double(accel_noise), C.c_double(init_angle), C.c_double(jolt),
-                                C.c_double(p0[0]), C.c_double(p0[1]), C.c_double(p0[2] if len(p0) > 2 else 0.0))
+        if p0 is None:  # the constructor without initialPosition: ML initialisation (KF.cpp:244-285)
+            h = lib().ref_k8_create_nofix(C.c_double(accel_noise), C.c_double(init_angle), C.c_double(jolt))
+        else:
+            h = lib().ref_k8_create(C.c_double(accel_noise), C.c_double(init_angle), C.c_double(jolt),
+                                    C.c_double(p0[0]), C.c_double(p0[1]), C.c_double(p0[2] if len(p0) > 2 else 0.0))
         if not h:
             raise RuntimeError("KalmanFilter::init() failed")
         self.h = C.c_void_p(h)
@@ -151,6 +156,9 @@ class RefK8:
         lib().ref_k8_get(self.h, _p(x), _p(P))
         return x, P.reshape(8, 8)
 
+    def tag_z(self):
+        return float(lib().ref_k8_tag_z(self.h))
+
     def __del__(self):
         if _LIB is not None and self.h:
             _LIB.ref_k8_destroy(self.h)
@@ -158,8 +166,11 @@ class RefK8:
 
 class RefT9:
     def __init__(self, accel_noise, jolt, p0):
-        self.h = C.c_void_p(lib().ref_t9_create(C.c_double(accel_noise), C.c_double(jolt), C.c_double(p0[0]),
-                                                C.c_double(p0[1]), C.c_double(p0[2])))
+        if p0 is None:  # the constructor without initialPosition (TOAIMU.cpp:6-24)
+            self.h = C.c_void_p(lib().ref_t9_create_nofix(C.c_double(accel_noise), C.c_double(jolt)))
+        else:
+            self.h = C.c_void_p(lib().ref_t9_create(C.c_double(accel_noise), C.c_double(jolt), C.c_double(p0[0]),
+                                                    C.c_double(p0[1]), C.c_double(p0[2])))
 
     def new_toa(self, dt, ranges, anchors, errs):
         r, a, e = valid_only(ranges, anchors, errs)

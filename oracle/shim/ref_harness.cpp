@@ -152,6 +152,21 @@ void *ref_k8_create(double accel_noise, double init_angle, double jolt, double x
     }
     return f;
 }
+// the constructor WITHOUT initialPosition (KF.cpp:6-32): what PosGenerator builds when the launch file
+// leaves useStartPosition at its default 0 (PG.cpp:519-528); the first epoch with rangings initialises
+// the filter through MLLocation (KF.cpp:244-285)
+void *ref_k8_create_nofix(double accel_noise, double init_angle, double jolt) {
+    KalmanFilter *f = new KalmanFilter(accel_noise, init_angle, jolt, "kfpos_pos", "kfpos_px4", "kfpos_tag",
+                                       "kfpos_imu", "kfpos_mag");
+    bool ok = false;
+    guarded([&] { ok = f->init(); });
+    if (!ok) {
+        delete f;
+        return 0;
+    }
+    return f;
+}
+double ref_k8_tag_z(void *h) { return ((KalmanFilter *)h)->mUWBtagZ; }
 void ref_k8_destroy(void *h) { delete (KalmanFilter *)h; }
 
 int ref_k8_toa(void *h, long long dt_ns, int n, const double *ranges, const double *anchors, const double *errs) {
@@ -208,6 +223,8 @@ void ref_k8_get(void *h, double *x8, double *P64) {
 void *ref_t9_create(double accel_noise, double jolt, double x, double y, double z) {
     return new KalmanFilterTOAIMU(accel_noise, jolt, make_v3(x, y, z));
 }
+// the constructor without initialPosition (TOAIMU.cpp:6-24), see ref_k8_create_nofix
+void *ref_t9_create_nofix(double accel_noise, double jolt) { return new KalmanFilterTOAIMU(accel_noise, jolt); }
 void ref_t9_destroy(void *h) { delete (KalmanFilterTOAIMU *)h; }
 int ref_t9_toa(void *h, long long dt_ns, int n, const double *ranges, const double *anchors, const double *errs) {
     KalmanFilterTOAIMU *f = (KalmanFilterTOAIMU *)h;

@@ -85,6 +85,13 @@ struct kfpos_batch {
     int32_t *d_xq = nullptr; // epochs handed to the exact-order solver (kfpos_exact.cu)
     int xq_cap = 0;
     int32_t *d_has = nullptr;
+    // ml_initial_position (K8 / T9): while a filter may still be uninitialised the replays run through the
+    // general kernel instantiation, which carries the ML-initialisation branch.  Every such launch leaves a
+    // flag behind (d_uninit: some filter still has a NaN position); it is copied to pinned host memory behind
+    // the launch and looked at -- without waiting -- by the next call.
+    bool uninit_possible = false, uninit_pending = false;
+    int *d_uninit = nullptr, *h_uninit = nullptr;
+    cudaEvent_t ev_uninit = nullptr;
     DevBuf scratch[N_SCRATCH];
     DevBuf stage[2];
     cudaStream_t copy_stream = nullptr;
@@ -217,6 +224,9 @@ extern "C" int kfpos_batch_create(kfpos_batch **out, int device, int model, int6
         alloc((void **)&b->d_latch, sizeof(double) * 16 * N);
         alloc((void **)&b->d_has, sizeof(int32_t) * N);
         alloc((void **)&b->d_latch_u, sizeof(double) * 16);
+        alloc((void **)&b->d_uninit, sizeof(int));
+        if (e == cudaSuccess) e = cudaHostAlloc((void **)&b->h_uninit, sizeof(int), cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_uninit, cudaEventDisableTiming);
     }
     if (model == KFPOS_MODEL_ML) {
         if (n_filters > 0x7fffffffLL) {
@@ -257,6 +267,9 @@ extern "C" void kfpos_batch_destroy(kfpos_batch *b) {
     cudaFree(b->d_latch);
     cudaFree(b->d_has);
     cudaFree(b->d_latch_u);
+    cudaFree(b->d_uninit);
+    if (b->h_uninit) cudaFreeHost(b->h_uninit);
+    if (b->ev_uninit) cudaEventDestroy(b->ev_uninit);
     cudaFree(b->d_mlq);
     cudaFree(b->d_mlq_count);
     cudaFree(b->d_xq);
@@ -313,6 +326,10 @@ extern "C" int kfpos_batch_set_state(kfpos_batch *b, const double *x, const doub
     if (b->d_has) CK(cudaMemsetAsync(b->d_has, 0, sizeof(int32_t) * N, s));
     if (b->d_latch) CK(cudaMemsetAsync(b->d_latch, 0, sizeof(double) * 16 * N, s));
     if (b->d_latch_u) CK(cudaMemsetAsync(b->d_latch_u, 0, sizeof(double) * 16, s));
+    if (b->model == KFPOS_MODEL_K8) // per-filter tag height (latch row 9): mUWBtagZ = fixedHeight until a 3-D ML init
+        CK(launch_fill(b->d_latch + 9 * N, b->N, b->cfg.fixed_height, s));
+    b->uninit_possible = b->cfg.ml_initial_position != 0 && (b->model == KFPOS_MODEL_K8 || b->model == KFPOS_MODEL_T9);
+    b->uninit_pending = false;
     b->imu_seen = false; // the latches are cleared above
     b->partials_fresh = false;
     b->out4_valid = false;
@@ -567,7 +584,31 @@ K8Cfg make_k8cfg(const kfpos_batch *b) {
     c.n_ignore = b->cfg.num_ignored_rangings;
     c.best_mode = b->cfg.best_mode;
     c.zero_tz = b->cfg.ml2d_zero_tentative_z != 0;
+    c.use_fixed_height = b->cfg.use_fixed_height != 0;
+    // after a 3-D initialisation the tag height is per filter: only the general instantiation carries it
+    c.ml_init = b->cfg.ml_initial_position != 0 && (b->uninit_possible || !c.use_fixed_height);
     return c;
+}
+
+// ml_initial_position: has the previous launch's "some filter is still uninitialised" flag arrived, and is it 0?
+void poll_uninit(kfpos_batch *b) {
+    if (!b->uninit_possible || !b->uninit_pending) return;
+    if (cudaEventQuery(b->ev_uninit) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    b->uninit_pending = false;
+    if (*b->h_uninit == 0) b->uninit_possible = false;
+}
+int arm_uninit(kfpos_batch *b, cudaStream_t s) {
+    CK(cudaMemsetAsync(b->d_uninit, 0, sizeof(int), s));
+    return KFPOS_OK;
+}
+int fetch_uninit(kfpos_batch *b, cudaStream_t s) {
+    CK(cudaMemcpyAsync(b->h_uninit, b->d_uninit, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CK(cudaEventRecord(b->ev_uninit, s));
+    b->uninit_pending = true;
+    return KFPOS_OK;
 }
 
 // events: HOST array; every data pointer already on the device
@@ -579,6 +620,12 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
     CK(b->scratch[7].reserve(sizeof(EventDesc) * (size_t)n));
     CK(cudaMemcpyAsync(b->scratch[7].p, events, sizeof(EventDesc) * (size_t)n, cudaMemcpyHostToDevice, s));
     const RangeStream rs = make_rs(b, d_ranges, fmt, err_scalar, d_err);
+    poll_uninit(b);
+    const bool track_uninit = b->uninit_possible;
+    if (track_uninit) {
+        int rc = arm_uninit(b, s);
+        if (rc) return rc;
+    }
     switch (b->model) {
     case KFPOS_MODEL_K8: {
         K8Params p;
@@ -595,6 +642,7 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.latch = b->d_latch;
         p.has = b->d_has;
         p.latch_u = b->d_latch_u;
+        p.uninit = track_uninit ? b->d_uninit : nullptr;
         p.dt_f = d_dt_f;
         p.traj = d_traj;
         p.counters = b->d_counters;
@@ -626,6 +674,8 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.variant = b->cfg.variant;
         p.n_ignore = b->cfg.num_ignored_rangings;
         p.best_mode = b->cfg.best_mode;
+        p.ml_init = track_uninit ? 1 : 0;
+        p.uninit = track_uninit ? b->d_uninit : nullptr;
         p.dt_f = d_dt_f;
         p.traj = d_traj;
         p.counters = b->d_counters;
@@ -637,6 +687,10 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         break;
     }
     default: return KFPOS_ERR_INVALID;
+    }
+    if (track_uninit) {
+        int rc = fetch_uninit(b, s);
+        if (rc) return rc;
     }
     // (the host event array may be a temporary of the caller: a copy from pageable memory has left the
     // caller's buffer when cudaMemcpyAsync returns, so no synchronisation is needed here)
@@ -811,7 +865,10 @@ extern "C" int kfpos_batch_get_pose_msg(kfpos_batch *b, double dt, double *pose1
     if ((rc = stage_out(b, 4, pose13, sizeof(double) * 13 * N, &d_pose, &c_pose))) return rc;
     if ((rc = stage_out(b, 5, cov36, sizeof(double) * 36 * N, &d_cov, &c_cov))) return rc;
     const int model = b->model == KFPOS_MODEL_T6 ? 1 : (b->model == KFPOS_MODEL_K8 ? 2 : 3);
-    CK(launch_pose_msg(model, b->N, b->cfg.fixed_height, dx, dP, (double *)d_pose, (double *)d_cov, s));
+    // K8 without useFixedHeight: the tag height of an ML-initialised filter is its own (KF.cpp:256-257, 328-332)
+    const double *tagz = (b->model == KFPOS_MODEL_K8 && b->cfg.ml_initial_position && !b->cfg.use_fixed_height)
+                             ? b->d_latch + 9 * N : nullptr;
+    CK(launch_pose_msg(model, b->N, b->cfg.fixed_height, tagz, dx, dP, (double *)d_pose, (double *)d_cov, s));
     if (c_pose) CK(cudaMemcpyAsync(pose13, d_pose, sizeof(double) * 13 * N, cudaMemcpyDeviceToHost, s));
     if (c_cov) CK(cudaMemcpyAsync(cov36, d_cov, sizeof(double) * 36 * N, cudaMemcpyDeviceToHost, s));
     if (c_pose || c_cov) CK(cudaStreamSynchronize(s));

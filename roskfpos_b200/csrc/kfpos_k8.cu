@@ -95,6 +95,9 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
         double carry = p.latch[8 * N + f];
         double ic00 = p.latch_u[0], ic01 = p.latch_u[1], ic11 = p.latch_u[2], icw = p.latch_u[3];
         int n_toa = 0;
+        // the tag height is per filter only after a 3-D ML initialisation (KF.cpp:256-257); general kernel only
+        const bool z_per_filter = SEL && p.cfg.ml_init && !p.cfg.use_fixed_height;
+        double tag_z = z_per_filter ? p.latch[9 * N + f] : p.cfg.tag_z;
 
         if (p.n_events > 0) prefetch_event(raw, land, p.events[0], m, p.rs, p.sensors, N, f);
         for (int e = 0; e < p.n_events; ++e) {
@@ -172,6 +175,39 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
             if (e + 1 < p.n_events) prefetch_event(raw, land, p.events[e + 1], m, p.rs, p.sensors, N, f);
             if (skip) {
                 carry += dt_ev;
+            } else if (SEL && p.cfg.ml_init && (isnan(px) || isnan(py))) {
+                // ---- the constructor without initialPosition (KF.cpp:244-285): the clock is read, the sample is
+                // latched (above), and an epoch with rangings initialises position and the 2x2 position block
+                // of the all-zero covariance from MLLocation; no predict, no update
+                carry = 0.0;
+                st.status |= 256u;
+                if (has_r) {
+                    const bool fh = p.cfg.use_fixed_height != 0;
+                    double p0[3] = {1.0, 1.0, fh ? tag_z : 4.0}, sse0, c0[6] = {0, 0, 0, 0, 0, 0};
+                    int irc;
+                    if (fh) irc = ml_solve2<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, c0, nullptr, p.cfg.zero_tz != 0);
+                    else irc = ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, c0);
+                    if (irc == ML_SINGULAR) {
+                        st.status |= 4u; // the solver throws before mPosition is assigned
+                    } else {
+                        px = p0[0]; py = p0[1];
+                        if (!fh) tag_z = p0[2];
+                        // too few rangings: the start point comes back with an EMPTY covariance matrix, whose
+                        // (0,0) throws after position (and tag height) have been assigned (KF.cpp:267)
+                        if (irc == ML_FEW) st.status |= 2u;
+                        else { Pm[0] = c0[0]; Pm[1] = c0[1]; Pm[2] = c0[2]; } // xx, yx, yy (both packings agree)
+                    }
+                }
+                if (st.status & ~(32u | 64u | 256u)) n_bad += 1;
+                status_or |= st.status;
+                if (ev.kind == EV_TOA) {
+                    if (p.traj) {
+                        p.traj[((int64_t)n_toa * 3 + 0) * N + f] = px;
+                        p.traj[((int64_t)n_toa * 3 + 1) * N + f] = py;
+                        p.traj[((int64_t)n_toa * 3 + 2) * N + f] = th;
+                    }
+                    ++n_toa;
+                }
             } else {
                 const double dt = dt_ev + carry;
                 carry = 0.0;
@@ -194,7 +230,7 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                 unsigned used = ep.valid;
                 if (SEL && has_r) {
                     const int n = __popc(ep.valid);
-                    const double start[3] = {xp[0], xp[1], p.cfg.tag_z};
+                    const double start[3] = {xp[0], xp[1], tag_z};
                     double p0[3] = {start[0], start[1], start[2]}, sse0, cov0[6];
                     if (p.cfg.variant == 1 && n > 0) {
                         if (ml_solve2<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, nullptr, nullptr,
@@ -212,7 +248,7 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                                                 cov0, used, grc, p.cfg.zero_tz != 0);
                     }
                 }
-                const int rc = k8_update<PME, MT>(p.anchors, p.cfg, ep, has_r, used, ms, dt, xp, Pm, Pw, dx, st,
+                const int rc = k8_update<PME, MT>(p.anchors, p.cfg, tag_z, ep, has_r, used, ms, dt, xp, Pm, Pw, dx, st,
                                                   SEL ? 0u : wmask);
                 if (rc == 0) {
                     px = xp[0] + dx[0]; py = xp[1] + dx[1];
@@ -248,13 +284,15 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
         for (int k = 0; k < 8; ++k) p.latch[(int64_t)k * N + f] = latch[k];
         p.has[f] = (int32_t)has;
         p.latch[8 * N + f] = carry;
+        if (z_per_filter) p.latch[9 * N + f] = tag_z;
+        if (SEL && p.uninit && (isnan(px) || isnan(py))) *p.uninit = 1;
         int32_t st_all = (int32_t)status_or;
         if (p.status) {
             st_all |= p.status[f];
             p.status[f] = st_all;
         }
         // planar filter: z is the configured tag height (KF.cpp:328-332)
-        if (p.truth) filter_error_terms(px, py, p.cfg.tag_z, p.truth, N, f, st_all != 0, errv);
+        if (p.truth) filter_error_terms(px, py, tag_z, p.truth, N, f, st_all != 0, errv);
         if (f == 0) {
             p.latch_u[0] = ic00; p.latch_u[1] = ic01; p.latch_u[2] = ic11; p.latch_u[3] = icw;
         }
@@ -280,7 +318,7 @@ static cudaError_t launch_k(const K8Params &p, cudaStream_t s) {
 
 cudaError_t launch_k8_replay(const K8Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
-    if (p.cfg.variant == 1 || p.cfg.variant == 2 || p.dt_f != nullptr) // the general instantiation
+    if (p.cfg.variant == 1 || p.cfg.variant == 2 || p.dt_f != nullptr || p.cfg.ml_init) // the general instantiation
         return p.rs.err != nullptr ? launch_k<true, 0, true>(p, s) : launch_k<false, 0, true>(p, s);
     if (p.rs.err != nullptr) return launch_k<true, 0>(p, s);
     if (p.rs.m_slots == 8 && !p.cfg.zero_tz) return launch_k<false, 8>(p, s);

@@ -62,14 +62,14 @@ struct K8Meas {
 // accelerometer pair as a 2x2 block: its covariance may carry off-diagonals, KF.cpp:431-434).
 // wmask: lanes that run this event together, re-converged after the Newton loop (0 = none).
 template <bool PME, int MT>
-KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const EpochT<PME, MT> &ep, bool has_r, unsigned used,
-                     const K8Meas &ms, double dt, const double (&xp)[8], const Col &Pm, Sym<8> &Pw, double (&dx)[8],
-                     StepStats &st, unsigned wmask) {
+KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, double tag_z, const EpochT<PME, MT> &ep, bool has_r,
+                     unsigned used, const K8Meas &ms, double dt, const double (&xp)[8], const Col &Pm, Sym<8> &Pw,
+                     double (&dx)[8], StepStats &st, unsigned wmask) {
     const unsigned mask = has_r ? used : 0u; // used = ep.valid, or the EKF-side variant's selection
     double sse = -1.0;
     int rc = ML_OK;
     if (has_r) { // inner ML 2-D solve from (x^-_0, x^-_1, tagZ) (KF.cpp:403-405)
-        double pml[3] = {xp[0], xp[1], cfg.tag_z};
+        double pml[3] = {xp[0], xp[1], tag_z};
         rc = ml_solve2<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr, nullptr, cfg.zero_tz != 0);
         if (mask == 0u) sse = -1.0; // estimationError of an empty list
         // has_r is a property of the event, common to the batch: every lane of wmask is here
@@ -99,7 +99,7 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, const EpochT<PME, M
         double c = 0.0, b[3] = {0.0, 0.0, 0.0}, G[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         if (mask) {
             const double dx3[3] = {dx[0], dx[1], 0.0};
-            iekf_pass<PME, MT, 2>(A, ep, mask, sse, xp[0] + dx[0], xp[1] + dx[1], cfg.tag_z, dx3, c, b, G);
+            iekf_pass<PME, MT, 2>(A, ep, mask, sse, xp[0] + dx[0], xp[1] + dx[1], tag_z, dx3, c, b, G);
             if (!PME) c *= invR0;
         }
         double sn = 0.0, cs = 1.0, sw = 0.0, cw = 1.0;

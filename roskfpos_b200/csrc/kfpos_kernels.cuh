@@ -143,6 +143,10 @@ struct K8Cfg {
     int imu_fix_acc, imu_fix_gyro;
     int variant, n_ignore, best_mode; // EKF-side NLOS variants (config_pos.xml; 0 = normal)
     int zero_tz;                      // ml2d_zero_tentative_z (App. B-1 as a zero-initialising build computes it)
+    // the constructor without initialPosition (kfpos_config.ml_initial_position, KF.cpp:244-285): a filter whose
+    // position is NaN initialises itself from its first epoch with rangings -- 2-D ML from (1, 1, tag height)
+    // when use_fixed_height, else 3-D ML from (1, 1, 4), whose z becomes THIS filter's tag height (latch row 9)
+    int ml_init, use_fixed_height;
 };
 
 struct K8Params {
@@ -156,8 +160,9 @@ struct K8Params {
     double *x;       // SoA [8][N]
     double *P;       // SoA [36][N] packed
     int32_t *status; // [N]
-    double *latch;   // SoA [8][N]: px4 vx,vy,gz,cv | imu ax,ay,wz | mag angle
+    double *latch;   // SoA [16][N]: px4 vx,vy,gz,cv | imu ax,ay,wz | mag angle | [8] dt carry | [9] tag height
     int32_t *has;    // [N] bit0 px4, bit1 imu, bit2 mag latched
+    int *uninit;     // null, or a flag set by every filter that is still uninitialised when the launch ends
     double *latch_u; // [4] batch-wide latched IMU covariances c00,c01,c11,cw
     const double *dt_f; // null, or per-filter time steps SoA [n_events][N] (see T9Params)
     double *traj;    // SoA [n_toa][3][N] (px, py, theta) after each TOA event, or null
@@ -191,6 +196,8 @@ struct T9Params {
                         // filter has no such event) -- the ragged epochs of kfpos_batch_replay_epochs
     int no_imu;      // host knowledge: no IMU sample latched and none in this schedule -> lean kernel
     int variant, n_ignore, best_mode; // EKF-side NLOS variants (config_pos.xml; 0 = normal)
+    int ml_init;     // the constructor without initialPosition (TOAIMU.cpp:118-162), see K8Cfg::ml_init
+    int *uninit;     // see K8Params
     double *traj;    // SoA [n_toa][3][N] or null
     unsigned long long *counters;
     const double *truth; // see T6Params
@@ -218,8 +225,10 @@ cudaError_t launch_error_stats(int64_t N, const double *x, int zrow, double zcon
 cudaError_t launch_error_stats_tree(int64_t n, double *part, double *out4, cudaStream_t s);
 
 // getPose report in the publisher's layout (kfpos_misc.cu); model 1 = T6, 2 = K8, 3 = T9
-cudaError_t launch_pose_msg(int model, int64_t N, double tag_z, const double *x_pred, const double *P_pred_full,
-                            double *pose13, double *cov36, cudaStream_t s);
+// tagz: null, or the per-filter tag height replacing tag_z (K8 after a 3-D ML initialisation)
+cudaError_t launch_pose_msg(int model, int64_t N, double tag_z, const double *tagz, const double *x_pred,
+                            const double *P_pred_full, double *pose13, double *cov36, cudaStream_t s);
+cudaError_t launch_fill(double *p, int64_t n, double v, cudaStream_t s);
 
 // epoch assembler (kfpos_assemble.cu): N logs of L messages, SoA [L][N]
 struct AssembleParams {

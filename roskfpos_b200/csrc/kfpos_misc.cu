@@ -138,10 +138,11 @@ cudaError_t measure_fp64_peak(double *flops_per_s) {
 // (Posgenerator.cpp:385-470): pose SoA [13][N] = x, y, z, rotX, rotY, rotZ, rotW, linearSpeed(3),
 // angularSpeed(3); cov SoA [36][N], cov[i] = covarianceMatrix(i), Armadillo's column-major index.
 // x: SoA [n][N] predicted state; Pf: SoA [n*n][N] predicted covariance, row-major.
-__global__ void pose_msg_kernel(int model, int64_t N, double tag_z, const double *x, const double *Pf, double *pose,
-                                double *cov) {
+__global__ void pose_msg_kernel(int model, int64_t N, double tag_z, const double *tagz, const double *x,
+                                const double *Pf, double *pose, double *cov) {
     const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (f >= N) return;
+    if (tagz) tag_z = tagz[f]; // per-filter tag height (K8 after a 3-D ML initialisation)
     const int n = model == 1 ? 6 : (model == 2 ? 8 : 9);
     auto X = [&](int i) { return x[(int64_t)i * N + f]; };
     auto P = [&](int i, int j) { return Pf[(int64_t)(i * n + j) * N + f]; };
@@ -189,10 +190,20 @@ __global__ void pose_msg_kernel(int model, int64_t N, double tag_z, const double
     }
 }
 
-cudaError_t launch_pose_msg(int model, int64_t N, double tag_z, const double *x_pred, const double *P_pred_full,
-                            double *pose13, double *cov36, cudaStream_t s) {
+cudaError_t launch_pose_msg(int model, int64_t N, double tag_z, const double *tagz, const double *x_pred,
+                            const double *P_pred_full, double *pose13, double *cov36, cudaStream_t s) {
     if (N <= 0) return cudaSuccess;
-    pose_msg_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(model, N, tag_z, x_pred, P_pred_full, pose13, cov36);
+    pose_msg_kernel<<<(unsigned)((N + 127) / 128), 128, 0, s>>>(model, N, tag_z, tagz, x_pred, P_pred_full, pose13, cov36);
+    return cudaGetLastError();
+}
+
+__global__ void fill_kernel(double *p, int64_t n, double v) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+cudaError_t launch_fill(double *p, int64_t n, double v, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    fill_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(p, n, v);
     return cudaGetLastError();
 }
 

@@ -268,6 +268,41 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
                     continue;
                 }
             }
+            if (SEL && p.ml_init && (isnan(pos[0]) || isnan(pos[1]))) {
+                // ---- the constructor without initialPosition (TOAIMU.cpp:118-162): the sample is latched, an
+                // epoch with rangings initialises the position from the 3-D ML estimate started at (1, 1, 4)
+                // and the 2x2 x-y block of the all-zero covariance from its covariance; no predict, no update
+                cp_async_wait_all();
+                st.status = 256u;
+                if (ev.kind == EV_TOA) {
+                    convert_epoch<PME, MT>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, ev.offset * N + f, N);
+                    if (e + 1 < p.n_events) prefetch(p.events[e + 1]);
+                    double p0[3] = {1.0, 1.0, 4.0}, sse0, c0[6] = {0, 0, 0, 0, 0, 0};
+                    const int irc = ml_solve3<PME, MT>(p.anchors, ep, ep.valid, p0, sse0, st.ml_iters, c0);
+                    if (irc == ML_SINGULAR) {
+                        st.status |= 4u; // the solver throws before mPosition is assigned
+                    } else {
+                        pos[0] = p0[0]; pos[1] = p0[1]; pos[2] = p0[2];
+                        if (irc == ML_FEW) st.status |= 2u; // empty covariance matrix: (0,0) throws (:133)
+                        else { Pm[0] = c0[0]; Pm[1] = c0[1]; Pm[2] = c0[2]; }
+                    }
+                    if (p.traj) {
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) p.traj[((int64_t)n_toa * 3 + k) * N + f] = pos[k];
+                    }
+                    ++n_toa;
+                } else {
+                    za[0] = land[0]; za[1] = land[1]; za[2] = land[2];
+                    Ra[0] = ev.aux[0]; Ra[1] = 0.5 * (ev.aux[1] + ev.aux[3]); Ra[2] = ev.aux[4];
+                    Ra[3] = 0.5 * (ev.aux[2] + ev.aux[6]); Ra[4] = 0.5 * (ev.aux[5] + ev.aux[7]); Ra[5] = ev.aux[8];
+                    asym = ev.aux[1] != ev.aux[3] || ev.aux[2] != ev.aux[6] || ev.aux[5] != ev.aux[7];
+                    has |= 2u;
+                    if (e + 1 < p.n_events) prefetch(p.events[e + 1]);
+                }
+                if (st.status & ~(32u | 64u | 256u)) n_bad += 1;
+                status_or |= st.status;
+                continue;
+            }
             // ---- predict (TOAIMU.cpp:165-180): a = 0 at the start of every step.  Done before the
             // event's payload is unpacked so that the epoch's ranges are not live across it.
             Sym<9> Pw;
@@ -363,6 +398,7 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
             p.status[f] = st_all;
         }
         if (p.truth) filter_error_terms(pos[0], pos[1], pos[2], p.truth, N, f, st_all != 0, errv);
+        if (SEL && p.uninit && (isnan(pos[0]) || isnan(pos[1]))) *p.uninit = 1;
         if (f == 0 && (has & 2u)) {
             // keep the symmetric part as the latched covariance
             p.latch_u[0] = Ra[0]; p.latch_u[1] = Ra[1]; p.latch_u[2] = Ra[3];
@@ -391,7 +427,7 @@ static cudaError_t launch_k(const T9Params &p, cudaStream_t s) {
 
 cudaError_t launch_t9_replay(const T9Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
-    if (p.variant == 1 || p.variant == 2 || p.dt_f != nullptr) // the general instantiation
+    if (p.variant == 1 || p.variant == 2 || p.dt_f != nullptr || p.ml_init) // the general instantiation
         return p.rs.err != nullptr ? launch_k<true, 0, true, true>(p, s) : launch_k<false, 0, true, true>(p, s);
     if (p.no_imu) {
         if (p.rs.err != nullptr) return launch_k<true, 0, false>(p, s);

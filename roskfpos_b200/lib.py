@@ -17,6 +17,7 @@ MODEL_ML, MODEL_T6, MODEL_K8, MODEL_T9 = 0, 1, 2, 3
 FMT_F64_M, FMT_I32_MM, FMT_U16_MM = 0, 1, 2
 ST_NO_MEAS, ST_ML_FEW, ST_SINGULAR, ST_NAN, ST_ML_NAN, ST_MAXITER, ST_ASYM_R = 1, 2, 4, 8, 16, 32, 64
 ST_Z_GATE = 128
+ST_UNINIT = 256
 
 
 class KfposConfig(C.Structure):
@@ -35,6 +36,7 @@ class KfposConfig(C.Structure):
         ("imu_use_fixed_cov_acc", C.c_int32), ("imu_use_fixed_cov_gyro_z", C.c_int32),
         ("imu_cov_acc", C.c_double), ("imu_cov_gyro_z", C.c_double),
         ("mag_angle_offset", C.c_double), ("mag_cov", C.c_double),
+        ("ml_initial_position", C.c_int32), ("_reserved0", C.c_int32),
     ]
 
 

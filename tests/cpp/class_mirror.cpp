@@ -47,6 +47,20 @@ int main() {
             const std::string pos = "<config><algorithm type=\"1\" variant=\"0\"/></config>";
             algo.reset(new KalmanFilter(a, ang, j, pos, px4, tag, imu, mag, Vector3(x, y, 0)));
             if (!algo->init()) { std::printf("init failed\n"); return 2; }
+        } else if (cmd == "t9_nofix") {
+            double a, j;
+            in >> a >> j;
+            algo.reset(new KalmanFilterTOAIMU(a, j));
+        } else if (cmd == "k8_nofix") { // the constructor without initialPosition; fh = useFixedHeight
+            double a, ang, j; int fh;
+            in >> a >> ang >> j >> fh;
+            const std::string px4 = "<config><px4flow armP0=\"1\" armP1=\"0\" sensorHeight=\"5\" covarianceVelocity=\"0.04\" covarianceGyroZ=\"0.02\"/></config>";
+            const std::string tag = std::string("<config><uwb useFixedHeight=\"") + (fh ? "1" : "0") + "\" fixedHeight=\"1.049\" tagId=\"0\"/></config>";
+            const std::string imu = "<config><imu useFixedCovarianceAcceleration=\"1\" covarianceAcceleration=\"0.003\" useFixedCovarianceAngularVelocityZ=\"1\" covarianceAngularVelocityZ=\"0.089\"/></config>";
+            const std::string mag = "<config><mag angleOffset=\"0\" covarianceMag=\"0.0001\"/></config>";
+            const std::string pos = "<config><algorithm type=\"1\" variant=\"0\"/></config>";
+            algo.reset(new KalmanFilter(a, ang, j, pos, px4, tag, imu, mag));
+            if (!algo->init()) { std::printf("init failed\n"); return 2; }
         } else if (cmd == "ml") {
             int use2d, variant, nign; double x, y, z;
             in >> use2d >> variant >> nign >> x >> y >> z;
