@@ -84,8 +84,15 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
         // written back: KF.cpp:287-291,315-318)
         double px = p.x[0 * N + f], py = p.x[1 * N + f], vx = p.x[2 * N + f], vy = p.x[3 * N + f];
         double th = p.x[6 * N + f], om = p.x[7 * N + f];
+        // the tuned instantiations keep the covariance in REGISTERS from event to event (Pr); Pm then only backs
+        // P^- up inside an event that fuses several sensors.  The general one keeps it in Pm between events.
+        Sym<8> Pr;
 #pragma unroll
-        for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = p.P[(int64_t)k * N + f];
+        for (int k = 0; k < Sym<8>::SZ; ++k) {
+            const double v = p.P[(int64_t)k * N + f];
+            if (SEL) Pm[k] = v;
+            else Pr.a[k] = v;
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) latch[k] = p.latch[(int64_t)k * N + f];
         unsigned has = (unsigned)p.has[f]; // bit0 px4, bit1 imu, bit2 mag latched
@@ -213,12 +220,18 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                 carry = 0.0;
 
                 // ---- predict (KF.cpp:287-305): a = 0 at the start of every step
-                Sym<8> Pw;
+                Sym<8> &Pw = Pr;
+                if (SEL) {
 #pragma unroll
-                for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k];
+                    for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k];
+                }
                 k8_predict_cov(Pw, dt, p.cfg.accel_noise, p.cfg.jolt);
+                // one sensor and no rangings: the deferred update on the register copy (k8_update_light)
+                const bool light = !SEL && (ev.kind == EV_IMU || ev.kind == EV_PX4 || ev.kind == EV_MAG);
+                if (!light) {
 #pragma unroll
-                for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = Pw.a[k];
+                    for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = Pw.a[k];
+                }
                 const double xp[8] = {px + dt * vx, py + dt * vy, vx, vy, 0.0, 0.0, wrap_angle(th + dt * om), om};
 
                 if (ms.has_imu) {
@@ -248,14 +261,27 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                                                 cov0, used, grc, p.cfg.zero_tz != 0);
                     }
                 }
-                const int rc = k8_update<PME, MT>(p.anchors, p.cfg, tag_z, ep, has_r, used, ms, dt, xp, Pm, Pw, dx, st,
-                                                  SEL ? 0u : wmask);
+                int rc = 0;
+                if (light) {
+                    if (ev.kind == EV_IMU) k8_update_light<EV_IMU>(p.cfg, ms, dt, xp, Pw, dx, st);
+                    else if (ev.kind == EV_PX4) k8_update_light<EV_PX4>(p.cfg, ms, dt, xp, Pw, dx, st);
+                    else k8_update_light<EV_MAG>(p.cfg, ms, dt, xp, Pw, dx, st);
+                } else {
+                    rc = k8_update<PME, MT>(p.anchors, p.cfg, tag_z, ep, has_r, used, ms, dt, xp, Pm, Pw, dx, st,
+                                            SEL ? 0u : wmask);
+                    if (!SEL && rc != 0) { // update skipped: P^- is what remains
+#pragma unroll
+                        for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k];
+                    }
+                }
                 if (rc == 0) {
                     px = xp[0] + dx[0]; py = xp[1] + dx[1];
                     vx = xp[2] + dx[2]; vy = xp[3] + dx[3];
                     th = xp[6] + dx[6]; om = xp[7] + dx[7]; // written back un-wrapped (KF.cpp:317)
+                    if (SEL) {
 #pragma unroll
-                    for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = Pw.a[k];
+                        for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = Pw.a[k];
+                    }
                     if (!(isfinite(px) && isfinite(py) && isfinite(vx) && isfinite(vy) && isfinite(th) && isfinite(om)))
                         st.status |= 8u;
                 } else {
@@ -279,7 +305,7 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
         p.x[0 * N + f] = px; p.x[1 * N + f] = py; p.x[2 * N + f] = vx; p.x[3 * N + f] = vy;
         p.x[4 * N + f] = 0.0; p.x[5 * N + f] = 0.0; p.x[6 * N + f] = th; p.x[7 * N + f] = om;
 #pragma unroll
-        for (int k = 0; k < Sym<8>::SZ; ++k) p.P[(int64_t)k * N + f] = Pm[k];
+        for (int k = 0; k < Sym<8>::SZ; ++k) p.P[(int64_t)k * N + f] = SEL ? Pm[k] : Pr.a[k];
 #pragma unroll
         for (int k = 0; k < 8; ++k) p.latch[(int64_t)k * N + f] = latch[k];
         p.has[f] = (int32_t)has;

@@ -207,4 +207,180 @@ KF_DEV int k8_update(const AnchorTable &A, const K8Cfg &cfg, double tag_z, const
     return 0;
 }
 
+// ---- kalmanStep3D for an event that fuses ONE sensor and no rangings (KF.cpp:100-193: a PX4Flow frame,
+// an IMU sample or a raw magnetometer sample; 13 of the 15 events of a kfpos_multi macro-step), with the
+// covariance held in REGISTERS across predict and update and the covariance update DEFERRED:
+// every such event runs exactly two gain steps and three cost evaluations (the first gain step's covariance
+// is discarded by the reference as well: each step restarts from P^-, KF.cpp:472-495), so a gain step here
+// computes only what the state increment needs -- the <= 3 vectors v_r = P_{r-1} h_r, obtained from the
+// columns of P^- and the earlier vectors instead of from an updated matrix -- and the sequential rank-1
+// updates are applied once, after the loop, from the vectors of the last gain step:
+//     P = fma(-k2_i, v2_j, fma(-k1_i, v1_j, fma(-k0_i, v0_j, P^-_ij)))        k_r = v_r / s_r
+// Entry for entry these are the operations of scalar_update / block2_update in the same order, so the
+// result is bit-identical to the sequential form (kfpos_math.cuh); the covariance never visits shared
+// memory, and the first gain step costs a third of a full one.
+//   KIND: EV_IMU (accelerometer pair as a 2x2 block + gyro row), EV_PX4 (two flow rows + gyro row), EV_MAG.
+template <int KIND>
+KF_DEV void k8_update_light(const K8Cfg &cfg, const K8Meas &ms, double dt, const double (&xp)[8], Sym<8> &P,
+                            double (&dx)[8], StepStats &st) {
+    // inverse of the IMU accelerometer block and the scalar variances, as in k8_update
+    const double idet = KIND == EV_IMU ? 1.0 / (ms.imu_c00 * ms.imu_c11 - ms.imu_c01 * ms.imu_c01) : 0.0;
+    const double ii00 = ms.imu_c11 * idet, ii01 = -ms.imu_c01 * idet, ii11 = ms.imu_c00 * idet;
+    const double px4_cv = KIND == EV_PX4 ? ms.latch[3] : 1.0;
+    const double i_cv = KIND == EV_PX4 ? 1.0 / px4_cv : 0.0, i_cg = KIND == EV_PX4 ? 1.0 / ms.px4_cg : 0.0;
+    const double i_cw = KIND == EV_IMU ? 1.0 / ms.imu_cw : 0.0, i_cm = KIND == EV_MAG ? 1.0 / ms.mag_c : 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dx[k] = 0.0;
+    double cost = 1e20, prior = 0.0;
+    bool broke = false;
+    // the vectors of the last gain step and their gains (IMU: k0, k1 are the 2x2 block's)
+    double v0[8], v1[8], v2[8], q00 = 0.0, q01 = 0.0, q11 = 0.0, q2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v0[k] = v1[k] = v2[k] = 0.0;
+    for (int iter = 0; iter < 20; ++iter) {
+        const double vx = xp[2] + dx[2], vy = xp[3] + dx[3];
+        const double ax = xp[4] + dx[4], ay = xp[5] + dx[5];
+        const double th = xp[6] + dx[6], om = xp[7] + dx[7];
+        double c = 0.0;
+        double sn = 0.0, cs = 1.0, sw = 0.0, cw = 1.0;
+        if (KIND != EV_MAG) fast_sincos(th, &sn, &cs);
+        double e0 = 0, e1 = 0, e2 = 0;
+        if (KIND == EV_PX4) { // px4flowOutput (KF.cpp:563-571)
+            fast_sincos(om * dt, &sw, &cw);
+            const double it = 1.0 / dt;
+            e0 = ms.latch[0] - (cs * vx + sn * vy + it * ((1.0 - cw) * cfg.arm1 - sw * cfg.arm2));
+            e1 = ms.latch[1] - (-sn * vx + cs * vy + it * (sw * cfg.arm1 + (1.0 - cw) * cfg.arm2));
+            e2 = ms.latch[2] - om;
+            c += (e0 * e0 + e1 * e1) * i_cv + e2 * e2 * i_cg;
+        } else if (KIND == EV_IMU) { // imuOutput (KF.cpp:573-581)
+            e0 = ms.latch[4] - (cs * ax + sn * ay);
+            e1 = ms.latch[5] - (-sn * ax + cs * ay);
+            e2 = ms.latch[6] - om;
+            c += e0 * (ii00 * e0 + ii01 * e1) + e1 * (ii01 * e0 + ii11 * e1) + e2 * e2 * i_cw;
+        } else { // residual wrapped once (KF.cpp:461-463)
+            e0 = wrap_angle(ms.latch[7] - th);
+            c += e0 * e0 * i_cm;
+        }
+        const double newCost = c + prior;
+        st.cost_evals += 1;
+        if (rel_change_lt(cost, newCost, 1e-4)) { broke = true; break; }
+        cost = newCost;
+        st.gain_evals += 1;
+
+        double dn[8];
+        if (KIND == EV_MAG) {
+            const double y = e0 + dx[6];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v0[i] = P.get(i, 6) * 1.0;
+            const double s = fma(1.0, v0[6], ms.mag_c), nu = y;
+            q00 = fast_rcp(s);
+            const double g = nu * q00;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dn[i] = fma(v0[i], g, 0.0);
+            const double wm = (y - dn[6]) * i_cm;
+            prior = fma(wm, dn[6], 0.0);
+        } else if (KIND == EV_IMU) {
+            const double j06 = -sn * ax + cs * ay, j16 = -cs * ax - sn * ay;
+            const double y0 = e0 + (cs * dx[4] + sn * dx[5] + j06 * dx[6]);
+            const double y1 = e1 + (-sn * dx[4] + cs * dx[5] + j16 * dx[6]);
+            const double y2 = e2 + dx[7];
+            // rows (cs, sn, j06) and (-sn, cs, j16) on states 4, 5, 6 as one 2x2 block (block2_update<8, 0x70>)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                v0[i] = fma(P.get(i, 6), j06, fma(P.get(i, 5), sn, fma(P.get(i, 4), cs, 0.0)));
+                v1[i] = fma(P.get(i, 6), j16, fma(P.get(i, 5), cs, fma(P.get(i, 4), -sn, 0.0)));
+            }
+            const double s00 = fma(j06, v0[6], fma(sn, v0[5], fma(cs, v0[4], ms.imu_c00)));
+            const double s01 = fma(j06, v1[6], fma(sn, v1[5], fma(cs, v1[4], ms.imu_c01)));
+            const double s11 = fma(j16, v1[6], fma(cs, v1[5], fma(-sn, v1[4], ms.imu_c11)));
+            const double id = fast_rcp(s00 * s11 - s01 * s01);
+            q00 = s11 * id; q01 = -s01 * id; q11 = s00 * id;
+            const double g0 = q00 * y0 + q01 * y1, g1 = q01 * y0 + q11 * y1;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dn[i] = fma(v0[i], g0, fma(v1[i], g1, 0.0));
+            // gyro row e_7 on the covariance after the block: its column 7, entry (7, i) of the packed matrix
+            const double k07 = v0[7] * q00 + v1[7] * q01, k17 = v0[7] * q01 + v1[7] * q11;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v2[i] = fma(-k07, v0[i], fma(-k17, v1[i], P.get(7, i))) * 1.0;
+            const double s2 = fma(1.0, v2[7], ms.imu_cw), nu2 = fma(-1.0, dn[7], y2);
+            q2 = fast_rcp(s2);
+            const double g2 = nu2 * q2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dn[i] = fma(v2[i], g2, dn[i]);
+            // prior term for the next cost: w = J^T R^-1 (y - J Delta), delta^T P^+ delta = w . Delta
+            const double r0 = y0 - (cs * dn[4] + sn * dn[5] + j06 * dn[6]);
+            const double r1 = y1 - (-sn * dn[4] + cs * dn[5] + j16 * dn[6]);
+            const double u0 = ii00 * r0 + ii01 * r1, u1 = ii01 * r0 + ii11 * r1;
+            const double u2 = (y2 - dn[7]) * i_cw;
+            const double w4 = 0.0 + (cs * u0 - sn * u1), w5 = 0.0 + (sn * u0 + cs * u1);
+            const double w6 = 0.0 + (j06 * u0 + j16 * u1), w7 = 0.0 + u2;
+            prior = fma(w7, dn[7], fma(w6, dn[6], fma(w5, dn[5], fma(w4, dn[4], 0.0))));
+        } else {
+            const double j06 = -sn * vx + cs * vy, j07 = cfg.arm1 * sw - cfg.arm2 * cw;
+            const double j16 = -cs * vx - sn * vy, j17 = cfg.arm1 * cw + cfg.arm2 * sw;
+            const double y0 = e0 + (cs * dx[2] + sn * dx[3] + j06 * dx[6] + j07 * dx[7]);
+            const double y1 = e1 + (-sn * dx[2] + cs * dx[3] + j16 * dx[6] + j17 * dx[7]);
+            const double y2 = e2 + dx[7];
+            // flow rows on states 2, 3, 6, 7, sequential (scalar_update<8, 0xCC> twice), then the gyro row e_7
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                v0[i] = fma(P.get(i, 7), j07, fma(P.get(i, 6), j06, fma(P.get(i, 3), sn, P.get(i, 2) * cs)));
+            const double s0 = fma(j07, v0[7], fma(j06, v0[6], fma(sn, v0[3], fma(cs, v0[2], px4_cv))));
+            q00 = fast_rcp(s0);
+            const double g0 = y0 * q00; // the increment is still zero: nu = y
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dn[i] = fma(v0[i], g0, 0.0);
+            double k0[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) k0[i] = v0[i] * q00;
+            // entry (i, j) of the covariance after row 0: fma(-k0[max], v0[min], P(i, j))
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                auto p1 = [&](int j) { return fma(-k0[i > j ? i : j], v0[i > j ? j : i], P.get(i, j)); };
+                v1[i] = fma(p1(7), j17, fma(p1(6), j16, fma(p1(3), cs, p1(2) * -sn)));
+            }
+            const double s1 = fma(j17, v1[7], fma(j16, v1[6], fma(cs, v1[3], fma(-sn, v1[2], px4_cv))));
+            q11 = fast_rcp(s1);
+            const double nu1 = fma(-j17, dn[7], fma(-j16, dn[6], fma(-cs, dn[3], fma(sn, dn[2], y1))));
+            const double g1 = nu1 * q11;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dn[i] = fma(v1[i], g1, dn[i]);
+            const double k17 = v1[7] * q11;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v2[i] = fma(-k17, v1[i], fma(-k0[7], v0[i], P.get(7, i))) * 1.0;
+            const double s2 = fma(1.0, v2[7], ms.px4_cg), nu2 = fma(-1.0, dn[7], y2);
+            q2 = fast_rcp(s2);
+            const double g2 = nu2 * q2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dn[i] = fma(v2[i], g2, dn[i]);
+            const double u0 = (y0 - (cs * dn[2] + sn * dn[3] + j06 * dn[6] + j07 * dn[7])) * i_cv;
+            const double u1 = (y1 - (-sn * dn[2] + cs * dn[3] + j16 * dn[6] + j17 * dn[7])) * i_cv;
+            const double u2 = (y2 - dn[7]) * i_cg;
+            const double w2 = 0.0 + (cs * u0 - sn * u1), w3 = 0.0 + (sn * u0 + cs * u1);
+            const double w6 = 0.0 + (j06 * u0 + j16 * u1), w7 = 0.0 + (j07 * u0 + j17 * u1 + u2);
+            prior = fma(w7, dn[7], fma(w6, dn[6], fma(w3, dn[3], fma(w2, dn[2], 0.0))));
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dx[k] = dn[k];
+    }
+    if (!broke) st.status |= 32u;
+    // ---- the covariance update of the last gain step, applied once
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        if (KIND == EV_MAG) {
+            const double k = v0[i] * q00;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) P.at(i, j) = fma(-k, v0[j], P.at(i, j));
+        } else if (KIND == EV_IMU) {
+            const double k0 = v0[i] * q00 + v1[i] * q01, k1 = v0[i] * q01 + v1[i] * q11, k2 = v2[i] * q2;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) P.at(i, j) = fma(-k2, v2[j], fma(-k0, v0[j], fma(-k1, v1[j], P.at(i, j))));
+        } else {
+            const double k0 = v0[i] * q00, k1 = v1[i] * q11, k2 = v2[i] * q2;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) P.at(i, j) = fma(-k2, v2[j], fma(-k1, v1[j], fma(-k0, v0[j], P.at(i, j))));
+        }
+    }
+}
+
 } // namespace kfpos

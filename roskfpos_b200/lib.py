@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "csrc", "libkfpos_b200.so")
+# KFPOS_B200_SO: another build of the same library (kernel variants under profiles/, never a different backend)
+SO_PATH = os.environ.get("KFPOS_B200_SO") or os.path.join(_HERE, "csrc", "libkfpos_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "kfpos_b200.h")
 
 MODEL_ML, MODEL_T6, MODEL_K8, MODEL_T9 = 0, 1, 2, 3
