@@ -40,6 +40,46 @@ def w_alg_t6(m, i_ml, i_c, i_g):
     return w_pred + i_ml * w_mlit + 12 * m + 2 * m + i_c * w_cost + i_g * w_gain
 
 
+K8_ROWS = {"px4": ((4, 4, 1), 24), "imu": ((3, 3, 1), 7), "mag": ((1,), 1)}  # nnz per row, c_q
+
+
+def w_alg_k8(m, sensors, i_ml, i_c, i_g):
+    """Algorithmic FLOP of one K8 event, SURVEY.md §8(d) formula W_alg (v1) for n = 8, d = 2: m valid rangings
+    (0 for a sensor-only event) fused with the sensor groups in `sensors`; the iteration counts are MEASURED means.
+    (Nominal counts reproduce the table of §8d: 1994 PX4-only, 726 mag-only, 8003 TOA + IMU + mag, 1790 IMU-only.)"""
+    n, d = 8, 2
+    rows = [d] * m + [z for s_ in sensors for z in K8_ROWS[s_][0]]
+    q = len(rows) - m
+    nnz_q = sum(rows[m:])
+    c_q = sum(K8_ROWS[s_][1] for s_ in sensors)
+    w_pred = 4 * 7 * n + 22 + 15 + 2 * 7
+    w_ml = (12 * m + i_ml * (46 * m + 25) + 12 * m) if m > 0 else 0.0
+    w_cost = 13 * m + q + c_q + (2 * d * m + 2 * nnz_q + 3 * len(rows)) + 3
+    w_gain = (1 + d) * m + (10 if q > 0 else 0) + sum(n * n + 2 * n * z + 4 * n + 4 * z + 3 for z in rows) + n
+    return w_pred + w_ml + 2 * m + (6 if len(rows) >= 3 else 0) + i_c * w_cost + i_g * w_gain
+
+
+def k8_roofline(events, full, m, N, cnt, seconds, peak):
+    """FP64 roofline block of a K8 replay: sum of W_alg over the schedule (what each event fuses follows from the
+    schedule: every sensor is latched by the first macro-step) with the measured mean iteration counts."""
+    from roskfpos_b200 import synth
+    n_upd = max(cnt["updates"], 1.0)
+    n_toa = sum(1 for e in events if e[0] == synth.EV_TOA)
+    i_c, i_g = cnt["cost_evals"] / n_upd, cnt["gain_evals"] / n_upd
+    i_ml = cnt["ml_iters"] / max(N * n_toa, 1)
+    latched = ("px4", "imu", "mag") if full else ("imu", "mag")
+    fused = {synth.EV_IMU: (0, ("imu",)), synth.EV_PX4: (0, ("px4",)), synth.EV_MAG: (0, ("mag",)),
+             synth.EV_COMPASS: (0, latched), synth.EV_TOA: (m, latched)}
+    w = sum(w_alg_k8(fused[e[0]][0], fused[e[0]][1], i_ml, i_c, i_g) for e in events)
+    ach = w * N / seconds
+    return {"bound": "fp64", "achieved": ach / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
+            "frac": ach / peak if peak else None, "flop_per_event_mean": w / len(events),
+            "mean_iters": {"ml_per_toa": i_ml, "cost": i_c, "gain": i_g}, "kernel": "k8_replay_kernel<false,8,false>",
+            "numerator": "SURVEY.md §8(d) W_alg v1 per event kind (IMU 3 rows, PX4 3 rows, compass = mag + latched "
+                         "sensors, TOA = 8 rangings + latched sensors) with the measured iteration counters",
+            "peak_source": "measured live: kfpos_measure_fp64_peak"}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -670,12 +710,15 @@ def bench_other_configs(local, dev, args):
                 b.set_state(w["x0"], None, stream=stream)
                 b.replay_events(w["events"], ranges=w["ranges"], sensors=w["sensors"], err=0.01, stream=stream)
             t = timed(run)
+            b.counters(reset=True)
+            run()
             c = b.counters()
             s4 = b.error_stats(w["truth_end"], stream=stream)
         out[name] = {"toa_updates_per_s": Nk * w["n_toa"] / t, "all_event_updates_per_s": Nk * w["n_events"] / t,
                      "ms": t * 1e3, "filters": Nk, "events": w["n_events"], "toa_events": w["n_toa"],
                      "rmse_xy_m": float(np.sqrt(s4[1] / max(s4[2], 1))), "bad_updates": c["bad"],
-                     "input_mb": (w["sensors"].numel() * 8 + w["ranges"].numel() * 4) / 1e6}
+                     "input_mb": (w["sensors"].numel() * 8 + w["ranges"].numel() * 4) / 1e6,
+                     "roofline": k8_roofline(w["events"], full, 8, Nk, c, t, C_double_peak(local))}
         del w
     # ---- config 5 at scale: 8 Mi filters (the per-GPU share of the 64 M-filter Monte Carlo on 8 GPUs), inputs
     # synthesised on the device chunk by chunk (kfpos_synth_k8) and replayed; generation is inside the timed region

@@ -189,14 +189,31 @@ int kfpos_batch_state_dim(const kfpos_batch *b); /* 3 (ML), 6, 8, 9 */
  * (PEA.h:16; built by PG.cpp:476-496 from the anchor index order).  xyz [n][3]. */
 int kfpos_batch_set_anchors(kfpos_batch *b, int n_anchors, const double *xyz);
 
-/* State and covariance (checkpoint/restore).  x: SoA [n][N]; P: SoA [n*n][N]
+/* State and covariance.  x: SoA [n][N]; P: SoA [n*n][N]
  * row-major full matrix, or NULL for the reference's initial P0 = 0.
+ * set_state RE-INITIALISES the filters (it is the constructor's initial position): latched sensor
+ * samples, their flags and the status words are cleared.  A checkpoint of a running K8 / T9 batch is
+ * get_state + kfpos_batch_get_latches, restored by set_state followed by kfpos_batch_set_latches.
+ * (T6 ignores rows 3..5 of x -- the velocity is zero at the start of every step, TOA.cpp:110-112 --
+ * and get_state returns them as zeros.)
  * State layouts: T6 [px,py,pz,vx,vy,vz]  (v is always 0: TOA.cpp:110-112)
  *                K8 [px,py,vx,vy,ax,ay,theta,omega]  (a always 0: KF.cpp:287-291)
  *                T9 [px,py,pz,vx,vy,vz,ax,ay,az]     (a always 0: TOAIMU.cpp:165-168)
  * Also clears the per-filter status, selection and latched-sensor flags.      */
 int kfpos_batch_set_state(kfpos_batch *b, const double *x, const double *P, void *stream);
 int kfpos_batch_get_state(kfpos_batch *b, double *x, double *P, int32_t *status, void *stream);
+
+/* The rest of a running K8 / T9 filter: the members the sensor callbacks latch (KF.h:92-130,
+ * KalmanFilterTOAIMU.h:60-70).  latch: SoA [16][N] -- K8 rows 0..3 lastPX4FlowMeasurement (vx, vy,
+ * gyroZ, covarianceVelocity), 4..6 lastImuMeasurement (ax, ay, angularVelocityZ), 7 lastMagMeasurement
+ * angle, 8 time carried over from PX4 frames of quality 0 (KF.cpp:111-113), 9 this filter's tag height
+ * (mUWBtagZ, see ml_initial_position); T9 rows 0..2 latched acceleration.  has: [N] bit0 PX4, bit1 IMU,
+ * bit2 magnetometer sample latched.  latch_u: 16 doubles common to the batch (the IMU covariances of
+ * the last sample: K8 c00, c01, c11, cw; T9 the 3x3 matrix row-major).  Any pointer may be NULL.
+ * Host or device pointers.                                                                        */
+int kfpos_batch_get_latches(kfpos_batch *b, double *latch, int32_t *has, double *latch_u, void *stream);
+int kfpos_batch_set_latches(kfpos_batch *b, const double *latch, const int32_t *has, const double *latch_u,
+                            void *stream);
 
 /* ---------------------------------------------------------------- EKF steps
  * One newTOAMeasurement per filter (PEA.h:16; TOA.cpp:43-61, KF.cpp:64-97,

@@ -121,6 +121,19 @@ class Batch:
                 "kfpos_batch_get_state")
         return x, P, st
 
+    def get_latches(self, stream=None):
+        """The latched sensor members of a running K8 / T9 batch: (latch [16][N], has [N], latch_u [16])."""
+        latch = np.empty((16, self.N)); has = np.empty(self.N, dtype=np.int32); u = np.empty(16)
+        L.check(L.lib().kfpos_batch_get_latches(self._h, C.c_void_p(latch.ctypes.data), C.c_void_p(has.ctypes.data),
+                                                C.c_void_p(u.ctypes.data), _stream_ptr(stream)), "kfpos_batch_get_latches")
+        return latch, has, u
+
+    def set_latches(self, latch, has, latch_u, stream=None):
+        a = [np.ascontiguousarray(latch, dtype=np.float64), np.ascontiguousarray(has, dtype=np.int32),
+             np.ascontiguousarray(latch_u, dtype=np.float64)]
+        L.check(L.lib().kfpos_batch_set_latches(self._h, C.c_void_p(a[0].ctypes.data), C.c_void_p(a[1].ctypes.data),
+                                                C.c_void_p(a[2].ctypes.data), _stream_ptr(stream)), "kfpos_batch_set_latches")
+
     def get_state_into(self, x=None, P=None, status=None, stream=None):
         """Device-to-device variant of get_state for torch tensors."""
         L.check(L.lib().kfpos_batch_get_state(self._h, _ptr(x)[0], _ptr(P)[0], _ptr(status)[0],

@@ -223,7 +223,7 @@ extern "C" int kfpos_batch_create(kfpos_batch **out, int device, int model, int6
     if (model == KFPOS_MODEL_K8 || model == KFPOS_MODEL_T9) {
         alloc((void **)&b->d_latch, sizeof(double) * 16 * N);
         alloc((void **)&b->d_has, sizeof(int32_t) * N);
-        alloc((void **)&b->d_latch_u, sizeof(double) * 16);
+        alloc((void **)&b->d_latch_u, sizeof(double) * 32); // [0..15] read by a launch, [16..31] written by it
         alloc((void **)&b->d_uninit, sizeof(int));
         if (e == cudaSuccess) e = cudaHostAlloc((void **)&b->h_uninit, sizeof(int), cudaHostAllocDefault);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b->ev_uninit, cudaEventDisableTiming);
@@ -325,7 +325,7 @@ extern "C" int kfpos_batch_set_state(kfpos_batch *b, const double *x, const doub
     CK(cudaMemsetAsync(b->d_status, 0, sizeof(int32_t) * N, s));
     if (b->d_has) CK(cudaMemsetAsync(b->d_has, 0, sizeof(int32_t) * N, s));
     if (b->d_latch) CK(cudaMemsetAsync(b->d_latch, 0, sizeof(double) * 16 * N, s));
-    if (b->d_latch_u) CK(cudaMemsetAsync(b->d_latch_u, 0, sizeof(double) * 16, s));
+    if (b->d_latch_u) CK(cudaMemsetAsync(b->d_latch_u, 0, sizeof(double) * 32, s));
     if (b->model == KFPOS_MODEL_K8) // per-filter tag height (latch row 9): mUWBtagZ = fixedHeight until a 3-D ML init
         CK(launch_fill(b->d_latch + 9 * N, b->N, b->cfg.fixed_height, s));
     b->uninit_possible = b->cfg.ml_initial_position != 0 && (b->model == KFPOS_MODEL_K8 || b->model == KFPOS_MODEL_T9);
@@ -335,6 +335,50 @@ extern "C" int kfpos_batch_set_state(kfpos_batch *b, const double *x, const doub
     b->out4_valid = false;
     b->stepped = P != nullptr; // a restored checkpoint is a running filter; P0 = 0 is a fresh one
     if (!xd || (P && !on_device(P))) CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
+extern "C" int kfpos_batch_get_latches(kfpos_batch *b, double *latch, int32_t *has, double *latch_u, void *stream) {
+    if (!b || !b->d_latch) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N;
+    bool sync = false;
+    auto out = [&](void *dst, const void *src, size_t bytes) {
+        if (!dst) return cudaSuccess;
+        const bool d = on_device(dst);
+        sync |= !d;
+        return cudaMemcpyAsync(dst, src, bytes, d ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, s);
+    };
+    CK(out(latch, b->d_latch, sizeof(double) * 16 * N));
+    CK(out(has, b->d_has, sizeof(int32_t) * N));
+    CK(out(latch_u, b->d_latch_u, sizeof(double) * 16));
+    if (sync) CK(cudaStreamSynchronize(s));
+    return KFPOS_OK;
+}
+
+extern "C" int kfpos_batch_set_latches(kfpos_batch *b, const double *latch, const int32_t *has, const double *latch_u,
+                                       void *stream) {
+    if (!b || !b->d_latch) return KFPOS_ERR_INVALID;
+    DeviceGuard g(b->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)b->N;
+    bool sync = false;
+    auto in = [&](void *dst, const void *src, size_t bytes) {
+        if (!src) return cudaSuccess;
+        const bool d = on_device(src);
+        sync |= !d;
+        return cudaMemcpyAsync(dst, src, bytes, d ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s);
+    };
+    CK(in(b->d_latch, latch, sizeof(double) * 16 * N));
+    CK(in(b->d_has, has, sizeof(int32_t) * N));
+    if (latch_u) {
+        CK(in(b->d_latch_u, latch_u, sizeof(double) * 16));
+        CK(in(b->d_latch_u + 16, latch_u, sizeof(double) * 16));
+    }
+    if (has) b->imu_seen = true; // T9: a restored filter may carry a latched IMU sample
+    b->stepped = true;
+    if (sync) CK(cudaStreamSynchronize(s));
     return KFPOS_OK;
 }
 
@@ -649,6 +693,7 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.truth = b->d_truth;
         p.partials = b->d_partials;
         CK(launch_k8_replay(p, s));
+        CK(cudaMemcpyAsync(b->d_latch_u, b->d_latch_u + 16, sizeof(double) * 16, cudaMemcpyDeviceToDevice, s));
         b->partials_fresh = b->d_truth != nullptr;
         b->out4_valid = false;
         break;
@@ -682,6 +727,7 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
         p.truth = b->d_truth;
         p.partials = b->d_partials;
         CK(launch_t9_replay(p, s));
+        CK(cudaMemcpyAsync(b->d_latch_u, b->d_latch_u + 16, sizeof(double) * 16, cudaMemcpyDeviceToDevice, s));
         b->partials_fresh = b->d_truth != nullptr;
         b->out4_valid = false;
         break;

@@ -320,7 +320,8 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
         // planar filter: z is the configured tag height (KF.cpp:328-332)
         if (p.truth) filter_error_terms(px, py, tag_z, p.truth, N, f, st_all != 0, errv);
         if (f == 0) {
-            p.latch_u[0] = ic00; p.latch_u[1] = ic01; p.latch_u[2] = ic11; p.latch_u[3] = icw;
+            // written to the OUT half: blocks of this launch that start later must still read the launch's input
+            p.latch_u[16] = ic00; p.latch_u[17] = ic01; p.latch_u[18] = ic11; p.latch_u[19] = icw;
         }
     }
     warp_accumulate(p.counters + CNT_UPDATES, n_updates);

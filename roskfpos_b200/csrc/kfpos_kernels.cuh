@@ -163,7 +163,7 @@ struct K8Params {
     double *latch;   // SoA [16][N]: px4 vx,vy,gz,cv | imu ax,ay,wz | mag angle | [8] dt carry | [9] tag height
     int32_t *has;    // [N] bit0 px4, bit1 imu, bit2 mag latched
     int *uninit;     // null, or a flag set by every filter that is still uninitialised when the launch ends
-    double *latch_u; // [4] batch-wide latched IMU covariances c00,c01,c11,cw
+    double *latch_u; // batch-wide latched IMU covariances c00,c01,c11,cw: read from [0..3], written to [16..19]
     const double *dt_f; // null, or per-filter time steps SoA [n_events][N] (see T9Params)
     double *traj;    // SoA [n_toa][3][N] (px, py, theta) after each TOA event, or null
     unsigned long long *counters;
@@ -191,7 +191,7 @@ struct T9Params {
     int32_t *status; // [N]
     double *latch;   // SoA rows 0..2: latched acceleration
     int32_t *has;    // [N] bit1: imu latched
-    double *latch_u; // [9] batch-wide latched 3x3 acceleration covariance
+    double *latch_u; // batch-wide latched 3x3 acceleration covariance: read from [0..8], written to [16..24]
     const double *dt_f; // null, or per-filter time steps SoA [n_events][N] replacing EventDesc::dt (< 0: the
                         // filter has no such event) -- the ragged epochs of kfpos_batch_replay_epochs
     int no_imu;      // host knowledge: no IMU sample latched and none in this schedule -> lean kernel

@@ -399,11 +399,13 @@ __global__ void __launch_bounds__(T9_BLOCK, IMU ? 2 : T9_LEAN_MINB) t9_replay_ke
         }
         if (p.truth) filter_error_terms(pos[0], pos[1], pos[2], p.truth, N, f, st_all != 0, errv);
         if (SEL && p.uninit && (isnan(pos[0]) || isnan(pos[1]))) *p.uninit = 1;
-        if (f == 0 && (has & 2u)) {
-            // keep the symmetric part as the latched covariance
-            p.latch_u[0] = Ra[0]; p.latch_u[1] = Ra[1]; p.latch_u[2] = Ra[3];
-            p.latch_u[3] = Ra[1]; p.latch_u[4] = Ra[2]; p.latch_u[5] = Ra[4];
-            p.latch_u[6] = Ra[3]; p.latch_u[7] = Ra[4]; p.latch_u[8] = Ra[5];
+        if (f == 0) {
+            // keep the symmetric part as the latched covariance; written to the OUT half (the host copies it over
+            // the input after the launch): blocks that start later must still read this launch's input
+            double *o = p.latch_u + 16;
+            o[0] = Ra[0]; o[1] = Ra[1]; o[2] = Ra[3];
+            o[3] = Ra[1]; o[4] = Ra[2]; o[5] = Ra[4];
+            o[6] = Ra[3]; o[7] = Ra[4]; o[8] = Ra[5];
         }
     }
     warp_accumulate(p.counters + CNT_UPDATES, n_updates);

@@ -70,6 +70,8 @@ SIGNATURES = {
     "kfpos_batch_set_anchors": (_I, [_VP, _I, _VP]),
     "kfpos_batch_set_state": (_I, [_VP, _VP, _VP, _VP]),
     "kfpos_batch_get_state": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "kfpos_batch_get_latches": (_I, [_VP, _VP, _VP, _VP, _VP]),
+    "kfpos_batch_set_latches": (_I, [_VP, _VP, _VP, _VP, _VP]),
     "kfpos_batch_step_toa": (_I, [_VP, _D, _VP, _I, _D, _VP, _VP]),
     "kfpos_batch_replay_toa": (_I, [_VP, _I, _VP, _VP, _I, _D, _VP, _VP, _VP, _VP]),
     "kfpos_batch_replay_epochs": (_I, [_VP, _I, _VP, _VP, _I, _D, _VP, _VP, _VP]),

@@ -171,3 +171,40 @@ def test_k8_ekf_side_nlos_variants(kflib, oracle, variant, n_ignore):
                         what=f"K8 variant {variant}")
     print("parity report K8 variant", variant, rep, cnt)
     assert cnt["updates"] == N * len(events)
+
+
+def test_k8_checkpoint_with_latches(kflib):
+    """get_state + get_latches / set_state + set_latches is a checkpoint of a running multi-sensor batch: the
+    restored batch continues bit-identically (latched PX4 / IMU / mag samples, their flags, the IMU covariances
+    and the time carried over from PX4 frames of quality 0 are all part of the filter)."""
+    from roskfpos_b200.batch import Batch
+    N = 1500
+    anc = synth.anchors_for(8)
+    w = synth.k8_workload(N, 4, anc, seed=123, full=True)
+    sens = w["sensors"].copy()
+    rng = np.random.default_rng(3)
+    for (kind, dt, off, aux) in w["events"]:
+        if kind == synth.EV_PX4:
+            sens[off + 4, rng.random(N) < 0.3] = 0.0  # quality 0: the frame is skipped, its dt carried
+    ev = w["events"]
+    # cut right after a PX4 frame: the filters that skipped it carry its dt into the next event
+    cut = next(i for i in range(len(ev) // 2, len(ev)) if ev[i][0] == synth.EV_PX4) + 1
+    kw = dict(anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5)
+    with Batch(kflib.MODEL_K8, N, **kw) as b:
+        b.set_state(w["x0"])
+        b.replay_events(ev, ranges=w["ranges"], sensors=sens, err=0.01)
+        x_ref, P_ref, _ = b.get_state()
+    with Batch(kflib.MODEL_K8, N, **kw) as b:
+        b.set_state(w["x0"])
+        b.replay_events(ev[:cut], ranges=w["ranges"], sensors=sens, err=0.01)
+        x1, P1, _ = b.get_state()
+        latches = b.get_latches()
+    assert latches[1].max() == 7 and np.abs(latches[0][8]).max() > 0  # every sensor latched, some dt carried
+    with Batch(kflib.MODEL_K8, N, **kw) as b:
+        b.set_state(x1, P1)
+        b.set_latches(*latches)
+        b.replay_events(ev[cut:], ranges=w["ranges"], sensors=sens, err=0.01)
+        x2, P2, _ = b.get_state()
+    assert np.array_equal(x2, x_ref)
+    # the covariance crosses the ABI as a full matrix and is packed again: symmetric, so nothing is lost
+    assert np.array_equal(P2, P_ref)
