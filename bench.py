@@ -40,6 +40,19 @@ def w_alg_t6(m, i_ml, i_c, i_g):
     return w_pred + i_ml * w_mlit + 12 * m + 2 * m + i_c * w_cost + i_g * w_gain
 
 
+def w_alg_t6_v2(m, i_ml, i_c, i_g):
+    """Algorithmic FLOP per T6 update of the formulation the kernel actually uses (information-form IEKF, one pass
+    per Newton / IEKF iteration, first pass shared, factored covariance update); DESIGN.md §4.0 "W_alg v2".  Same
+    conventions as SURVEY.md §8(d): add / mul / rsqrt / rcp = 1, FMA = 2."""
+    w_pred = 105
+    pass_ml = 37 * m + 60          # distances, residual, gradient, 5 of 6 Hessian sums, 3x3 solve, stop test
+    pass_first = 49 * m + 60       # + the 5 sums of u u^T that the first IEKF iteration reuses
+    pass_iekf = 32 * m + 20        # cost, b, 5 of 6 sums of G, G dx
+    gain = 184                     # N = I + G A, cofactors, s, dx, M, prior, scaling by 1/R
+    apply = 216                    # P^- - B M B^T on the packed 6x6
+    return w_pred + 2 * m + pass_first + i_ml * pass_ml + (i_c - 1) * pass_iekf + 5 * i_c + i_g * gain + apply
+
+
 K8_ROWS = {"px4": ((4, 4, 1), 24), "imu": ((3, 3, 1), 7), "mag": ((1,), 1)}  # nnz per row, c_q (SURVEY.md §8d)
 
 
@@ -349,78 +362,68 @@ def run_b200(args):
     if not args.no_e2e:
         # the host log holds the first Te epochs of the same workload (pinned host memory is bounded: 1000
         # epochs would be 33.5 GB per rank); the per-update rate is what is compared
+        import ctypes as C
         Te = min(T, args.e2e_tsteps)
-        h_ranges = torch.empty((Te,) + tuple(ranges.shape[1:]), dtype=ranges.dtype, pin_memory=True)
-        h_ranges.copy_(ranges[:Te])
         h_x0 = torch.empty(x0_full.shape, dtype=torch.float64, pin_memory=True)
         h_x0.copy_(x0_full)
         h_truth = torch.empty(truth_end.shape, dtype=torch.float64, pin_memory=True)
         h_truth.copy_(truth_end)
         h_pos = torch.empty((6, N), dtype=torch.float64, pin_memory=True)
-        hr, hx, ht, hp = h_ranges.numpy(), h_x0.numpy(), h_truth.numpy(), h_pos.numpy()
-        import ctypes as C
-
-        def step_e2e():
-            batch.set_state(hx, None, stream=stream)                      # H2D x0
-            batch.replay_toa(0.1, hr, err=0.01, stream=stream)            # H2D range log, chunked+overlapped
-            s_ = batch.error_stats(ht, stream=stream)                     # H2D truth, D2H 4 doubles
-            L.check(L.lib().kfpos_batch_get_state(batch._h, C.c_void_p(hp.ctypes.data), None, None,
-                                                  C.c_void_p(stream.cuda_stream)), "get_state")  # D2H x
-            return s_
-        for _ in range(max(1, min(W, 2))):
-            step_e2e()
-        barrier()
+        hx, ht, hp = h_x0.numpy(), h_truth.numpy(), h_pos.numpy()
         Ke = max(1, min(K, 3))
-        t0 = time.perf_counter()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record(stream)
-        for _ in range(Ke):
-            s2 = step_e2e()
-        f1.record(stream)
-        barrier()
-        wall = (time.perf_counter() - t0) * 1e3
-        ems = max(f0.elapsed_time(f1), 0.0)
-        te = torch.tensor([max(ems, wall if world == 1 else ems)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        h2d = int(h_ranges.numel() * h_ranges.element_size() + 8 * 6 * N + 8 * 3 * N)
-        e2e = {"value": world * N * Te * Ke / (float(te.item()) * 1e-3), "unit": UNIT,
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * 6 * N + 32), "steps": Ke,
-               "epochs_per_step": Te,
-               "ms_per_step": float(te.item()) / Ke,
-               "h2d_gbs": h2d * Ke / (float(te.item()) * 1e-3) / 1e9,
-               "note": "host range log in the reference's int32-mm table format; the step is bound by the "
-                       "host-to-device copy (h2d_gbs), which the replay kernel overlaps chunk by chunk"}
-        h_shape = tuple(h_ranges.shape)
-        del h_ranges, hr
-        # the same step with the host log in the library's uint16-mm wire format (ranges < 65.5 m)
-        try:
-            h16 = torch.empty(h_shape, dtype=torch.uint16, pin_memory=True)
-            h16.copy_(ranges[:Te].to(torch.uint16))
-            hr16 = h16.numpy()
 
-            def step_e2e16():
-                batch.set_state(hx, None, stream=stream)
-                batch.replay_toa(0.1, hr16, err=0.01, stream=stream)
-                s_ = batch.error_stats(ht, stream=stream)
+        def e2e_leg(h_log):
+            hr = h_log.numpy()
+
+            def step_e2e():
+                batch.set_state(hx, None, stream=stream)                      # H2D x0
+                batch.replay_toa(0.1, hr, err=0.01, stream=stream)            # H2D range log, chunked + overlapped
+                s_ = batch.error_stats(ht, stream=stream)                     # H2D truth, D2H 4 doubles
                 L.check(L.lib().kfpos_batch_get_state(batch._h, C.c_void_p(hp.ctypes.data), None, None,
-                                                      C.c_void_p(stream.cuda_stream)), "get_state")
+                                                      C.c_void_p(stream.cuda_stream)), "get_state")  # D2H x
                 return s_
-            step_e2e16()
+            for _ in range(max(1, min(W, 2))):
+                step_e2e()
             barrier()
             t0 = time.perf_counter()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
             for _ in range(Ke):
-                s3 = step_e2e16()
+                s_last = step_e2e()
+            f1.record(stream)
             barrier()
-            wall16 = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+            wall = (time.perf_counter() - t0) * 1e3
+            ems = max(f0.elapsed_time(f1), 0.0)
+            te = torch.tensor([max(ems, wall if world == 1 else ems)], device=dev, dtype=torch.float64)
             if world > 1:
-                dist.all_reduce(wall16, op=dist.ReduceOp.MAX)
-            e2e["uint16_wire_format"] = {"value": world * N * Te * Ke / (float(wall16.item()) * 1e-3),
-                                         "h2d_bytes_per_step": int(h16.numel() * 2 + 8 * 9 * N),
-                                         "rmse_equal": bool(abs(s3[0] - s2[0]) <= 1e-12 * abs(s2[0]))}
-            del h16, hr16
+                dist.all_reduce(te, op=dist.ReduceOp.MAX)
+            h2d = int(h_log.numel() * h_log.element_size() + 8 * 6 * N + 8 * 3 * N)
+            ms_e = float(te.item())
+            return {"value": world * N * Te * Ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": int(8 * 6 * N + 32), "steps": Ke, "epochs_per_step": Te,
+                    "ms_per_step": ms_e / Ke, "h2d_gbs": h2d * Ke / (ms_e * 1e-3) / 1e9}, s_last
+
+        # the library's wire format for host-resident range logs: uint16 millimetres (every UWB range is < 65.5 m);
+        # the step is bound by the host-to-device copy, and the box's PCIe / host memory gives what it gives
+        # (profiles/r02_h2d_ngpu.txt: 55.5 GB/s per GPU alone, 23-36 GB/s with 8 GPUs copying), so the width of
+        # the wire format is the one lever -- the kernel converts either format to metres bit-identically
+        h16 = torch.empty((Te,) + tuple(ranges.shape[1:]), dtype=torch.uint16, pin_memory=True)
+        h16.copy_(ranges[:Te].to(torch.uint16))
+        e2e, s16 = e2e_leg(h16)
+        e2e["wire_format"] = "uint16 mm (KFPOS_FMT_U16_MM)"
+        e2e["note"] = ("host range log in the library's uint16-mm wire format; the step is bound by the host-to-device "
+                       "copy (h2d_gbs), which the replay kernel overlaps chunk by chunk; int32_table_format = the same "
+                       "step with the log in the reference's int32-mm table format (PG.cpp:213)")
+        del h16
+        try:
+            h32 = torch.empty((Te,) + tuple(ranges.shape[1:]), dtype=ranges.dtype, pin_memory=True)
+            h32.copy_(ranges[:Te])
+            leg32, s32 = e2e_leg(h32)
+            leg32["rmse_equal"] = bool(abs(s32[0] - s16[0]) <= 1e-12 * abs(s16[0]))
+            e2e["int32_table_format"] = leg32
+            del h32
         except Exception as exc:  # an extra, never fatal
-            e2e["uint16_wire_format"] = {"error": repr(exc)}
+            e2e["int32_table_format"] = {"error": repr(exc)}
 
     # ---- roofline of the dominant kernel (t6_replay_kernel): FP64 CUDA-core bound
     upd = max(cnt["updates"], 1.0)
@@ -447,6 +450,10 @@ def run_b200(args):
             "peak_source": "measured live: kfpos_measure_fp64_peak (DFMA-only kernel, best of 5)",
             "kernel": "t6_replay_kernel<8,false,false>", "kernel_ms": kernel_ms,
             "flop_per_update": w_alg, "mean_iters": {"ml": i_ml, "cost": i_c, "gain": i_g},
+            "flop_per_update_v2": w_alg_t6_v2(M, i_ml, i_c, i_g),
+            "frac_v2": w_alg_t6_v2(M, i_ml, i_c, i_g) * N * T / (kernel_ms * 1e-3) / peak if peak else None,
+            "v2_note": "W_alg v2 = the algorithmic count of the information-form formulation the kernel uses (DESIGN.md "
+                       "§4.0); frac >= frac_executed >= frac_v2 bracket the useful share of the FP64 peak",
             "numerator": "SURVEY.md §8(d) W_alg v1 (sequential-scalar IEKF count) with the measured iteration "
                          "counters; the kernel's information-form IEKF executes fewer flops than that count "
                          "(profiles/README.md: executed FP64 instructions per update from ncu)",

@@ -289,6 +289,16 @@ int kfpos_batch_replay_events(kfpos_batch *b, int n_events, const kfpos_event *e
                               int fmt, double err_scalar, const double *err_var, const double *sensors,
                               int64_t sensor_rows, double *traj, void *stream);
 
+/* The same with PER-FILTER time steps: dt_per_filter SoA [n_events][N] replaces kfpos_event::dt; a
+ * value < 0 means "filter f has no such event" (nothing is latched, predicted or updated; a TOA slot's
+ * trajectory row repeats the current state).  This is how N tags whose sensor messages arrive in
+ * different orders and numbers share one launch: kfpos_merge_streams lays their streams onto a common
+ * schedule (K8 / T9, general kernel instantiation).                                              */
+int kfpos_batch_replay_events_ragged(kfpos_batch *b, int n_events, const kfpos_event *events,
+                                     const double *dt_per_filter, const void *ranges, int fmt, double err_scalar,
+                                     const double *err_var, const double *sensors, int64_t sensor_rows,
+                                     double *traj, void *stream);
+
 /* getPose (PEA.h:14; TOA.cpp:438-473, KF.cpp:709-747, TOAIMU.cpp:476-510):
  * predict-only to `dt` after the last update, state untouched.  x_pred SoA
  * [n][N], P_pred SoA [n*n][N] (either may be NULL).                              */
@@ -344,6 +354,43 @@ int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs, int n_anch
                           const uint8_t *seq, const int32_t *range_mm, const double *err, const double *t,
                           int64_t max_epochs, int flags, double first_dt, int32_t *ranges_out, double *err_out,
                           double *dt_out, int32_t *n_epochs, void *stream);
+
+/* The assembler with the REPORT TIMES as well: t_out SoA [max_epochs][N] = the time at which each
+ * report reaches newTOAMeasurement (the arrival time of the ranging that started the next sequence
+ * number, or last ranging + 0.05 s when the timer sent it); -1 for epochs a log does not have.  NULL
+ * = kfpos_assemble_epochs.                                                                       */
+int kfpos_assemble_epochs_t(int device, int64_t n_logs, int64_t n_msgs, int n_anchors, const uint8_t *anchor,
+                            const uint8_t *seq, const int32_t *range_mm, const double *err, const double *t,
+                            int64_t max_epochs, int flags, double first_dt, int32_t *ranges_out, double *err_out,
+                            double *dt_out, int32_t *n_epochs, double *t_out, void *stream);
+
+/* ------------------------------------------------------------ stream merger
+ * PosGenerator runs every callback of a tag on one thread (Posgenerator.cpp:92-140): ranging reports
+ * (from the aggregation above) and PX4Flow / IMU / magnetometer / compass samples reach the filter in
+ * ARRIVAL ORDER, and the filter takes the time since its previous callback as dt (0.1 s for the first
+ * one, KF.cpp:232-243).  This call does that interleaving for N tags at once and lays the N sequences
+ * onto ONE schedule of n_slots events for kfpos_batch_replay_events_ragged: slot s has kind
+ * slot_kind[s] (KFPOS_EV_*, host array, any pattern -- e.g. the tags' nominal message pattern
+ * repeated); a tag's next event takes the next slot of its kind; slots it passes over get dt = -1
+ * ("this filter has no such event").  Equal time stamps: sensor samples in KFPOS_EV_* order, then
+ * the ranging report.
+ *   t_epoch SoA [n_epochs][N], ranges int32 SoA [n_epochs][n_anchors][N], err f64 same shape or NULL:
+ *       outputs of kfpos_assemble_epochs_t;
+ *   sensor streams q = 0..3 (PX4, IMU, MAG, COMPASS): n_samples[q], t_sensor[q] SoA [n_samples][N]
+ *       arrival times (a negative or NaN value ends the tag's stream), payload[q] SoA
+ *       [n_samples][rows][N] with the rows of kfpos_event (5 / 3 / 2 / 1); NULL / 0 = no such stream;
+ *   imu_aux: the 9 aux doubles every IMU slot gets (covariances, common to the batch), or NULL;
+ *   outputs: events_out HOST [n_slots] (kind, offset; dt unused); dt_out SoA [n_slots][N];
+ *       ranges_out int32 SoA [n_anchors * #TOA slots][N] (-1 where no event); err_out same shape or
+ *       NULL; sensors_out f64 SoA [sum of the sensor slots' rows][N]; n_dropped [N] or NULL = events of
+ *       a tag that found no slot left (raise n_slots).
+ * Host or device pointers for the tensors; the call synchronises `stream` before returning.       */
+int kfpos_merge_streams(int device, int64_t n_logs, int n_anchors, int64_t n_epochs, const double *t_epoch,
+                        const int32_t *ranges, const double *err, const int64_t n_samples[4],
+                        const double *const t_sensor[4], const double *const payload[4], int n_slots,
+                        const int32_t *slot_kind, double first_dt, const double *imu_aux,
+                        kfpos_event *events_out, double *dt_out, int32_t *ranges_out, double *err_out,
+                        double *sensors_out, int32_t *n_dropped, void *stream);
 
 /* ------------------------------------------------------------- diagnostics
  * Work counters accumulated on the device since the last reset, as doubles:

@@ -206,11 +206,15 @@ void ko_pose_msg(int model, const double *x, const double *P, double tag_z, doub
 int64_t ko_assemble(int64_t L, int M, int64_t stride, const uint8_t *anchor, const uint8_t *seq,
                     const int32_t *range_mm, const double *err, const double *t, int64_t max_epochs,
                     int fix_b12, double first_dt, int64_t out_stride, int32_t *ranges_out, double *err_out,
-                    double *dt_out);
+                    double *dt_out, double *t_out);
 void ko_assemble_batch(int64_t N, int64_t L, int M, const uint8_t *anchor, const uint8_t *seq,
                        const int32_t *range_mm, const double *err, const double *t, int64_t max_epochs,
                        int fix_b12, double first_dt, int32_t *ranges_out, double *err_out, double *dt_out,
-                       int32_t *n_epochs);
+                       int32_t *n_epochs, double *t_out);
+void ko_merge_batch(int64_t N, int M, const int64_t L[5], const double *const t_src[5], const int32_t *ranges,
+                    const double *err_src, const double *const src[5], int S, const int32_t *slot_kind,
+                    const int64_t *slot_row, double first_dt, double *dt_f, int32_t *ranges_out, double *err_out,
+                    double *sensors_out, int32_t *n_dropped);
 
 #ifdef __cplusplus
 }

@@ -34,7 +34,7 @@
 int64_t ko_assemble(int64_t L, int M, int64_t stride, const uint8_t *anchor, const uint8_t *seq,
                     const int32_t *range_mm, const double *err, const double *t, int64_t max_epochs,
                     int fix_b12, double first_dt, int64_t out_stride, int32_t *ranges_out, double *err_out,
-                    double *dt_out) {
+                    double *dt_out, double *t_out /* NULL, or the time of every report */) {
     int32_t(*val)[KO_MAX_ANCHORS] = malloc(sizeof(int32_t) * 256 * KO_MAX_ANCHORS);
     double(*ee)[KO_MAX_ANCHORS] = malloc(sizeof(double) * 256 * KO_MAX_ANCHORS);
     memset(val, 0xff, sizeof(int32_t) * 256 * KO_MAX_ANCHORS); /* :505 */
@@ -54,6 +54,7 @@ int64_t ko_assemble(int64_t L, int M, int64_t stride, const uint8_t *anchor, con
                     if (err_out) err_out[(n_ep * M + a) * out_stride] = ee[range_seq][a];            \
                 }                                                                                    \
                 dt_out[n_ep * out_stride] = flushed_once ? (tnow) - t_prev_flush : first_dt;         \
+                if (t_out) t_out[n_ep * out_stride] = (tnow);                                        \
             }                                                                                        \
             n_ep += 1;                                                                               \
             t_prev_flush = (tnow);                                                                   \
@@ -101,7 +102,7 @@ int64_t ko_assemble(int64_t L, int M, int64_t stride, const uint8_t *anchor, con
 void ko_assemble_batch(int64_t N, int64_t L, int M, const uint8_t *anchor, const uint8_t *seq,
                        const int32_t *range_mm, const double *err, const double *t, int64_t max_epochs,
                        int fix_b12, double first_dt, int32_t *ranges_out, double *err_out, double *dt_out,
-                       int32_t *n_epochs) {
+                       int32_t *n_epochs, double *t_out /* [max_epochs][N] or NULL */) {
 #pragma omp parallel for schedule(static)
     for (int64_t f = 0; f < N; ++f) {
         for (int64_t k = 0; k < max_epochs; ++k) {
@@ -110,9 +111,71 @@ void ko_assemble_batch(int64_t N, int64_t L, int M, const uint8_t *anchor, const
                 if (err_out) err_out[(k * M + a) * N + f] = 0.0;
             }
             dt_out[k * N + f] = -1.0;
+            if (t_out) t_out[k * N + f] = -1.0;
         }
         n_epochs[f] = (int32_t)ko_assemble(L, M, N, anchor + f, seq + f, range_mm + f, err ? err + f : 0, t + f,
                                            max_epochs, fix_b12, first_dt, N, ranges_out + f,
-                                           err_out ? err_out + f : 0, dt_out + f);
+                                           err_out ? err_out + f : 0, dt_out + f, t_out ? t_out + f : 0);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Stream merger: what PosGenerator's single callback thread does with one tag's messages when they
+ * come from several topics (Posgenerator.cpp:92-140): the ranging reports (ko_assemble, at their report
+ * times) and the PX4Flow / IMU / magnetometer / compass samples reach the filter in ARRIVAL ORDER, and
+ * the filter takes the time since its previous callback as dt (0.1 s for the first one, KF.cpp:232-243).
+ * For a batch, the N per-tag sequences are laid onto ONE schedule of S slots (slot s has kind
+ * slot_kind[s]; KO event kinds 0 TOA, 1 PX4, 2 IMU, 3 MAG, 4 COMPASS): a tag's next event takes the next
+ * slot of its kind, slots it passes over are marked "no event" (dt = -1) -- the ragged-replay
+ * convention of kfpos_batch_replay_events_ragged.  Equal time stamps: sensor samples in kind order,
+ * then the ranging report (a timer that is due exactly when a message arrives fires after it).
+ *   t_src[k]   : [L_k][N] arrival times of stream k (k = 0: report times from ko_assemble); a value that
+ *                is negative or NaN ends the stream
+ *   src[k]     : k = 0: int32 ranges [L_0][M][N] (+ err_src [L_0][M][N] or NULL); k > 0: f64 [L_k][rows_k][N]
+ *   slot_row[s]: first output row of slot s (rows of ranges_out for TOA slots, of sensors_out otherwise)
+ *   outputs    : dt_f [S][N]; ranges_out / err_out [*][N]; sensors_out [*][N]; n_dropped [N] = events that
+ *                found no slot left
+ */
+static const int ko_event_rows[5] = {0, 5, 3, 2, 1};
+void ko_merge_batch(int64_t N, int M, const int64_t L[5], const double *const t_src[5], const int32_t *ranges,
+                    const double *err_src, const double *const src[5], int S, const int32_t *slot_kind,
+                    const int64_t *slot_row, double first_dt, double *dt_f, int32_t *ranges_out, double *err_out,
+                    double *sensors_out, int32_t *n_dropped) {
+#pragma omp parallel for schedule(static)
+    for (int64_t f = 0; f < N; ++f) {
+        int64_t ptr[5] = {0, 0, 0, 0, 0};
+        int slot = 0, dropped = 0, first = 1;
+        double t_prev = 0.0;
+        for (int s = 0; s < S; ++s) dt_f[(int64_t)s * N + f] = -1.0;
+        for (;;) {
+            int k = -1;
+            double tk = 0.0;
+            for (int qq = 1; qq <= 5; ++qq) { /* equal time stamps: sensor samples in kind order, then the report */
+                const int q = qq % 5;
+                if (!t_src[q] || ptr[q] >= L[q]) continue;
+                const double tq = t_src[q][ptr[q] * N + f];
+                if (!(tq >= 0.0)) continue; /* negative or NaN: the stream has ended */
+                if (k < 0 || tq < tk) { k = q; tk = tq; }
+            }
+            if (k < 0) break;
+            int s = slot;
+            while (s < S && slot_kind[s] != k) ++s;
+            const int64_t j = ptr[k]++;
+            if (s >= S) { dropped += 1; continue; }
+            dt_f[(int64_t)s * N + f] = first ? first_dt : tk - t_prev;
+            first = 0;
+            t_prev = tk;
+            if (k == 0) {
+                for (int a = 0; a < M; ++a) {
+                    ranges_out[(slot_row[s] + a) * N + f] = ranges[(j * M + a) * N + f];
+                    if (err_out) err_out[(slot_row[s] + a) * N + f] = err_src ? err_src[(j * M + a) * N + f] : 0.0;
+                }
+            } else {
+                for (int r = 0; r < ko_event_rows[k]; ++r)
+                    sensors_out[(slot_row[s] + r) * N + f] = src[k][(j * ko_event_rows[k] + r) * N + f];
+            }
+            slot = s + 1;
+        }
+        if (n_dropped) n_dropped[f] = dropped;
     }
 }

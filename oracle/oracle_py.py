@@ -403,11 +403,62 @@ def assemble(anchor, seq, range_mm, t, n_anchors, max_epochs, err=None, fix_b12=
     ro = np.empty((T, M, N), dtype=np.int32)
     eo = np.empty((T, M, N))
     dt = np.empty((T, N))
+    tt = np.empty((T, N))
     ne = np.empty(N, dtype=np.int32)
     lib().ko_assemble_batch(C.c_int64(N), C.c_int64(L), M, _p(anchor, C.c_uint8), _p(seq, C.c_uint8),
                             _p(range_mm, C.c_int32), _p(e), _p(t), C.c_int64(T), int(fix_b12),
-                            C.c_double(first_dt), _p(ro, C.c_int32), _p(eo), _p(dt), _p(ne, C.c_int32))
-    return dict(ranges=ro, err=eo, dt=dt, n_epochs=ne)
+                            C.c_double(first_dt), _p(ro, C.c_int32), _p(eo), _p(dt), _p(ne, C.c_int32), _p(tt))
+    return dict(ranges=ro, err=eo, dt=dt, n_epochs=ne, t=tt)
+
+
+EVENT_ROWS = {1: 5, 2: 3, 3: 2, 4: 1}
+
+
+def slot_rows(slot_kind, n_anchors):
+    """First output row of every slot of a merged schedule: TOA slots count rows of the range tensor
+    (n_anchors each), the others rows of the sensor tensor.  Returns (rows int64 [S], range_rows, sensor_rows)."""
+    rows, nr, ns = [], 0, 0
+    for k in slot_kind:
+        if k == 0:
+            rows.append(nr); nr += n_anchors
+        else:
+            rows.append(ns); ns += EVENT_ROWS[int(k)]
+    return np.array(rows, dtype=np.int64), nr, ns
+
+
+def merge_streams(t_epoch, ranges, err, sensors, slot_kind, first_dt=0.1):
+    """ko_merge_batch.  t_epoch [T][N], ranges int32 [T][M][N], err [T][M][N] or None; sensors = {kind: (t [L][N],
+    payload [L][rows][N])}; slot_kind: the S kinds of the common schedule.  Returns dict(dt [S][N], ranges
+    int32 [range_rows][N], err, sensors [sensor_rows][N], n_dropped [N], slot_row)"""
+    t_epoch = np.ascontiguousarray(t_epoch, dtype=np.float64)
+    ranges = np.ascontiguousarray(ranges, dtype=np.int32)
+    T, M, N = ranges.shape
+    err = None if err is None else np.ascontiguousarray(err, dtype=np.float64)
+    sk = np.ascontiguousarray(slot_kind, dtype=np.int32)
+    S = len(sk)
+    row, nr, ns = slot_rows(sk, M)
+    Ls = (C.c_int64 * 5)(T, 0, 0, 0, 0)
+    tp = (C.POINTER(C.c_double) * 5)()
+    sp = (C.POINTER(C.c_double) * 5)()
+    keep = []
+    tp[0] = _p(t_epoch)
+    for k, (tk, pk) in sensors.items():
+        tk = np.ascontiguousarray(tk, dtype=np.float64)
+        pk = np.ascontiguousarray(pk, dtype=np.float64)
+        assert pk.shape == (tk.shape[0], EVENT_ROWS[k], N)
+        keep += [tk, pk]
+        Ls[k] = tk.shape[0]
+        tp[k] = _p(tk)
+        sp[k] = _p(pk)
+    dt = np.empty((S, N))
+    ro = np.full((max(nr, 1), N), -1, dtype=np.int32)
+    eo = None if err is None else np.zeros((max(nr, 1), N))
+    so = np.zeros((max(ns, 1), N))
+    nd = np.empty(N, dtype=np.int32)
+    lib().ko_merge_batch(C.c_int64(N), M, Ls, tp, _p(ranges, C.c_int32), _p(err), sp, S, _p(sk, C.c_int32),
+                         _p(row, C.c_int64), C.c_double(first_dt), _p(dt), _p(ro, C.c_int32), _p(eo), _p(so),
+                         _p(nd, C.c_int32))
+    return dict(dt=dt, ranges=ro, err=eo, sensors=so, n_dropped=nd, slot_row=row)
 
 
 # ------------------------------------------------------------------ pose message

@@ -195,8 +195,11 @@ class Batch:
         L.check(L.lib().kfpos_batch_step_imu(self._h, float(dt), a[0][0], cp[0], a[1][0], cp[1],
                                              _stream_ptr(stream)), "kfpos_batch_step_imu")
 
-    def replay_events(self, events, ranges=None, sensors=None, err=0.01, traj=None, want_traj=False, stream=None):
-        """events: list of (kind, dt, offset_row[, aux]) ; ranges [T][M][N] (or [rows][N]); sensors [R][N] f64."""
+    def replay_events(self, events, ranges=None, sensors=None, err=0.01, traj=None, want_traj=False, stream=None,
+                      dt_per_filter=None):
+        """events: list of (kind, dt, offset_row[, aux]) ; ranges [T][M][N] (or [rows][N]); sensors [R][N] f64.
+        dt_per_filter [n_events][N]: per-filter time steps (< 0 = the filter has no such event), the ragged replay
+        of schedules merged by merge_streams (kfpos_batch_replay_events_ragged)."""
         n = len(events)
         arr = (L.KfposEvent * n)()
         n_toa = 0
@@ -213,6 +216,12 @@ class Batch:
         if traj is None and want_traj:
             traj = np.empty((n_toa, 3, self.N))
         fmt = _fmt_of(ranges) if ranges is not None else L.FMT_F64_M
+        if dt_per_filter is not None:
+            pd, kd = _ptr(dt_per_filter, np.float64)
+            L.check(L.lib().kfpos_batch_replay_events_ragged(self._h, n, C.cast(arr, C.c_void_p), pd, pr, fmt, es, ep, ps,
+                                                             C.c_int64(srows), _ptr(traj)[0], _stream_ptr(stream)),
+                    "kfpos_batch_replay_events_ragged")
+            return traj
         L.check(L.lib().kfpos_batch_replay_events(self._h, n, C.cast(arr, C.c_void_p), pr, fmt, es, ep, ps,
                                                   C.c_int64(srows), _ptr(traj)[0], _stream_ptr(stream)),
                 "kfpos_batch_replay_events")
@@ -300,18 +309,58 @@ def assemble_epochs(anchor, seq, range_mm, t, n_anchors, max_epochs, err=None, f
                     device=0, out=None, stream=None):
     """Ranging aggregation of PosGenerator for N logs of L messages (SoA [L][N]; numpy or CUDA torch
     tensors: uint8 anchor index, uint8 seq, int32 range_mm, f64 arrival time, optional f64 err).
-    Returns dict(ranges int32 [T][M][N], err [T][M][N] or None, dt [T][N], n_epochs [N]); `out` may
-    supply device tensors under the same keys."""
+    Returns dict(ranges int32 [T][M][N], err [T][M][N] or None, dt [T][N], n_epochs [N], t [T][N] = the report
+    times); `out` may supply device tensors under the same keys."""
     Lm, N = int(anchor.shape[0]), int(anchor.shape[1])
     M, T = int(n_anchors), int(max_epochs)
     if out is None:
         out = dict(ranges=np.empty((T, M, N), dtype=np.int32), err=None if err is None else np.empty((T, M, N)),
-                   dt=np.empty((T, N)), n_epochs=np.empty(N, dtype=np.int32))
+                   dt=np.empty((T, N)), n_epochs=np.empty(N, dtype=np.int32), t=np.empty((T, N)))
     keep = [_ptr(anchor, np.uint8), _ptr(seq, np.uint8), _ptr(range_mm, np.int32), _ptr(err, np.float64),
             _ptr(t, np.float64)]
-    L.check(L.lib().kfpos_assemble_epochs(int(device), N, Lm, M, keep[0][0], keep[1][0], keep[2][0], keep[3][0],
-                                          keep[4][0], T, L.ASM_FIX_ROW_CLEAR if fix_row_clear else 0, float(first_dt),
-                                          _ptr(out["ranges"])[0], _ptr(out.get("err"))[0], _ptr(out["dt"])[0],
-                                          _ptr(out.get("n_epochs"))[0], _stream_ptr(stream)),
-            "kfpos_assemble_epochs")
+    L.check(L.lib().kfpos_assemble_epochs_t(int(device), N, Lm, M, keep[0][0], keep[1][0], keep[2][0], keep[3][0],
+                                            keep[4][0], T, L.ASM_FIX_ROW_CLEAR if fix_row_clear else 0, float(first_dt),
+                                            _ptr(out["ranges"])[0], _ptr(out.get("err"))[0], _ptr(out["dt"])[0],
+                                            _ptr(out.get("n_epochs"))[0], _ptr(out.get("t"))[0], _stream_ptr(stream)),
+            "kfpos_assemble_epochs_t")
+    return out
+
+
+def merge_streams(t_epoch, ranges, err, sensors, slot_kind, first_dt=0.1, imu_aux=None, device=0, stream=None):
+    """kfpos_merge_streams: N tags' ranging reports (t_epoch [T][N], ranges int32 [T][M][N], err [T][M][N] or None:
+    the assembler's outputs) and sensor samples (sensors = {EV kind: (t [L][N], payload [L][rows][N])}) in arrival
+    order, laid onto the common schedule `slot_kind` (list of EV kinds).  numpy arrays in, numpy arrays out:
+    dict(events = list for Batch.replay_events, dt [S][N], ranges int32 [rows][N], err, sensors [rows][N], n_dropped)."""
+    ranges = np.ascontiguousarray(ranges, dtype=np.int32)
+    T, M, N = ranges.shape
+    t_epoch = np.ascontiguousarray(t_epoch, dtype=np.float64)
+    err = None if err is None else np.ascontiguousarray(err, dtype=np.float64)
+    sk = np.ascontiguousarray(slot_kind, dtype=np.int32)
+    S = len(sk)
+    n_toa = int((sk == L.EV_TOA).sum())
+    srows = int(sum(L.EV_ROWS[int(k)] for k in sk if k != L.EV_TOA))
+    ns = (C.c_int64 * 4)(0, 0, 0, 0)
+    tp = (C.c_void_p * 4)()
+    pp = (C.c_void_p * 4)()
+    keep = []
+    for k, (tk, pk) in sensors.items():
+        tk = np.ascontiguousarray(tk, dtype=np.float64)
+        pk = np.ascontiguousarray(pk, dtype=np.float64)
+        assert pk.shape == (tk.shape[0], L.EV_ROWS[k], N)
+        keep += [tk, pk]
+        ns[k - 1] = tk.shape[0]
+        tp[k - 1] = tk.ctypes.data
+        pp[k - 1] = pk.ctypes.data
+    aux = None if imu_aux is None else np.ascontiguousarray(list(imu_aux) + [0.0] * (9 - len(imu_aux)), dtype=np.float64)
+    ev = (L.KfposEvent * S)()
+    out = dict(dt=np.empty((S, N)), ranges=np.empty((max(n_toa * M, 1), N), dtype=np.int32),
+               err=None if err is None else np.empty((max(n_toa * M, 1), N)), sensors=np.empty((max(srows, 1), N)),
+               n_dropped=np.empty(N, dtype=np.int32))
+    vp = lambda a: None if a is None else C.c_void_p(a.ctypes.data)
+    L.check(L.lib().kfpos_merge_streams(int(device), N, M, T, vp(t_epoch), vp(ranges), vp(err), C.cast(ns, C.c_void_p),
+                                        C.cast(tp, C.c_void_p), C.cast(pp, C.c_void_p), S, vp(sk),
+                                        float(first_dt), vp(aux), C.cast(ev, C.c_void_p), vp(out["dt"]), vp(out["ranges"]),
+                                        vp(out["err"]), vp(out["sensors"]), vp(out["n_dropped"]), _stream_ptr(stream)),
+            "kfpos_merge_streams")
+    out["events"] = [(int(e.kind), 0.0, int(e.offset), list(e.aux) if e.kind == L.EV_IMU else None) for e in ev]
     return out

@@ -745,9 +745,9 @@ int run_events(kfpos_batch *b, int n, const kfpos_event *events, const void *d_r
 
 } // namespace
 
-extern "C" int kfpos_batch_replay_events(kfpos_batch *b, int n_events, const kfpos_event *events, const void *ranges,
-                                         int fmt, double err_scalar, const double *err_var, const double *sensors,
-                                         int64_t sensor_rows, double *traj, void *stream) {
+static int replay_events_impl(kfpos_batch *b, int n_events, const kfpos_event *events, const double *dt_per_filter,
+                              const void *ranges, int fmt, double err_scalar, const double *err_var,
+                              const double *sensors, int64_t sensor_rows, double *traj, void *stream) {
     if (!b || (b->model != KFPOS_MODEL_K8 && b->model != KFPOS_MODEL_T9) || n_events < 0 || !events)
         return KFPOS_ERR_INVALID;
     if (fmt < 0 || fmt > 2) return KFPOS_ERR_INVALID;
@@ -781,14 +781,32 @@ extern "C" int kfpos_batch_replay_events(kfpos_batch *b, int n_events, const kfp
     bool copy_traj = false;
     rc = stage_out(b, 2, traj, sizeof(double) * 3 * N * (size_t)n_toa, &d_traj, &copy_traj);
     if (rc) return rc;
+    const void *d_dtf = nullptr;
+    if ((rc = stage_in(b, 1, dt_per_filter, sizeof(double) * N * (size_t)n_events, s, &d_dtf))) return rc;
     rc = run_events(b, n_events, events, d_r, fmt, err_scalar, (const double *)d_e, (const double *)d_s,
-                    (double *)d_traj, s);
+                    (double *)d_traj, s, (const double *)d_dtf);
     if (rc) return rc;
     if (copy_traj) {
         CK(cudaMemcpyAsync(traj, d_traj, sizeof(double) * 3 * N * (size_t)n_toa, cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
     }
     return KFPOS_OK;
+}
+
+extern "C" int kfpos_batch_replay_events(kfpos_batch *b, int n_events, const kfpos_event *events, const void *ranges,
+                                         int fmt, double err_scalar, const double *err_var, const double *sensors,
+                                         int64_t sensor_rows, double *traj, void *stream) {
+    return replay_events_impl(b, n_events, events, nullptr, ranges, fmt, err_scalar, err_var, sensors, sensor_rows, traj,
+                              stream);
+}
+
+extern "C" int kfpos_batch_replay_events_ragged(kfpos_batch *b, int n_events, const kfpos_event *events,
+                                                const double *dt_per_filter, const void *ranges, int fmt,
+                                                double err_scalar, const double *err_var, const double *sensors,
+                                                int64_t sensor_rows, double *traj, void *stream) {
+    if (!dt_per_filter) return KFPOS_ERR_INVALID;
+    return replay_events_impl(b, n_events, events, dt_per_filter, ranges, fmt, err_scalar, err_var, sensors, sensor_rows,
+                              traj, stream);
 }
 
 namespace {
@@ -1018,6 +1036,14 @@ extern "C" int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs,
                                      const uint8_t *seq, const int32_t *range_mm, const double *err, const double *t,
                                      int64_t max_epochs, int flags, double first_dt, int32_t *ranges_out,
                                      double *err_out, double *dt_out, int32_t *n_epochs, void *stream) {
+    return kfpos_assemble_epochs_t(device, n_logs, n_msgs, n_anchors, anchor, seq, range_mm, err, t, max_epochs, flags,
+                                   first_dt, ranges_out, err_out, dt_out, n_epochs, nullptr, stream);
+}
+
+extern "C" int kfpos_assemble_epochs_t(int device, int64_t n_logs, int64_t n_msgs, int n_anchors, const uint8_t *anchor,
+                                       const uint8_t *seq, const int32_t *range_mm, const double *err, const double *t,
+                                       int64_t max_epochs, int flags, double first_dt, int32_t *ranges_out,
+                                       double *err_out, double *dt_out, int32_t *n_epochs, double *t_out, void *stream) {
     if (n_logs <= 0 || n_msgs < 0 || n_anchors <= 0 || n_anchors > KFPOS_MAX_ANCHORS || max_epochs <= 0)
         return KFPOS_ERR_INVALID;
     if (!anchor || !seq || !range_mm || !t || !ranges_out || !dt_out) return KFPOS_ERR_INVALID;
@@ -1031,7 +1057,7 @@ extern "C" int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs,
     cudaStream_t s = (cudaStream_t)stream;
     const size_t N = (size_t)n_logs, L = (size_t)n_msgs, M = (size_t)n_anchors, T = (size_t)max_epochs;
     TmpIn i_a, i_s, i_r, i_e, i_t;
-    TmpOut o_r, o_e, o_dt, o_n;
+    TmpOut o_r, o_e, o_dt, o_n, o_t;
     CK(i_a.set(anchor, L * N, s));
     CK(i_s.set(seq, L * N, s));
     CK(i_r.set(range_mm, 4 * L * N, s));
@@ -1041,6 +1067,7 @@ extern "C" int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs,
     CK(o_e.set(err_out, 8 * T * M * N));
     CK(o_dt.set(dt_out, 8 * T * N));
     CK(o_n.set(n_epochs, 4 * N));
+    CK(o_t.set(t_out, 8 * T * N));
     const int fix = (flags & KFPOS_ASM_FIX_ROW_CLEAR) ? 1 : 0;
     const size_t rows = fix ? 1 : 256;
     // the sequence-number table: per-device scratch that is kept between calls (grown on demand)
@@ -1060,7 +1087,9 @@ extern "C" int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs,
     p.tbl_r = (int32_t *)tr.p; p.tbl_e = (double *)te.p;
     p.ranges_out = (int32_t *)o_r.d; p.err_out = (double *)o_e.d; p.dt_out = (double *)o_dt.d;
     p.n_epochs = (int32_t *)o_n.d;
+    p.t_out = (double *)o_t.d;
     CK(launch_assemble(p, s));
+    CK(o_t.back(s));
     CK(o_r.back(s));
     CK(o_e.back(s));
     CK(o_dt.back(s));
@@ -1069,9 +1098,105 @@ extern "C" int kfpos_assemble_epochs(int device, int64_t n_logs, int64_t n_msgs,
     // pointers only, the call is asynchronous on `stream` like the rest of the API (the table
     // is reused by the next call on the same device, which is ordered behind this one only if it
     // uses the same stream: callers on different streams must synchronise themselves).
-    if (i_a.own || i_s.own || i_r.own || i_e.own || i_t.own || o_r.own || o_e.own || o_dt.own || o_n.own)
+    if (i_a.own || i_s.own || i_r.own || i_e.own || i_t.own || o_r.own || o_e.own || o_dt.own || o_n.own || o_t.own)
         CK(cudaStreamSynchronize(s));
     return KFPOS_OK;
+}
+
+extern "C" int kfpos_merge_streams(int device, int64_t n_logs, int n_anchors, int64_t n_epochs, const double *t_epoch,
+                                   const int32_t *ranges, const double *err, const int64_t n_samples[4],
+                                   const double *const t_sensor[4], const double *const payload[4], int n_slots,
+                                   const int32_t *slot_kind, double first_dt, const double *imu_aux,
+                                   kfpos_event *events_out, double *dt_out, int32_t *ranges_out, double *err_out,
+                                   double *sensors_out, int32_t *n_dropped, void *stream) {
+    if (n_logs <= 0 || n_anchors <= 0 || n_anchors > KFPOS_MAX_ANCHORS || n_epochs < 0 || n_slots <= 0 || !slot_kind ||
+        !dt_out)
+        return KFPOS_ERR_INVALID;
+    static const int rows_of[5] = {0, 5, 3, 2, 1};
+    int64_t range_rows = 0, sensor_rows = 0;
+    std::vector<int64_t> slot_row((size_t)n_slots);
+    for (int sidx = 0; sidx < n_slots; ++sidx) {
+        const int k = slot_kind[sidx];
+        if (k < KFPOS_EV_TOA || k > KFPOS_EV_COMPASS) return KFPOS_ERR_INVALID;
+        if (k == KFPOS_EV_TOA) {
+            slot_row[sidx] = range_rows;
+            range_rows += n_anchors;
+        } else {
+            slot_row[sidx] = sensor_rows;
+            sensor_rows += rows_of[k];
+        }
+        if (events_out) {
+            memset(&events_out[sidx], 0, sizeof(kfpos_event));
+            events_out[sidx].kind = k;
+            events_out[sidx].dt = 0.0; // the per-filter time steps replace it
+            events_out[sidx].offset = slot_row[sidx];
+            if (k == KFPOS_EV_IMU && imu_aux) memcpy(events_out[sidx].aux, imu_aux, sizeof(double) * 9);
+        }
+    }
+    if ((range_rows > 0 && (!ranges_out || (n_epochs > 0 && (!t_epoch || !ranges)))) || (sensor_rows > 0 && !sensors_out))
+        return KFPOS_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return KFPOS_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return KFPOS_ERR_CUDA;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = (size_t)n_logs, M = (size_t)n_anchors;
+    MergeParams p;
+    memset(&p, 0, sizeof p);
+    p.N = n_logs; p.M = n_anchors; p.n_slots = n_slots; p.first_dt = first_dt;
+    TmpIn i_t[5], i_p[5], i_e, i_k, i_row;
+    TmpOut o_dt, o_r, o_e, o_s, o_n;
+    p.L[0] = n_epochs;
+    CK(i_t[0].set(t_epoch, 8 * (size_t)n_epochs * N, s));
+    CK(i_p[0].set(ranges, 4 * (size_t)n_epochs * M * N, s));
+    CK(i_e.set(err, 8 * (size_t)n_epochs * M * N, s));
+    p.t_src[0] = (const double *)i_t[0].d; p.ranges = (const int32_t *)i_p[0].d; p.err_src = (const double *)i_e.d;
+    for (int k = 1; k < 5; ++k) {
+        const int64_t Lk = n_samples ? n_samples[k - 1] : 0;
+        if (Lk <= 0 || !t_sensor || !payload || !t_sensor[k - 1] || !payload[k - 1]) continue;
+        p.L[k] = Lk;
+        CK(i_t[k].set(t_sensor[k - 1], 8 * (size_t)Lk * N, s));
+        CK(i_p[k].set(payload[k - 1], 8 * (size_t)Lk * rows_of[k] * N, s));
+        p.t_src[k] = (const double *)i_t[k].d; p.src[k] = (const double *)i_p[k].d;
+    }
+    CK(i_k.set(nullptr, 0, s)); // (slot tables are small host arrays: always copied)
+    int32_t *d_kind = nullptr;
+    int64_t *d_row = nullptr;
+    CK(cudaMalloc((void **)&d_kind, sizeof(int32_t) * (size_t)n_slots));
+    cudaError_t e2 = cudaMalloc((void **)&d_row, sizeof(int64_t) * (size_t)n_slots);
+    if (e2 != cudaSuccess) { cudaFree(d_kind); return map_cuda_err(e2); }
+    auto cleanup = [&]() { cudaFree(d_kind); cudaFree(d_row); };
+    auto fail = [&](cudaError_t e) { cudaStreamSynchronize(s); cleanup(); return map_cuda_err(e); };
+    cudaError_t e = cudaMemcpyAsync(d_kind, slot_kind, sizeof(int32_t) * (size_t)n_slots, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_row, slot_row.data(), sizeof(int64_t) * (size_t)n_slots, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = o_dt.set(dt_out, 8 * (size_t)n_slots * N);
+    if (e == cudaSuccess) e = o_r.set(ranges_out, 4 * (size_t)(range_rows > 0 ? range_rows : 1) * N);
+    if (e == cudaSuccess) e = o_e.set(err_out, 8 * (size_t)(range_rows > 0 ? range_rows : 1) * N);
+    if (e == cudaSuccess) e = o_s.set(sensors_out, 8 * (size_t)(sensor_rows > 0 ? sensor_rows : 1) * N);
+    if (e == cudaSuccess) e = o_n.set(n_dropped, 4 * N);
+    if (e != cudaSuccess) return fail(e);
+    // slots nobody takes keep "no ranging" / zero payloads
+    if (o_r.d) e = cudaMemsetAsync(o_r.d, 0xff, 4 * (size_t)(range_rows > 0 ? range_rows : 1) * N, s);
+    if (e == cudaSuccess && o_e.d) e = cudaMemsetAsync(o_e.d, 0, 8 * (size_t)(range_rows > 0 ? range_rows : 1) * N, s);
+    if (e == cudaSuccess && o_s.d) e = cudaMemsetAsync(o_s.d, 0, 8 * (size_t)(sensor_rows > 0 ? sensor_rows : 1) * N, s);
+    if (e != cudaSuccess) return fail(e);
+    p.slot_kind = d_kind; p.slot_row = d_row;
+    p.dt_f = (double *)o_dt.d; p.ranges_out = (int32_t *)o_r.d; p.err_out = (double *)o_e.d;
+    p.sensors_out = (double *)o_s.d; p.n_dropped = (int32_t *)o_n.d;
+    e = launch_merge(p, s);
+    if (e == cudaSuccess) e = o_dt.back(s);
+    if (e == cudaSuccess) e = o_r.back(s);
+    if (e == cudaSuccess) e = o_e.back(s);
+    if (e == cudaSuccess) e = o_s.back(s);
+    if (e == cudaSuccess) e = o_n.back(s);
+    if (e != cudaSuccess) return fail(e);
+    // the slot tables (and any staged host arrays) are freed on return: finish the work first
+    e = cudaStreamSynchronize(s);
+    cleanup();
+    return e == cudaSuccess ? KFPOS_OK : map_cuda_err(e);
 }
 
 // ----------------------------------------------------------------- diagnostics

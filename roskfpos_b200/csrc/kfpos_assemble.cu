@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleParams p) {
                 if (p.err_out) p.err_out[(n_ep * M + a) * N + f] = te[(row + a) * N];
             }
             p.dt_out[n_ep * N + f] = flushed_once ? tnow - t_prev : p.first_dt;
+            if (p.t_out) p.t_out[n_ep * N + f] = tnow; // the time newTOAMeasurement is called (stream merger)
         }
         n_ep += 1;
         t_prev = tnow;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleParams p) {
             if (p.err_out) p.err_out[(k * M + a) * N + f] = 0.0;
         }
         p.dt_out[k * N + f] = -1.0;
+        if (p.t_out) p.t_out[k * N + f] = -1.0;
     }
     if (p.n_epochs) p.n_epochs[f] = (int32_t)(n_ep > 0x7fffffff ? 0x7fffffff : n_ep);
 }
@@ -100,6 +102,76 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleParams p) {
 cudaError_t launch_assemble(const AssembleParams &p, cudaStream_t s) {
     if (p.N <= 0) return cudaSuccess;
     assemble_kernel<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+// ---- stream merger: the arrival-order interleaving of one tag's ranging reports and sensor samples
+// (PosGenerator's single callback thread, Posgenerator.cpp:92-140), N tags at once, laid onto ONE schedule of
+// slots for the ragged replay (kfpos_batch_replay_events_ragged).  One thread per tag does a 5-way merge by
+// time stamp over its streams (heads in registers, SoA loads and stores with the tag index fastest): its next
+// event takes the next slot of its kind, dt = time since its previous event (first_dt for the first one,
+// KF.cpp:232-243), slots passed over stay "no event" (dt = -1).  Byte / integer shuffling: HBM-bound.
+__global__ void __launch_bounds__(128) merge_kernel(const MergeParams p) {
+    const int64_t f = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (f >= p.N) return;
+    const int64_t N = p.N;
+    const int M = p.M;
+    int64_t ptr[5] = {0, 0, 0, 0, 0};
+    double head[5];
+    auto load_head = [&](int q) { // negative / NaN = the stream has ended
+        head[q] = (p.t_src[q] && ptr[q] < p.L[q]) ? p.t_src[q][ptr[q] * N + f] : -1.0;
+    };
+#pragma unroll
+    for (int q = 0; q < 5; ++q) load_head(q);
+    int slot = 0, next_unmarked = 0, dropped = 0;
+    bool first = true;
+    double t_prev = 0.0;
+    for (;;) {
+        int k = -1;
+        double tk = 0.0;
+#pragma unroll
+        for (int qq = 1; qq <= 5; ++qq) { // equal time stamps: sensor samples in kind order, then the report
+            const int q = qq % 5;
+            const double tq = head[q];
+            if (!(tq >= 0.0)) continue;
+            if (k < 0 || tq < tk) { k = q; tk = tq; }
+        }
+        if (k < 0) break;
+        int s = slot;
+        while (s < p.n_slots && p.slot_kind[s] != k) ++s;
+        const int64_t j = ptr[k];
+        // advance stream k (a select chain keeps ptr / head in registers)
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            if (q == k) {
+                ptr[q] += 1;
+                load_head(q);
+            }
+        if (s >= p.n_slots) { dropped += 1; continue; }
+        for (; next_unmarked < s; ++next_unmarked) p.dt_f[(int64_t)next_unmarked * N + f] = -1.0;
+        p.dt_f[(int64_t)s * N + f] = first ? p.first_dt : tk - t_prev;
+        next_unmarked = s + 1;
+        first = false;
+        t_prev = tk;
+        const int64_t row = p.slot_row[s];
+        if (k == 0) {
+            for (int a = 0; a < M; ++a) {
+                p.ranges_out[(row + a) * N + f] = p.ranges[(j * M + a) * N + f];
+                if (p.err_out) p.err_out[(row + a) * N + f] = p.err_src ? p.err_src[(j * M + a) * N + f] : 0.0;
+            }
+        } else {
+            const int rows = k == 1 ? 5 : (k == 2 ? 3 : (k == 3 ? 2 : 1));
+            for (int r = 0; r < rows; ++r) p.sensors_out[(row + r) * N + f] = p.src[k][(j * rows + r) * N + f];
+        }
+        slot = s + 1;
+    }
+    for (; next_unmarked < p.n_slots; ++next_unmarked) p.dt_f[(int64_t)next_unmarked * N + f] = -1.0;
+    if (p.n_dropped) p.n_dropped[f] = dropped;
+}
+
+cudaError_t launch_merge(const MergeParams &p, cudaStream_t s) {
+    if (p.N <= 0) return cudaSuccess;
+    merge_kernel<<<(unsigned)((p.N + 127) / 128), 128, 0, s>>>(p);
     return cudaGetLastError();
 }
 

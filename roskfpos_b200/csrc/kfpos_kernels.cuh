@@ -243,8 +243,29 @@ struct AssembleParams {
     int32_t *ranges_out;
     double *err_out, *dt_out;
     int32_t *n_epochs;
+    double *t_out; // [max_epochs][N] or null: the time of every report (-1 = no such epoch)
 };
 cudaError_t launch_assemble(const AssembleParams &p, cudaStream_t s);
+
+// stream merger (kfpos_assemble.cu): stream 0 = ranging reports, 1..4 = PX4 / IMU / MAG / COMPASS samples
+struct MergeParams {
+    int64_t N;
+    int M, n_slots;
+    int64_t L[5];
+    const double *t_src[5];   // [L_k][N] arrival times; negative / NaN ends the stream
+    const int32_t *ranges;    // [L_0][M][N]
+    const double *err_src;    // [L_0][M][N] or null
+    const double *src[5];     // k > 0: [L_k][rows_k][N]
+    const int32_t *slot_kind; // device [n_slots]
+    const int64_t *slot_row;  // device [n_slots]: first output row of the slot
+    double first_dt;
+    double *dt_f;             // [n_slots][N]
+    int32_t *ranges_out;      // [range rows][N]
+    double *err_out;          // [range rows][N] or null
+    double *sensors_out;      // [sensor rows][N]
+    int32_t *n_dropped;       // [N] or null
+};
+cudaError_t launch_merge(const MergeParams &p, cudaStream_t s);
 
 cudaError_t launch_selftest_math(int64_t n, const double *x, double *rcp, double *rsq, double *sn, double *cs,
                                  cudaStream_t s);

@@ -138,3 +138,68 @@ def test_ml_log_to_report(kflib):
             assert out["status"][j] == 0
             assert np.abs(out["pos"][:, j] - g["ml_pose"][j, v, :3]).max() < 1e-9, (j, v)
             assert relP(out["cov"][:, j].reshape(3, 3), g["ml_cov"][j, v].reshape(6, 6)[:3, :3]) < 1e-9, (j, v)
+
+
+def test_k8_multi_sensor_logs_to_report(kflib, oracle):
+    """The whole multi-sensor chain through the C ABI: six tags' raw ranging logs and PX4Flow / IMU / magnetometer /
+    compass message logs (each tag in its own order) -> kfpos_assemble_epochs_t -> kfpos_merge_streams ->
+    kfpos_batch_replay_events_ragged -> kfpos_batch_get_pose_msg, against the report the reference NODE published
+    for each tag (tests/golden/node_k8.npz, produced by PosGenerator + KalmanFilter fed message by message)."""
+    from roskfpos_b200.batch import Batch, assemble_epochs, merge_streams
+    g = np.load(os.path.join(os.path.dirname(GOLD), "node_k8.npz"))
+    k = np.load(os.path.join(os.path.dirname(GOLD), "k8_multi.npz"))
+    M, N = 8, g["anchor"].shape[1]
+    ep = assemble_epochs(g["anchor"], g["seq"], g["range_mm"], g["t"], M, 64, err=g["err"])
+    ref_ep = oracle.assemble(g["anchor"], g["seq"], g["range_mm"], g["t"], M, 64, err=g["err"])
+    for key in ("ranges", "err", "dt", "n_epochs", "t"):
+        assert np.array_equal(ep[key], ref_ep[key]), key
+    # the node was polled before the 50 ms timer sent each log's last epoch
+    ep["t"][ep["t"] > g["t_report"][None, :]] = -1.0
+    sensors = {1: (g["px4_t"], g["px4"]), 2: (g["imu_t"], g["imu"]), 3: (g["mag_t"], g["mag"]),
+               4: (g["compass_t"], g["compass"])}
+    slots = [2, 0, 1, 2, 3, 4, 0, 2] * 70
+    mg = merge_streams(ep["t"], ep["ranges"], ep["err"], sensors, slots, imu_aux=g["imu_aux"])
+    ref_mg = oracle.merge_streams(ep["t"], ep["ranges"], ep["err"], sensors, slots)
+    for key in ("dt", "ranges", "err", "sensors", "n_dropped"):
+        assert np.array_equal(mg[key], ref_mg[key]), key
+    assert mg["n_dropped"].max() == 0
+    xml = [str(k[n]) for n in ("xml_pos", "xml_px4", "xml_tag", "xml_imu", "xml_mag")]
+    x0 = np.zeros((8, N)); x0[:2] = g["x0"]; x0[6] = g["ang0"]
+    n_rng = mg["ranges"].shape[0] // M
+    with Batch(kflib.MODEL_K8, N, anchors=g["anchors"], xml=xml, accel_noise=float(g["accel_noise"]),
+               jolt=float(g["jolt"]), ml2d_zero_tentative_z=1) as b:
+        b.set_state(x0)
+        b.replay_events(mg["events"], ranges=mg["ranges"].reshape(n_rng, M, N), sensors=mg["sensors"], err=mg["err"],
+                        dt_per_filter=mg["dt"])
+        for f in range(N):
+            last = [ep["t"][:, f].max(), g["imu_t"][:, f].max(), g["mag_t"][:, f].max(), g["compass_t"][:, f].max()]
+            ok = (g["px4_t"][:, f] >= 0) & (g["px4"][:, 4, f] != 0)
+            if ok.any():
+                last.append(g["px4_t"][ok, f].max())
+            pose, cov = b.get_pose_msg(float(g["t_report"][f]) - max(last))
+            assert np.abs(pose[:, f] - g["pose"][:, f]).max() < 1e-9, f
+            assert np.abs(cov[:, f] - g["cov"][:, f]).max() <= 1e-9 * np.abs(g["cov"][:, f]).max(), f
+
+
+def test_stream_merger_bit_exact_at_scale(kflib, oracle):
+    """4000 tags with ragged, differently ordered streams (missing sensors, ended streams, too few slots for some):
+    the merge kernel equals the oracle merger bit for bit."""
+    from roskfpos_b200.batch import merge_streams
+    rng = np.random.default_rng(11)
+    N, M, T = 4000, 8, 12
+    def stream(Lk, rate):
+        t = np.cumsum(rng.uniform(0.2, 1.8, (Lk, N)) * rate, axis=0).round(4)
+        n = rng.integers(0, Lk + 1, N)
+        t[np.arange(Lk)[:, None] >= n[None, :]] = -1.0
+        return t
+    t_epoch = stream(T, 0.1)
+    ranges = rng.integers(-1, 20000, (T, M, N)).astype(np.int32)
+    err = rng.uniform(0.01, 0.03, (T, M, N))
+    sensors = {2: (stream(40, 0.03), rng.normal(size=(40, 3, N))), 1: (stream(15, 0.08), rng.normal(size=(15, 5, N))),
+               4: (stream(9, 0.13), rng.normal(size=(9, 1, N)))}
+    slots = [2, 2, 1, 2, 0, 4, 3] * 14  # the magnetometer slots stay empty; some tags run out of slots
+    got = merge_streams(t_epoch, ranges, err, sensors, slots)
+    ref = oracle.merge_streams(t_epoch, ranges, err, sensors, slots)
+    for key in ("dt", "ranges", "err", "sensors", "n_dropped"):
+        assert np.array_equal(got[key], ref[key]), key
+    assert ref["n_dropped"].max() > 0 and (ref["n_dropped"] == 0).mean() > 0.3

@@ -269,3 +269,67 @@ def test_t9_ml_initialisation_golden(oracle, case):
         assert relP(o.P, g[case + "/P"][t]) < TOL_INIT, t
         assert (g[case + "/rc"][t] == 2) == bool((info.status & 256) and (info.status & 2)), t
     assert not np.isnan(o.x).any()
+
+
+def _node_slots(n_cycles):
+    """A common schedule for the merged streams: any order of a tag's events fits when every kind comes round
+    often enough (the merger gives an event the next slot of its kind)."""
+    return [2, 0, 1, 2, 3, 4, 0, 2] * n_cycles  # IMU, TOA, PX4, IMU, MAG, COMPASS, TOA, IMU
+
+
+def test_node_chain_assembler_merger_replay_report(oracle):
+    """Six tags, each with its own ranging log and its own PX4Flow / IMU / magnetometer / compass messages in its
+    own order: raw logs -> ranging aggregation (with report times) -> stream merger -> ragged replay -> report,
+    against what the reference NODE (PosGenerator + KalmanFilter, fed message by message) publishes."""
+    g = np.load(os.path.join(GOLD, "node_k8.npz"))
+    M, N = 8, g["anchor"].shape[1]
+    ep = oracle.assemble(g["anchor"], g["seq"], g["range_mm"], g["t"], M, 64, err=g["err"])
+    # the offline assembler also sends the last epoch (its 50 ms timer); the node was polled before that timer fired
+    assert np.array_equal(ep["n_epochs"], g["n_epochs"] + 1)
+    ep["t"][ep["t"] > g["t_report"][None, :]] = -1.0
+    sensors = {1: (g["px4_t"], g["px4"]), 2: (g["imu_t"], g["imu"]), 3: (g["mag_t"], g["mag"]),
+               4: (g["compass_t"], g["compass"])}
+    slots = _node_slots(70)
+    mg = oracle.merge_streams(ep["t"], ep["ranges"], ep["err"], sensors, slots)
+    assert mg["n_dropped"].max() == 0
+    n_events = sum(int((t >= 0).sum(axis=0).sum()) for t, _ in sensors.values()) + int(g["n_epochs"].sum())
+    assert int((mg["dt"] >= 0).sum()) == n_events
+    aux = g["imu_aux"]
+    cac = np.zeros(9); cav = np.zeros(9)
+    cac[0], cac[1], cac[3], cac[4], cav[8] = aux
+    for f in range(N):
+        o = oracle.K8(float(g["accel_noise"]), float(g["ang0"][f]), float(g["jolt"]), g["x0"][:, f], **CFG_K8)
+        carry, t_abs, seen = 0.0, None, 0
+        for s, kind in enumerate(slots):
+            dt = mg["dt"][s, f]
+            if dt < 0:
+                continue
+            row = mg["slot_row"][s]
+            if kind == 1 and int(mg["sensors"][row + 4, f]) == 0:  # skipped before the clock is read (KF.cpp:111-113)
+                carry += dt
+                continue
+            dt, carry = dt + carry, 0.0
+            seen += 1
+            if kind == 0:
+                rr = mg["ranges"][row:row + M, f] / 1000.0
+                o.new_toa(dt, np.where(rr > 0, rr, 0.0), g["anchors"], mg["err"][row:row + M, f], b1_zero_z=True)
+            elif kind == 1:
+                p = mg["sensors"][row:row + 5, f]
+                o.new_px4(dt, p[0], p[1], p[2], p[3], int(p[4]))
+            elif kind == 2:
+                p = mg["sensors"][row:row + 3, f]
+                o.new_imu(dt, [0, 0, p[0]], cav, [p[1], p[2], 0], cac)
+            elif kind == 3:
+                p = mg["sensors"][row:row + 2, f]
+                o.new_mag(dt, [p[0], p[1], 0.0])
+            else:
+                o.new_compass(dt, mg["sensors"][row, f])
+        # the filter's clock stopped at its last callback that read it
+        last = [ep["t"][:, f].max(), g["imu_t"][:, f].max(), g["mag_t"][:, f].max(), g["compass_t"][:, f].max()]
+        ok = (g["px4_t"][:, f] >= 0) & (g["px4"][:, 4, f] != 0)
+        if ok.any():
+            last.append(g["px4_t"][ok, f].max())
+        xp, Pp = o.get_pose(float(g["t_report"][f]) - max(last))
+        po, co = oracle.pose_msg(2, xp, Pp, tag_z=CFG_K8["tag_z"])
+        assert np.abs(po - g["pose"][:, f]).max() < 1e-10, f
+        assert relP(co, g["cov"][:, f]) < 1e-10, f
