@@ -75,3 +75,85 @@ def test_k8_million_filters_sampled_against_the_oracle(kflib, oracle, full):
                            w["sensors"][:, tidx].cpu().numpy(), anc, 0.01, cfg)
     assert rel_err_state(xg[:, tidx].cpu().numpy(), ref["x"]) < REL_TOL
     assert rel_err_cov(Pg[:, tidx].cpu().numpy(), ref["P"]) < REL_TOL
+
+
+def test_k8_config3_full_horizon_sampled_against_the_oracle(kflib, oracle):
+    """BASELINE config 3 ITSELF: 1,048,576 K8 filters x 1000 macro-steps (12 000 events each: 10 IMU, compass, TOA),
+    inputs generated on the device chunk by chunk (never resident: 280 GB in total).  A sample of the filters
+    keeps its inputs and is replayed through the oracle over the whole horizon."""
+    import torch
+    from roskfpos_b200.batch import Batch
+    dev = torch.device("cuda", 0)
+    N, n_macro, chunk = 1 << 20, 1000, 10
+    anc = synth.anchors_for(8)
+    idx = np.sort(np.random.default_rng(2).choice(N, 72, replace=False))
+    tidx = torch.as_tensor(idx, device=dev)
+    events, rng_keep, sen_keep = [], [], []
+    rows_r = rows_s = 0
+    with Batch(kflib.MODEL_K8, N, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5) as b:
+        bufs = synth.k8_montecarlo_chunk(N, 0, chunk, anc, dev, seed=synth.SEED, full=False, want_x0=True)
+        x0 = bufs["x0"].clone()
+        b.set_state(x0)
+        for m0 in range(0, n_macro, chunk):
+            bufs = synth.k8_montecarlo_chunk(N, m0, chunk, anc, dev, seed=synth.SEED, full=False, out=bufs)
+            b.replay_events(bufs["events"], ranges=bufs["ranges"], sensors=bufs["sensors"], err=0.01)
+            r = bufs["ranges"].reshape(-1, N)[:, tidx].cpu().numpy()
+            s = bufs["sensors"][:, tidx].cpu().numpy()
+            for (kind, dt, off, aux) in bufs["events"]:  # the chunk's rows appended to the sample's whole log
+                events.append((kind, dt, off + (rows_r if kind == synth.EV_TOA else rows_s), aux))
+            rows_r += r.shape[0]; rows_s += s.shape[0]
+            rng_keep.append(r); sen_keep.append(s)
+        xg = torch.empty((8, N), device=dev, dtype=torch.float64)
+        Pg = torch.empty((64, N), device=dev, dtype=torch.float64)
+        st = torch.empty(N, device=dev, dtype=torch.int32)
+        b.get_state_into(xg, Pg, st)
+        cnt = b.counters()
+        stats = b.error_stats(bufs["truth_end"])
+    assert cnt["updates"] == N * n_macro * len(synth.MACRO_IMU_MAG) and cnt["bad"] == 0
+    assert int((st & ~32).abs().sum().item()) == 0
+    assert stats[2] == N and np.sqrt(stats[1] / N) < 0.1
+    cfg = oracle.k8_cfg(0.5, 0.5, **synth.K8_ORACLE_CFG)
+    ref = oracle.k8_replay(x0[:, tidx].cpu().numpy(), None, events, np.concatenate(rng_keep).reshape(-1, 8, len(idx)),
+                           np.concatenate(sen_keep), anc, 0.01, cfg)
+    assert ref["counters"][4] == len(idx) * n_macro * len(synth.MACRO_IMU_MAG)
+    assert rel_err_state(xg[:, tidx].cpu().numpy(), ref["x"]) < REL_TOL
+    assert rel_err_cov(Pg[:, tidx].cpu().numpy(), ref["P"]) < REL_TOL
+
+
+def test_ml_config4a_full_size_sampled_against_the_oracle(kflib, oracle):
+    """BASELINE config 4a at its stated size: 4,194,304 epochs, 16 anchors on the 4 x 4 grid, 15 % NLOS rangings
+    (bias ~ Exp(0.8 m)), ML variant 1 ignoring the 2 worst rangings; position, dropped-anchor mask and status of
+    131 072 sampled epochs against the oracle (selection bit-exact on every oracle-stable epoch)."""
+    import torch
+    from roskfpos_b200.batch import Batch
+    from tests.util import assert_parity, to_metres, ulp_perturbations
+    dev = torch.device("cuda", 0)
+    N, M = 1 << 22, 16
+    anc = synth.anchors_for(M)
+    r, _, _ = synth.device_ranges_mm(N, 1, anc, 0.1, dev, seed=synth.SEED + 60)
+    r = r[0].contiguous()
+    g = torch.Generator(device=dev)
+    g.manual_seed(61)
+    nlos = torch.rand((M, N), generator=g, device=dev) < 0.15
+    bias = -0.8 * torch.log1p(-torch.rand((M, N), generator=g, device=dev, dtype=torch.float64))
+    r = torch.where(nlos, r + torch.floor(bias * 1000.0).to(torch.int32), r).contiguous()
+    out = dict(pos=torch.empty((3, N), device=dev, dtype=torch.float64), cov=torch.empty((9, N), device=dev, dtype=torch.float64),
+               iters=torch.empty(N, device=dev, dtype=torch.int32), sel=torch.empty((2, N), device=dev, dtype=torch.int32),
+               status=torch.empty(N, device=dev, dtype=torch.int32))
+    with Batch(kflib.MODEL_ML, N, anchors=anc, variant=1, num_ignored_rangings=2, ml_start=[1.0, 1.0, 4.0]) as b:
+        b.ml_solve(r, err=0.01, out=out)
+        cnt = b.counters()
+    assert cnt["updates"] == N
+    lo = 3 * (1 << 20) + 12345  # a block of the batch that does not start at a launch boundary
+    n = 1 << 17
+    rs = r[:, lo:lo + n].cpu().numpy()
+    start = [1.0, 1.0, 4.0]
+    ref = oracle.ml_batch(rs, anc, 0.01, start, variant=1, n_ignore=2)
+    per = [oracle.ml_batch(rp, anc, 0.01, start, variant=1, n_ignore=2) for rp in ulp_perturbations(to_metres(rs), n_random=2)]
+    got = {k: out[k][..., lo:lo + n].cpu().numpy() for k in ("pos", "sel", "status")}
+    # the first solve starts at (1, 1, 4), far from the tags: a handful of epochs in a million reach another local
+    # minimum when any intermediate moves by one ulp, and survive the six perturbations that define "stable";
+    # they are counted in the parity report (observed: 1 of 131072)
+    rep = assert_parity(got, ref, per, float_keys=("pos",), int_keys=("status", "sel"), min_stable=0.97,
+                        max_tie_frac=5e-5, tie_tol=0.1, what="config 4a full size (sample of 131072 of 4 Mi epochs)")
+    print("config 4a full size", rep)
