@@ -49,11 +49,9 @@ def test_config1a_t6_ten_thousand_steps_step_by_step(kflib, oracle):
     where the reference itself is chaotic (tests/util.py).  So the 10 000 steps are checked one at a
     time: every step must match the oracle to 1e-9 unless the oracle's own inner solve went wild on
     that step, in which case the GPU filter is re-synchronised (the tests/test_oracle_golden.py rule).
-    The bar here is 1e-8: with exactly four anchors the vertical geometry is poor, the covariance spans
-    seven decades, and rounding differences of 1e-16 are amplified to a few 1e-9 (bounded, no drift:
-    the worst step over the whole run is printed); the 1e-9 bar of the north star is asserted on the
-    8- and 16-anchor geometries (tests/test_gpu_t6.py, tests/test_gpu_full_size.py)."""
-    tol = 1e-8
+    The bar is the north star's 1e-9 (round 1 needed 1e-8 here; measured now: no wild step, worst regular
+    step 3.7e-11 over the 10 000 steps, printed)."""
+    tol = 1e-9
     from roskfpos_b200.batch import Batch
     anc, truth, r = config1_inputs(seed=11)
     o = oracle.T6(0.5, False, 0.0, truth[0][:, 0])
@@ -78,4 +76,4 @@ def test_config1a_t6_ten_thousand_steps_step_by_step(kflib, oracle):
         cnt = b.counters()
     print("config 1a: wild steps", n_wild, "worst regular step", worst)
     assert cnt["updates"] == T
-    assert n_wild <= 60, n_wild
+    assert n_wild <= 10, n_wild
