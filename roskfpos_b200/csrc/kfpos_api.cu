@@ -481,8 +481,14 @@ extern "C" int kfpos_batch_replay_toa(kfpos_batch *b, int n_steps, const double 
     } else if (!r_dev && err_var == nullptr) {
         // HOST range log: stream it through two device staging buffers, the copy
         // of chunk c+1 overlapping the replay kernel of chunk c.
+        // Chunk size: the replay of the LAST chunk is the only kernel time the copies do not hide, so chunks are
+        // 1/32 of the log, within [32 MB, 256 MB] (a chunk launch re-reads and re-writes the 192 B of filter state,
+        // which bounds how small a chunk is worth making).
         const size_t step_bytes = M * N * fmt_size(fmt);
-        size_t chunk_steps = (size_t)(((size_t)256 << 20) / (step_bytes ? step_bytes : 1));
+        size_t chunk_bytes = step_bytes * (size_t)T / 32;
+        if (chunk_bytes < ((size_t)32 << 20)) chunk_bytes = (size_t)32 << 20;
+        if (chunk_bytes > ((size_t)256 << 20)) chunk_bytes = (size_t)256 << 20;
+        size_t chunk_steps = chunk_bytes / (step_bytes ? step_bytes : 1);
         if (chunk_steps < 1) chunk_steps = 1;
         if (chunk_steps > (size_t)T) chunk_steps = (size_t)T;
         for (int i = 0; i < 2; ++i) CK(b->stage[i].reserve(chunk_steps * step_bytes));
