@@ -448,7 +448,9 @@ int kfpos_measure_fp64_peak(int device, double *flops_per_s);
  * 0.003); KFPOS_EV_PX4 the five PX4Flow fields (33.333 ms, height 5 m, quality 200);
  * KFPOS_EV_COMPASS heading + N(0, 0.01^2) -- the payload layouts of kfpos_batch_replay_events.
  * events: HOST array; x0 (SoA [8][N], state at t = 0) and truth_end (SoA [3][N], position at
- * t_end) optional.  Synchronises `stream` before returning.                                    */
+ * t_end) optional.  Asynchronous on `stream` when every output is a device pointer (so that the next
+ * chunk can be generated on one stream while the current one is replayed on another), else it
+ * synchronises `stream` before returning.                                    */
 typedef struct kfpos_synth_event {
     int32_t kind;         /* kfpos_event_kind                                   */
     int32_t global_index; /* index of the event in the whole run (RNG counter)  */

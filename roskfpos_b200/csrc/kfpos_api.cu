@@ -1372,11 +1372,23 @@ extern "C" int kfpos_synth_k8(int device, int64_t n_filters, int64_t first_filte
     CK(o_s.set(sensors, 8 * (size_t)sensor_rows * N));
     CK(o_x.set(x0, 8 * 8 * N));
     CK(o_t.set(truth_end, 8 * 3 * N));
+    // the schedule goes through a small per-device ring of scratch buffers (a pageable source has left the caller's
+    // array when cudaMemcpyAsync returns): with device outputs the call is then asynchronous on `stream`, so that a
+    // caller can generate chunk c + 1 on one stream while chunk c is replayed on another
     void *d_ev = nullptr;
     if (n_events > 0) {
-        CK(cudaMalloc(&d_ev, sizeof(SynthEvent) * (size_t)n_events));
-        cudaError_t e = cudaMemcpyAsync(d_ev, events, sizeof(SynthEvent) * (size_t)n_events, cudaMemcpyHostToDevice, s);
-        if (e != cudaSuccess) { cudaFree(d_ev); return map_cuda_err(e); }
+        static std::mutex mtx;
+        static DevBuf ring[64][8];
+        static unsigned next[64];
+        std::lock_guard<std::mutex> lock(mtx);
+        DevBuf &slot = ring[device & 63][next[device & 63]++ & 7];
+        if (slot.cap < sizeof(SynthEvent) * (size_t)n_events) {
+            CK(cudaStreamSynchronize(s)); // growing a slot frees the old one: nothing may still read it
+            CK(cudaDeviceSynchronize());
+            CK(slot.reserve(sizeof(SynthEvent) * (size_t)(n_events < 256 ? 256 : n_events)));
+        }
+        d_ev = slot.p;
+        CK(cudaMemcpyAsync(d_ev, events, sizeof(SynthEvent) * (size_t)n_events, cudaMemcpyHostToDevice, s));
     }
     SynthK8Params p;
     memset(&p.anchors, 0, sizeof p.anchors);
@@ -1393,11 +1405,9 @@ extern "C" int kfpos_synth_k8(int device, int64_t n_filters, int64_t first_filte
     if (e == cudaSuccess) e = o_s.back(s);
     if (e == cudaSuccess) e = o_x.back(s);
     if (e == cudaSuccess) e = o_t.back(s);
-    // the schedule copy (and any host staging) is freed on return
-    cudaError_t e2 = cudaStreamSynchronize(s);
-    if (d_ev) cudaFree(d_ev);
     if (e != cudaSuccess) return map_cuda_err(e);
-    if (e2 != cudaSuccess) return map_cuda_err(e2);
+    // host staging is freed on return: finish the work first; device outputs: asynchronous on `stream`
+    if (o_r.own || o_s.own || o_x.own || o_t.own) CK(cudaStreamSynchronize(s));
     return KFPOS_OK;
 }
 
