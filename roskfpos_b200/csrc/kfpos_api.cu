@@ -635,7 +635,8 @@ K8Cfg make_k8cfg(const kfpos_batch *b) {
     c.best_mode = b->cfg.best_mode;
     c.zero_tz = b->cfg.ml2d_zero_tentative_z != 0;
     c.use_fixed_height = b->cfg.use_fixed_height != 0;
-    // after a 3-D initialisation the tag height is per filter: only the general instantiation carries it
+    // after a 3-D initialisation the tag height is per filter (latch row 9), so the flag stays on in that mode;
+    // in 2-D mode it is dropped once a launch has ended with every filter initialised (poll_uninit)
     c.ml_init = b->cfg.ml_initial_position != 0 && (b->uninit_possible || !c.use_fixed_height);
     return c;
 }

@@ -48,7 +48,8 @@ KF_DEV void prefetch_event(const RawColPriv &raw, const Col &land, const EventDe
 // at a TOA event the 2-D ML estimator, started at the predicted position, selects the rangings --
 // variant 1 drops the N with the largest residual, variant 2 keeps the best THREE anchors -- and the
 // update runs on the survivors.
-template <bool PME, int MT, bool SEL = false>
+// MLI: the ML-initialisation branch and the per-filter tag height (kfpos_config.ml_initial_position) are compiled in.
+template <bool PME, int MT, bool SEL = false, bool MLI = SEL>
 __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __grid_constant__ K8Params p) {
     extern __shared__ double smem[];
     const int64_t f = (int64_t)blockIdx.x * K8_BLOCK + threadIdx.x;
@@ -84,15 +85,11 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
         // written back: KF.cpp:287-291,315-318)
         double px = p.x[0 * N + f], py = p.x[1 * N + f], vx = p.x[2 * N + f], vy = p.x[3 * N + f];
         double th = p.x[6 * N + f], om = p.x[7 * N + f];
-        // the tuned instantiations keep the covariance in REGISTERS from event to event (Pr); Pm then only backs
-        // P^- up inside an event that fuses several sensors.  The general one keeps it in Pm between events.
+        // the covariance lives in REGISTERS from event to event (Pr); Pm only backs P^- up inside an event that
+        // fuses several sensors
         Sym<8> Pr;
 #pragma unroll
-        for (int k = 0; k < Sym<8>::SZ; ++k) {
-            const double v = p.P[(int64_t)k * N + f];
-            if (SEL) Pm[k] = v;
-            else Pr.a[k] = v;
-        }
+        for (int k = 0; k < Sym<8>::SZ; ++k) Pr.a[k] = p.P[(int64_t)k * N + f];
 #pragma unroll
         for (int k = 0; k < 8; ++k) latch[k] = p.latch[(int64_t)k * N + f];
         unsigned has = (unsigned)p.has[f]; // bit0 px4, bit1 imu, bit2 mag latched
@@ -102,8 +99,8 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
         double carry = p.latch[8 * N + f];
         double ic00 = p.latch_u[0], ic01 = p.latch_u[1], ic11 = p.latch_u[2], icw = p.latch_u[3];
         int n_toa = 0;
-        // the tag height is per filter only after a 3-D ML initialisation (KF.cpp:256-257); general kernel only
-        const bool z_per_filter = SEL && p.cfg.ml_init && !p.cfg.use_fixed_height;
+        // the tag height is per filter only after a 3-D ML initialisation (KF.cpp:256-257)
+        const bool z_per_filter = MLI && p.cfg.ml_init && !p.cfg.use_fixed_height;
         double tag_z = z_per_filter ? p.latch[9 * N + f] : p.cfg.tag_z;
 
         if (p.n_events > 0) prefetch_event(raw, land, p.events[0], m, p.rs, p.sensors, N, f);
@@ -180,9 +177,13 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
             }
             }
             if (e + 1 < p.n_events) prefetch_event(raw, land, p.events[e + 1], m, p.rs, p.sensors, N, f);
+            // lanes that re-converge after the inner Newton loop of a ranging event: every lane of the warp, except
+            // the filters that are still uninitialised (ML initialisation) -- and nobody in a ragged replay
+            unsigned umask = (SEL && p.dt_f) ? 0u : wmask;
+            if (MLI && umask && p.cfg.ml_init && ev.kind == EV_TOA) umask = __ballot_sync(wmask, !(isnan(px) || isnan(py)));
             if (skip) {
                 carry += dt_ev;
-            } else if (SEL && p.cfg.ml_init && (isnan(px) || isnan(py))) {
+            } else if (MLI && p.cfg.ml_init && (isnan(px) || isnan(py))) {
                 // ---- the constructor without initialPosition (KF.cpp:244-285): the clock is read, the sample is
                 // latched (above), and an epoch with rangings initialises position and the 2x2 position block
                 // of the all-zero covariance from MLLocation; no predict, no update
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                         // too few rangings: the start point comes back with an EMPTY covariance matrix, whose
                         // (0,0) throws after position (and tag height) have been assigned (KF.cpp:267)
                         if (irc == ML_FEW) st.status |= 2u;
-                        else { Pm[0] = c0[0]; Pm[1] = c0[1]; Pm[2] = c0[2]; } // xx, yx, yy (both packings agree)
+                        else { Pr.a[0] = c0[0]; Pr.a[1] = c0[1]; Pr.a[2] = c0[2]; } // xx, yx, yy (both packings agree)
                     }
                 }
                 if (st.status & ~(32u | 64u | 256u)) n_bad += 1;
@@ -221,13 +222,9 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
 
                 // ---- predict (KF.cpp:287-305): a = 0 at the start of every step
                 Sym<8> &Pw = Pr;
-                if (SEL) {
-#pragma unroll
-                    for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k];
-                }
                 k8_predict_cov(Pw, dt, p.cfg.accel_noise, p.cfg.jolt);
                 // one sensor and no rangings: the deferred update on the register copy (k8_update_light)
-                const bool light = !SEL && (ev.kind == EV_IMU || ev.kind == EV_PX4 || ev.kind == EV_MAG);
+                const bool light = ev.kind == EV_IMU || ev.kind == EV_PX4 || ev.kind == EV_MAG;
                 if (!light) {
 #pragma unroll
                     for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = Pw.a[k];
@@ -267,9 +264,8 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                     else if (ev.kind == EV_PX4) k8_update_light<EV_PX4>(p.cfg, ms, dt, xp, Pw, dx, st);
                     else k8_update_light<EV_MAG>(p.cfg, ms, dt, xp, Pw, dx, st);
                 } else {
-                    rc = k8_update<PME, MT>(p.anchors, p.cfg, tag_z, ep, has_r, used, ms, dt, xp, Pm, Pw, dx, st,
-                                            SEL ? 0u : wmask);
-                    if (!SEL && rc != 0) { // update skipped: P^- is what remains
+                    rc = k8_update<PME, MT>(p.anchors, p.cfg, tag_z, ep, has_r, used, ms, dt, xp, Pm, Pw, dx, st, umask);
+                    if (rc != 0) { // update skipped: P^- is what remains
 #pragma unroll
                         for (int k = 0; k < Sym<8>::SZ; ++k) Pw.a[k] = Pm[k];
                     }
@@ -278,10 +274,6 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                     px = xp[0] + dx[0]; py = xp[1] + dx[1];
                     vx = xp[2] + dx[2]; vy = xp[3] + dx[3];
                     th = xp[6] + dx[6]; om = xp[7] + dx[7]; // written back un-wrapped (KF.cpp:317)
-                    if (SEL) {
-#pragma unroll
-                        for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = Pw.a[k];
-                    }
                     if (!(isfinite(px) && isfinite(py) && isfinite(vx) && isfinite(vy) && isfinite(th) && isfinite(om)))
                         st.status |= 8u;
                 } else {
@@ -300,18 +292,18 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                 }
 
             }
-            if (!SEL) __syncwarp(wmask); // the IEKF trip count differs per lane
+            if (!(SEL && p.dt_f)) __syncwarp(wmask); // the IEKF trip count differs per lane
         }
         p.x[0 * N + f] = px; p.x[1 * N + f] = py; p.x[2 * N + f] = vx; p.x[3 * N + f] = vy;
         p.x[4 * N + f] = 0.0; p.x[5 * N + f] = 0.0; p.x[6 * N + f] = th; p.x[7 * N + f] = om;
 #pragma unroll
-        for (int k = 0; k < Sym<8>::SZ; ++k) p.P[(int64_t)k * N + f] = SEL ? Pm[k] : Pr.a[k];
+        for (int k = 0; k < Sym<8>::SZ; ++k) p.P[(int64_t)k * N + f] = Pr.a[k];
 #pragma unroll
         for (int k = 0; k < 8; ++k) p.latch[(int64_t)k * N + f] = latch[k];
         p.has[f] = (int32_t)has;
         p.latch[8 * N + f] = carry;
         if (z_per_filter) p.latch[9 * N + f] = tag_z;
-        if (SEL && p.uninit && (isnan(px) || isnan(py))) *p.uninit = 1;
+        if (MLI && p.uninit && (isnan(px) || isnan(py))) *p.uninit = 1;
         int32_t st_all = (int32_t)status_or;
         if (p.status) {
             st_all |= p.status[f];
@@ -333,23 +325,29 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
     if (p.truth) block_stats_partial(errv, smem, p.partials + (int64_t)blockIdx.x * 4);
 }
 
-template <bool PME, int MT, bool SEL = false>
+template <bool PME, int MT, bool SEL, bool MLI>
 static cudaError_t launch_k(const K8Params &p, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + K8_BLOCK - 1) / K8_BLOCK);
     const size_t smem = (size_t)k8_smem_rows(p.rs.m_slots, p.rs.fmt, PME, MT > 0) * K8_BLOCK * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(k8_replay_kernel<PME, MT, SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k8_replay_kernel<PME, MT, SEL, MLI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
     if (e != cudaSuccess) return e;
-    k8_replay_kernel<PME, MT, SEL><<<grid, K8_BLOCK, smem, s>>>(p);
+    k8_replay_kernel<PME, MT, SEL, MLI><<<grid, K8_BLOCK, smem, s>>>(p);
     return cudaGetLastError();
+}
+
+template <bool PME, int MT>
+static cudaError_t launch_tuned(const K8Params &p, cudaStream_t s) {
+    return p.cfg.ml_init ? launch_k<PME, MT, false, true>(p, s) : launch_k<PME, MT, false, false>(p, s);
 }
 
 cudaError_t launch_k8_replay(const K8Params &p, cudaStream_t s) {
     if (p.N <= 0 || p.n_events <= 0) return cudaSuccess;
-    if (p.cfg.variant == 1 || p.cfg.variant == 2 || p.dt_f != nullptr || p.cfg.ml_init) // the general instantiation
-        return p.rs.err != nullptr ? launch_k<true, 0, true>(p, s) : launch_k<false, 0, true>(p, s);
-    if (p.rs.err != nullptr) return launch_k<true, 0>(p, s);
-    if (p.rs.m_slots == 8 && !p.cfg.zero_tz) return launch_k<false, 8>(p, s);
-    return launch_k<false, 0>(p, s);
+    if (p.cfg.variant == 1 || p.cfg.variant == 2 || p.dt_f != nullptr) // the general instantiation
+        return p.rs.err != nullptr ? launch_k<true, 0, true, true>(p, s) : launch_k<false, 0, true, true>(p, s);
+    if (p.rs.err != nullptr) return launch_tuned<true, 0>(p, s);
+    if (p.rs.m_slots == 8 && !p.cfg.zero_tz) return launch_tuned<false, 8>(p, s);
+    return launch_tuned<false, 0>(p, s);
 }
 
 // getPose (KF.cpp:709-747): predict-only, state untouched
