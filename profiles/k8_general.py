@@ -18,3 +18,16 @@ for full in (False, True):
                 e1.record(stream); torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1))
             t = min(ms[1:])
             print(f"{'config5' if full else 'config3'} {name:40s} {t:8.3f} ms {N*len(w['events'])/t/1e6:8.3f} G events/s", flush=True)
+# ---- the ragged replay (per-filter time steps) through the general instantiation, same schedule, every filter present
+    import numpy as np
+    dtf = torch.tensor(np.array([[e[1]] * 1 for e in w["events"]]), device=dev, dtype=torch.float64).repeat(1, N).contiguous()
+    with Batch(L.MODEL_K8, N, device=0, anchors=anc, xml=synth.K8_XML, accel_noise=0.5, jolt=0.5) as b:
+        ms = []
+        for k in range(4):
+            b.set_state(w["x0"], None, stream=stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            b.replay_events(w["events"], ranges=w["ranges"], sensors=w["sensors"], err=0.01, stream=stream, dt_per_filter=dtf)
+            e1.record(stream); torch.cuda.synchronize(); ms.append(e0.elapsed_time(e1))
+        t = min(ms[1:])
+        print(f"{'config5' if full else 'config3'} {'ragged replay (general instantiation)':40s} {t:8.3f} ms {N*len(w['events'])/t/1e6:8.3f} G events/s", flush=True)
