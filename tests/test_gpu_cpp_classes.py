@@ -91,3 +91,28 @@ def test_cpp_ml_and_t9(exe, oracle):
     t9.new_toa(0.1, r, anc, 0.01)
     t9.new_toa(0.1, r, anc, 0.01)
     assert np.abs(np.array(poses[1][6:8]) - t9.x[3:5]).max() < 1e-9  # velocities persisted
+
+
+def test_plain_c_caller_of_the_stats_collective(kflib, tmp_path):
+    """tests/cpp/stats_c_abi.c is compiled as C against include/kfpos_b200.h and calls the boundary the way a
+    maintainer's code would, ending in kfpos_stats_allreduce; same numbers as the Python host side."""
+    from roskfpos_b200.batch import Batch
+    out = str(tmp_path / "stats_c_abi")
+    subprocess.check_call(["gcc", "-std=c99", "-O1", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "stats_c_abi.c"), L.SO_PATH,
+                           "-Wl,-rpath," + os.path.dirname(L.SO_PATH), "-o", out])
+    N, T, M = 300, 5, 8
+    anc = synth.anchors_for(M)
+    truth = synth.truth_lissajous(N, T, 0.1, seed=31)
+    r = synth.ranges_mm(truth[1:], anc, seed=32).astype(np.float64) / 1000
+    x0 = np.zeros((6, N)); x0[:3] = truth[0]
+    text = f"{N} {T} {M}\n" + "\n".join(" ".join(repr(float(v)) for v in a.ravel()) for a in (anc, x0, truth[-1], r)) + "\n"
+    p = subprocess.run([out], input=text, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    got = np.array([float(v) for v in p.stdout.split()[1:]])
+    with Batch(kflib.MODEL_T6, N, anchors=anc, accel_noise=0.5) as b:
+        b.set_state(x0)
+        b.replay_toa(0.1, r, err=0.01)
+        ref = b.error_stats(truth[-1])
+    assert np.array_equal(got[:4], ref[:4])
+    assert got[4] == np.sqrt(ref[0] / ref[2]) and got[2] == N
