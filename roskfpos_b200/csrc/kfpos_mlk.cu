@@ -173,7 +173,10 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_coop_kernel(const __grid_constant
                 if (PME) v[K - 1] = fma(c2 * dz, dz, v[K - 1]);
             }
             group_sum<K, L>(tile + (round & 1u) * COOP_TILE, lane, v);
-            if (!done) {
+            {
+                // straight-line: every lane evaluates the stop test and the 3x3 solve (same operations and order
+                // as rel_change_gt / solve_sym3), the results are committed with selects -- the iteration is one
+                // serial dependency chain, and every divergent region on it cost a reconvergence barrier
                 const double wcost = v[0];
                 double c1s = v[4], h5;
                 if (PME) {
@@ -183,22 +186,27 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_coop_kernel(const __grid_constant
                     c1s = nvalid - c1s;
                 }
                 const double newCost = PME ? wcost : wcost * inv_e0;
-                if (!(rel_change_gt(cost, newCost) && iter < 10000u)) {
-                    done = true;
-                } else {
-                    const double H[6] = {v[5] + c1s, v[6], v[7] + c1s, v[8], v[9], h5 + c1s};
-                    const double g[3] = {v[1], v[2], v[3]};
-                    double s[3];
-                    if (!solve_sym3(H, g, s)) {
-                        done = true; // left to the one-thread solver, which reports it
-                    } else {
-                        iter += 1;
-                        cost = newCost;
-                        px -= s[0]; py -= s[1]; pz -= s[2];
-                    }
-                }
+                const double q = fabs(cost - newCost), thr = 1e-3 * cost;
+                bool changed = q > thr * 1.000000001;
+                if (!(cost > 0.0) || !(changed || q < thr * 0.999999999)) changed = q / cost > 1e-3; // within 1e-9 of the threshold
+                const double Ha = v[5] + c1s, Hb = v[6], Hd = v[7] + c1s, Hc = v[8], He = v[9], Hf = h5 + c1s;
+                const double c00 = Hd * Hf - He * He, c01 = Hc * He - Hb * Hf, c02 = Hb * He - Hc * Hd;
+                const double det = Ha * c00 + Hb * c01 + Hc * c02;
+                const double c11 = Ha * Hf - Hc * Hc, c12 = Hb * Hc - Ha * He, c22 = Ha * Hd - Hb * Hb;
+                const double id = fast_rcp(det);
+                const double s0 = (c00 * v[1] + c01 * v[2] + c02 * v[3]) * id;
+                const double s1 = (c01 * v[1] + c11 * v[2] + c12 * v[3]) * id;
+                const double s2 = (c02 * v[1] + c12 * v[2] + c22 * v[3]) * id;
+                // a singular system is left to the one-thread solver, which reports it
+                const bool step = !done && changed && iter < 10000u && usable_det(det);
+                done = !step;
+                iter += step ? 1u : 0u;
+                cost = step ? newCost : cost;
+                px = step ? px - s0 : px; py = step ? py - s1 : py; pz = step ? pz - s2 : pz;
             }
-            if (__all_sync(0xffffffffu, done)) break;
+            // the warp vote costs ~100 cycles of a ~1200-cycle iteration: taken every fourth iteration (a finished
+            // record just idles in between; nothing it holds changes)
+            if ((round & 3u) == 3u && __all_sync(0xffffffffu, done)) break;
         }
         if (gl == 0 && live) {
             rec->p[0] = px; rec->p[1] = py; rec->p[2] = pz;
