@@ -13,7 +13,13 @@
 
 namespace kfpos {
 
-__global__ void __launch_bounds__(128) assemble_kernel(const AssembleParams p) {
+#ifndef ASM_D
+#define ASM_D 4
+#endif
+#ifndef ASM_MINB
+#define ASM_MINB 1
+#endif
+__global__ void __launch_bounds__(128, ASM_MINB) assemble_kernel(const AssembleParams p) {
     const int64_t f = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (f >= p.N) return;
     const int64_t N = p.N;
@@ -42,24 +48,26 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleParams p) {
         armed = false; // timerRanging.stop() (:174)
     };
 
-    // software pipeline: the fields of message i + 1 are in flight while message i is processed
-    int a_n = 0xff, s_n = 0;
-    int32_t r_n = 0;
-    double e_n = 0.0, t_n = 0.0;
-    auto load = [&](int64_t i) {
-        a_n = p.anchor[i * N + f];
-        s_n = p.seq[i * N + f];
-        r_n = p.range_mm[i * N + f];
-        e_n = p.err ? p.err[i * N + f] : 0.0;
-        t_n = p.t[i * N + f];
+    // software pipeline: the fields of the NEXT D messages are in flight while D messages are processed
+    // (one message ahead left the kernel latency-bound at 55 % of the copy bandwidth)
+    constexpr int D = ASM_D;
+    int a_n[D], s_n[D];
+    int32_t r_n[D];
+    double e_n[D], t_n[D];
+    auto load = [&](int64_t i0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const int64_t i = i0 + d;
+            const bool in = i < p.L;
+            a_n[d] = in ? p.anchor[i * N + f] : 0xff;
+            s_n[d] = in ? p.seq[i * N + f] : 0;
+            r_n[d] = in ? p.range_mm[i * N + f] : 0;
+            e_n[d] = (in && p.err) ? p.err[i * N + f] : 0.0;
+            t_n[d] = in ? p.t[i * N + f] : 0.0;
+        }
     };
-    if (p.L > 0) load(0);
-    for (int64_t i = 0; i < p.L; ++i) {
-        const int a = a_n, s = s_n;
-        const int32_t r = r_n;
-        const double e = e_n, ti = t_n;
-        if (i + 1 < p.L) load(i + 1);
-        if (a == 0xff || a >= M) continue; // padding of a ragged log
+    auto message = [&](int a, int s, int32_t r, double e, double ti) {
+        if (a == 0xff || a >= M) return; // padding of a ragged log
         // the one-shot timer fires 0.05 s after the last ranging if nothing arrived before (:143-152)
         if (have_last && armed && ti - t_last > 0.05) flush(t_last + 0.05);
         if (range_seq == s) { // a ranging of the current sequence number (:229-239)
@@ -85,6 +93,19 @@ __global__ void __launch_bounds__(128) assemble_kernel(const AssembleParams p) {
         t_last = ti; // timerRanging.stop(); timerRanging.start() (:270-273)
         have_last = true;
         armed = true;
+    };
+    if (p.L > 0) load(0);
+    for (int64_t i0 = 0; i0 < p.L; i0 += D) {
+        int a_c[D], s_c[D];
+        int32_t r_c[D];
+        double e_c[D], t_c[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            a_c[d] = a_n[d]; s_c[d] = s_n[d]; r_c[d] = r_n[d]; e_c[d] = e_n[d]; t_c[d] = t_n[d];
+        }
+        if (i0 + D < p.L) load(i0 + D);
+#pragma unroll
+        for (int d = 0; d < D; ++d) message(a_c[d], s_c[d], r_c[d], e_c[d], t_c[d]);
     }
     if (have_last && armed) flush(t_last + 0.05); // the timer after the last ranging of the log
     // epochs this log did not produce: no ranging, dt < 0 = "no step" for the replay
