@@ -35,7 +35,10 @@ constexpr int ML_BLOCK = 128;
 constexpr unsigned ML_FIRST_CAP = 32u;
 // queue length up to which the one-lane-per-anchor form is used (measured on 16 anchors: 6.4 ms flat up
 // to ~2700 records, then 2.3 us per record; the 4-lanes-per-record form: 11 ms at 7800 records)
-constexpr int COOP_WIDE_MAX = 4000;
+#ifndef KF_COOP_WIDE_MAX
+#define KF_COOP_WIDE_MAX 4000
+#endif
+constexpr int COOP_WIDE_MAX = KF_COOP_WIDE_MAX;
 
 // parked Newton state of one epoch (one 64-byte record)
 struct MlParked {
@@ -75,7 +78,7 @@ KF_DEV int ml_any(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask
 // iterations so that one __syncwarp per hand-over is enough.
 constexpr int COOP_STRIDE = 34;                       // doubles per row: rows 16-byte aligned, four banks apart
 constexpr int COOP_TOT = 12 * COOP_STRIDE;            // totals: [group][12]
-constexpr int COOP_TILE = COOP_TOT + 8 * 12;          // doubles per tile
+constexpr int COOP_TILE = COOP_TOT + 16 * 12;         // doubles per tile (up to 16 groups per warp)
 template <int K, int L>
 KF_DEV void group_sum(double *tile, int lane, double (&v)[K]) {
     const int grp = lane / L, gl = lane % L;
@@ -87,13 +90,18 @@ KF_DEV void group_sum(double *tile, int lane, double (&v)[K]) {
         const int j = j0 + gl;
         if (j < K) {
             const double2 *row = reinterpret_cast<const double2 *>(tile + j * COOP_STRIDE + grp * L);
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+            if (L == 2) {
+                const double2 lo = row[0];
+                tile[COOP_TOT + grp * 12 + j] = lo.x + lo.y;
+            } else {
+                double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
 #pragma unroll
-            for (int i = 0; i < L / 4; ++i) {
-                const double2 lo = row[2 * i], hi = row[2 * i + 1];
-                a0 += lo.x; a1 += lo.y; a2 += hi.x; a3 += hi.y;
+                for (int i = 0; i < L / 4; ++i) {
+                    const double2 lo = row[2 * i], hi = row[2 * i + 1];
+                    a0 += lo.x; a1 += lo.y; a2 += hi.x; a3 += hi.y;
+                }
+                tile[COOP_TOT + grp * 12 + j] = (a0 + a1) + (a2 + a3);
             }
-            tile[COOP_TOT + grp * 12 + j] = (a0 + a1) + (a2 + a3);
         }
     }
     __syncwarp();
@@ -364,7 +372,15 @@ static cudaError_t launch_k(const MlParams &p0, cudaStream_t s) {
     const int rounds = p.variant == 1 ? 2 : 1; // IGNORE_N solves twice
     for (int q = 0; q < rounds; ++q) {
         p.q_in = p.queue[q]; p.q_in_count = p.queue_count + q;
+#ifdef KF_COOP_FORCE_L // profiling builds: one form for every queue length (0 = no cooperative advance)
+        p.coop_min = 0; p.coop_max = 0x7fffffff;
+#if KF_COOP_FORCE_L > 0
+        ml_coop_kernel<PME, KF_COOP_FORCE_L, 16 / KF_COOP_FORCE_L><<<coop_grid, ML_BLOCK, 0, s>>>(p);
+#endif
+        if (false) {
+#else
         if (m <= 16) {
+#endif
             p.coop_min = 0; p.coop_max = COOP_WIDE_MAX;
             // 8 lanes x 2 anchors measured 8 % faster than 16 x 1 on the 16-anchor batch (12.4 -> 11.5 ms at 1 Mi
             // epochs; 4 x 4: 15.2 ms): the iteration is a serial chain, a shorter group sum buys more than
