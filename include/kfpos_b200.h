@@ -468,6 +468,13 @@ int kfpos_synth_k8(int device, int64_t n_filters, int64_t first_filter, uint64_t
 int kfpos_selftest_math(int device, int64_t n, const double *x, double *rcp, double *rsqrt, double *sn,
                         double *cs);
 
+/* Self-test of the exact-order solver's branch-free IEEE division and square root (kfpos_exact.cu: the
+ * compiler's own fast-path sequences with the operand-range test accumulated into a flag): a[i] / b[i] and
+ * sqrt(a[i]) through them (plain operator when the flag says so) next to the plain operators, so that a test
+ * can compare the two BIT FOR BIT; flags bit 0 / 1 = the fast path was taken.  Outputs may be NULL.        */
+int kfpos_selftest_ieee(int device, int64_t n, const double *a, const double *b, double *div_fast,
+                        double *div_ieee, double *sqrt_fast, double *sqrt_ieee, int32_t *flags);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,7 +3,7 @@
 BestGroup 2-D (best 3 of 16) and 3-D (best 4 of 16) on the exact 4 x 4 grid (where most epochs end at the first
 collinear triple, as the reference's exception does) and on a jittered grid (every epoch enumerates all subsets).
 
-    [KFPOS_B200_SO=build/variants/libX.so] python profiles/ml_variants.py [ign] [best]
+    [KFPOS_B200_SO=build/variants/libX.so] python profiles/ml_variants.py [ign] [best2] [best3]
 """
 import os
 import sys
@@ -20,7 +20,7 @@ from roskfpos_b200.batch import Batch  # noqa: E402
 dev = torch.device("cuda", 0)
 torch.cuda.set_device(0)
 stream = torch.cuda.current_stream()
-which = sys.argv[1:] or ["ign", "best"]
+which = sys.argv[1:] or ["ign", "best2", "best3"]
 REPS = 3
 
 
@@ -49,7 +49,7 @@ if "ign" in which:
         with Batch(L.MODEL_ML, Nm, device=0, anchors=anc16, use2d=0, variant=1, num_ignored_rangings=2) as b:
             timed(f"ignore2 3-D {Nm >> 20} Mi", lambda: b.ml_solve(rm, err=0.01, out=o4, stream=stream), Nm)
         del rm, o4
-if "best" in which:
+if "best2" in which or "best3" in which:
     Nb = int(os.environ.get("KF_NB", 1 << 17))
     for nm, anc in (("grid", anc16), ("jittered", jit)):
         rb, _, _ = synth.device_ranges_mm(Nb, 1, anc, 0.1, dev, seed=synth.SEED + 6)
@@ -58,7 +58,7 @@ if "best" in which:
                   iters=torch.empty(Nb, device=dev, dtype=torch.int32),
                   sel=torch.empty((2, Nb), device=dev, dtype=torch.int32),
                   status=torch.empty(Nb, device=dev, dtype=torch.int32))
-        for use2d in (1, 0):
+        for use2d in [u for u, w in ((1, "best2"), (0, "best3")) if w in which]:
             with Batch(L.MODEL_ML, Nb, device=0, anchors=anc, use2d=use2d, variant=2,
                        ml_start=[1.0, 1.0, 1.0 if use2d else 4.0]) as b:
                 timed(f"best {'3 2-D' if use2d else '4 3-D'} {nm}", lambda: b.ml_solve(rb, err=0.01, out=ob, stream=stream),

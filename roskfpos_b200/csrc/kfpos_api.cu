@@ -1433,3 +1433,28 @@ extern "C" int kfpos_selftest_math(int device, int64_t n, const double *x, doubl
     CK(cudaStreamSynchronize(nullptr));
     return KFPOS_OK;
 }
+
+extern "C" int kfpos_selftest_ieee(int device, int64_t n, const double *a, const double *b, double *div_fast,
+                                   double *div_ieee, double *sqrt_fast, double *sqrt_ieee, int32_t *flags) {
+    if (n <= 0 || !a || !b) return KFPOS_ERR_INVALID;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+        cudaGetLastError();
+        return KFPOS_ERR_CUDA;
+    }
+    DeviceGuard g(device);
+    if (!g.ok) return KFPOS_ERR_CUDA;
+    TmpIn i_a, i_b;
+    TmpOut o[4], o_f;
+    double *outs[4] = {div_fast, div_ieee, sqrt_fast, sqrt_ieee};
+    CK(i_a.set(a, 8 * (size_t)n, nullptr));
+    CK(i_b.set(b, 8 * (size_t)n, nullptr));
+    for (int k = 0; k < 4; ++k) CK(o[k].set(outs[k], 8 * (size_t)n));
+    CK(o_f.set(flags, 4 * (size_t)n));
+    CK(launch_selftest_ieee(n, (const double *)i_a.d, (const double *)i_b.d, (double *)o[0].d, (double *)o[1].d,
+                            (double *)o[2].d, (double *)o[3].d, (int32_t *)o_f.d, nullptr));
+    for (int k = 0; k < 4; ++k) CK(o[k].back(nullptr));
+    CK(o_f.back(nullptr));
+    CK(cudaStreamSynchronize(nullptr));
+    return KFPOS_OK;
+}

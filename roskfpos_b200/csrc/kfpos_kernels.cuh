@@ -177,6 +177,8 @@ cudaError_t launch_k8_get_pose(int64_t N, double dt, double accel_noise, double 
                                const double *P, double *x_pred, double *P_pred_full, cudaStream_t s);
 cudaError_t launch_ml_solve(const MlParams &p, cudaStream_t s);
 cudaError_t launch_ml_exact(const MlParams &p, bool queued, cudaStream_t s); // kfpos_exact.cu
+cudaError_t launch_selftest_ieee(int64_t n, const double *a, const double *b, double *div_fast, double *div_ieee,
+                                 double *sqrt_fast, double *sqrt_ieee, int32_t *flags, cudaStream_t s);
 
 struct T9Params {
     AnchorTable anchors;

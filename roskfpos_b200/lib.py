@@ -90,6 +90,7 @@ SIGNATURES = {
     "kfpos_measure_fp64_peak": (_I, [_I, C.POINTER(C.c_double)]),
     "kfpos_synth_k8": (_I, [_I, _I64, _I64, C.c_uint64, _I, _VP, _D, _D, _I, _VP, _D, _I64, _I64, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_selftest_math": (_I, [_I, _I64, _VP, _VP, _VP, _VP, _VP]),
+    "kfpos_selftest_ieee": (_I, [_I, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_assemble_epochs": (_I, [_I, _I64, _I64, _I, _VP, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_assemble_epochs_t": (_I, [_I, _I64, _I64, _I, _VP, _VP, _VP, _VP, _VP, _I64, _I, _D, _VP, _VP, _VP, _VP, _VP, _VP]),
     "kfpos_merge_streams": (_I, [_I, _I64, _I, _I64, _VP, _VP, _VP, _VP, _VP, _VP, _I, _VP, _D, _VP, _VP, _VP, _VP, _VP,

@@ -53,3 +53,55 @@ def test_sincos_within_one_ulp(kflib):
     tol = np.maximum(1.0 * np.spacing(np.abs(ref_c)), 0.5 * np.spacing(np.abs(x)))
     assert np.all(np.abs(cs - ref_c) <= tol), float((np.abs(cs - ref_c) / tol).max())
     assert np.abs(sn ** 2 + cs ** 2 - 1).max() < 5e-16
+
+
+def run_ieee(kflib, a, b):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    b = np.ascontiguousarray(b, dtype=np.float64)
+    out = [np.empty_like(a) for _ in range(4)]
+    flags = np.empty(a.size, dtype=np.int32)
+    kflib.check(kflib.lib().kfpos_selftest_ieee(0, a.size, C.c_void_p(a.ctypes.data), C.c_void_p(b.ctypes.data),
+                                                *[C.c_void_p(o.ctypes.data) for o in out],
+                                                C.c_void_p(flags.ctypes.data)), "kfpos_selftest_ieee")
+    return out, flags
+
+
+def bits_equal(x, y):
+    return (x.view(np.uint64) == y.view(np.uint64)) | (np.isnan(x) & np.isnan(y))
+
+
+def test_branch_free_ieee_division_and_sqrt_are_bit_exact(kflib):
+    """kfpos_exact.cu's xf_div / xf_sqrt (the compiler's fast-path sequences, range test accumulated instead of
+    branched on) against the plain operators: identical bits on every operand pair -- ordinary magnitudes, values
+    next to powers of two, subnormals, huge values, zeros, infinities and NaNs (where the flag must send the
+    operation to the plain operator) -- and against numpy's correctly rounded results."""
+    rng = np.random.default_rng(7)
+    n = 4_000_000
+    a = np.concatenate([
+        rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-30, 30, n),
+        np.ldexp(1.0 + rng.integers(0, 8, n // 4) * 2.0 ** -52, rng.integers(-60, 60, n // 4)),
+        rng.uniform(0, 1, n // 4) * 10.0 ** rng.uniform(-320, -290, n // 4),
+        rng.uniform(0, 1, n // 4) * 10.0 ** rng.uniform(290, 308, n // 4),
+        np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, 4.0, 2.0 ** -1022, 5e-324, 1.7976931348623157e308] * 10),
+    ])
+    b = np.concatenate([
+        rng.uniform(-1, 1, n) * 10.0 ** rng.uniform(-30, 30, n),
+        np.ldexp(1.0 + rng.integers(0, 8, n // 4) * 2.0 ** -52, rng.integers(-60, 60, n // 4)),
+        rng.uniform(0, 1, n // 4) * 10.0 ** rng.uniform(290, 308, n // 4),
+        rng.uniform(0, 1, n // 4) * 10.0 ** rng.uniform(-320, -290, n // 4),
+        np.repeat(np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1.0, 3.0, 2.0 ** -1022, 5e-324, 1.7976931348623157e308]), 10),
+    ])
+    (qf, q, sf, s), flags = run_ieee(kflib, a, b)
+    assert bits_equal(qf, q).all(), int((~bits_equal(qf, q)).sum())
+    assert bits_equal(sf, s).all(), int((~bits_equal(sf, s)).sum())
+    with np.errstate(all="ignore"):
+        assert bits_equal(q, a / b).all()
+        assert bits_equal(s, np.sqrt(a)).all()
+    # the fast path is what runs on ordinary operands (positive a for the square root) ...
+    ordinary = slice(0, n)
+    assert (flags[ordinary] & 1).mean() > 0.999
+    assert ((flags[ordinary] & 2) != 0)[a[ordinary] > 0].mean() > 0.999
+    # ... and never on operands it cannot round correctly
+    special = ~np.isfinite(a) | ~np.isfinite(b) | (b == 0) | (np.abs(a) < 2.0 ** -1000)
+    assert not (flags[special] & 1).any()
+    assert not (flags[(a <= 0) | ~np.isfinite(a) | (a < 2.0 ** -1000)] & 2).any()
