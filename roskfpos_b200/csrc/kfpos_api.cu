@@ -999,6 +999,14 @@ extern "C" int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt,
     p.xq = b->d_xq;
     p.xq_count = b->d_mlq_count + 2;
     p.xq_cap = b->xq_cap;
+    p.xw_scratch = nullptr;
+    p.xw_scratch_bytes = 0;
+    if (p.variant == 2 && !p.use2d && p.exact_mode >= 0) { // parked subset solves of the 3-D BestGroup scan
+        const size_t bytes = ml_exact_scratch_bytes(ml_exact_scratch_epochs(b->N));
+        CK(b->scratch[7].reserve(bytes));
+        p.xw_scratch = b->scratch[7].p;
+        p.xw_scratch_bytes = bytes;
+    }
     CK(launch_ml_solve(p, s));
     if (c_pos) CK(cudaMemcpyAsync(pos, d_pos, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, s));
     if (c_cov) CK(cudaMemcpyAsync(cov, d_cov, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, s));

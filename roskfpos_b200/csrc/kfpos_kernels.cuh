@@ -109,6 +109,9 @@ struct MlParams {
     int xq_cap;
     int32_t *xq;
     int *xq_count;
+    // scratch of the warp-per-epoch BestGroup kernels (parked 3-D subset solves), see ml_exact_scratch_bytes
+    void *xw_scratch;
+    size_t xw_scratch_bytes;
 };
 constexpr int KFPOS_MAX_ANCHORS_DEV = 32;
 // relative margin below which the fast solver does not trust its own order of two squared residuals
@@ -177,6 +180,8 @@ cudaError_t launch_k8_get_pose(int64_t N, double dt, double accel_noise, double 
                                const double *P, double *x_pred, double *P_pred_full, cudaStream_t s);
 cudaError_t launch_ml_solve(const MlParams &p, cudaStream_t s);
 cudaError_t launch_ml_exact(const MlParams &p, bool queued, cudaStream_t s); // kfpos_exact.cu
+size_t ml_exact_scratch_bytes(int64_t epochs);
+int64_t ml_exact_scratch_epochs(int64_t N);
 cudaError_t launch_selftest_ieee(int64_t n, const double *a, const double *b, double *div_fast, double *div_ieee,
                                  double *sqrt_fast, double *sqrt_ieee, int32_t *flags, cudaStream_t s);
 

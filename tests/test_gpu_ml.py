@@ -230,3 +230,18 @@ def test_ml_z_gate(kflib):
     assert 0.05 < out.mean() < 0.95
     assert np.array_equal((gated["status"] & kflib.ST_Z_GATE) != 0, out)
     assert np.array_equal(gated["status"] & ~kflib.ST_Z_GATE, plain["status"])
+
+
+def test_ml_best_group_3d_parked_solves_overflow(kflib, oracle, monkeypatch):
+    """3-D BestGroup parks long subset solves in task records; when the records run out (forced here with a
+    capacity of 40 tasks) the warp finishes its parked solves in place: same bits either way."""
+    N, m = 160, 16
+    anc, truth, r = epochs(m, N, seed=616, p_nlos=0.15)
+    ref = oracle.ml_batch(r, anc, 0.01, start_for(0), use2d=0, variant=2, best_mode=0)
+    keys = ("sel", "status", "iters", "pos", "cov")
+    got = gpu_ml(kflib, anc, r, use2d=0, variant=2, best_mode=0, ml_start=start_for(0))
+    assert_bit_equal(got, ref, keys, "BestGroup 3-D parked")
+    assert ref["iters"].max() > 10000, "the workload no longer has subset solves that run to the cap"
+    monkeypatch.setenv("KFPOS_XW_TASK_CAP", "40")
+    got = gpu_ml(kflib, anc, r, use2d=0, variant=2, best_mode=0, ml_start=start_for(0))
+    assert_bit_equal(got, ref, keys, "BestGroup 3-D parked, task records exhausted")
