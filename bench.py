@@ -655,15 +655,31 @@ def bench_other_configs(local, dev, args):
     with Batch(L.MODEL_ML, N4, device=local, anchors=anc16, use2d=0, variant=1, num_ignored_rangings=2) as b:
         t = timed(lambda: b.ml_solve(r16, err=0.01, out=o4, stream=stream))
     out["config4a_ml_ignore2_16anchors"] = {"epochs_per_s": N4 / t, "ms": t * 1e3, "epochs": N4}
-    Nb = 1 << 17
-    ob = dict(pos=torch.empty((3, Nb), device=dev, dtype=torch.float64), cov=None, iters=None,
-              sel=torch.empty((2, Nb), device=dev, dtype=torch.int32), status=None)
-    rb = r16[:, :Nb].contiguous()
-    with Batch(L.MODEL_ML, Nb, device=local, anchors=anc16, use2d=1, variant=2, ml_start=[1.0, 1.0, 1.0]) as b:
-        t = timed(lambda: b.ml_solve(rb, err=0.01, out=ob, stream=stream), reps=1)
-    out["config4b_ml_best3_of_16_2d"] = {"epochs_per_s": Nb / t, "ms": t * 1e3, "epochs": Nb,
-                                         "subset_solves_per_epoch": 560 + 1}
-    del r16, rb, o4, ob
+    # variant 2 (BestGroup, exact-order solver, a warp per epoch): the BASELINE size on the BASELINE geometry (the 4 x 4
+    # grid, where the scan of most epochs ends at the first collinear triple the way the reference's exception
+    # does), a jittered grid on which every epoch enumerates all 560 subsets, and the 3-D scan (1820 subsets of 4)
+    import numpy as np
+    jit = anc16.copy()
+    jit[:, :2] += np.random.default_rng(3).uniform(-0.3, 0.3, size=(16, 2))
+    rj, _, _ = synth.device_ranges_mm(1 << 20, 1, jit, 0.1, dev, seed=synth.SEED + 6)
+    rj = rj[0].contiguous()
+    for key, ranges, a, Nb, use2d in (("config4b_ml_best3_of_16_2d", r16, anc16, N4, 1),
+                                      ("config4b_ml_best3_of_16_2d_jittered_grid", rj, jit, 1 << 20, 1),
+                                      ("config4b_ml_best4_of_16_3d", r16, anc16, 1 << 17, 0)):
+        ob = dict(pos=torch.empty((3, Nb), device=dev, dtype=torch.float64), cov=None, iters=None,
+                  sel=torch.empty((2, Nb), device=dev, dtype=torch.int32), status=None)
+        rb = ranges[:, :Nb].contiguous()
+        with Batch(L.MODEL_ML, Nb, device=local, anchors=a, use2d=use2d, variant=2,
+                   ml_start=[1.0, 1.0, 1.0 if use2d else 4.0]) as b:
+            t = timed(lambda: b.ml_solve(rb, err=0.01, out=ob, stream=stream), reps=1)
+            c = b.counters()
+        out[key] = {"epochs_per_s": Nb / t, "ms": t * 1e3, "epochs": Nb,
+                    "subsets_per_epoch": 560 if use2d else 1820,
+                    "mean_newton_iters_per_epoch": c["ml_iters"] / max(c["updates"], 1),
+                    "epochs_where_the_scan_throws": c["bad"] / max(c["updates"], 1)}
+        del ob, rb
+    del rj
+    del r16, o4
     # ---- config 4c: T6 leave-one-out (ignoreWorstAnchorMode), 16 anchors
     Nl, Tl = 1 << 18, 10
     rl, x0l, _ = synth.device_ranges_mm(Nl, Tl, anc16, 0.1, dev, seed=synth.SEED + 7)
