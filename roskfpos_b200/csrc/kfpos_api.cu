@@ -1001,6 +1001,7 @@ extern "C" int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt,
     p.xq_cap = b->xq_cap;
     p.xw_scratch = nullptr;
     p.xw_scratch_bytes = 0;
+    p.stream_counter = b->d_mlq_count + 3;
     if (p.variant == 2 && !p.use2d && p.exact_mode >= 0) { // parked subset solves of the 3-D BestGroup scan
         const size_t bytes = ml_exact_scratch_bytes(ml_exact_scratch_epochs(b->N));
         CK(b->scratch[7].reserve(bytes));

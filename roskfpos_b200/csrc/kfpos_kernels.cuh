@@ -112,6 +112,7 @@ struct MlParams {
     // scratch of the warp-per-epoch BestGroup kernels (parked 3-D subset solves), see ml_exact_scratch_bytes
     void *xw_scratch;
     size_t xw_scratch_bytes;
+    int *stream_counter; // device int: the epoch counter of ml_stream3_kernel
 };
 constexpr int KFPOS_MAX_ANCHORS_DEV = 32;
 // relative margin below which the fast solver does not trust its own order of two squared residuals

@@ -348,6 +348,163 @@ __global__ void __launch_bounds__(ML_BLOCK) ml_solve_kernel(const __grid_constan
     warp_accumulate(p.counters + CNT_BAD, bad);
 }
 
+// ---- NORMAL-mode 3-D epochs as a stream (BASELINE config 2).  In ml_solve_kernel a thread owns one epoch and
+// a warp lasts as long as its slowest lane: the Newton trip counts from the fixed start point spread between 5
+// and 12 (mean 7.7 at 8 anchors), and ncu shows 20 of 32 lanes active on average.  Here warps are persistent and
+// every LANE is a state machine: one Newton pass per trip of a warp-uniform loop; a lane whose solve has ended
+// writes its epoch (covariance, outputs) and takes the next one from a global counter when ML_STREAM_FIN lanes
+// wait or nobody iterates, its raw rangings already in registers (fetched one epoch ahead).  Per epoch the
+// arithmetic is ml_solve3's, operation for operation: outputs are bit-identical to ml_solve_kernel's.  An epoch
+// that needs more than `first_cap` iterations is parked in the straggler queue exactly as there.
+#ifndef ML_STREAM_FIN_N
+#define ML_STREAM_FIN_N 24
+#endif
+constexpr int ML_STREAM_FIN = ML_STREAM_FIN_N;
+template <int MT>
+__global__ void __launch_bounds__(ML_BLOCK, 4) ml_stream3_kernel(const __grid_constant__ MlParams p, int *next_epoch) {
+    const int64_t N = p.N;
+    const int fmt = p.rs.fmt; // 1: int32 mm, 2: uint16 mm
+    MlParked *queue = reinterpret_cast<MlParked *>(p.q_out);
+    enum { FETCH = 0, RUN = 1, FIN = 2, DONE = 3 };
+    int phase = FETCH;
+    int64_t f = -1, f_next = -1;
+    unsigned raw_next[MT];
+    EpochT<false, MT> ep;
+    ep.e0 = p.rs.err_scalar;
+    ep.m_slots = MT;
+    ep.valid = 0u;
+    auto load_raw = [&](int64_t fe) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int64_t at = (int64_t)i * N + fe;
+            raw_next[i] = fmt == 1 ? (unsigned)__ldg(reinterpret_cast<const int32_t *>(p.rs.ranges) + at)
+                                   : (unsigned)__ldg(reinterpret_cast<const uint16_t *>(p.rs.ranges) + at);
+        }
+    };
+    {
+        const int64_t t = atomicAdd(next_epoch, 1);
+        if (t < N) { f_next = t; load_raw(t); }
+    }
+    double pos[3] = {0, 0, 0}, cost = 1e20;
+    unsigned iter = 0, nvalid = 0, iters_sum = 0, n_done = 0, n_bad = 0;
+    bool first = true;
+    int rc = ML_OK;
+    MlPass3 ps;
+    for (;;) {
+        const unsigned waiting = __ballot_sync(0xffffffffu, phase == FIN || phase == FETCH);
+        const unsigned running = __ballot_sync(0xffffffffu, phase == RUN);
+        if (waiting == 0u && running == 0u) break;
+        if (waiting != 0u && (running == 0u || __popc(waiting) >= ML_STREAM_FIN)) {
+            if (phase == FIN) {
+                double cv[6] = {0, 0, 0, 0, 0, 0};
+                bool parked = false, have_cov = false;
+                if (rc == ML_MORE) { // park; a full queue: finish in place
+                    const int slot = queue ? atomicAdd(p.q_out_count, 1) : p.queue_cap;
+                    if (slot < p.queue_cap) {
+                        MlParked rec;
+                        rec.idx = (int32_t)f; rec.phase = 0; rec.used = ep.valid; rec.iter = iter; rec.iters = 0u;
+                        rec._pad = 0u; rec.cost = cost; rec.p[0] = pos[0]; rec.p[1] = pos[1]; rec.p[2] = pos[2];
+                        rec._pad2 = 0.0;
+                        queue[slot] = rec;
+                        parked = true;
+                    } else {
+                        MlResume rs = {cost, iter};
+                        double sse_r;
+                        unsigned it_r = 0;
+                        rc = ml_solve3<false, MT>(p.anchors, ep, ep.valid, pos, sse_r, it_r, cv, nullptr, 10000u, &rs);
+                        iter = it_r;
+                        have_cov = true;
+                    }
+                }
+                if (!parked) {
+                    // estimatePosition ends with the covariance (ML.cpp:229-254); a singular J^T W^-1 J fails the epoch
+                    if (rc == ML_OK && !have_cov) rc = ml_cov3<false, MT>(p.anchors, ep, ep.valid, pos, ps.sse, cv);
+                    if (p.cov) {
+                        const bool ok = rc == ML_OK;
+                        const double c00 = ok ? cv[0] : 0.0, c01 = ok ? cv[1] : 0.0, c11 = ok ? cv[2] : 0.0;
+                        const double c02 = ok ? cv[3] : 0.0, c12 = ok ? cv[4] : 0.0, c22 = ok ? cv[5] : 0.0;
+                        p.cov[0 * N + f] = c00; p.cov[1 * N + f] = c01; p.cov[2 * N + f] = c02;
+                        p.cov[3 * N + f] = c01; p.cov[4 * N + f] = c11; p.cov[5 * N + f] = c12;
+                        p.cov[6 * N + f] = c02; p.cov[7 * N + f] = c12; p.cov[8 * N + f] = c22;
+                    }
+                    if (p.pos) {
+#pragma unroll
+                        for (int q = 0; q < 3; ++q) p.pos[(int64_t)q * N + f] = pos[q];
+                    }
+                    if (p.iters) p.iters[f] = (int32_t)iter;
+                    if (p.sel) {
+                        p.sel[f] = (int32_t)ep.valid;
+                        p.sel[N + f] = -1;
+                    }
+                    int stv = rc == ML_OK ? 0 : (rc == ML_FEW ? 2 : 4);
+                    if (p.max_z > p.min_z && (pos[2] < p.min_z || pos[2] > p.max_z)) stv |= 128;
+                    if (p.status) p.status[f] = stv;
+                    n_bad += (stv & ~128) != 0;
+                    n_done += 1;
+                    iters_sum += iter;
+                }
+                phase = FETCH;
+            }
+            if (phase == FETCH) {
+                if (f_next < 0) {
+                    phase = DONE;
+                } else {
+                    f = f_next;
+                    unsigned valid = 0u;
+#pragma unroll
+                    for (int i = 0; i < MT; ++i) {
+                        const double r = mm_to_m(fmt == 1 ? (double)(int)raw_next[i] : (double)raw_next[i]);
+                        ep.zr[i] = r;
+                        if (r > 0) valid |= 1u << i;
+                    }
+                    ep.valid = valid;
+                    nvalid = __popc(valid);
+                    const int64_t t = atomicAdd(next_epoch, 1);
+                    f_next = -1;
+                    if (t < N) { f_next = t; load_raw(t); }
+                    pos[0] = p.start[0]; pos[1] = p.start[1]; pos[2] = p.start[2];
+                    cost = 1e20; iter = 0; first = true; rc = ML_OK;
+                    phase = RUN;
+                }
+            }
+        }
+        if (phase == RUN) { // one trip of ml_solve3's loop
+            ml_pass3<false, MT>(p.anchors, ep, ep.valid, (int)nvalid, pos, ps);
+            double newCost = 1.0;
+            bool stop = false;
+            if (first) {
+                first = false;
+                if (nvalid < 4) { rc = ML_FEW; stop = true; }
+                else if (ep.e0 == 0.0) { rc = ML_SINGULAR; stop = true; }
+            } else {
+                newCost = ps.wcost;
+            }
+            if (!stop) {
+                if (!(rel_change_gt(cost, newCost) && iter < 10000u)) {
+                    stop = true;
+                } else if (iter >= p.first_cap) {
+                    rc = ML_MORE;
+                    stop = true;
+                } else {
+                    iter += 1;
+                    cost = newCost;
+                    double sv[3];
+                    if (!solve_sym3(ps.H, ps.g, sv)) {
+                        rc = ML_SINGULAR;
+                        stop = true;
+                    } else {
+                        pos[0] -= sv[0]; pos[1] -= sv[1]; pos[2] -= sv[2];
+                    }
+                }
+            }
+            if (stop) phase = FIN;
+        }
+    }
+    warp_accumulate(p.counters + CNT_UPDATES, n_done);
+    warp_accumulate(p.counters + CNT_ML_ITERS, iters_sum);
+    warp_accumulate(p.counters + CNT_BAD, n_bad);
+}
+
 template <bool PME, int MT>
 static cudaError_t launch_k(const MlParams &p0, cudaStream_t s) {
     MlParams p = p0;
@@ -363,7 +520,24 @@ static cudaError_t launch_k(const MlParams &p0, cudaStream_t s) {
     p.q_in = nullptr; p.q_in_count = nullptr;
     p.q_out = parks ? p.queue[0] : nullptr; p.q_out_count = p.queue_count;
     p.first_cap = parks ? ML_FIRST_CAP : 10000u;
-    ml_solve_kernel<PME, MT, false><<<(unsigned)((p.N + ML_BLOCK - 1) / ML_BLOCK), ML_BLOCK, smem, s>>>(p);
+    bool streamed = false;
+    if constexpr (!PME && MT > 0) {
+        // NORMAL mode, 3-D, integer wire formats: the persistent per-lane state machines (ml_stream3_kernel)
+#ifndef ML_NO_STREAM
+        if (p.variant == 0 && !p.use2d && p.rs.fmt != 0 && p.stream_counter != nullptr && p.N < 0x7fffffff) {
+            e = cudaMemsetAsync(p.stream_counter, 0, sizeof(int), s);
+            if (e != cudaSuccess) return e;
+            int dev = 0, sms = 148;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            const int64_t want = (p.N + ML_BLOCK - 1) / ML_BLOCK;
+            const unsigned grid = (unsigned)std::min<int64_t>(want, (int64_t)sms * 4);
+            ml_stream3_kernel<MT><<<grid, ML_BLOCK, 0, s>>>(p, p.stream_counter);
+            streamed = true;
+        }
+#endif
+    }
+    if (!streamed) ml_solve_kernel<PME, MT, false><<<(unsigned)((p.N + ML_BLOCK - 1) / ML_BLOCK), ML_BLOCK, smem, s>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess || !parks) return e;
     // the parked epochs: grids sized for the whole queue (warps / blocks beyond the count exit at once)

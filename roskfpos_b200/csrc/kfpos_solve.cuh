@@ -166,7 +166,26 @@ template <bool PME, int MT>
 KF_DEV int ml_cov3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, const double (&p)[3], double sse,
                    double *cov) {
     double M[6] = {0, 0, 0, 0, 0, 0};
-    for (int i = 0; i < ep.m_slots; ++i) {
+    if (MT > 0) {
+        // compile-time anchor count: unrolled, a missing ranging weighs 0, one MUFU-seeded reciprocal per ranging
+        // (<= 1 ulp, kfpos_math.cuh) instead of two IEEE divisions with their slow-path branches -- the eight
+        // chains interleave (the rolled form below waits ~200 cycles per ranging on its own divisions)
+#pragma unroll
+        for (int i = 0; i < (MT > 0 ? MT : 1); ++i) {
+            const bool on = (mask >> i) & 1u;
+            const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            const double wr = fast_rcp(d2 * fmax(ep.err(i), sse));
+            const double w = on ? wr : 0.0;
+            M[0] = fma(w * dx, dx, M[0]);
+            M[1] = fma(w * dx, dy, M[1]);
+            M[2] = fma(w * dy, dy, M[2]);
+            M[3] = fma(w * dx, dz, M[3]);
+            M[4] = fma(w * dy, dz, M[4]);
+            M[5] = fma(w * dz, dz, M[5]);
+        }
+    }
+    for (int i = 0; i < (MT > 0 ? 0 : ep.m_slots); ++i) {
         if (!((mask >> i) & 1u)) continue;
         const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
         const double id2 = 1.0 / (dx * dx + dy * dy + dz * dz);
@@ -190,7 +209,20 @@ template <bool PME, int MT>
 KF_DEV int ml_cov2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, const double (&p)[3], double sse,
                    double *cov) {
     double m00 = 0, m01 = 0, m11 = 0;
-    for (int i = 0; i < ep.m_slots; ++i) {
+    if (MT > 0) { // unrolled, one MUFU-seeded reciprocal per ranging (see ml_cov3)
+#pragma unroll
+        for (int i = 0; i < (MT > 0 ? MT : 1); ++i) {
+            const bool on = (mask >> i) & 1u;
+            const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
+            const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
+            const double wr = fast_rcp(d2 * fmax(ep.err(i), sse));
+            const double w = on ? wr : 0.0;
+            m00 = fma(w * dx, dx, m00);
+            m01 = fma(w * dx, dy, m01);
+            m11 = fma(w * dy, dy, m11);
+        }
+    }
+    for (int i = 0; i < (MT > 0 ? 0 : ep.m_slots); ++i) {
         if (!((mask >> i) & 1u)) continue;
         const double dx = p[0] - A.x[i], dy = p[1] - A.y[i], dz = p[2] - A.z[i];
         const double id2 = 1.0 / (dx * dx + dy * dy + dz * dz);
