@@ -32,11 +32,18 @@
 namespace kfpos {
 
 constexpr int ML_BLOCK = 128;
-constexpr unsigned ML_FIRST_CAP = 32u;
+// Newton iterations an epoch gets in the main launch before it is parked.  Measured (16 anchors, variant 1,
+// 1 Mi / 4 Mi epochs): 32 -> 10.4 / 21.5 ms, 64 -> 10.5 / 17.8, 80 -> 9.6 / 18.1, 128 -> 9.9 / 18.9, 256 -> 10.6 / 20.8:
+// about half of the epochs that pass 32 iterations end before 80, and every record less shortens the advance
+// of a long queue, which is bound by throughput as much as by latency.
+#ifndef ML_FIRST_CAP_N
+#define ML_FIRST_CAP_N 80
+#endif
+constexpr unsigned ML_FIRST_CAP = ML_FIRST_CAP_N;
 // queue length up to which the one-lane-per-anchor form is used (measured on 16 anchors: 6.4 ms flat up
 // to ~2700 records, then 2.3 us per record; the 4-lanes-per-record form: 11 ms at 7800 records)
 #ifndef KF_COOP_WIDE_MAX
-#define KF_COOP_WIDE_MAX 4000
+#define KF_COOP_WIDE_MAX 6000
 #endif
 constexpr int COOP_WIDE_MAX = KF_COOP_WIDE_MAX;
 
