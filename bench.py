@@ -642,9 +642,19 @@ def bench_other_configs(local, dev, args):
                    ml_start=[1.0, 1.0, 1.0 if use2d else 4.0]) as b:
             t = timed(lambda: b.ml_solve(r, err=0.01, out=outs, stream=stream))
             c = b.counters()
+        i_ml = c["ml_iters"] / max(c["updates"], 1)
+        # ML standalone epoch = W_ml0 + I_ml W_mlit(d, m) + (15 + d + 1.5 d (d + 1)) m + (8 | 40)
+        d, m = (2, 8) if use2d else (3, 8)
+        w_epoch = ((12 * m if d == 2 else 0) + i_ml * ((46 * m + 25) if d == 2 else (59 * m + 60))
+                   + (15 + d + 1.5 * d * (d + 1)) * m + (8 if d == 2 else 40))
+        peak = C_double_peak(local)
         out[f"config2_ml_{'2d' if use2d else '3d'}"] = {
-            "epochs_per_s": N / t, "ms": t * 1e3, "epochs": N, "anchors": 8,
-            "mean_newton_iters": c["ml_iters"] / max(c["updates"], 1)}
+            "epochs_per_s": N / t, "ms": t * 1e3, "epochs": N, "anchors": 8, "mean_newton_iters": i_ml,
+            "roofline": {"bound": "fp64", "achieved": w_epoch * N / t / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s",
+                         "frac": w_epoch * N / t / peak if peak else None, "flop_per_epoch": w_epoch,
+                         "numerator": "SURVEY.md §8(d) W_alg of a standalone ML epoch with the measured Newton iterations",
+                         "kernel": "ml_solve_kernel<false,8,false>" if use2d else "ml_stream3_kernel<8>",
+                         "peak_source": "measured live: kfpos_measure_fp64_peak"}}
     # ---- config 4a/4b: NLOS variants, 16 anchors
     anc16 = synth.anchors_for(16)
     N4 = 1 << 22

@@ -323,7 +323,10 @@ int kfpos_batch_get_pose_msg(kfpos_batch *b, double dt, double *pose13, double *
  * pos SoA [3][N]; cov SoA [9][N] (3x3 row-major, the 2x2 block top-left when
  * use2d); iters [N] total Newton iterations; sel SoA [2][N]: row 0 = bit mask of
  * the anchor slots used by the final solve, row 1 = #dropped (variant 1) or the
- * subset index in prev_permutation order (variant 2); status [N].               */
+ * subset index in prev_permutation order (variant 2); status [N].
+ * Variant 2 runs in the exact-order solver (ml_exact_order >= 0) with one warp per epoch; the 3-D
+ * scan parks its long subset solves in device scratch that the batch allocates on first use
+ * (~190 MB, independent of N: epochs go through in chunks of 131072).             */
 int kfpos_batch_ml_solve(kfpos_batch *b, const void *ranges, int fmt, double err_scalar,
                          const double *err_var, double *pos, double *cov, int32_t *iters,
                          int32_t *sel, int32_t *status, void *stream);
