@@ -245,3 +245,19 @@ def test_ml_best_group_3d_parked_solves_overflow(kflib, oracle, monkeypatch):
     monkeypatch.setenv("KFPOS_XW_TASK_CAP", "40")
     got = gpu_ml(kflib, anc, r, use2d=0, variant=2, best_mode=0, ml_start=start_for(0))
     assert_bit_equal(got, ref, keys, "BestGroup 3-D parked, task records exhausted")
+
+
+def test_ml_best_group_3d_chunks_ragged_per_ranging_errors(kflib, oracle, monkeypatch):
+    """The 3-D scan goes through the batch in chunks (131072 epochs; forced to 48 here so that a 200-epoch batch takes
+    five passes with a short last one), with missing rangings, per-ranging error estimates and all three wire formats."""
+    N, m = 200, 12
+    anc, truth, r = epochs(m, N, seed=640, p_missing=0.25, p_nlos=0.1)
+    r[:, :6] = 0
+    err = np.random.default_rng(4).uniform(0.005, 0.05, size=r.shape)
+    keys = ("sel", "status", "iters", "pos", "cov")
+    monkeypatch.setenv("KFPOS_XW_CHUNK", "48")
+    for e, rr in ((0.01, r), (err, r), (0.01, r.astype(np.uint16)), (0.02, r.astype(np.float64) / 1000)):
+        for best_mode in (0, 1):
+            ref = oracle.ml_batch(rr, anc, e, start_for(0), use2d=0, variant=2, best_mode=best_mode)
+            got = gpu_ml(kflib, anc, rr, err=e, use2d=0, variant=2, best_mode=best_mode, ml_start=start_for(0))
+            assert_bit_equal(got, ref, keys, f"BestGroup 3-D chunks {rr.dtype} pme={not np.isscalar(e)} mode={best_mode}")
