@@ -24,6 +24,9 @@ __host__ __device__ inline int k8_smem_rows(int m, int fmt, bool pme, bool in_re
     return 36 + 8 + k8_land_rows(m, fmt) + (in_regs ? 0 : m) + (pme ? m : 0);
 }
 
+// (the raw-magnetometer event's atan2, ~140 instructions, kept out of the replay loop's code)
+static __device__ __noinline__ double atan2_out_of_line(double y, double x) { return atan2(y, x); }
+
 KF_DEV int event_rows(int kind) {
     switch (kind) {
     case EV_PX4: return 5;
@@ -163,7 +166,7 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                 break;
             }
             case EV_MAG: { // newMAGMeasurement (KF.cpp:179-193): mag only, angle not normalised
-                latch[7] = atan2(land[1], land[0]) - p.cfg.mag_offset;
+                latch[7] = atan2_out_of_line(land[1], land[0]) - p.cfg.mag_offset;
                 has |= 4u;
                 ms.has_mag = true;
                 break;
@@ -224,8 +227,8 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                 Sym<8> &Pw = Pr;
                 k8_predict_cov(Pw, dt, p.cfg.accel_noise, p.cfg.jolt);
                 // one sensor and no rangings: the deferred update on the register copy (k8_update_light)
-                const bool light = ev.kind == EV_IMU || ev.kind == EV_PX4 || ev.kind == EV_MAG;
-                if (!light) {
+                bool light = ev.kind == EV_IMU || ev.kind == EV_PX4 || ev.kind == EV_MAG;
+                if (!light || ev.kind == EV_IMU) { // (the IMU event's straight-line form keeps P^- there as its backup)
 #pragma unroll
                     for (int k = 0; k < Sym<8>::SZ; ++k) Pm[k] = Pw.a[k];
                 }
@@ -259,8 +262,13 @@ __global__ void __launch_bounds__(K8_BLOCK, K8_MINB) k8_replay_kernel(const __gr
                     }
                 }
                 int rc = 0;
+                if (ev.kind == EV_IMU) {
+                    // speculation failed (the break tests did not come out as continue, continue, stop): the general
+                    // form below repeats the event from the backed-up P^-
+                    if (!k8_update_imu_fast(ms, xp, Pw, dx, st)) light = false;
+                }
                 if (light) {
-                    if (ev.kind == EV_IMU) k8_update_light<EV_IMU>(p.cfg, ms, dt, xp, Pw, dx, st);
+                    if (ev.kind == EV_IMU) { /* done above */ }
                     else if (ev.kind == EV_PX4) k8_update_light<EV_PX4>(p.cfg, ms, dt, xp, Pw, dx, st);
                     else k8_update_light<EV_MAG>(p.cfg, ms, dt, xp, Pw, dx, st);
                 } else {

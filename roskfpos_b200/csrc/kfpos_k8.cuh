@@ -383,4 +383,89 @@ KF_DEV void k8_update_light(const K8Cfg &cfg, const K8Meas &ms, double dt, const
     }
 }
 
+
+// ---- the IMU event (10 of the 12 / 15 events of a macro-step) as STRAIGHT-LINE code.  Every such event runs
+// three cost evaluations and two gain steps (measured 3.000 / 2.000); written as a loop, each evaluation ends a
+// basic block at its break test, so the covariance prediction cannot overlap the first evaluation's sincos chain
+// and the deferred covariance update cannot overlap the third evaluation.  Here the sequence
+//   eval0, gain1, eval1, gain2, [P <- update], eval2
+// is one block: the update is applied SPECULATIVELY after the second gain step (the caller has backed P^- up in
+// the filter's shared-memory column).  If the break tests do not come out as (continue, continue, stop) the
+// function returns false and the caller runs the event through k8_update from the backed-up P^- -- the general
+// form, same operations in the same order -- so results and counters are those of the loop form in every case.
+KF_DEV bool k8_update_imu_fast(const K8Meas &ms, const double (&xp)[8], Sym<8> &P, double (&dx)[8], StepStats &st) {
+    const double idet = 1.0 / (ms.imu_c00 * ms.imu_c11 - ms.imu_c01 * ms.imu_c01);
+    const double ii00 = ms.imu_c11 * idet, ii01 = -ms.imu_c01 * idet, ii11 = ms.imu_c00 * idet;
+    const double i_cw = 1.0 / ms.imu_cw;
+    const double la4 = ms.latch[4], la5 = ms.latch[5], la6 = ms.latch[6];
+    double v0[8], v1[8], v2[8], q00, q01, q11, q2, prior;
+    double sn, cs, e0, e1, e2;
+    auto eval = [&](const double(&d)[8]) { // imuOutput and cost at x^- + d (KF.cpp:451-469, 573-581)
+        const double ax = xp[4] + d[4], ay = xp[5] + d[5], th = xp[6] + d[6], om = xp[7] + d[7];
+        fast_sincos(th, &sn, &cs);
+        e0 = la4 - (cs * ax + sn * ay);
+        e1 = la5 - (-sn * ax + cs * ay);
+        e2 = la6 - om;
+        return 0.0 + (e0 * (ii00 * e0 + ii01 * e1) + e1 * (ii01 * e0 + ii11 * e1) + e2 * e2 * i_cw);
+    };
+    auto gain = [&](const double(&d)[8], double(&dn)[8]) { // the EV_IMU gain step of k8_update_light, operation for operation
+        const double ax = xp[4] + d[4], ay = xp[5] + d[5];
+        const double j06 = -sn * ax + cs * ay, j16 = -cs * ax - sn * ay;
+        const double y0 = e0 + (cs * d[4] + sn * d[5] + j06 * d[6]);
+        const double y1 = e1 + (-sn * d[4] + cs * d[5] + j16 * d[6]);
+        const double y2 = e2 + d[7];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            v0[i] = fma(P.get(i, 6), j06, fma(P.get(i, 5), sn, fma(P.get(i, 4), cs, 0.0)));
+            v1[i] = fma(P.get(i, 6), j16, fma(P.get(i, 5), cs, fma(P.get(i, 4), -sn, 0.0)));
+        }
+        const double s00 = fma(j06, v0[6], fma(sn, v0[5], fma(cs, v0[4], ms.imu_c00)));
+        const double s01 = fma(j06, v1[6], fma(sn, v1[5], fma(cs, v1[4], ms.imu_c01)));
+        const double s11 = fma(j16, v1[6], fma(cs, v1[5], fma(-sn, v1[4], ms.imu_c11)));
+        const double id = fast_rcp(s00 * s11 - s01 * s01);
+        q00 = s11 * id; q01 = -s01 * id; q11 = s00 * id;
+        const double g0 = q00 * y0 + q01 * y1, g1 = q01 * y0 + q11 * y1;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dn[i] = fma(v0[i], g0, fma(v1[i], g1, 0.0));
+        const double k07 = v0[7] * q00 + v1[7] * q01, k17 = v0[7] * q01 + v1[7] * q11;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v2[i] = fma(-k07, v0[i], fma(-k17, v1[i], P.get(7, i))) * 1.0;
+        const double s2 = fma(1.0, v2[7], ms.imu_cw), nu2 = fma(-1.0, dn[7], y2);
+        q2 = fast_rcp(s2);
+        const double g2 = nu2 * q2;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dn[i] = fma(v2[i], g2, dn[i]);
+        const double r0 = y0 - (cs * dn[4] + sn * dn[5] + j06 * dn[6]);
+        const double r1 = y1 - (-sn * dn[4] + cs * dn[5] + j16 * dn[6]);
+        const double u0 = ii00 * r0 + ii01 * r1, u1 = ii01 * r0 + ii11 * r1;
+        const double u2 = (y2 - dn[7]) * i_cw;
+        const double w4 = 0.0 + (cs * u0 - sn * u1), w5 = 0.0 + (sn * u0 + cs * u1);
+        const double w6 = 0.0 + (j06 * u0 + j16 * u1), w7 = 0.0 + u2;
+        prior = fma(w7, dn[7], fma(w6, dn[6], fma(w5, dn[5], fma(w4, dn[4], 0.0))));
+    };
+    const double z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double d1[8], d2[8];
+    const double c0 = eval(z) + 0.0;
+    const bool stop0 = rel_change_lt(1e20, c0, 1e-4);
+    gain(z, d1);
+    const double c1 = eval(d1) + prior;
+    const bool stop1 = rel_change_lt(c0, c1, 1e-4);
+    gain(d1, d2);
+    // the covariance update of the second gain step (k8_update_light's, entry for entry), before the third evaluation
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const double k0 = v0[i] * q00 + v1[i] * q01, k1 = v0[i] * q01 + v1[i] * q11, k2 = v2[i] * q2;
+#pragma unroll
+        for (int j = 0; j <= i; ++j) P.at(i, j) = fma(-k2, v2[j], fma(-k0, v0[j], fma(-k1, v1[j], P.at(i, j))));
+    }
+    const double c2 = eval(d2) + prior;
+    const bool stop2 = rel_change_lt(c1, c2, 1e-4);
+    if (stop0 || stop1 || !stop2) return false;
+    st.cost_evals += 3;
+    st.gain_evals += 2;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) dx[k] = d2[k];
+    return true;
+}
+
 } // namespace kfpos

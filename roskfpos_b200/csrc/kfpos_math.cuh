@@ -66,9 +66,18 @@ KF_DEV double fast_rsqrt(double x) {
 // (error ~ |k| 2^-110), then the fdlibm kernels on [-pi/4, pi/4] (< 1 ulp): ~27 FP64
 // instructions and a handful of selects instead of the ~200 instructions of the library
 // sincos with its Payne-Hanek branch; larger or non-finite arguments take the library path.
+// (the library path out of line: inlined, its Payne-Hanek reduction costs ~150 instructions and a stack frame at
+// every call site of a kernel whose code is already three times the instruction cache)
+static __device__ __noinline__ double2 library_sincos(double x) {
+    double s, c;
+    sincos(x, &s, &c);
+    return make_double2(s, c);
+}
 KF_DEV void fast_sincos(double x, double *sn, double *cs) {
     if (!(fabs(x) < 1.0e5)) {
-        sincos(x, sn, cs);
+        const double2 sc = library_sincos(x);
+        *sn = sc.x;
+        *cs = sc.y;
         return;
     }
     const double kd = rint(x * 0.63661977236758138243); // 2/pi

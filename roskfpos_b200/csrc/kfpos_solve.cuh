@@ -46,6 +46,10 @@ struct EpochT {
 
 // fabs(cost - newCost) / cost > 1e-3  (ML.cpp:67,165), bit-exact without the division
 // unless the quotient is within 1e-9 of the threshold.
+// (the division itself out of line: it is reached when the quotient is within 1e-9 of the threshold or the cost is
+// not positive, and inlined it costs ~40 instructions at each of a dozen call sites of kernels whose code is
+// several times the instruction cache)
+static __device__ __noinline__ double rel_change_quotient(double q, double cost) { return q / cost; }
 KF_DEV bool rel_change_gt(double cost, double newCost) {
     const double q = fabs(cost - newCost);
     if (cost > 0.0) {
@@ -53,7 +57,7 @@ KF_DEV bool rel_change_gt(double cost, double newCost) {
         if (q > t * 1.000000001) return true;
         if (q < t * 0.999999999) return false;
     }
-    return q / cost > 1e-3;
+    return rel_change_quotient(q, cost) > 1e-3;
 }
 // fabs(cost - newCost) / cost < tol  (TOA.cpp:307, KF.cpp:470, TOAIMU.cpp:312)
 KF_DEV bool rel_change_lt(double cost, double newCost, double tol) {
@@ -63,7 +67,7 @@ KF_DEV bool rel_change_lt(double cost, double newCost, double tol) {
         if (q < t * 0.999999999) return true;
         if (q > t * 1.000000001) return false;
     }
-    return q / cost < tol;
+    return rel_change_quotient(q, cost) < tol;
 }
 
 // Exact shortcut for Newton iterations that never meet the stop test.  The iteration is a
