@@ -50,6 +50,8 @@ struct EpochT {
 // not positive, and inlined it costs ~40 instructions at each of a dozen call sites of kernels whose code is
 // several times the instruction cache)
 static __device__ __noinline__ double rel_change_quotient(double q, double cost) { return q / cost; }
+// (likewise the counters of rare events inside the replay loops)
+static __device__ __noinline__ void count_rare_event(unsigned long long *c) { atomicAdd(c, 1ull); }
 KF_DEV bool rel_change_gt(double cost, double newCost) {
     const double q = fabs(cost - newCost);
     if (cost > 0.0) {
@@ -345,10 +347,10 @@ KF_DEV int ml_solve3_ekf(const AnchorTable &A, const EpochT<false, MT> &ep, unsi
         } else if (p[0] == cyc_ref[0] && p[1] == cyc_ref[1] && p[2] == cyc_ref[2]) {
             const unsigned per = iter - (1u << (31 - __clz(iter)));
             iter = 10000u - (10000u - iter) % per;
-            if (cnt) atomicAdd(cnt + CNT_ML_CYCLES, 1ull);
+            if (cnt) count_rare_event(cnt + CNT_ML_CYCLES);
         }
     }
-    if (cnt && iter >= 10000u) atomicAdd(cnt + CNT_ML_CAPPED, 1ull);
+    if (cnt && iter >= 10000u) count_rare_event(cnt + CNT_ML_CAPPED);
     iters += iter;
     sse_out = ps.sse;
     return ML_OK;

@@ -29,9 +29,13 @@ __host__ __device__ inline int t6_smem_rows(int m, int fmt, bool pme, bool in_re
 // largest residual at its solution (ML.cpp:307-347), variant 2 keeps the 4-anchor group with the
 // smallest covariance criterion (ML.cpp:351-414, bestMode) -- and the iterated update runs on the
 // survivors.  The mask of the slots used goes to `sel`.
-template <bool PME, bool LOO, int MT, bool SEL = false>
+// FMT: the wire format as a compile-time constant (the tuned instantiation: the per-epoch prefetch / conversion code of
+// the other two formats -- a third of the replay loop's 2300 instructions, against a 32 KB instruction cache -- is
+// not generated); -1 = read from the parameters.
+template <bool PME, bool LOO, int MT, bool SEL = false, int FMT = -1>
 __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __grid_constant__ T6Params p) {
     extern __shared__ double smem[];
+    const int fmt = FMT >= 0 ? FMT : p.rs.fmt;
     const int64_t f = (int64_t)blockIdx.x * T6_BLOCK + threadIdx.x;
     const bool active = f < p.N;
     const unsigned wmask = __ballot_sync(0xffffffffu, active);
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
         ep.e0 = p.rs.err_scalar;
         ep.m_slots = m;
         // landing zone of the cp.async prefetch of the next epoch
-        const RawCol raw = make_raw(smem + (size_t)row * T6_BLOCK, p.rs.fmt, threadIdx.x, T6_BLOCK);
+        const RawCol raw = make_raw(smem + (size_t)row * T6_BLOCK, fmt, threadIdx.x, T6_BLOCK);
 
         double pos[3];
 #pragma unroll
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
         for (int k = 0; k < Sym<6>::SZ; ++k) Pm[k] = p.P[(int64_t)k * N + f];
         unsigned status_or = 0;
 
-        prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, f, N);
+        prefetch_epoch(raw, m, p.rs.ranges, fmt, f, N);
         double dt_next = p.dt_f ? __ldg(p.dt_f + f) : 0.0;
         for (int t = 0; t < p.T; ++t) {
             // per-filter time steps (assembled logs): a negative dt = this filter has no epoch t.
@@ -78,7 +82,7 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
             const unsigned emask = p.dt_f ? __ballot_sync(wmask, stepping) : wmask;
             if (!stepping) { // keep the landing zone protocol going, touch nothing else
                 cp_async_wait_all();
-                if (t + 1 < p.T) prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, (int64_t)(t + 1) * m * N + f, N);
+                if (t + 1 < p.T) prefetch_epoch(raw, m, p.rs.ranges, fmt, (int64_t)(t + 1) * m * N + f, N);
                 if (p.traj) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k) p.traj[((int64_t)t * 3 + k) * N + f] = pos[k];
@@ -100,8 +104,8 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
             }
             // ---- this epoch's rangings (landed during the previous epoch); start the next fetch
             cp_async_wait_all();
-            convert_epoch<PME, MT>(ep, raw, p.rs.ranges, p.rs.fmt, p.rs.err, (int64_t)t * m * N + f, N);
-            if (t + 1 < p.T) prefetch_epoch(raw, m, p.rs.ranges, p.rs.fmt, (int64_t)(t + 1) * m * N + f, N);
+            convert_epoch<PME, MT>(ep, raw, p.rs.ranges, fmt, p.rs.err, (int64_t)t * m * N + f, N);
+            if (t + 1 < p.T) prefetch_epoch(raw, m, p.rs.ranges, fmt, (int64_t)(t + 1) * m * N + f, N);
 
             st.status = 0u;
             if (ep.valid == 0u) st.status |= 1u;
@@ -202,15 +206,24 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
     if (p.truth) block_stats_partial(errv, smem, p.partials + (int64_t)blockIdx.x * 4);
 }
 
-template <bool PME, bool LOO, int MT, bool SEL = false>
+template <bool PME, bool LOO, int MT, bool SEL = false, int FMT = -1>
 static cudaError_t launch_k(const T6Params &p, cudaStream_t s) {
     const unsigned grid = (unsigned)((p.N + T6_BLOCK - 1) / T6_BLOCK);
     const size_t smem = (size_t)t6_smem_rows(p.rs.m_slots, p.rs.fmt, PME, MT > 0) * T6_BLOCK * sizeof(double);
-    cudaError_t e = cudaFuncSetAttribute(t6_replay_kernel<PME, LOO, MT, SEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(t6_replay_kernel<PME, LOO, MT, SEL, FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)smem);
     if (e != cudaSuccess) return e;
-    t6_replay_kernel<PME, LOO, MT, SEL><<<grid, T6_BLOCK, smem, s>>>(p);
+    t6_replay_kernel<PME, LOO, MT, SEL, FMT><<<grid, T6_BLOCK, smem, s>>>(p);
     return cudaGetLastError();
+}
+// the plain replay with a compile-time anchor count: one instantiation per wire format
+template <int MT>
+static cudaError_t launch_tuned(const T6Params &p, cudaStream_t s) {
+    switch (p.rs.fmt) {
+    case 1: return launch_k<false, false, MT, false, 1>(p, s);
+    case 2: return launch_k<false, false, MT, false, 2>(p, s);
+    default: return launch_k<false, false, MT, false, 0>(p, s);
+    }
 }
 
 cudaError_t launch_t6_replay(const T6Params &p, cudaStream_t s) {
@@ -229,8 +242,8 @@ cudaError_t launch_t6_replay(const T6Params &p, cudaStream_t s) {
     }
     if (pme) return launch_k<true, false, 0>(p, s);
     if (m == 4) return launch_k<false, false, 4>(p, s);
-    if (m == 8) return launch_k<false, false, 8>(p, s);
-    if (m == 16) return launch_k<false, false, 16>(p, s);
+    if (m == 8) return launch_tuned<8>(p, s);
+    if (m == 16) return launch_tuned<16>(p, s);
     return launch_k<false, false, 0>(p, s);
 }
 
