@@ -316,6 +316,9 @@ def run_b200(args):
     sampler.start()  # every rank watches its own GPU
     for _ in range(W):
         step_resident()
+    # the warm-up includes the job's collective: the first call on a fresh NCCL communicator sets up its
+    # connections (6-140 ms from box to box), which is not part of a step
+    batch.stats_allreduce(comm, stream=stream)
     batch.counters(reset=True)
     barrier()
     t_start = time.perf_counter()
