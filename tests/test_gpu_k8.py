@@ -208,3 +208,37 @@ def test_k8_checkpoint_with_latches(kflib):
     assert np.array_equal(x2, x_ref)
     # the covariance crosses the ABI as a full matrix and is packed again: symmetric, so nothing is lost
     assert np.array_equal(P2, P_ref)
+
+
+def test_k8_imu_event_break_patterns(kflib, oracle):
+    """The IMU event runs as straight-line code that assumes the break tests come out as (continue, continue, stop)
+    and repeats the event in the general form otherwise.  Filters whose IMU sample equals the predicted output
+    exactly (zero cost: the relative-change quotient is 0 / 0, the loop runs to its 20-iteration cap) and filters
+    with gross outliers take that other path: state, covariance, status and the iteration counters must be the
+    oracle's either way."""
+    N = 4096
+    anc = synth.anchors_for(8)
+    w = synth.k8_workload(N, 3, anc, seed=91, full=False)
+    sens = w["sensors"].copy()
+    first = True
+    for (kind, dt, off, aux) in w["events"]:
+        if kind != synth.EV_IMU:
+            continue
+        if first:  # first IMU event: omega is still x0's, the predicted accelerations are 0
+            sens[off, 0::4] = w["x0"][7, 0::4]
+            sens[off + 1, 0::4] = 0.0
+            sens[off + 2, 0::4] = 0.0
+            first = False
+        else:  # later ones: gross outliers for another quarter of the filters
+            sens[off, 1::4] += 50.0
+            sens[off + 1, 1::4] -= 80.0
+    w2 = dict(w, sensors=sens)
+    ref = oracle_k8(oracle, w2, anc)
+    got = gpu_k8(kflib, w2, anc)
+    assert ref["counters"][1] != 3 * ref["counters"][4] or ref["counters"][2] != 2 * ref["counters"][4], \
+        "every event still runs 3 cost evaluations and 2 gain steps: the workload does not leave the fast path"
+    assert rel_err_state(got["x"], ref["x"]) < REL_TOL
+    assert rel_err_cov(got["P"], ref["P"]) < REL_TOL
+    c = got["counters"]
+    assert [c["updates"], c["ml_iters"], c["cost_evals"], c["gain_evals"]] == [ref["counters"][4], *ref["counters"][:3]]
+    assert np.array_equal(got["status"], ref["status"])
