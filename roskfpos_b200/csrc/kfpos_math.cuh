@@ -61,6 +61,17 @@ KF_DEV double fast_rsqrt(double x) {
     return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
+// 1/sqrt(x) for an unrolled anchor slot that may hold no ranging: `on` false seeds the refinement with rsqrt(+inf) = 0,
+// and every term of the correction is a multiple of the seed, so the result is exactly 0 -- one 32-bit select on the
+// operand's high word (all the MUFU unit reads) instead of two on the 64-bit result.
+KF_DEV double fast_rsqrt_masked(double x, bool on) {
+    const double xs = __hiloint2double(on ? __double2hiint(x) : 0x7ff00000, __double2loint(x));
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(xs));
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
+}
+
 // sin and cos together for the angles of this path (heading, omega * dt: a few radians).
 // |x| < 1e5: quadrant k = rint(x 2/pi), Cody-Waite reduction with a three-part pi/2 in FMAs
 // (error ~ |k| 2^-110), then the fdlibm kernels on [-pi/4, pi/4] (< 1 ulp): ~27 FP64

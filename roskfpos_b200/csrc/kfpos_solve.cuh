@@ -109,12 +109,9 @@ KF_DEV void ml_pass3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
         if (MT == 0 && !on) continue;
         const double dx = A.x[i] - p[0], dy = A.y[i] - p[1], dz = A.z[i] - p[2];
         const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        double invd = fast_rsqrt(d2);
+        double invd = MT > 0 ? fast_rsqrt_masked(d2, on) : fast_rsqrt(d2); // a missing ranging contributes exact zeros
         double r = ep.r(i);
-        if (MT > 0) { // a missing ranging contributes exact zeros
-            invd = on ? invd : 0.0;
-            r = on ? r : 0.0;
-        }
+        if (MT > 0) r = on ? r : 0.0;
         const double res = fma(-d2, invd, r);
         const double rid = r * invd;
         if (PME) {
@@ -373,12 +370,9 @@ KF_DEV void ml_pass2(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
         if (MT == 0 && !on) continue;
         const double dx = A.x[i] - px, dy = A.y[i] - py, dz = A.z[i] - pz;
         const double d2 = fma(dz, dz, fma(dy, dy, dx * dx));
-        double invd = fast_rsqrt(d2);
+        double invd = MT > 0 ? fast_rsqrt_masked(d2, on) : fast_rsqrt(d2);
         double r = ep.r(i);
-        if (MT > 0) {
-            invd = on ? invd : 0.0;
-            r = on ? r : 0.0;
-        }
+        if (MT > 0) r = on ? r : 0.0;
         const double res = fma(-d2, invd, r);
         const double rid = r * invd;
         sse = fma(res, res, sse);
@@ -594,12 +588,9 @@ KF_DEV void iekf_pass(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned 
         if (MT == 0 && !on) continue;
         const double ex = px - A.x[i], ey = py - A.y[i], ez = pz - A.z[i];
         const double d2 = fma(ez, ez, fma(ey, ey, ex * ex));
-        double id = fast_rsqrt(d2);
+        double id = MT > 0 ? fast_rsqrt_masked(d2, on) : fast_rsqrt(d2);
         double r = ep.r(i);
-        if (MT > 0) {
-            id = on ? id : 0.0;
-            r = on ? r : 0.0;
-        }
+        if (MT > 0) r = on ? r : 0.0;
         const double e = fma(-d2, id, r);
         const double h0 = ex * id, h1 = ey * id, h2 = D == 3 ? ez * id : 0.0;
         // b = sum h (eps + h . dx) / R = sum h eps / R + G dx: the second term is added after the loop
