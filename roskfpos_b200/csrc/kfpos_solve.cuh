@@ -52,6 +52,8 @@ struct EpochT {
 static __device__ __noinline__ double rel_change_quotient(double q, double cost) { return q / cost; }
 // (likewise the counters of rare events inside the replay loops)
 static __device__ __noinline__ void count_rare_event(unsigned long long *c) { atomicAdd(c, 1ull); }
+// (and the jump over whole periods when Brent's cycle detection fires: an integer modulo)
+static __device__ __noinline__ unsigned skip_whole_periods(unsigned iter, unsigned per) { return 10000u - (10000u - iter) % per; }
 KF_DEV bool rel_change_gt(double cost, double newCost) {
     const double q = fabs(cost - newCost);
     if (cost > 0.0) {
@@ -301,7 +303,7 @@ KF_DEV int ml_solve3(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
                 c[0] = p[0]; c[1] = p[1]; c[2] = p[2];
             } else if (p[0] == c[0] && p[1] == c[1] && p[2] == c[2]) {
                 const unsigned per = iter - (1u << (31 - __clz(iter)));
-                iter = 10000u - (10000u - iter) % per;
+                iter = skip_whole_periods(iter, per);
             }
         }
     }
@@ -343,7 +345,7 @@ KF_DEV int ml_solve3_ekf(const AnchorTable &A, const EpochT<false, MT> &ep, unsi
             cyc_ref[0] = p[0]; cyc_ref[1] = p[1]; cyc_ref[2] = p[2];
         } else if (p[0] == cyc_ref[0] && p[1] == cyc_ref[1] && p[2] == cyc_ref[2]) {
             const unsigned per = iter - (1u << (31 - __clz(iter)));
-            iter = 10000u - (10000u - iter) % per;
+            iter = skip_whole_periods(iter, per);
             if (cnt) count_rare_event(cnt + CNT_ML_CYCLES);
         }
     }

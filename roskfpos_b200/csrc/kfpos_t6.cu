@@ -36,6 +36,8 @@ template <bool PME, bool LOO, int MT, bool SEL = false, int FMT = -1>
 __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __grid_constant__ T6Params p) {
     extern __shared__ double smem[];
     const int fmt = FMT >= 0 ? FMT : p.rs.fmt;
+    // per-filter time steps (assembled logs of different length) only in the FMT = -1 instantiations: the launcher routes them there
+    const double *dt_f = FMT >= 0 ? nullptr : p.dt_f;
     const int64_t f = (int64_t)blockIdx.x * T6_BLOCK + threadIdx.x;
     const bool active = f < p.N;
     const unsigned wmask = __ballot_sync(0xffffffffu, active);
@@ -72,14 +74,14 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
         unsigned status_or = 0;
 
         prefetch_epoch(raw, m, p.rs.ranges, fmt, f, N);
-        double dt_next = p.dt_f ? __ldg(p.dt_f + f) : 0.0;
+        double dt_next = dt_f ? __ldg(dt_f + f) : 0.0;
         for (int t = 0; t < p.T; ++t) {
             // per-filter time steps (assembled logs): a negative dt = this filter has no epoch t.
             // The lanes that do step are the ones that re-converge below.
-            const double dt = p.dt_f ? dt_next : __ldg(p.dt + t);
-            if (p.dt_f && t + 1 < p.T) dt_next = __ldg(p.dt_f + (int64_t)(t + 1) * N + f);
-            const bool stepping = !(dt < 0.0);
-            const unsigned emask = p.dt_f ? __ballot_sync(wmask, stepping) : wmask;
+            const double dt = dt_f ? dt_next : __ldg(p.dt + t);
+            if (dt_f && t + 1 < p.T) dt_next = __ldg(dt_f + (int64_t)(t + 1) * N + f);
+            const bool stepping = !dt_f || !(dt < 0.0);
+            const unsigned emask = dt_f ? __ballot_sync(wmask, stepping) : wmask;
             if (!stepping) { // keep the landing zone protocol going, touch nothing else
                 cp_async_wait_all();
                 if (t + 1 < p.T) prefetch_epoch(raw, m, p.rs.ranges, fmt, (int64_t)(t + 1) * m * N + f, N);
@@ -219,6 +221,7 @@ static cudaError_t launch_k(const T6Params &p, cudaStream_t s) {
 // the plain replay with a compile-time anchor count: one instantiation per wire format
 template <int MT>
 static cudaError_t launch_tuned(const T6Params &p, cudaStream_t s) {
+    if (p.dt_f != nullptr) return launch_k<false, false, MT>(p, s); // per-filter time steps
     switch (p.rs.fmt) {
     case 1: return launch_k<false, false, MT, false, 1>(p, s);
     case 2: return launch_k<false, false, MT, false, 2>(p, s);
