@@ -106,9 +106,21 @@ KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
 #pragma unroll
             for (int k = 0; k < 6; ++k) G[k] = Gu_xp[k];
         } else {
+#ifndef T6_NO_COST_FIRST
+            if constexpr (!PME && MT > 0) {
+                if (iter >= 2) { // the evaluation that usually ends the loop: the cost alone first (iekf_cost_only)
+                    const double c2 = iekf_cost_only<MT>(A, ep, mask, xp[0] + dx[0], xp[1] + dx[1], xp[2] + dx[2]);
+                    if (rel_change_lt(cost, fma(c2, invR0, prior), 1e-3)) {
+                        st.cost_evals += 1;
+                        broke = true;
+                        break;
+                    }
+                }
+            }
+#endif
             iekf_pass<PME, MT, 3>(A, ep, mask, sse, xp[0] + dx[0], xp[1] + dx[1], xp[2] + dx[2], dx, c, b, G);
         }
-        const double newCost = (PME ? c : c * invR0) + prior;
+        const double newCost = PME ? c + prior : fma(c, invR0, prior);
         st.cost_evals += 1;
         if (rel_change_lt(cost, newCost, 1e-3)) { broke = true; break; }
         cost = newCost;
