@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(T6_BLOCK, T6_MINB) t6_replay_kernel(const __gr
                 rc = t6_update<PME, MT>(p.anchors, ep, used, pos, Pm, res, st, 0u, &cyc);
                 ignored = (int)used;
             } else if (!LOO) {
-                rc = t6_update<PME, MT>(p.anchors, ep, ep.valid, pos, Pm, res, st, emask, &cyc, p.counters);
+                rc = t6_update<PME, MT, !LOO>(p.anchors, ep, ep.valid, pos, Pm, res, st, emask, &cyc, p.counters);
                 __syncwarp(emask);
             } else {
                 // kalmanStep3DCanIgnoreAnAnchor (TOA.cpp:185-238): the all-anchor solve (i = -1),

@@ -59,7 +59,8 @@ struct T6Result {
 // wmask != 0: the lanes in wmask all call this function together; they are re-converged
 // after the Newton loop (whose trip count differs per lane) so that the IEKF loop is issued
 // once per warp and not once per group of lanes that left the Newton loop together.
-template <bool PME, int MT>
+// COSTFIRST: the evaluations that usually end the Newton and the IEKF loop form the cost alone first (plain replay only)
+template <bool PME, int MT, bool COSTFIRST = false>
 KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned mask, const double (&xp)[3],
                      const Col &Pm, T6Result &out, StepStats &st, unsigned wmask = 0u, const Col *cyc_ref = nullptr,
                      unsigned long long *cnt = nullptr) {
@@ -71,7 +72,7 @@ KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
     double g_xp[3] = {0.0, 0.0, 0.0}, Gu_xp[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     int rc;
     if constexpr (PME) rc = ml_solve3<PME, MT>(A, ep, mask, pml, sse, st.ml_iters, nullptr, &sse_xp, 10000u, nullptr, cyc_ref);
-    else rc = ml_solve3_ekf<MT>(A, ep, mask, pml, sse, st.ml_iters, sse_xp, g_xp, Gu_xp, *cyc_ref, cnt);
+    else rc = ml_solve3_ekf<MT, COSTFIRST>(A, ep, mask, pml, sse, st.ml_iters, sse_xp, g_xp, Gu_xp, *cyc_ref, cnt);
     if (wmask) __syncwarp(wmask);
     if (rc == ML_FEW) st.status |= 2u;
     if (rc == ML_SINGULAR) return ML_SINGULAR;
@@ -106,8 +107,7 @@ KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
 #pragma unroll
             for (int k = 0; k < 6; ++k) G[k] = Gu_xp[k];
         } else {
-#ifndef T6_NO_COST_FIRST
-            if constexpr (!PME && MT > 0) {
+            if constexpr (COSTFIRST && !PME && MT > 0) {
                 if (iter >= 2) { // the evaluation that usually ends the loop: the cost alone first (iekf_cost_only)
                     const double c2 = iekf_cost_only<MT>(A, ep, mask, xp[0] + dx[0], xp[1] + dx[1], xp[2] + dx[2]);
                     if (rel_change_lt(cost, fma(c2, invR0, prior), 1e-3)) {
@@ -117,7 +117,6 @@ KF_DEV int t6_update(const AnchorTable &A, const EpochT<PME, MT> &ep, unsigned m
                     }
                 }
             }
-#endif
             iekf_pass<PME, MT, 3>(A, ep, mask, sse, xp[0] + dx[0], xp[1] + dx[1], xp[2] + dx[2], dx, c, b, G);
         }
         const double newCost = PME ? c + prior : fma(c, invR0, prior);
