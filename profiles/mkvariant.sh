@@ -1,7 +1,9 @@
 #!/bin/bash
-# usage: build/mkvariant.sh NAME file.cu "-DX=1 ..."   -> build/variants/libNAME.so (other objects reused from csrc/)
+# usage: profiles/mkvariant.sh NAME file.cu "-DX=1 ..."   -> build/variants/libNAME.so (other objects reused from csrc/)
 set -e
-cd $(git rev-parse --show-toplevel)/roskfpos_b200/csrc
+ROOT=$(git rev-parse --show-toplevel)
+mkdir -p "$ROOT/build/variants"
+cd "$ROOT/roskfpos_b200/csrc"
 NAME=$1; SRC=$2; DEFS=$3
 FMAD=--fmad=true; [ "$SRC" = kfpos_exact.cu ] && FMAD=--fmad=false
 /usr/local/cuda/bin/nvcc -O3 -std=c++17 -lineinfo -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC $FMAD $DEFS -c $SRC -o /tmp/var_$NAME.o
