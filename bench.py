@@ -451,7 +451,7 @@ def run_b200(args):
                              "of the committed ncu capture / updates of that launch, times this run's update rate",
             "algorithmic_bytes": alg_bytes,
             "peak_source": "measured live: kfpos_measure_fp64_peak (DFMA-only kernel, best of 5)",
-            "kernel": "t6_replay_kernel<8,false,false>", "kernel_ms": kernel_ms,
+            "kernel": "t6_replay_kernel<PME=0,LOO=0,MT=8,SEL=0,FMT=1 (int32 mm)>", "kernel_ms": kernel_ms,
             "flop_per_update": w_alg, "mean_iters": {"ml": i_ml, "cost": i_c, "gain": i_g},
             "flop_per_update_v2": w_alg_t6_v2(M, i_ml, i_c, i_g),
             "frac_v2": w_alg_t6_v2(M, i_ml, i_c, i_g) * N * T / (kernel_ms * 1e-3) / peak if peak else None,
